@@ -1,0 +1,278 @@
+"""deltapq_b200 -- thin ctypes binding over libdpq.so (the C ABI in include/dpq.h).
+
+This is plumbing for tests and bench.py, not the product: the product is the CUDA library
+and the C++ command-line tools built from deltapq_b200/csrc.  There is no CPU fallback; if
+libdpq.so is missing or no GPU is visible the calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdpq.so")
+
+# every symbol include/dpq.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "dpq_version", "dpq_last_error", "dpq_device_count", "dpq_set_device",
+    "dpq_index_open", "dpq_index_open_file", "dpq_index_set_codebook", "dpq_index_set_option",
+    "dpq_index_search", "dpq_index_search_device", "dpq_index_sync", "dpq_merge_topk_device",
+    "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",
+    "dpq_free_host", "dpq_index_stat", "dpq_index_close", "dpq_adc_tables", "dpq_encode",
+    "dpq_find_edges", "dpq_edge_diffs", "dpq_groundtruth_begin", "dpq_groundtruth_chunk",
+    "dpq_groundtruth_finish", "dpq_program_compile", "dpq_program_size", "dpq_program_copy",
+    "dpq_program_free",
+]
+
+
+class DpqError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libdpq.so in tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise DpqError("building libdpq.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DpqError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    L.dpq_last_error.restype = C.c_char_p
+    L.dpq_index_open.argtypes = [vp, i64, i64, i32, i32, vp, i32, i32, C.POINTER(vp)]
+    L.dpq_index_open_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(vp)]
+    L.dpq_index_set_codebook.argtypes = [vp, vp, i32]
+    L.dpq_index_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.dpq_index_search.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.dpq_index_search_device.argtypes = [vp, vp, i32, i32, vp]
+    L.dpq_index_sync.argtypes = [vp]
+    L.dpq_merge_topk_device.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.dpq_malloc.argtypes = [C.POINTER(vp), sz]
+    L.dpq_free.argtypes = [vp]
+    L.dpq_memcpy_h2d.argtypes = [vp, vp, sz]
+    L.dpq_memcpy_d2h.argtypes = [vp, vp, sz]
+    L.dpq_malloc_host.argtypes = [C.POINTER(vp), sz]
+    L.dpq_free_host.argtypes = [vp]
+    L.dpq_index_stat.restype = i64
+    L.dpq_index_stat.argtypes = [vp, C.c_char_p]
+    L.dpq_index_close.argtypes = [vp]
+    L.dpq_index_close.restype = None
+    L.dpq_adc_tables.argtypes = [vp, i32, i32, i32, vp, i32, vp]
+    L.dpq_encode.argtypes = [vp, i32, i32, i32, vp, i64, i32, vp]
+    L.dpq_find_edges.argtypes = [vp, i64, i32, i32, i32, i32, vp, C.POINTER(C.c_uint32)]
+    L.dpq_edge_diffs.argtypes = [vp, i64, i32, vp, i64, vp, C.POINTER(i64)]
+    L.dpq_groundtruth_begin.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    L.dpq_groundtruth_chunk.argtypes = [vp, vp, i64, i64]
+    L.dpq_groundtruth_finish.argtypes = [vp, vp, vp]
+    L.dpq_program_compile.argtypes = [vp, i64, i64, i32, i32, i32, i32, i32, C.POINTER(vp)]
+    L.dpq_program_size.restype = i64
+    L.dpq_program_size.argtypes = [vp, C.c_char_p]
+    L.dpq_program_copy.argtypes = [vp, C.c_char_p, vp]
+    L.dpq_program_free.argtypes = [vp]
+    L.dpq_program_free.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise DpqError(f"libdpq error {rc}: {lib().dpq_last_error().decode()}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return lib().dpq_device_count()
+
+
+def set_device(dev):
+    _check(lib().dpq_set_device(dev))
+
+
+class DeviceBuffer:
+    """Raw device allocation through the C ABI (no torch / cuda-python needed)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        self.nbytes = nbytes
+        _check(lib().dpq_malloc(C.byref(self.ptr), max(nbytes, 16)))
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _check(lib().dpq_memcpy_h2d(self.ptr, _ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, dtype, shape):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        _check(lib().dpq_memcpy_d2h(_ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().dpq_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def unpack_keys(keys):
+    """uint64 keys (float bits << 32 | pos) -> (pos uint32, dist float32)."""
+    keys = np.asarray(keys, np.uint64)
+    pos = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    dist = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    return pos, dist
+
+
+class DeltaTreeIndex:
+    """Host mirror of the reference's query entry points (DCAT.h:2805 / :3731): open a
+    compressed DeltaTree, set the codebook, search batches of queries."""
+
+    def __init__(self, payload, n_codes, M, K, pos2id=None, rank=0, n_ranks=1):
+        payload = np.ascontiguousarray(payload, np.uint8)
+        self.M, self.K = M, K
+        self._h = C.c_void_p()
+        p2i = None
+        if pos2id is not None:
+            self._p2i = np.ascontiguousarray(pos2id, np.uint32)
+            p2i = _ptr(self._p2i)
+        _check(lib().dpq_index_open(_ptr(payload), payload.nbytes, n_codes, M, K, p2i, rank, n_ranks,
+                                    C.byref(self._h)))
+        self.Ds = None
+
+    @classmethod
+    def from_file(cls, tree_path, M, K, qnode_path=None, rank=0, n_ranks=1):
+        self = cls.__new__(cls)
+        self.M, self.K = M, K
+        self._h = C.c_void_p()
+        _check(lib().dpq_index_open_file(tree_path.encode(), qnode_path.encode() if qnode_path else None,
+                                         M, K, rank, n_ranks, C.byref(self._h)))
+        self.Ds = None
+        return self
+
+    def set_codebook(self, cw):
+        cw = np.ascontiguousarray(cw, np.float32)
+        assert cw.shape[0] == self.M and cw.shape[1] == self.K
+        self.Ds = cw.shape[2]
+        _check(lib().dpq_index_set_codebook(self._h, _ptr(cw), self.Ds))
+
+    def set_option(self, name, value):
+        _check(lib().dpq_index_set_option(self._h, name.encode(), int(value)))
+
+    def stat(self, name):
+        return int(lib().dpq_index_stat(self._h, name.encode()))
+
+    def search(self, queries, topk):
+        """Host buffers in, host buffers out: (pos [Q][k], id [Q][k], dist [Q][k])."""
+        q = np.ascontiguousarray(queries, np.float32)
+        Q = q.shape[0]
+        pos = np.empty((Q, topk), np.uint32)
+        ids = np.empty((Q, topk), np.uint32)
+        dist = np.empty((Q, topk), np.float32)
+        _check(lib().dpq_index_search(self._h, _ptr(q), Q, topk, _ptr(pos), _ptr(ids), _ptr(dist)))
+        return pos, ids, dist
+
+    def search_device(self, d_queries_ptr, Q, topk, d_out_ptr):
+        _check(lib().dpq_index_search_device(self._h, d_queries_ptr, Q, topk, d_out_ptr))
+
+    def merge_device(self, d_keys_ptr, n_lists, Q, topk, d_out_ptr):
+        _check(lib().dpq_merge_topk_device(self._h, d_keys_ptr, n_lists, Q, topk, d_out_ptr))
+
+    def sync(self):
+        _check(lib().dpq_index_sync(self._h))
+
+    def close(self):
+        if self._h:
+            lib().dpq_index_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def adc_tables(cw, queries):
+    cw = np.ascontiguousarray(cw, np.float32)
+    q = np.ascontiguousarray(queries, np.float32)
+    M, K, Ds = cw.shape
+    out = np.empty((q.shape[0], M, K), np.float32)
+    _check(lib().dpq_adc_tables(_ptr(cw), M, K, Ds, _ptr(q), q.shape[0], _ptr(out)))
+    return out
+
+
+def encode(cw, x):
+    cw = np.ascontiguousarray(cw, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    M, K, Ds = cw.shape
+    codes = np.empty((x.shape[0], M), np.uint8)
+    _check(lib().dpq_encode(_ptr(cw), M, K, Ds, _ptr(x), x.shape[0], x.shape[1], _ptr(codes)))
+    return codes
+
+
+def find_edges(codes, K=256, h=1, method=1):
+    codes = np.ascontiguousarray(codes, np.uint8)
+    n, M = codes.shape
+    edges = np.zeros((max(n - 1, 1), 2), np.uint32)
+    root = C.c_uint32(0)
+    _check(lib().dpq_find_edges(_ptr(codes), n, M, K, h, method, _ptr(edges), C.byref(root)))
+    return edges[: n - 1], int(root.value)
+
+
+def edge_diffs(codes, edges):
+    codes = np.ascontiguousarray(codes, np.uint8)
+    edges = np.ascontiguousarray(edges, np.uint32)
+    bm = np.empty(edges.shape[0], np.uint32)
+    nd = C.c_int64(0)
+    _check(lib().dpq_edge_diffs(_ptr(codes), codes.shape[0], codes.shape[1], _ptr(edges), edges.shape[0],
+                                _ptr(bm), C.byref(nd)))
+    return bm, int(nd.value)
+
+
+def groundtruth(base, queries, topk, chunk=100000):
+    base = np.ascontiguousarray(base, np.float32)
+    q = np.ascontiguousarray(queries, np.float32)
+    st = C.c_void_p()
+    _check(lib().dpq_groundtruth_begin(_ptr(q), q.shape[0], q.shape[1], topk, C.byref(st)))
+    for s in range(0, base.shape[0], chunk):
+        blk = base[s:s + chunk]
+        _check(lib().dpq_groundtruth_chunk(st, _ptr(blk), blk.shape[0], s))
+    ids = np.empty((q.shape[0], topk), np.uint32)
+    dist = np.empty((q.shape[0], topk), np.float32)
+    _check(lib().dpq_groundtruth_finish(st, _ptr(ids), _ptr(dist)))
+    return ids, dist
+
+
+def compile_program(payload, n_codes, M, K, rank=0, n_ranks=1, chunk_nodes=256):
+    """Host-only: the device scan program of one shard as numpy arrays (for tests)."""
+    payload = np.ascontiguousarray(payload, np.uint8)
+    h = C.c_void_p()
+    _check(lib().dpq_program_compile(_ptr(payload), payload.nbytes, n_codes, M, K, rank, n_ranks,
+                                     chunk_nodes, C.byref(h)))
+    try:
+        out = {}
+        for name, dt in (("ops", np.uint32), ("chunks", np.uint32), ("anc", np.uint8), ("codes", np.uint8)):
+            nb = lib().dpq_program_size(h, name.encode())
+            arr = np.empty(nb // np.dtype(dt).itemsize, dt)
+            if nb:
+                _check(lib().dpq_program_copy(h, name.encode(), _ptr(arr)))
+            out[name] = arr
+        for name in ("n_local", "base_pos", "rb", "levels", "n_bytes", "n_diffs", "n_chunks"):
+            out[name] = int(lib().dpq_program_size(h, name.encode()))
+        out["chunks"] = out["chunks"].reshape(-1, 4)
+        out["codes"] = out["codes"].reshape(-1, M)
+        out["anc"] = out["anc"].reshape(-1, out["levels"], M)
+        return out
+    finally:
+        lib().dpq_program_free(h)

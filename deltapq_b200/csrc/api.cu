@@ -1,0 +1,534 @@
+// C ABI of libdpq.so (include/dpq.h): handle management, buffer plumbing, kernel sequencing.
+// No compute happens on the host here; without a usable CUDA device every entry point
+// fails with DPQ_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dpq.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = 0;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int check_device();
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(DPQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return DPQ_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(DPQ_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return DPQ_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+}  // namespace
+
+struct dpq_index {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // total begin, scan begin, scan end, total end
+    dpq::ScanProgram prog;  // host copy (ops/codes released after upload)
+    int Ds = 0;
+    // device-resident tree
+    DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw;
+    int n_chunks = 0;
+    size_t ops_bytes = 0;
+    bool has_pos2id = false;
+    std::vector<uint32_t> pos2id_host;  // local slice
+    // options
+    int opt_slices = 0, opt_pack = 1, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
+    int chunk_nodes = 256;
+    // scratch
+    DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_fbuf,
+        d_fcnt, d_key;
+    void* h_stage = nullptr;  // pinned staging for the host-buffer path
+    size_t h_stage_cap = 0;
+    // stats
+    int last_launches = 0;
+    int64_t last_fallback = 0;
+    bool timing_valid = false;
+};
+
+namespace {
+
+int choose_geometry(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
+    const dpq::ScanProgram& P = ix->prog;
+    g->M = P.M;
+    g->K = P.K;
+    g->rb = P.fmt.rb;
+    g->pack = ix->opt_pack == 2 ? 2 : 1;
+    g->levels = P.fmt.levels();
+    g->n_warps = std::max(1, std::min(16, ix->opt_warps));
+    const size_t rows_bytes = (size_t)4 << g->rb;
+    const size_t overhead = (size_t)g->n_warps * g->levels * 128 + 32 * g->pack * 4 + 64;
+    int qgl = (int)((dpq::kMaxSmem - overhead) / rows_bytes);
+    qgl = std::min(qgl, 32);
+    if (qgl < 1) return fail(DPQ_ERR_ARG, "ADC table does not fit in shared memory");
+    // do not spread a small batch over more lanes than needed
+    int need = (Q + g->pack - 1) / g->pack;
+    if (need < qgl) qgl = std::max(1, need);
+    g->qgl = qgl;
+    g->qpg = qgl * g->pack;
+    g->n_groups = (Q + g->qpg - 1) / g->qpg;
+    int slack = ix->opt_slack >= 0 ? ix->opt_slack : std::max(6, topk / 4);
+    g->kp = std::min(256, topk + slack);
+    if (topk > 256 - 0 || g->kp < topk) return fail(DPQ_ERR_ARG, "topk must be <= 256");
+    int n_slices = ix->opt_slices;
+    if (n_slices <= 0) {
+        int by_fill = (148 * 6 + g->n_groups - 1) / g->n_groups;
+        int by_work = std::max(1, ix->n_chunks / (2 * g->n_warps));
+        n_slices = std::max(1, std::min(by_fill, by_work));
+    }
+    n_slices = std::min(n_slices, std::max(1, ix->n_chunks));
+    while ((int64_t)n_slices * g->n_warps > 2048) --n_slices;
+    g->n_slices = n_slices;
+    g->smem_bytes = (size_t)qgl * rows_bytes + overhead;
+    return DPQ_OK;
+}
+
+int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
+    int rc = b.ensure(std::max<size_t>(bytes, 16));
+    if (rc) return rc;
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+    return DPQ_OK;
+}
+
+int finish_open(dpq_index* ix, const uint32_t* pos2id) {
+    dpq::ScanProgram& P = ix->prog;
+    CU(cudaSetDevice(ix->device));
+    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto& e : ix->ev) CU(cudaEventCreate(&e));
+    int rc;
+    if ((rc = upload(ix->d_ops, P.ops.data(), P.ops.size() * 4, ix->stream))) return rc;
+    if ((rc = upload(ix->d_chunks, P.chunks.data(), P.chunks.size() * sizeof(dpq::ChunkDesc), ix->stream)))
+        return rc;
+    if ((rc = upload(ix->d_anc, P.anc.data(), P.anc.size(), ix->stream))) return rc;
+    if ((rc = upload(ix->d_codes, P.codes.data(), P.codes.size(), ix->stream))) return rc;
+    ix->n_chunks = (int)P.chunks.size();
+    ix->ops_bytes = P.ops.size() * 4;
+    if (pos2id) {
+        ix->has_pos2id = true;
+        ix->pos2id_host.assign(pos2id + P.base_pos, pos2id + P.base_pos + P.n_local);
+    }
+    CU(cudaStreamSynchronize(ix->stream));
+    // the device copy is authoritative from here on
+    std::vector<uint32_t>().swap(P.ops);
+    std::vector<uint8_t>().swap(P.codes);
+    std::vector<uint8_t>().swap(P.anc);
+    std::vector<dpq::ChunkDesc>().swap(P.chunks);
+    return DPQ_OK;
+}
+
+int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return fail(DPQ_ERR_CUDA, "no CUDA device available (libdpq has no CPU fallback)");
+    }
+    if (g_device >= n) return fail(DPQ_ERR_CUDA, "selected device index out of range");
+    return DPQ_OK;
+}
+
+}  // namespace
+
+namespace dpq {  // shared with secondary.cu / edges.cu
+int api_fail(int code, const std::string& msg) { return fail(code, msg); }
+int api_check_device() { return check_device(); }
+int api_device() { return g_device; }
+}  // namespace dpq
+
+extern "C" {
+
+int dpq_version(void) { return 100; }
+const char* dpq_last_error(void) { return g_err.c_str(); }
+
+int dpq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dpq_set_device(int device) {
+    int n = dpq_device_count();
+    if (device < 0 || device >= n) return fail(DPQ_ERR_CUDA, "dpq_set_device: no such device");
+    g_device = device;
+    CU(cudaSetDevice(device));
+    return DPQ_OK;
+}
+
+int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                   const uint32_t* pos2id, int rank, int n_ranks, dpq_index** out) {
+    if (!payload || !out) return fail(DPQ_ERR_ARG, "dpq_index_open: null argument");
+    *out = nullptr;
+    int rc = check_device();
+    if (rc) return rc;
+    dpq_index* ix = new dpq_index();
+    ix->device = g_device;
+    std::string err = dpq::compile_program(payload, n_bytes, n_codes, M, K, rank, n_ranks,
+                                           ix->chunk_nodes, &ix->prog);
+    if (!err.empty()) {
+        delete ix;
+        return fail(DPQ_ERR_FORMAT, "dpq_index_open: " + err);
+    }
+    rc = finish_open(ix, pos2id);
+    if (rc) {
+        dpq_index_close(ix);
+        return rc;
+    }
+    *out = ix;
+    return DPQ_OK;
+}
+
+int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,
+                        int n_ranks, dpq_index** out) {
+    if (!tree_path || !out) return fail(DPQ_ERR_ARG, "dpq_index_open_file: null argument");
+    FILE* f = fopen(tree_path, "rb");
+    if (!f) return fail(DPQ_ERR_IO, std::string("cannot open ") + tree_path);
+    int64_t hdr[2];
+    if (fread(hdr, 8, 2, f) != 2) {
+        fclose(f);
+        return fail(DPQ_ERR_FORMAT, "tree file shorter than its header");
+    }
+    if (hdr[0] < 1 || hdr[1] < M) {
+        fclose(f);
+        return fail(DPQ_ERR_FORMAT, "bad tree file header");
+    }
+    std::vector<uint8_t> payload((size_t)hdr[1]);
+    size_t got = fread(payload.data(), 1, payload.size(), f);
+    fclose(f);
+    if (got != payload.size()) return fail(DPQ_ERR_FORMAT, "tree file truncated");
+    std::vector<uint32_t> pos2id;
+    if (qnode_path) {  // 60-byte QNode records, vec_id at offset 0 (DCAT.h:79-101)
+        FILE* q = fopen(qnode_path, "rb");
+        if (!q) return fail(DPQ_ERR_IO, std::string("cannot open ") + qnode_path);
+        pos2id.resize((size_t)hdr[0]);
+        std::vector<uint8_t> rec(60 * 4096);
+        size_t done = 0;
+        while (done < pos2id.size()) {
+            size_t want = std::min<size_t>(4096, pos2id.size() - done);
+            if (fread(rec.data(), 60, want, q) != want) {
+                fclose(q);
+                return fail(DPQ_ERR_FORMAT, "QNode file truncated");
+            }
+            for (size_t i = 0; i < want; ++i) memcpy(&pos2id[done + i], rec.data() + 60 * i, 4);
+            done += want;
+        }
+        fclose(q);
+    }
+    return dpq_index_open(payload.data(), hdr[1], hdr[0], M, K, qnode_path ? pos2id.data() : nullptr,
+                          rank, n_ranks, out);
+}
+
+int dpq_index_set_codebook(dpq_index* ix, const float* cw, int Ds) {
+    if (!ix || !cw || Ds < 1) return fail(DPQ_ERR_ARG, "dpq_index_set_codebook: bad argument");
+    CU(cudaSetDevice(ix->device));
+    ix->Ds = Ds;
+    int rc = upload(ix->d_cw, cw, (size_t)ix->prog.M * ix->prog.K * Ds * sizeof(float), ix->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ix->stream));
+    return DPQ_OK;
+}
+
+int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
+    if (!ix || !name) return fail(DPQ_ERR_ARG, "dpq_index_set_option: null argument");
+    std::string n(name);
+    if (n == "slices") ix->opt_slices = (int)v;
+    else if (n == "pack") ix->opt_pack = (int)v;
+    else if (n == "warps") ix->opt_warps = (int)v;
+    else if (n == "slack") ix->opt_slack = (int)v;
+    else if (n == "force_fallback") ix->opt_force_fallback = (int)v;
+    else return fail(DPQ_ERR_ARG, "unknown option " + n);
+    return DPQ_OK;
+}
+
+int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int topk,
+                            uint64_t* d_out_key) {
+    if (!ix || !d_queries || !d_out_key) return fail(DPQ_ERR_ARG, "dpq_index_search: null argument");
+    if (Q < 1 || topk < 1) return fail(DPQ_ERR_ARG, "dpq_index_search: Q and topk must be >= 1");
+    if (ix->Ds < 1) return fail(DPQ_ERR_ARG, "dpq_index_search: codebook not set");
+    CU(cudaSetDevice(ix->device));
+    dpq::ScanGeom g;
+    int rc = choose_geometry(ix, Q, topk, &g);
+    if (rc) return rc;
+    const dpq::ScanProgram& P = ix->prog;
+    const size_t MK = (size_t)P.M * P.K;
+    const size_t rows = (size_t)1 << g.rb;
+    const size_t LW = 32 * (size_t)g.pack;
+    const size_t n_items = (size_t)g.n_groups * g.n_slices;
+    const int max_flagged = std::min(Q, 4096);
+    const int fcap = 2048;
+    if ((rc = ix->d_lutf.ensure((size_t)Q * MK * 4))) return rc;
+    if ((rc = ix->d_scale.ensure((size_t)g.n_groups * g.qpg * 8))) return rc;
+    if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * g.qgl * rows * 4))) return rc;
+    if ((rc = ix->d_cand.ensure(n_items * g.n_warps * g.kp * LW * 8))) return rc;
+    if ((rc = ix->d_cnt.ensure(n_items * g.n_warps * LW * 4))) return rc;
+    if ((rc = ix->d_flagged.ensure((size_t)max_flagged * 4))) return rc;
+    if ((rc = ix->d_ctrl.ensure(64))) return rc;
+    if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
+    if ((rc = ix->d_fbuf.ensure((size_t)max_flagged * fcap * 8))) return rc;
+    if ((rc = ix->d_fcnt.ensure((size_t)max_flagged * 4))) return rc;
+    cudaStream_t st = ix->stream;
+    uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();  // [0] n_flagged, [1] overflow
+    CU(cudaEventRecord(ix->ev[0], st));
+    CU(cudaMemsetAsync(ctrl, 0, 64, st));
+    CU(cudaMemsetAsync(ix->d_fcnt.p, 0, (size_t)max_flagged * 4, st));
+    dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
+                    ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), g, st);
+    dpq::ScanArgs sa;
+    sa.g = g;
+    sa.ops = ix->d_ops.as<uint4>();
+    sa.chunks = ix->d_chunks.as<dpq::ChunkDesc>();
+    sa.anc = ix->d_anc.as<uint8_t>();
+    sa.n_chunks = ix->n_chunks;
+    sa.qlut = ix->d_qlut.as<uint32_t>();
+    sa.cand = ix->d_cand.as<uint64_t>();
+    sa.cand_cnt = ix->d_cnt.as<uint32_t>();
+    sa.Q = Q;
+    CU(cudaEventRecord(ix->ev[1], st));
+    CU(dpq::launch_scan(sa, st));
+    CU(cudaEventRecord(ix->ev[2], st));
+    dpq::SelectArgs se;
+    se.g = g;
+    se.cand = sa.cand;
+    se.cand_cnt = sa.cand_cnt;
+    se.lutf = ix->d_lutf.as<float>();
+    se.scale = ix->d_scale.as<double>();
+    se.codes = ix->d_codes.as<uint8_t>();
+    se.base_pos = P.base_pos;
+    se.n_local = P.n_local;
+    se.Q = Q;
+    se.topk = topk;
+    se.out_key = d_out_key;
+    se.flagged = ix->d_flagged.as<uint32_t>();
+    se.n_flagged = ctrl;
+    se.max_flagged = max_flagged;
+    se.bound = ix->d_bound.as<float>();
+    se.force_fallback = ix->opt_force_fallback;
+    dpq::launch_select(se, st);
+    dpq::FallbackArgs fa;
+    fa.flagged = se.flagged;
+    fa.n_flagged = ctrl;
+    fa.max_flagged = max_flagged;
+    fa.lutf = se.lutf;
+    fa.bound = se.bound;
+    fa.codes = se.codes;
+    fa.base_pos = P.base_pos;
+    fa.n_local = P.n_local;
+    fa.M = P.M;
+    fa.K = P.K;
+    fa.topk = topk;
+    fa.buf = ix->d_fbuf.as<uint64_t>();
+    fa.buf_cnt = ix->d_fcnt.as<uint32_t>();
+    fa.cap = fcap;
+    fa.out_key = d_out_key;
+    fa.overflow = ctrl + 1;
+    dpq::launch_fallback(fa, st);
+    CU(cudaEventRecord(ix->ev[3], st));
+    CU(cudaGetLastError());
+    ix->last_launches = 5;  // lut, scan, select, fallback collect, fallback finish
+    ix->timing_valid = true;
+    return DPQ_OK;
+}
+
+int dpq_index_sync(dpq_index* ix) {
+    if (!ix) return fail(DPQ_ERR_ARG, "dpq_index_sync: null");
+    CU(cudaSetDevice(ix->device));
+    CU(cudaStreamSynchronize(ix->stream));
+    if (ix->d_ctrl.p) {
+        uint32_t ctrl[2] = {0, 0};
+        CU(cudaMemcpy(ctrl, ix->d_ctrl.p, 8, cudaMemcpyDeviceToHost));
+        ix->last_fallback = ctrl[0];
+        if (ctrl[1]) return fail(DPQ_ERR_NOMEM, "exact fallback overflowed its buffers (massive ties)");
+    }
+    return DPQ_OK;
+}
+
+int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint32_t* out_pos,
+                     uint32_t* out_id, float* out_dist) {
+    if (!ix || !queries) return fail(DPQ_ERR_ARG, "dpq_index_search: null argument");
+    if (Q < 1 || topk < 1) return fail(DPQ_ERR_ARG, "dpq_index_search: Q and topk must be >= 1");
+    CU(cudaSetDevice(ix->device));
+    const size_t D = (size_t)ix->prog.M * ix->Ds;
+    const size_t qbytes = (size_t)Q * D * 4, kbytes = (size_t)Q * topk * 8;
+    if (ix->h_stage_cap < qbytes + kbytes) {
+        if (ix->h_stage) cudaFreeHost(ix->h_stage);
+        ix->h_stage = nullptr;
+        ix->h_stage_cap = 0;
+        CU(cudaMallocHost(&ix->h_stage, qbytes + kbytes));
+        ix->h_stage_cap = qbytes + kbytes;
+    }
+    int rc;
+    if ((rc = ix->d_queries.ensure(qbytes))) return rc;
+    if ((rc = ix->d_key.ensure(kbytes))) return rc;
+    float* hq = reinterpret_cast<float*>(ix->h_stage);
+    uint64_t* hk = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes);
+    memcpy(hq, queries, qbytes);
+    CU(cudaMemcpyAsync(ix->d_queries.p, hq, qbytes, cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = dpq_index_search_device(ix, ix->d_queries.as<float>(), Q, topk, ix->d_key.as<uint64_t>())))
+        return rc;
+    CU(cudaMemcpyAsync(hk, ix->d_key.p, kbytes, cudaMemcpyDeviceToHost, ix->stream));
+    if ((rc = dpq_index_sync(ix))) return rc;
+    const int64_t base = ix->prog.base_pos;
+    for (size_t i = 0; i < (size_t)Q * topk; ++i) {
+        uint32_t pos = (uint32_t)hk[i];
+        uint32_t bits = (uint32_t)(hk[i] >> 32);
+        float d;
+        memcpy(&d, &bits, 4);
+        if (out_pos) out_pos[i] = pos;
+        if (out_dist) out_dist[i] = d;
+        if (out_id) out_id[i] = (ix->has_pos2id && pos != 0xFFFFFFFFu) ? ix->pos2id_host[(size_t)(pos - base)] : pos;
+    }
+    return DPQ_OK;
+}
+
+int dpq_merge_topk_device(dpq_index* ix, const uint64_t* d_keys, int n_lists, int Q, int topk,
+                          uint64_t* d_out_key) {
+    if (!ix || !d_keys || !d_out_key) return fail(DPQ_ERR_ARG, "dpq_merge_topk_device: null");
+    if (n_lists < 1 || n_lists > 64) return fail(DPQ_ERR_ARG, "dpq_merge_topk_device: 1..64 lists");
+    CU(cudaSetDevice(ix->device));
+    dpq::launch_merge(d_keys, n_lists, Q, topk, d_out_key, ix->stream);
+    CU(cudaGetLastError());
+    return DPQ_OK;
+}
+
+int dpq_malloc(void** dptr, size_t bytes) {
+    if (!dptr) return fail(DPQ_ERR_ARG, "dpq_malloc: null");
+    int rc = check_device();
+    if (rc) return rc;
+    CU(cudaSetDevice(g_device));
+    CU(cudaMalloc(dptr, bytes));
+    return DPQ_OK;
+}
+int dpq_free(void* dptr) {
+    CU(cudaFree(dptr));
+    return DPQ_OK;
+}
+int dpq_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return DPQ_OK;
+}
+int dpq_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return DPQ_OK;
+}
+int dpq_malloc_host(void** hptr, size_t bytes) {
+    if (!hptr) return fail(DPQ_ERR_ARG, "dpq_malloc_host: null");
+    int rc = check_device();
+    if (rc) return rc;
+    CU(cudaMallocHost(hptr, bytes));
+    return DPQ_OK;
+}
+int dpq_free_host(void* hptr) {
+    CU(cudaFreeHost(hptr));
+    return DPQ_OK;
+}
+
+int64_t dpq_index_stat(dpq_index* ix, const char* name) {
+    if (!ix || !name) return -1;
+    std::string n(name);
+    const dpq::ScanProgram& P = ix->prog;
+    if (n == "n_codes") return P.n_codes;
+    if (n == "n_bytes") return P.local_bytes;
+    if (n == "n_bytes_total") return P.n_bytes;
+    if (n == "n_local") return P.n_local;
+    if (n == "base_pos") return P.base_pos;
+    if (n == "n_diffs") return P.n_diffs;
+    if (n == "n_chunks") return ix->n_chunks;
+    if (n == "ops_bytes") return (int64_t)ix->ops_bytes;
+    if (n == "last_launches") return ix->last_launches;
+    if (n == "last_fallback") return ix->last_fallback;
+    if (n.rfind("depth_hist_", 0) == 0) {
+        size_t d = (size_t)atoi(n.c_str() + 11);
+        return d < P.depth_hist.size() ? P.depth_hist[d] : 0;
+    }
+    if (n == "last_scan_us" || n == "last_total_us" || n == "last_lut_us") {
+        if (!ix->timing_valid) return -1;
+        cudaSetDevice(ix->device);
+        if (cudaEventSynchronize(ix->ev[3]) != cudaSuccess) return -1;
+        float ms = 0;
+        cudaEvent_t a = n == "last_scan_us" ? ix->ev[1] : ix->ev[0];
+        cudaEvent_t b = n == "last_scan_us" ? ix->ev[2] : (n == "last_lut_us" ? ix->ev[1] : ix->ev[3]);
+        if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return -1;
+        return (int64_t)(ms * 1000.0f + 0.5f);
+    }
+    return -1;
+}
+
+void dpq_index_close(dpq_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (DevBuf* b : {&ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+                      &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
+                      &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_fbuf, &ix->d_fcnt, &ix->d_key})
+        b->release();
+    if (ix->h_stage) cudaFreeHost(ix->h_stage);
+    for (auto& e : ix->ev)
+        if (e) cudaEventDestroy(e);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    (void)cudaGetLastError();
+    delete ix;
+}
+
+int dpq_adc_tables(const float* cw, int M, int K, int Ds, const float* queries, int Q, float* lut) {
+    if (!cw || !queries || !lut || M < 1 || M > 16 || K < 1 || K > 256 || Ds < 1 || Q < 1)
+        return fail(DPQ_ERR_ARG, "dpq_adc_tables: bad argument");
+    int rc = check_device();
+    if (rc) return rc;
+    CU(cudaSetDevice(g_device));
+    DevBuf d_cw, d_q, d_l;
+    size_t cwb = (size_t)M * K * Ds * 4, qb = (size_t)Q * M * Ds * 4, lb = (size_t)Q * M * K * 4;
+    if ((rc = d_cw.ensure(cwb)) || (rc = d_q.ensure(qb)) || (rc = d_l.ensure(lb))) return rc;
+    CU(cudaMemcpy(d_cw.p, cw, cwb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_q.p, queries, qb, cudaMemcpyHostToDevice));
+    dpq::launch_lut_plain(d_cw.as<float>(), M, K, Ds, d_q.as<float>(), Q, d_l.as<float>(), 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(lut, d_l.p, lb, cudaMemcpyDeviceToHost));
+    d_cw.release();
+    d_q.release();
+    d_l.release();
+    return DPQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// Internal declarations shared by the host-side tree compiler and the CUDA kernels.
+// Nothing here crosses the C ABI (include/dpq.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace dpq {
+
+// ---------------------------------------------------------------------------------------
+// Device layout of one DeltaTree shard: the "scan program".
+//
+// The on-disk stream (reference writer DCAT.h:1765-1842) is a strictly
+// sequential byte code: variable-length records, each node's parent found through a
+// depth stack.  At open time the host decodes it once and emits, per chunk of
+// `chunk_nodes` consecutive DFS positions, a flat array of 32-bit delta ops that a warp can
+// execute with no further decoding:
+//
+//   op = from_row4 | to_row4 << (RB+2) | LEVEL | KIND | LAST
+//     from_row4 / to_row4 : (m*K + centroid) * 4, byte offset of the ADC-table row of the
+//                           subspace this edge changes: old centroid / new centroid
+//     LAST  (bit 31)      : last op of a node -> the accumulator now holds the node distance
+//     KIND  (bits 29..30) : what the NEXT node's parent is: 0 sibling (same parent),
+//                           2 child (this node), 3 child + store this distance to the
+//                           per-warp depth stack, 1 pop (reload stack[LEVEL])
+//     LEVEL               : stack level for store / pop
+//
+// Every chunk also records the codes of the ancestors of its first node, so a warp starts a
+// chunk with full M-term table sums for those ancestors ("full M-term lookup at each root")
+// and needs nothing from other chunks.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t OP_LAST = 1u << 31;
+constexpr uint32_t OP_CHILD = 1u << 30;
+constexpr uint32_t OP_AUX = 1u << 29;  // with CHILD: store; without: pop
+
+struct OpFormat {
+    int rb;  // row bits: 11 (M*K <= 2048) or 12 (M*K <= 4096)
+    uint32_t fmask() const { return ((1u << rb) - 1u) << 2; }
+    int tshift() const { return rb + 2; }
+    int levels() const { return rb == 11 ? 8 : 16; }
+    uint32_t level_bits(uint32_t lev) const {
+        if (rb == 11) return lev << 26;                  // bits 26..28
+        return (lev & 3u) | ((lev >> 2) << 14);          // bits 0..1 and 14..15
+    }
+};
+
+struct ChunkDesc {
+    uint32_t quad_begin;   // first uint4 of this chunk in the op array
+    uint32_t n_quads;
+    uint32_t first_pos;    // global DFS position of the first node executed by the ops
+    uint32_t n_anc_flags;  // bits 0..7: number of ancestor levels; bit 8: also emit the root
+};
+constexpr uint32_t CHUNK_EMIT_ROOT = 1u << 8;
+
+struct ScanProgram {
+    int M = 0, K = 0;
+    OpFormat fmt{11};
+    int64_t n_codes = 0;       // nodes in the whole tree
+    int64_t n_bytes = 0;       // stream bytes of the whole tree
+    int64_t base_pos = 0;      // first global position held by this shard
+    int64_t n_local = 0;       // nodes held by this shard (contiguous positions)
+    int64_t local_bytes = 0;   // algorithmic stream bytes of this shard
+    int64_t n_diffs = 0;       // changed subspaces over this shard's nodes
+    std::vector<uint32_t> ops;        // multiple of 4 words per chunk
+    std::vector<ChunkDesc> chunks;
+    std::vector<uint8_t> anc;         // [n_chunks][levels][M]
+    std::vector<uint8_t> codes;       // [n_local][M] decoded codes, by position - base_pos
+    std::vector<int64_t> depth_hist;  // nodes per depth (this shard)
+};
+
+// Decodes `payload` and builds the program for shard `rank` of `n_ranks`.
+// Returns empty string on success, else an error message.
+std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                            int rank, int n_ranks, int chunk_nodes, ScanProgram* out);
+
+}  // namespace dpq

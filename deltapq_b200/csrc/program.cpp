@@ -1,0 +1,195 @@
+// Host-side tree compiler: DeltaTree byte stream -> device scan program (see
+// dpq_internal.h).  The stream format is the reference's (writer
+// DCAT.h:1765-1842, reader DCAT.h:3773-3882): int64 header stripped by the caller, M root
+// bytes, then per pair of nodes one depth byte (two nibbles) followed by each node's
+// changed-subspace bitmap and new centroid bytes; a trailing single node carries a full
+// depth byte.  M > 8 uses the extension format (ceil(M/8) bitmap bytes, little-endian;
+// 4-bit depths) because the reference's own M = 16 output is invalid.
+#include "dpq_internal.h"
+
+#include <cstring>
+
+namespace dpq {
+namespace {
+
+struct Emitter {
+    ScanProgram* p;
+    int M, K, levels;
+    OpFormat fmt;
+    int chunk_nodes;
+    // current chunk
+    bool open = false;
+    int nodes_in_chunk = 0;
+    size_t chunk_op_begin = 0;
+    long prev_last = -1;  // op index of the previous node's LAST op (this chunk), or -1
+    int prev_depth = 0;
+    std::vector<long> level_idx;  // op index of LAST op of the in-chunk node at each depth
+
+    void begin(uint32_t first_pos, int depth, const uint8_t* stack, bool emit_root) {
+        ChunkDesc c;
+        chunk_op_begin = p->ops.size();
+        c.quad_begin = (uint32_t)(chunk_op_begin / 4);
+        c.n_quads = 0;
+        c.first_pos = first_pos;
+        c.n_anc_flags = (uint32_t)depth | (emit_root ? CHUNK_EMIT_ROOT : 0u);
+        p->chunks.push_back(c);
+        size_t a0 = p->anc.size();
+        p->anc.resize(a0 + (size_t)levels * M, 0);
+        memcpy(p->anc.data() + a0, stack, (size_t)depth * M);
+        level_idx.assign((size_t)levels + 1, -1);
+        prev_last = -1;
+        nodes_in_chunk = 0;
+        open = true;
+    }
+    void end() {
+        if (!open) return;
+        while (p->ops.size() % 4) p->ops.push_back(0u);  // no-op: row 0 minus row 0, not LAST
+        p->chunks.back().n_quads = (uint32_t)((p->ops.size() - chunk_op_begin) / 4);
+        open = false;
+    }
+    // node at `depth` whose parent code is `par`, own code `cur`
+    void node(int depth, const uint8_t* par, const uint8_t* cur) {
+        if (prev_last >= 0) {  // now the previous node's successor is known: patch its KIND
+            uint32_t& w = p->ops[(size_t)prev_last];
+            if (depth == prev_depth + 1) {
+                w |= OP_CHILD;
+            } else if (depth < prev_depth) {
+                int lev = depth - 1;
+                w |= OP_AUX | fmt.level_bits((uint32_t)lev);
+                long owner = level_idx[(size_t)lev];
+                if (owner >= 0)  // the ancestor at `lev` lives in this chunk: make it store
+                    p->ops[(size_t)owner] |= OP_AUX | fmt.level_bits((uint32_t)lev);
+            }
+        }
+        int n = 0;
+        for (int m = 0; m < M; ++m)
+            if (par[m] != cur[m]) {
+                uint32_t fr = (uint32_t)(m * K + par[m]) << 2;
+                uint32_t to = (uint32_t)(m * K + cur[m]) << 2;
+                p->ops.push_back(fr | (to << fmt.tshift()));
+                ++n;
+            }
+        if (n == 0) p->ops.push_back(0u);
+        p->ops.back() |= OP_LAST;
+        prev_last = (long)p->ops.size() - 1;
+        prev_depth = depth;
+        level_idx[(size_t)depth] = prev_last;
+        ++nodes_in_chunk;
+    }
+};
+
+}  // namespace
+
+std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                            int rank, int n_ranks, int chunk_nodes, ScanProgram* out) {
+    if (M < 1 || M > 16 || K < 1 || K > 256) return "unsupported M/K (need 1<=M<=16, 1<=K<=256)";
+    if (n_codes < 1) return "empty tree";
+    if (n_codes >= 0x7FFFFFFFLL) return "n_codes must be < 2^31-1 (DCAT.h:982)";
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return "bad rank / n_ranks";
+    if (n_bytes < M) return "stream shorter than the root code";
+    ScanProgram& P = *out;
+    P = ScanProgram();
+    P.M = M;
+    P.K = K;
+    P.fmt.rb = (M * K <= 2048) ? 11 : 12;
+    if (M * K > 4096) return "M*K > 4096 not supported";
+    P.n_codes = n_codes;
+    P.n_bytes = n_bytes;
+    const int levels = P.fmt.levels();
+    const int bmb = (M + 7) / 8;
+    const int dmask = M > 8 ? 15 : 7;  // DCAT.h:3794 masks nibbles with &7
+    P.depth_hist.assign((size_t)levels + 1, 0);
+    if (chunk_nodes < 4) chunk_nodes = 4;
+
+    std::vector<uint8_t> stack((size_t)(levels + 1) * M, 0);
+    int64_t off = 0;
+    memcpy(stack.data(), payload, (size_t)M);
+    off = M;
+
+    Emitter E;
+    E.p = &P;
+    E.M = M;
+    E.K = K;
+    E.levels = levels;
+    E.fmt = P.fmt;
+    E.chunk_nodes = chunk_nodes;
+
+    bool have_base = false;
+    bool pending_root = (rank == 0);
+    if (rank == 0) {
+        P.base_pos = 0;
+        have_base = true;
+        P.codes.insert(P.codes.end(), payload, payload + M);
+        P.n_local = 1;
+        P.local_bytes = M;
+        P.depth_hist[0] = 1;
+    }
+    int cur_rank = 0;
+    int depths = 0;
+    int last_depth = 0;
+    int64_t local_nodes_records = 0;
+    for (int64_t i = 1; i < n_codes; ++i) {
+        int64_t rec_begin = off;
+        int d;
+        if (i & 1) {
+            if (off >= n_bytes) return "stream truncated (depth byte)";
+            depths = payload[off++];
+            d = (i == n_codes - 1) ? depths : (depths & dmask);  // DCAT.h:3861 unmasked tail
+        } else {
+            d = (depths >> 4) & dmask;
+        }
+        if (d < 1 || d > levels - 1 || d > last_depth + 1) return "bad depth in stream";
+        last_depth = d;
+        if (off + bmb > n_bytes) return "stream truncated (bitmap)";
+        uint32_t bitmap = 0;
+        for (int b = 0; b < bmb; ++b) bitmap |= (uint32_t)payload[off++] << (8 * b);
+        if (M < 32 && (bitmap >> M)) return "bitmap has bits above M";
+        uint8_t* cur = stack.data() + (size_t)d * M;
+        const uint8_t* par = stack.data() + (size_t)(d - 1) * M;
+        memcpy(cur, par, (size_t)M);
+        int nd = 0;
+        for (int m = 0; m < M; ++m)
+            if ((bitmap >> m) & 1) {
+                if (off >= n_bytes) return "stream truncated (centroid byte)";
+                uint8_t c = payload[off++];
+                if (c >= K) return "centroid id >= K in stream";
+                cur[m] = c;
+                ++nd;
+            }
+        if (d == 1) {  // a depth-1 subtree starts: pick its owner by stream byte offset
+            cur_rank = (int)((__int128)rec_begin * n_ranks / n_bytes);
+            if (cur_rank >= n_ranks) cur_rank = n_ranks - 1;
+        }
+        if (cur_rank != rank) {
+            if (E.open) E.end();
+            continue;
+        }
+        if (!have_base) {
+            P.base_pos = i;
+            have_base = true;
+        }
+        if (!E.open || E.nodes_in_chunk >= chunk_nodes) {
+            E.end();
+            E.begin((uint32_t)i, d, stack.data(), pending_root);
+            pending_root = false;
+        }
+        E.node(d, par, cur);
+        P.codes.insert(P.codes.end(), cur, cur + M);
+        P.n_local++;
+        P.n_diffs += nd;
+        P.local_bytes += bmb + nd;
+        local_nodes_records++;
+        P.depth_hist[(size_t)d]++;
+    }
+    E.end();
+    if (off != n_bytes) return "stream has trailing or missing bytes (n_bytes mismatch)";
+    P.local_bytes += (local_nodes_records + 1) / 2;  // depth nibbles
+    if (pending_root) {  // root only (n_codes == 1, or rank 0 owns no subtree)
+        E.begin(1u, 1, stack.data(), true);
+        E.end();
+    }
+    if (!have_base) P.base_pos = n_codes;
+    return std::string();
+}
+
+}  // namespace dpq

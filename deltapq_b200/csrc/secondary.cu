@@ -1,0 +1,394 @@
+// Secondary kernels of the DeltaPQ pipeline (in scope per BASELINE.json north_star):
+//   encode_kernel        PQTree::EncodePlain nearest-centroid argmin (pq_tree.cpp:215-237)
+//   edge_diff_kernel     per-edge changed-subspace bitmap / diff count (DCAT.h:196-238)
+//   gt_dist / gt_select  exact brute-force ground truth (pmain:138-166)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dpq.h"
+
+namespace dpq {
+int api_fail(int code, const std::string& msg);  // api_common.cu
+int api_check_device();
+int api_device();
+}  // namespace dpq
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return dpq::api_fail(DPQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------------ encode -------
+// Block = 256 vectors x one subspace.  The subspace's K x Ds codebook slice sits in shared
+// memory (every thread reads the same word: broadcast); each thread keeps its Ds-float
+// sub-vector in registers.  Arithmetic is the reference's, op for op: float subtract, float
+// multiply, float add (no FMA: __f*_rn intrinsics are never contracted), strict <, so ties
+// go to the lowest centroid id and the codes are bit-exact.
+template <int DS>
+__global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ cw, int M, int K,
+                                                     const float* __restrict__ x, int64_t n, int D,
+                                                     uint8_t* __restrict__ codes) {
+    extern __shared__ float s_cw[];  // [K][DS]
+    const int m = blockIdx.y;
+    for (int i = threadIdx.x; i < K * DS; i += blockDim.x) s_cw[i] = cw[(size_t)m * K * DS + i];
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    float xr[DS];
+#pragma unroll
+    for (int d = 0; d < DS; ++d) {
+        int col = m * DS + d;
+        xr[d] = col < D ? x[(size_t)v * D + col] : 0.0f;  // zero padding (pq_tree.cpp:194-198)
+    }
+    float best = FLT_MAX;
+    int best_k = 0;
+    for (int k = 0; k < K; ++k) {
+        const float* c = s_cw + k * DS;
+        float dist = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DS; ++d) {
+            float diff = __fsub_rn(xr[d], c[d]);
+            dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+        }
+        if (dist < best) {
+            best = dist;
+            best_k = k;
+        }
+    }
+    codes[(size_t)v * M + m] = (uint8_t)best_k;
+}
+
+// any Ds: sub-vector staged in shared memory as [d][thread]
+__global__ void __launch_bounds__(256) encode_kernel_any(const float* __restrict__ cw, int M, int K,
+                                                         int Ds, const float* __restrict__ x,
+                                                         int64_t n, int D, uint8_t* __restrict__ codes) {
+    extern __shared__ float s_mem[];
+    float* s_cw = s_mem;            // [K][Ds]
+    float* s_x = s_mem + K * Ds;    // [Ds][256]
+    const int m = blockIdx.y;
+    for (int i = threadIdx.x; i < K * Ds; i += blockDim.x) s_cw[i] = cw[(size_t)m * K * Ds + i];
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int d = 0; d < Ds; ++d) {
+        int col = m * Ds + d;
+        s_x[d * 256 + threadIdx.x] = (v < n && col < D) ? x[(size_t)v * D + col] : 0.0f;
+    }
+    __syncthreads();
+    if (v >= n) return;
+    float best = FLT_MAX;
+    int best_k = 0;
+    for (int k = 0; k < K; ++k) {
+        const float* c = s_cw + k * Ds;
+        float dist = 0.0f;
+        for (int d = 0; d < Ds; ++d) {
+            float diff = __fsub_rn(s_x[d * 256 + threadIdx.x], c[d]);
+            dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+        }
+        if (dist < best) {
+            best = dist;
+            best_k = k;
+        }
+    }
+    codes[(size_t)v * M + m] = (uint8_t)best_k;
+}
+
+cudaError_t launch_encode(const float* d_cw, int M, int K, int Ds, const float* d_x, int64_t n, int D,
+                          uint8_t* d_codes, cudaStream_t st) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)M), block(256);
+    size_t sm = (size_t)K * Ds * 4;
+#define DPQ_ENC(DSV)                                                                              \
+    case DSV:                                                                                     \
+        cudaFuncSetAttribute(encode_kernel<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        encode_kernel<DSV><<<grid, block, sm, st>>>(d_cw, M, K, d_x, n, D, d_codes);             \
+        break;
+    switch (Ds) {
+        DPQ_ENC(4)
+        DPQ_ENC(8)
+        DPQ_ENC(16)
+        DPQ_ENC(32)
+        DPQ_ENC(60)
+        default: {
+            size_t sm2 = sm + (size_t)Ds * 256 * 4;
+            if (sm2 > 227 * 1024) return cudaErrorInvalidValue;
+            cudaFuncSetAttribute(encode_kernel_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+            encode_kernel_any<<<grid, block, sm2, st>>>(d_cw, M, K, Ds, d_x, n, D, d_codes);
+        }
+    }
+#undef DPQ_ENC
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------ edge diffs ---
+__global__ void edge_diff_kernel(const uint8_t* __restrict__ codes, int M, const uint32_t* __restrict__ edges,
+                                 int64_t n_edges, uint32_t* __restrict__ bitmaps,
+                                 unsigned long long* __restrict__ total) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int nd = 0;
+    if (e < n_edges) {
+        const uint8_t* a = codes + (size_t)edges[2 * e] * M;
+        const uint8_t* b = codes + (size_t)edges[2 * e + 1] * M;
+        uint32_t bm = 0;
+        if (M == 8) {  // XOR of the packed codes, then a per-byte non-zero mask
+            uint64_t xa = *reinterpret_cast<const uint64_t*>(a) ^ *reinterpret_cast<const uint64_t*>(b);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) bm |= ((xa >> (8 * m)) & 0xFFull) ? (1u << m) : 0u;
+        } else {
+            for (int m = 0; m < M; ++m) bm |= (a[m] != b[m]) ? (1u << m) : 0u;
+        }
+        bitmaps[e] = bm;
+        nd = __popc(bm);
+    }
+    for (int o = 16; o; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
+    if ((threadIdx.x & 31) == 0 && nd) atomicAdd(total, (unsigned long long)nd);
+}
+
+// ------------------------------------------------------------------------ ground truth -
+// Distances in the reference's arithmetic (pmain:150-156): float difference, float product,
+// double running sum over d ascending; narrowed to float when it enters the heap.
+// Tile: 128 base vectors x 8 queries per block, base tile staged through shared memory.
+constexpr int GT_TB = 128, GT_TQ = 8;
+__global__ void __launch_bounds__(GT_TB) gt_dist_kernel(const float* __restrict__ base, int64_t n,
+                                                        const float* __restrict__ queries, int Q, int D,
+                                                        float* __restrict__ dist /*[Q][n]*/) {
+    extern __shared__ float s_q[];  // [GT_TQ][D]
+    const int q0 = blockIdx.y * GT_TQ;
+    for (int i = threadIdx.x; i < GT_TQ * D; i += blockDim.x) {
+        int qq = q0 + i / D;
+        s_q[i] = qq < Q ? queries[(size_t)qq * D + i % D] : 0.0f;
+    }
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * GT_TB + threadIdx.x;
+    if (v >= n) return;
+    double acc[GT_TQ];
+#pragma unroll
+    for (int j = 0; j < GT_TQ; ++j) acc[j] = 0.0;
+    const float* x = base + (size_t)v * D;
+    for (int d = 0; d < D; ++d) {
+        float xv = x[d];
+#pragma unroll
+        for (int j = 0; j < GT_TQ; ++j) {
+            float diff = __fsub_rn(xv, s_q[j * D + d]);
+            acc[j] = __dadd_rn(acc[j], (double)__fmul_rn(diff, diff));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < GT_TQ; ++j)
+        if (q0 + j < Q) dist[(size_t)(q0 + j) * n + v] = (float)acc[j];
+}
+
+// One block per query: merge this chunk's distances into the running sorted top-k
+// (keys = float bits << 32 | id; ascending; ties keep the lower id like the reference's
+// strict < against the heap top while ids arrive in ascending order).
+constexpr int GT_SEL_T = 256, GT_BUF = 2048;
+__global__ void __launch_bounds__(GT_SEL_T) gt_select_kernel(const float* __restrict__ dist, int64_t n,
+                                                             int64_t id0, int topk,
+                                                             unsigned long long* __restrict__ state /*[Q][topk]*/) {
+    __shared__ unsigned long long s_buf[GT_BUF];
+    __shared__ int s_n;
+    __shared__ unsigned long long s_bound;
+    const int q = blockIdx.x;
+    unsigned long long* st = state + (size_t)q * topk;
+    // buffer starts with the current state
+    for (int i = threadIdx.x; i < topk; i += blockDim.x) s_buf[i] = st[i];
+    if (threadIdx.x == 0) {
+        s_n = topk;
+        s_bound = st[topk - 1];
+    }
+    __syncthreads();
+    const float* dq = dist + (size_t)q * n;
+    auto compact = [&]() {  // sort s_buf[0..s_n) ascending, keep topk, refresh bound
+        int cnt = s_n;
+        int np2 = 1;
+        while (np2 < cnt) np2 <<= 1;
+        for (int i = cnt + threadIdx.x; i < np2; i += blockDim.x) s_buf[i] = ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        unsigned long long a = s_buf[i], b = s_buf[ixj];
+                        bool up = (i & k) == 0;
+                        if ((a > b) == up) {
+                            s_buf[i] = b;
+                            s_buf[ixj] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        if (threadIdx.x == 0) {
+            s_n = topk;
+            s_bound = s_buf[topk - 1];
+        }
+        __syncthreads();
+    };
+    for (int64_t base_i = 0; base_i < n; base_i += GT_SEL_T) {
+        int64_t i = base_i + threadIdx.x;
+        unsigned long long key = ~0ull;
+        if (i < n) key = ((unsigned long long)__float_as_uint(dq[i]) << 32) | (unsigned)(id0 + i);
+        bool take = key < s_bound;
+        // at most GT_SEL_T pushes per step: compact first if they might not fit
+        if (s_n + GT_SEL_T > GT_BUF) {
+            __syncthreads();
+            compact();
+            take = key < s_bound;
+        }
+        if (take) {
+            int slot = atomicAdd(&s_n, 1);
+            s_buf[slot] = key;
+        }
+        __syncthreads();
+    }
+    compact();
+    for (int i = threadIdx.x; i < topk; i += blockDim.x) st[i] = s_buf[i];
+}
+
+struct Buf {
+    void* p = nullptr;
+    ~Buf() {
+        if (p) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+struct dpq_gt {
+    int Q, D, topk;
+    float* d_q = nullptr;
+    unsigned long long* d_state = nullptr;
+    float* d_base = nullptr;
+    float* d_dist = nullptr;
+    size_t base_cap = 0, dist_cap = 0;
+};
+
+extern "C" {
+
+int dpq_encode(const float* cw, int M, int K, int Ds, const float* x, int64_t n, int D, uint8_t* codes) {
+    if (!cw || !x || !codes || M < 1 || M > 64 || K < 1 || K > 256 || Ds < 1 || n < 0 || D < 1 ||
+        D > M * Ds)
+        return dpq::api_fail(DPQ_ERR_ARG, "dpq_encode: bad argument");
+    int rc = dpq::api_check_device();
+    if (rc) return rc;
+    if (n == 0) return DPQ_OK;
+    CU(cudaSetDevice(dpq::api_device()));
+    Buf d_cw, d_x, d_c;
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 20);
+    CU(cudaMalloc(&d_cw.p, (size_t)M * K * Ds * 4));
+    CU(cudaMalloc(&d_x.p, (size_t)chunk * D * 4));
+    CU(cudaMalloc(&d_c.p, (size_t)chunk * M));
+    CU(cudaMemcpy(d_cw.p, cw, (size_t)M * K * Ds * 4, cudaMemcpyHostToDevice));
+    for (int64_t s = 0; s < n; s += chunk) {
+        int64_t c = std::min(chunk, n - s);
+        CU(cudaMemcpy(d_x.p, x + (size_t)s * D, (size_t)c * D * 4, cudaMemcpyHostToDevice));
+        CU(launch_encode((const float*)d_cw.p, M, K, Ds, (const float*)d_x.p, c, D, (uint8_t*)d_c.p, 0));
+        CU(cudaMemcpy(codes + (size_t)s * M, d_c.p, (size_t)c * M, cudaMemcpyDeviceToHost));
+    }
+    return DPQ_OK;
+}
+
+int dpq_edge_diffs(const uint8_t* codes, int64_t n_codes, int M, const uint32_t* edges, int64_t n_edges,
+                   uint32_t* bitmaps, int64_t* n_diffs) {
+    if (!codes || !edges || M < 1 || M > 32 || n_edges < 0)
+        return dpq::api_fail(DPQ_ERR_ARG, "dpq_edge_diffs: bad argument");
+    int rc = dpq::api_check_device();
+    if (rc) return rc;
+    CU(cudaSetDevice(dpq::api_device()));
+    if (n_diffs) *n_diffs = 0;
+    if (n_edges == 0) return DPQ_OK;
+    Buf d_codes, d_edges, d_bm, d_tot;
+    CU(cudaMalloc(&d_codes.p, (size_t)n_codes * M + 8));
+    CU(cudaMalloc(&d_edges.p, (size_t)n_edges * 8));
+    CU(cudaMalloc(&d_bm.p, (size_t)n_edges * 4));
+    CU(cudaMalloc(&d_tot.p, 8));
+    CU(cudaMemcpy(d_codes.p, codes, (size_t)n_codes * M, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_edges.p, edges, (size_t)n_edges * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemset(d_tot.p, 0, 8));
+    edge_diff_kernel<<<(unsigned)((n_edges + 255) / 256), 256>>>((const uint8_t*)d_codes.p, M,
+                                                                (const uint32_t*)d_edges.p, n_edges,
+                                                                (uint32_t*)d_bm.p,
+                                                                (unsigned long long*)d_tot.p);
+    CU(cudaGetLastError());
+    if (bitmaps) CU(cudaMemcpy(bitmaps, d_bm.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost));
+    unsigned long long tot = 0;
+    CU(cudaMemcpy(&tot, d_tot.p, 8, cudaMemcpyDeviceToHost));
+    if (n_diffs) *n_diffs = (int64_t)tot;
+    return DPQ_OK;
+}
+
+int dpq_groundtruth_begin(const float* queries, int Q, int D, int topk, dpq_gt** out) {
+    if (!queries || !out || Q < 1 || D < 1 || topk < 1 || topk > 1024)
+        return dpq::api_fail(DPQ_ERR_ARG, "dpq_groundtruth_begin: bad argument");
+    int rc = dpq::api_check_device();
+    if (rc) return rc;
+    CU(cudaSetDevice(dpq::api_device()));
+    dpq_gt* st = new dpq_gt();
+    st->Q = Q;
+    st->D = D;
+    st->topk = topk;
+    CU(cudaMalloc(&st->d_q, (size_t)Q * D * 4));
+    CU(cudaMalloc(&st->d_state, (size_t)Q * topk * 8));
+    CU(cudaMemcpy(st->d_q, queries, (size_t)Q * D * 4, cudaMemcpyHostToDevice));
+    // (FLT_MAX, 0xFFFFFFFF) sentinels: results[i][j].second = FLT_MAX (pmain:609-611)
+    std::vector<unsigned long long> init((size_t)Q * topk, ((unsigned long long)0x7F7FFFFFu << 32) | 0xFFFFFFFFull);
+    CU(cudaMemcpy(st->d_state, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    *out = st;
+    return DPQ_OK;
+}
+
+int dpq_groundtruth_chunk(dpq_gt* st, const float* base, int64_t n, int64_t id0) {
+    if (!st || !base || n < 0) return dpq::api_fail(DPQ_ERR_ARG, "dpq_groundtruth_chunk: bad argument");
+    CU(cudaSetDevice(dpq::api_device()));
+    const int64_t step = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)256 << 20) / ((int64_t)st->Q * 4)));
+    for (int64_t s = 0; s < n; s += step) {
+        int64_t c = std::min(step, n - s);
+        size_t bb = (size_t)c * st->D * 4, db = (size_t)c * st->Q * 4;
+        if (bb > st->base_cap) {
+            if (st->d_base) cudaFree(st->d_base);
+            CU(cudaMalloc(&st->d_base, bb));
+            st->base_cap = bb;
+        }
+        if (db > st->dist_cap) {
+            if (st->d_dist) cudaFree(st->d_dist);
+            CU(cudaMalloc(&st->d_dist, db));
+            st->dist_cap = db;
+        }
+        CU(cudaMemcpy(st->d_base, base + (size_t)s * st->D, bb, cudaMemcpyHostToDevice));
+        dim3 grid((unsigned)((c + GT_TB - 1) / GT_TB), (unsigned)((st->Q + GT_TQ - 1) / GT_TQ));
+        size_t sm = (size_t)GT_TQ * st->D * 4;
+        cudaFuncSetAttribute(gt_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        gt_dist_kernel<<<grid, GT_TB, sm>>>(st->d_base, c, st->d_q, st->Q, st->D, st->d_dist);
+        gt_select_kernel<<<st->Q, GT_SEL_T>>>(st->d_dist, c, id0 + s, st->topk, st->d_state);
+        CU(cudaGetLastError());
+    }
+    CU(cudaDeviceSynchronize());
+    return DPQ_OK;
+}
+
+int dpq_groundtruth_finish(dpq_gt* st, uint32_t* out_id, float* out_dist) {
+    if (!st) return dpq::api_fail(DPQ_ERR_ARG, "dpq_groundtruth_finish: null");
+    std::vector<unsigned long long> keys((size_t)st->Q * st->topk);
+    cudaError_t e = cudaMemcpy(keys.data(), st->d_state, keys.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(st->d_q);
+    cudaFree(st->d_state);
+    if (st->d_base) cudaFree(st->d_base);
+    if (st->d_dist) cudaFree(st->d_dist);
+    delete st;
+    if (e != cudaSuccess) return dpq::api_fail(DPQ_ERR_CUDA, cudaGetErrorString(e));
+    for (size_t i = 0; i < keys.size(); ++i) {
+        uint32_t bits = (uint32_t)(keys[i] >> 32);
+        if (out_id) out_id[i] = (uint32_t)keys[i];
+        if (out_dist) memcpy(&out_dist[i], &bits, 4);
+    }
+    return DPQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+/* dpq.h -- C ABI of the B200-native DeltaPQ query hot path (libdpq.so).
+ *
+ * The reference (RunhuiWang/DeltaPQ) has no plugin/FFI layer: its hot path is a set of free
+ * functions in deltapq_create_approx_tree.h ("DCAT.h") called from the per-query loop of
+ * deltapq_approx_tree_main.cpp ("dmain") and main.cpp ("pmain").  Each entry point below
+ * names the reference function / call site it replaces.  Plain C: opaque handles, int
+ * status returns (0 = ok, negative = error, text via dpq_last_error()), caller-owned
+ * buffers, no C++ or torch types.  One handle is used from one host thread at a time.
+ * There is no CPU fallback: every compute entry point fails with DPQ_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef DPQ_H
+#define DPQ_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPQ_OK 0
+#define DPQ_ERR_ARG (-1)    /* bad argument / unsupported shape */
+#define DPQ_ERR_CUDA (-2)   /* CUDA runtime error or no device */
+#define DPQ_ERR_FORMAT (-3) /* malformed tree stream / file */
+#define DPQ_ERR_IO (-4)
+#define DPQ_ERR_NOMEM (-5)
+
+typedef struct dpq_index dpq_index;
+
+/* ---- library ------------------------------------------------------------------------ */
+int dpq_version(void);
+const char* dpq_last_error(void); /* thread-local text of the last failure */
+int dpq_device_count(void);       /* number of visible CUDA devices (0 without a GPU) */
+int dpq_set_device(int device);   /* device used by handles created afterwards */
+
+/* ---- DeltaTree index (the scan operand) --------------------------------------------- */
+/* Opens a compressed DeltaTree ("DTC"; writer DCAT.h:1765-1842) that is
+ * already in host memory.  payload = the stream WITHOUT its 16-byte header, exactly what
+ * query_processing_scan_compressed_codes_opt_in_memory (DCAT.h:3731) takes.  pos2id maps a
+ * DFS position to the vector id (QNode.vec_id, DCAT.h:79) and may be NULL.
+ * The tree is decoded once, re-laid out for the device and uploaded.
+ *
+ * rank / n_ranks shard the tree by whole depth-1 subtrees balanced by stream bytes
+ * (SURVEY 8e): rank r keeps only its subtrees, prefixed by the global root code; reported
+ * positions stay GLOBAL.  Rank 0 also scores the root.  Use rank=0,n_ranks=1 for the
+ * whole tree. */
+int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                   const uint32_t* pos2id, int rank, int n_ranks, dpq_index** out);
+
+/* Same, reading "<dataset>/M{M}K{K}_Approx_compressed_codes_opt_N{N}" style files
+ * (header int64 n_codes, int64 n_bytes; DCAT.h:2822-2824).  qnode_path (the 60-byte/node
+ * "..._Approx_TreeNodesDFS_N{N}" file, DCAT.h:1484) may be NULL. */
+int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,
+                        int n_ranks, dpq_index** out);
+
+/* Codebook [M][K][Ds] as PQ::ReadCodewords returns it (pq.cpp:288-312). */
+int dpq_index_set_codebook(dpq_index* idx, const float* codewords, int Ds);
+
+/* Tuning knobs (optional): "slices", "chunk_nodes", "pack" (1 = 32-bit, 2 = 2x16-bit
+ * filter), "warps", "slack" (extra candidates re-scored exactly). */
+int dpq_index_set_option(dpq_index* idx, const char* name, int64_t value);
+
+/* Replaces the per-query loop dmain:328-344 calling
+ * query_processing_scan_compressed_codes_opt_o_direct (DCAT.h:2805) /
+ * ..._in_memory (DCAT.h:3731): ADC table build, DeltaTree scan, top-k.
+ * queries [Q][M*Ds] host floats; outputs [Q][topk], ascending distance, ties by lower
+ * position: out_pos = DFS position (what the reference returns), out_id = pos2id[pos]
+ * (NULL allowed), out_dist = float(sum of the node's M table entries), i.e. the value
+ * the reference's double accumulation rounds to.  Entries beyond the number of nodes in
+ * the shard are (0xFFFFFFFF, FLT_MAX). */
+int dpq_index_search(dpq_index* idx, const float* queries, int Q, int topk, uint32_t* out_pos,
+                     uint32_t* out_id, float* out_dist);
+
+/* Device-resident variant: all pointers are DEVICE pointers, work is enqueued on the
+ * index stream; call dpq_index_sync() before reading.  Used by bench.py ("value": inputs
+ * resident in HBM) and by the multi-GPU driver, which all-gathers out_key over NCCL.
+ * out_key [Q][topk] = (uint64) float_bits(dist) << 32 | pos, ascending. */
+int dpq_index_search_device(dpq_index* idx, const float* d_queries, int Q, int topk,
+                            uint64_t* d_out_key);
+int dpq_index_sync(dpq_index* idx);
+
+/* Merge n_lists sorted top-k key lists per query (device pointers; [n_lists][Q][topk])
+ * into one [Q][topk]: the post-gather step of the sharded scan. */
+int dpq_merge_topk_device(dpq_index* idx, const uint64_t* d_keys, int n_lists, int Q, int topk,
+                          uint64_t* d_out_key);
+
+/* Raw device allocation helpers for hosts without a CUDA binding (ctypes, cgo, JNI). */
+int dpq_malloc(void** dptr, size_t bytes);
+int dpq_free(void* dptr);
+int dpq_memcpy_h2d(void* dst, const void* src, size_t bytes);
+int dpq_memcpy_d2h(void* dst, const void* src, size_t bytes);
+int dpq_malloc_host(void** hptr, size_t bytes); /* pinned */
+int dpq_free_host(void* hptr);
+
+/* Introspection: "n_codes", "n_bytes" (algorithmic stream bytes of this shard),
+ * "n_local" (nodes scanned by this rank), "n_diffs", "n_chunks", "ops_bytes",
+ * "last_launches" (kernels launched by the last search), "last_fallback" (queries that
+ * took the exact fallback in the last search), "last_scan_us" (scan kernel time of the
+ * last search, CUDA events), "last_total_us". */
+int64_t dpq_index_stat(dpq_index* idx, const char* name);
+
+void dpq_index_close(dpq_index* idx);
+
+/* Host-only introspection of the tree compiler (no GPU needed): compiles the stream exactly
+ * as dpq_index_open does and lets a test copy the device program out and interpret it.
+ * `what`: "ops" (uint32), "chunks" (4 x uint32 each), "anc" (uint8), "codes" (uint8),
+ * scalars "n_ops", "n_chunks", "n_local", "base_pos", "rb", "levels", "n_bytes", "n_diffs". */
+typedef struct dpq_program dpq_program;
+int dpq_program_compile(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                        int rank, int n_ranks, int chunk_nodes, dpq_program** out);
+int64_t dpq_program_size(dpq_program* p, const char* what); /* bytes for arrays, value for scalars */
+int dpq_program_copy(dpq_program* p, const char* what, void* dst);
+void dpq_program_free(dpq_program* p);
+
+/* ---- stand-alone kernels ------------------------------------------------------------- */
+/* ADC tables of Q queries, lut[Q][M][K] (DCAT.h:2841-2849 / :3750-3758), host buffers. */
+int dpq_adc_tables(const float* codewords, int M, int K, int Ds, const float* queries, int Q,
+                   float* lut);
+
+/* PQTree::EncodePlain (pq_tree.cpp:192-253) over n vectors x[n][D], D <= M*Ds (zero
+ * padded): codes[n][M], bit-exact (sequential FP32, no FMA, strict <). */
+int dpq_encode(const float* codewords, int M, int K, int Ds, const float* x, int64_t n, int D,
+               uint8_t* codes);
+
+/* find_edges_by_diff_approx (DCAT.h:1207-1332) with the canonical stable-sort tie rule:
+ * edges[n_codes-1][2] = (parent id, child id) in emission order, *root_id. */
+int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_height_folds,
+                   int method, uint32_t* edges, uint32_t* root_id);
+
+/* check_num_diffs / dfs_node_layout diff extraction (DCAT.h:196-238, 1156-1183): for each
+ * edge the changed-subspace bitmap (bit m set <=> codes differ in subspace m);
+ * returns the total number of diffs through *n_diffs. */
+int dpq_edge_diffs(const uint8_t* codes, int64_t n_codes, int M, const uint32_t* edges,
+                   int64_t n_edges, uint32_t* bitmaps, int64_t* n_diffs);
+
+/* Exact brute-force ground truth (pmain:138-166, 569-669): base[n][D] (ids id0..),
+ * queries[Q][D]; accumulates into a state created by dpq_groundtruth_begin. */
+typedef struct dpq_gt dpq_gt;
+int dpq_groundtruth_begin(const float* queries, int Q, int D, int topk, dpq_gt** out);
+int dpq_groundtruth_chunk(dpq_gt* st, const float* base, int64_t n, int64_t id0);
+int dpq_groundtruth_finish(dpq_gt* st, uint32_t* out_id, float* out_dist); /* frees st */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

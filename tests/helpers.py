@@ -1,0 +1,71 @@
+"""Shared parity helpers: tie-aware top-k comparison and a numpy interpreter of the device
+scan program (test-only; mirrors scan_kernel in deltapq_b200/csrc/kernels.cu)."""
+import numpy as np
+
+REL_TOL = 1e-5  # BASELINE.json north_star: ties within 1e-5 relative distance
+
+
+def assert_topk_equal(pos_a, dist_a, pos_b, dist_b, node_dist=None, rel=REL_TOL):
+    """Distances equal within `rel`; id sets equal after removing ids that tie (within `rel`)
+    with the k-th distance; never compares id order inside a tie group."""
+    pos_a, pos_b = np.asarray(pos_a, np.int64), np.asarray(pos_b, np.int64)
+    dist_a, dist_b = np.asarray(dist_a, np.float64), np.asarray(dist_b, np.float64)
+    assert pos_a.shape == pos_b.shape
+    np.testing.assert_allclose(dist_a, dist_b, rtol=rel, atol=0)
+    if pos_a.ndim == 1:
+        pos_a, pos_b, dist_a, dist_b = pos_a[None], pos_b[None], dist_a[None], dist_b[None]
+    for q in range(pos_a.shape[0]):
+        kth = max(dist_a[q, -1], dist_b[q, -1])
+        strict_a = {int(p) for p, d in zip(pos_a[q], dist_a[q]) if d < kth * (1 - rel)}
+        strict_b = {int(p) for p, d in zip(pos_b[q], dist_b[q]) if d < kth * (1 - rel)}
+        assert strict_a == strict_b, (q, sorted(strict_a ^ strict_b))
+        if node_dist is not None:  # every reported id really has the reported distance
+            nd = np.asarray(node_dist[q] if np.ndim(node_dist) == 2 else node_dist, np.float64)
+            np.testing.assert_allclose(nd[pos_a[q]], dist_a[q], rtol=rel)
+
+
+def interpret_program(prog, table_q):
+    """Runs the op program for ONE query on the CPU.  table_q: integer or float table
+    [M*K].  Returns (positions, distances) of every node the program emits, in order."""
+    rb = prog["rb"]
+    fmask = ((1 << rb) - 1) << 2
+    tsh = rb + 2
+    M = prog["codes"].shape[1]
+    K = len(table_q) // M
+    ops, chunks, anc = prog["ops"], prog["chunks"], prog["anc"]
+    out_pos, out_d = [], []
+    for c in range(chunks.shape[0]):
+        qb, nq, first_pos, naf = (int(v) for v in chunks[c])
+        n_anc, emit_root = naf & 0xFF, bool(naf & 0x100)
+        stack = {}
+        par = 0
+        for lev in range(n_anc):
+            d = sum(table_q[m * K + int(anc[c, lev, m])] for m in range(M))
+            stack[lev] = d
+            par = d
+            if lev == 0 and emit_root:
+                out_pos.append(0)
+                out_d.append(d)
+        acc, pos = par, first_pos
+        for w in ops[qb * 4:(qb + nq) * 4]:
+            w = int(w)
+            fr = (w & fmask) >> 2
+            to = ((w >> tsh) & fmask) >> 2
+            acc = acc + table_q[to] - table_q[fr]
+            if w & 0x80000000:
+                d = acc
+                out_pos.append(pos)
+                out_d.append(d)
+                if rb == 11:
+                    lev = (w >> 26) & 7
+                else:
+                    lev = (w & 3) | (((w >> 14) & 3) << 2)
+                if w & 0x40000000:
+                    par = d
+                    if w & 0x20000000:
+                        stack[lev] = d
+                elif w & 0x20000000:
+                    par = stack[lev]
+                acc = par
+                pos += 1
+    return np.array(out_pos, np.int64), np.array(out_d)

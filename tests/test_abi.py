@@ -1,0 +1,113 @@
+"""CPU: the C-ABI library loads, exports every symbol include/dpq.h declares, fails loudly
+without a GPU, and its host-side tree compiler is correct (interpreted on the CPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import deltapq_b200 as dpq
+from helpers import interpret_program
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dpq.h")).read()
+    declared = set(re.findall(r"\b(dpq_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = dpq.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libdpq.so does not export {name}"
+    assert declared == set(dpq.SYMBOLS)
+    assert L.dpq_version() >= 100
+
+
+def test_fails_loudly_without_gpu(golden1501):
+    if dpq.device_count() > 0:
+        pytest.skip("a GPU is present")
+    g = golden1501
+    with pytest.raises(dpq.DpqError, match="no CUDA device"):
+        dpq.DeltaTreeIndex(g["payload"], int(g["n"]), 8, 256)
+    with pytest.raises(dpq.DpqError, match="no CUDA device"):
+        dpq.encode(g["cw"], g["base_head"])
+    with pytest.raises(dpq.DpqError, match="no CUDA device"):
+        dpq.adc_tables(g["cw"], g["queries"])
+
+
+def test_rejects_malformed_stream(golden1501):
+    g = golden1501
+    n = int(g["n"])
+    with pytest.raises(dpq.DpqError, match="trunc|mismatch|missing"):
+        dpq.compile_program(g["payload"][:-3], n, 8, 256)
+    bad = g["payload"].copy()
+    bad[8] = 0x77  # depth jump 0 -> 7
+    with pytest.raises(dpq.DpqError, match="depth"):
+        dpq.compile_program(bad, n, 8, 256)
+    with pytest.raises(dpq.DpqError):
+        dpq.compile_program(g["payload"], n, 33, 256)
+
+
+@pytest.mark.parametrize("chunk_nodes", [4, 37, 256, 100000])
+def test_program_reproduces_every_node_distance(golden4000, chunk_nodes):
+    """The compiled op program, interpreted on the CPU with an integer table, reproduces the
+    oracle's per-node sums exactly, for any chunking."""
+    g = golden4000
+    n = int(g["n"])
+    prog = dpq.compile_program(g["payload"], n, 8, 256, chunk_nodes=chunk_nodes)
+    assert prog["n_local"] == n and prog["base_pos"] == 0
+    assert prog["n_bytes"] == len(g["payload"])
+    assert np.array_equal(prog["codes"], g["codes"][g["vec_id"]])
+    rng = np.random.default_rng(3)
+    table = rng.integers(0, 1 << 20, 8 * 256).astype(np.int64)
+    pos, d = interpret_program(prog, table)
+    assert np.array_equal(np.sort(pos), np.arange(n))
+    want = table.reshape(8, 256)[np.arange(8)[None, :], prog["codes"]].sum(1)
+    assert np.array_equal(d[np.argsort(pos)], want)
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+def test_shards_partition_the_tree(golden4000, n_ranks):
+    g = golden4000
+    n = int(g["n"])
+    codes_dfs = g["codes"][g["vec_id"]]
+    table = np.arange(8 * 256, dtype=np.int64) * 7 + 1
+    want = table.reshape(8, 256)[np.arange(8)[None, :], codes_dfs].sum(1)
+    seen = np.zeros(n, np.int32)
+    total_bytes = 0
+    next_base = 0
+    for r in range(n_ranks):
+        prog = dpq.compile_program(g["payload"], n, 8, 256, rank=r, n_ranks=n_ranks, chunk_nodes=64)
+        if prog["n_local"] == 0:
+            continue
+        assert prog["base_pos"] == next_base  # contiguous position ranges
+        next_base = prog["base_pos"] + prog["n_local"]
+        assert np.array_equal(prog["codes"], codes_dfs[prog["base_pos"]:next_base])
+        pos, d = interpret_program(prog, table)
+        seen[pos] += 1
+        assert np.array_equal(d, want[pos])
+        total_bytes += prog["n_bytes"]
+    assert next_base == n and np.all(seen == 1)
+    # every shard repeats the root code and may round its depth nibbles up
+    assert len(g["payload"]) <= total_bytes <= len(g["payload"]) + n_ranks * 9
+
+
+def test_m16_program(golden_m16):
+    g = golden_m16
+    codes, cw = g["codes"], g["cw"]
+    _, _, lay, payload = po.build_tree(codes, cw)
+    prog = dpq.compile_program(payload, len(codes), 16, 256, chunk_nodes=50)
+    assert prog["rb"] == 12 and prog["levels"] == 16
+    table = np.random.default_rng(5).integers(0, 1 << 18, 16 * 256).astype(np.int64)
+    pos, d = interpret_program(prog, table)
+    want = table.reshape(16, 256)[np.arange(16)[None, :], codes[lay["vec_id"]]].sum(1)
+    assert np.array_equal(d[np.argsort(pos)], want)
+
+
+def test_single_node_tree():
+    payload = np.arange(8, dtype=np.uint8)
+    prog = dpq.compile_program(payload, 1, 8, 256)
+    pos, d = interpret_program(prog, np.arange(2048, dtype=np.int64))
+    assert list(pos) == [0] and d[0] == sum(m * 256 + m for m in range(8))

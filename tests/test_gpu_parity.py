@@ -1,0 +1,220 @@
+"""GPU: the CUDA path (through the C ABI, libdpq.so) against the oracle and the reference
+fixtures.  Integer/byte results bit-exact; distances bit-exact where the reference's double
+accumulation is exact, else within 1e-5 relative; ids modulo ties at 1e-5."""
+import numpy as np
+import pytest
+
+import datagen as dg
+import deltapq_b200 as dpq
+from helpers import assert_topk_equal, REL_TOL
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _open(g, **opts):
+    ix = dpq.DeltaTreeIndex(g["payload"], int(g["n"]), int(g["M"]), int(g["K"]), pos2id=g["vec_id"])
+    ix.set_codebook(g["cw"])
+    for k, v in opts.items():
+        ix.set_option(k, v)
+    return ix
+
+
+def test_adc_tables_bit_exact(golden4000):
+    g = golden4000
+    lut = dpq.adc_tables(g["cw"], g["queries"])
+    for i in range(len(g["ref_lut"])):
+        assert np.array_equal(lut[i], g["ref_lut"][i])          # vs the reference itself
+    for i, q in enumerate(g["queries"]):
+        assert np.array_equal(lut[i], po.lut(g["cw"], q))        # vs the oracle
+
+
+@pytest.mark.parametrize("pack", [1, 2])
+@pytest.mark.parametrize("fixture", ["golden4000", "golden1501"])
+def test_search_matches_reference_fixture(request, fixture, pack):
+    g = request.getfixturevalue(fixture)
+    n, k = int(g["n"]), int(g["topk"])
+    ix = _open(g, pack=pack)
+    pos, ids, dist = ix.search(g["queries"], k)
+    ref_pos = np.where(g["ref_pos"] == n, n - 1, g["ref_pos"])
+    assert np.array_equal(dist, g["ref_dist"])                   # bit-exact distances
+    assert_topk_equal(pos, dist, ref_pos, g["ref_dist"])
+    assert np.array_equal(ids, g["vec_id"][pos])
+    ix.close()
+
+
+@pytest.mark.parametrize("pack,slices,warps", [(1, 1, 16), (1, 5, 3), (2, 3, 8), (2, 0, 16)])
+def test_search_vs_oracle_all_nodes(golden4000, pack, slices, warps):
+    """k = 64: deep into the candidate lists; every reported (pos, dist) is checked against
+    the oracle's per-node distance, and the sets against the oracle's top-k."""
+    g = golden4000
+    n = int(g["n"])
+    ix = _open(g, pack=pack, slices=slices, warps=warps)
+    k = 64
+    pos, _, dist = ix.search(g["queries"], k)
+    for i, q in enumerate(g["queries"]):
+        opos, odist, nd = po.scan(g["payload"], n, g["cw"], q, k, want_node_dist=True)
+        assert np.array_equal(dist[i], odist)
+        assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+        assert len(set(pos[i])) == k
+    ix.close()
+
+
+def test_forced_exact_fallback(golden4000):
+    g = golden4000
+    a = _open(g)
+    b = _open(g, force_fallback=1)
+    pa = a.search(g["queries"], 10)
+    pb = b.search(g["queries"], 10)
+    assert b.stat("last_fallback") == len(g["queries"]) and a.stat("last_fallback") == 0
+    assert np.array_equal(pa[2], pb[2]) and np.array_equal(pa[0], pb[0])
+    a.close(), b.close()
+
+
+def test_duplicates_and_ties():
+    """Heavy exact ties: many duplicate codes.  Distances must match the oracle exactly and
+    ids modulo ties; own tie rule = lower position first."""
+    rng = np.random.default_rng(7)
+    M, K, n = 8, 256, 3000
+    uniq = rng.integers(0, K, (40, M)).astype(np.uint8)
+    codes = uniq[rng.integers(0, 40, n)]
+    cw = dg.roundtrip_codebook((rng.random((M, K, 4)) * 50).astype(np.float32))
+    _, _, lay, payload = po.build_tree(codes, cw)
+    ix = dpq.DeltaTreeIndex(payload, n, M, K)
+    ix.set_codebook(cw)
+    queries = (rng.random((9, M * 4)) * 50).astype(np.float32)
+    for pack in (1, 2):
+        ix.set_option("pack", pack)
+        pos, _, dist = ix.search(queries, 20)
+        for i, q in enumerate(queries):
+            opos, odist, nd = po.scan(payload, n, cw, q, 20, want_node_dist=True)
+            assert np.array_equal(dist[i], odist)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+            # deterministic tie rule: (distance, position) ascending
+            order = np.lexsort((pos[i], dist[i]))
+            assert np.array_equal(order, np.arange(20))
+    ix.close()
+
+
+def test_tiny_trees():
+    rng = np.random.default_rng(9)
+    M, K = 8, 256
+    cw = dg.roundtrip_codebook((rng.random((M, K, 2)) * 9).astype(np.float32))
+    for n in (1, 2, 3, 7):
+        codes = rng.integers(0, K, (n, M)).astype(np.uint8)
+        if n > 1:
+            _, _, lay, payload = po.build_tree(codes, cw)
+        else:
+            payload = codes[0].copy()
+        ix = dpq.DeltaTreeIndex(payload, n, M, K)
+        ix.set_codebook(cw)
+        q = (rng.random((3, M * 2)) * 9).astype(np.float32)
+        pos, _, dist = ix.search(q, 4)
+        for i in range(3):
+            opos, odist = po.scan(payload, n, cw, q[i], min(4, n))
+            assert np.array_equal(dist[i][: min(4, n)], odist)
+            assert np.all(pos[i][min(4, n):] == 0xFFFFFFFF)
+        ix.close()
+
+
+def test_sharded_search_merges_to_whole(golden4000):
+    """SURVEY 8e on one GPU: 4 shards opened as 4 indexes, local top-k lists merged by the
+    merge kernel == the unsharded result (positions are global)."""
+    g = golden4000
+    n, k, R = int(g["n"]), 10, 4
+    Q = len(g["queries"])
+    whole = _open(g)
+    wpos, _, wdist = whole.search(g["queries"], k)
+    dq = dpq.DeviceBuffer(g["queries"].nbytes).upload(g["queries"])
+    dk = dpq.DeviceBuffer(R * Q * k * 8)
+    do = dpq.DeviceBuffer(Q * k * 8)
+    shards = []
+    for r in range(R):
+        ix = dpq.DeltaTreeIndex(g["payload"], n, 8, 256, rank=r, n_ranks=R)
+        ix.set_codebook(g["cw"])
+        ix.search_device(dq.ptr, Q, k, dk.ptr.value + r * Q * k * 8)
+        ix.sync()
+        shards.append(ix)
+    assert sum(s.stat("n_local") for s in shards) == n
+    shards[0].merge_device(dk.ptr, R, Q, k, do.ptr)
+    shards[0].sync()
+    pos, dist = dpq.unpack_keys(do.download(np.uint64, (Q, k)))
+    assert np.array_equal(dist, wdist) and np.array_equal(pos, wpos)
+    for s in shards:
+        s.close()
+    whole.close()
+
+
+def test_m16_extension_search(golden_m16):
+    """Configs 3/4 (M=16): no reference tree oracle exists; parity is
+    against the generalised restatement, top-100."""
+    g = golden_m16
+    codes, cw = g["codes"], g["cw"]
+    _, _, lay, payload = po.build_tree(codes, cw)
+    ix = dpq.DeltaTreeIndex(payload, len(codes), 16, 256, pos2id=lay["vec_id"])
+    ix.set_codebook(cw)
+    for pack in (1, 2):
+        ix.set_option("pack", pack)
+        pos, ids, dist = ix.search(g["queries"], 100)
+        for i, q in enumerate(g["queries"]):
+            opos, odist, nd = po.scan(payload, len(codes), cw, q, 100, want_node_dist=True)
+            np.testing.assert_allclose(dist[i], odist, rtol=REL_TOL)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+    ix.close()
+
+
+def test_encode_bit_exact(golden4000, golden_m16):
+    for g in (golden4000, golden_m16):
+        assert np.array_equal(dpq.encode(g["cw"], g["base_head"]), g["codes"][:256])
+    rng = np.random.default_rng(2)
+    cw = dg.roundtrip_codebook(rng.random((16, 256, 60)).astype(np.float32))  # GIST shape
+    x = rng.random((700, 960)).astype(np.float32)
+    assert np.array_equal(dpq.encode(cw, x), po.encode(cw, x))
+    cw = dg.roundtrip_codebook(rng.random((4, 100, 7)).astype(np.float32))   # odd Ds, padding
+    x = rng.random((33, 27)).astype(np.float32)
+    assert np.array_equal(dpq.encode(cw, x), po.encode(cw, x))
+
+
+def test_edge_diffs(golden4000):
+    g = golden4000
+    bm, nd = dpq.edge_diffs(g["codes"], g["edges"])
+    a, b = g["codes"][g["edges"][:, 0]], g["codes"][g["edges"][:, 1]]
+    want = ((a != b) * (1 << np.arange(8))).sum(1).astype(np.uint32)
+    assert np.array_equal(bm, want)
+    assert nd == int((a != b).sum()) == len(g["payload"]) - 8 - (3 * (int(g["n"]) - 1) + 1) // 2
+
+
+def test_groundtruth_exact():
+    base = dg.sift_like(20000, 128, seed=4)
+    qs = dg.sift_like(12, 128, seed=5)
+    ids, dist = dpq.groundtruth(base, qs, 10, chunk=7000)
+    oid, odist = po.groundtruth(base, qs, 10, chunk=7000)
+    assert np.array_equal(dist, odist)
+    assert_topk_equal(ids, dist, oid, odist)
+    g = dg.gist_like(3000, 960, seed=6)
+    gq = dg.gist_like(5, 960, seed=7)
+    ids, dist = dpq.groundtruth(g, gq, 5)
+    oid, odist = po.groundtruth(g, gq, 5)
+    assert np.array_equal(dist, odist)
+    assert_topk_equal(ids, dist, oid, odist)
+
+
+def test_medium_tree_end_to_end():
+    """50K codes: encode on the GPU (bit-exact), oracle-built tree, search vs oracle."""
+    base = dg.sift_like(50000, 128, seed=21)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(8000, 128, seed=22), 8, 256, iters=4))
+    codes = dpq.encode(cw, base)
+    assert np.array_equal(codes[:2000], po.encode(cw, base[:2000]))
+    _, _, lay, payload = po.build_tree(codes, cw)
+    ix = dpq.DeltaTreeIndex(payload, len(codes), 8, 256, pos2id=lay["vec_id"])
+    ix.set_codebook(cw)
+    queries = dg.sift_like(64, 128, seed=23)
+    for pack in (1, 2):
+        ix.set_option("pack", pack)
+        pos, ids, dist = ix.search(queries, 10)
+        assert ix.stat("last_fallback") <= 2
+        for i in range(0, 64, 7):
+            opos, odist, nd = po.scan(payload, len(codes), cw, queries[i], 10, want_node_dist=True)
+            assert np.array_equal(dist[i], odist)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+    ix.close()
