@@ -74,10 +74,10 @@ struct dpq_index {
     std::vector<uint32_t> pos2id_host;  // local slice
     // options
     int opt_slices = 0, opt_pack = 1, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
-    int chunk_nodes = 256;
+    int chunk_nodes = 512;
     // scratch
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_fbuf,
-        d_fcnt, d_key;
+        d_fcnt, d_key, d_gthr;
     void* h_stage = nullptr;  // pinned staging for the host-buffer path
     size_t h_stage_cap = 0;
     // stats
@@ -97,7 +97,12 @@ int choose_geometry(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     g->levels = P.fmt.levels();
     g->n_warps = std::max(1, std::min(16, ix->opt_warps));
     const size_t rows_bytes = (size_t)4 << g->rb;
-    const size_t overhead = (size_t)g->n_warps * g->levels * 128 + 32 * g->pack * 4 + 64;
+    int slack = ix->opt_slack >= 0 ? ix->opt_slack : std::max(6, topk / 4);
+    g->kp = std::min(256, topk + slack);
+    if (topk > 256 || g->kp < topk) return fail(DPQ_ERR_ARG, "topk must be <= 256");
+    g->kps = g->kp <= 32 ? g->kp : 0;
+    g->bcap = std::min(512, ((g->kp + 31) / 32) * 32 + 32);
+    const size_t overhead = (size_t)g->n_warps * (g->levels * 128 + 512) + 32 * g->pack * 4 * (1 + g->kps) + 64;
     int qgl = (int)((dpq::kMaxSmem - overhead) / rows_bytes);
     qgl = std::min(qgl, 32);
     if (qgl < 1) return fail(DPQ_ERR_ARG, "ADC table does not fit in shared memory");
@@ -107,9 +112,6 @@ int choose_geometry(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     g->qgl = qgl;
     g->qpg = qgl * g->pack;
     g->n_groups = (Q + g->qpg - 1) / g->qpg;
-    int slack = ix->opt_slack >= 0 ? ix->opt_slack : std::max(6, topk / 4);
-    g->kp = std::min(256, topk + slack);
-    if (topk > 256 - 0 || g->kp < topk) return fail(DPQ_ERR_ARG, "topk must be <= 256");
     int n_slices = ix->opt_slices;
     if (n_slices <= 0) {
         int by_fill = (148 * 6 + g->n_groups - 1) / g->n_groups;
@@ -301,7 +303,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_lutf.ensure((size_t)Q * MK * 4))) return rc;
     if ((rc = ix->d_scale.ensure((size_t)g.n_groups * g.qpg * 8))) return rc;
     if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * g.qgl * rows * 4))) return rc;
-    if ((rc = ix->d_cand.ensure(n_items * g.n_warps * g.kp * LW * 8))) return rc;
+    if ((rc = ix->d_cand.ensure(n_items * g.n_warps * g.bcap * LW * 8))) return rc;
+    if ((rc = ix->d_gthr.ensure((size_t)g.n_groups * g.qpg * 4))) return rc;
     if ((rc = ix->d_cnt.ensure(n_items * g.n_warps * LW * 4))) return rc;
     if ((rc = ix->d_flagged.ensure((size_t)max_flagged * 4))) return rc;
     if ((rc = ix->d_ctrl.ensure(64))) return rc;
@@ -314,7 +317,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaMemsetAsync(ctrl, 0, 64, st));
     CU(cudaMemsetAsync(ix->d_fcnt.p, 0, (size_t)max_flagged * 4, st));
     dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
-                    ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), g, st);
+                    ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);
     dpq::ScanArgs sa;
     sa.g = g;
     sa.ops = ix->d_ops.as<uint4>();
@@ -324,6 +327,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     sa.qlut = ix->d_qlut.as<uint32_t>();
     sa.cand = ix->d_cand.as<uint64_t>();
     sa.cand_cnt = ix->d_cnt.as<uint32_t>();
+    sa.gthr = ix->d_gthr.as<uint32_t>();
     sa.Q = Q;
     CU(cudaEventRecord(ix->ev[1], st));
     CU(dpq::launch_scan(sa, st));
@@ -501,7 +505,8 @@ void dpq_index_close(dpq_index* ix) {
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
-                      &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_fbuf, &ix->d_fcnt, &ix->d_key})
+                      &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_fbuf, &ix->d_fcnt, &ix->d_key,
+                      &ix->d_gthr})
         b->release();
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
     for (auto& e : ix->ev)

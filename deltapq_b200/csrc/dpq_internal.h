@@ -13,35 +13,35 @@ namespace dpq {
 // The on-disk stream (reference writer DCAT.h:1765-1842) is a strictly
 // sequential byte code: variable-length records, each node's parent found through a
 // depth stack.  At open time the host decodes it once and emits, per chunk of
-// `chunk_nodes` consecutive DFS positions, a flat array of 32-bit delta ops that a warp can
-// execute with no further decoding:
+// `chunk_nodes` consecutive DFS positions, a flat array of node RECORDS that a warp can
+// execute with no further decoding.  A record is 1..4 quads (uint4) of 32-bit delta ops,
+// one op per subspace the node's edge changes, unused slots zero (a zero op reads table
+// row 0 twice and cancels):
 //
-//   op = from_row4 | to_row4 << (RB+2) | LEVEL | KIND | LAST
+//   op = from_row4 | to_row4 << (RB+2)
 //     from_row4 / to_row4 : (m*K + centroid) * 4, byte offset of the ADC-table row of the
 //                           subspace this edge changes: old centroid / new centroid
-//     LAST  (bit 31)      : last op of a node -> the accumulator now holds the node distance
-//     KIND  (bits 29..30) : what the NEXT node's parent is: 0 sibling (same parent),
-//                           2 child (this node), 3 child + store this distance to the
-//                           per-warp depth stack, 1 pop (reload stack[LEVEL])
-//     LEVEL               : stack level for store / pop
+//   the FIRST word of a record also carries, in bits no op field uses:
+//     NQ-1  (bits 30..31) : quads in this record
+//     CHILD (bit 29)      : the NEXT node is this node's child (its parent distance = ours)
+//     AUX   (bit 28)      : with CHILD: also store our distance to the per-warp depth stack
+//                           at LEVEL; without CHILD: the next node's parent is stack[LEVEL]
+//                           (neither bit: the next node is a sibling, same parent)
+//     LEVEL               : bits 0..1 and RB+2..RB+3 (4 bits)
 //
 // Every chunk also records the codes of the ancestors of its first node, so a warp starts a
 // chunk with full M-term table sums for those ancestors ("full M-term lookup at each root")
 // and needs nothing from other chunks.
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t OP_LAST = 1u << 31;
-constexpr uint32_t OP_CHILD = 1u << 30;
-constexpr uint32_t OP_AUX = 1u << 29;  // with CHILD: store; without: pop
+constexpr uint32_t OP_CHILD = 1u << 29;
+constexpr uint32_t OP_AUX = 1u << 28;  // with CHILD: store; without: pop
 
 struct OpFormat {
     int rb;  // row bits: 11 (M*K <= 2048) or 12 (M*K <= 4096)
     uint32_t fmask() const { return ((1u << rb) - 1u) << 2; }
     int tshift() const { return rb + 2; }
     int levels() const { return rb == 11 ? 8 : 16; }
-    uint32_t level_bits(uint32_t lev) const {
-        if (rb == 11) return lev << 26;                  // bits 26..28
-        return (lev & 3u) | ((lev >> 2) << 14);          // bits 0..1 and 14..15
-    }
+    uint32_t level_bits(uint32_t lev) const { return (lev & 3u) | ((lev >> 2) << (rb + 2)); }
 };
 
 struct ChunkDesc {
@@ -61,7 +61,7 @@ struct ScanProgram {
     int64_t n_local = 0;       // nodes held by this shard (contiguous positions)
     int64_t local_bytes = 0;   // algorithmic stream bytes of this shard
     int64_t n_diffs = 0;       // changed subspaces over this shard's nodes
-    std::vector<uint32_t> ops;        // multiple of 4 words per chunk
+    std::vector<uint32_t> ops;        // node records, each a multiple of 4 words
     std::vector<ChunkDesc> chunks;
     std::vector<uint8_t> anc;         // [n_chunks][levels][M]
     std::vector<uint8_t> codes;       // [n_local][M] decoded codes, by position - base_pos

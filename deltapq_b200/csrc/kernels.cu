@@ -72,7 +72,8 @@ __device__ __forceinline__ float adc_entry(const float* __restrict__ c, const fl
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ cw, int M, int K, int Ds,
                                                   const float* __restrict__ queries, int Q,
                                                   float* __restrict__ lutf, double* __restrict__ scale,
-                                                  uint32_t* __restrict__ qlut, ScanGeom g) {
+                                                  uint32_t* __restrict__ qlut, uint32_t* __restrict__ gthr,
+                                                  ScanGeom g) {
     extern __shared__ float s_q[];  // M*Ds
     __shared__ int s_max[16];
     const int vq = blockIdx.x;  // virtual query (padding lanes of the last group included)
@@ -111,7 +112,10 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ cw, 
     for (int m = 0; m < M; ++m) sum += (double)__int_as_float(s_max[m]);
     const double qmax = g.pack == 1 ? (double)(1u << 30) : (double)(32767 - 16);
     const double s = sum > 0.0 ? qmax / sum : 1.0;
-    if (k == 0) scale[vq] = s;
+    if (k == 0) {
+        scale[vq] = s;
+        gthr[vq] = g.pack == 1 ? kInf31 : 0x8000u;
+    }
     // rows beyond M*K are never addressed; entry (m,k) lives at word (row ^ lane)
     if (k < K)
         for (int m = 0; m < M; ++m) {
@@ -123,11 +127,11 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ cw, 
 }
 
 void launch_lut(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q,
-                float* d_lutf, double* d_scale, uint32_t* d_qlut, const ScanGeom& g,
+                float* d_lutf, double* d_scale, uint32_t* d_qlut, uint32_t* d_gthr, const ScanGeom& g,
                 cudaStream_t st) {
     int nvq = g.n_groups * g.qpg;
     lut_kernel<<<nvq, 256, (size_t)M * Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf,
-                                                              d_scale, d_qlut, g);
+                                                              d_scale, d_qlut, d_gthr, g);
 }
 void launch_lut_plain(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q,
                       float* d_lutf, cudaStream_t st) {
@@ -137,35 +141,151 @@ void launch_lut_plain(const float* d_cw, int M, int K, int Ds, const float* d_qu
     g.qgl = 1;
     g.qpg = 1;
     lut_kernel<<<Q, 256, (size_t)M * Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf,
-                                                            nullptr, nullptr, g);
+                                                            nullptr, nullptr, nullptr, g);
 }
 
 // ------------------------------------------------------------------------ scan ---------
 // CTA = (query group, tree slice).  Shared memory: the group's fixed-point ADC table,
 // [lane][row ^ lane] so that the 32 lanes of a warp, all reading the SAME row, hit 32
-// different banks; per-warp depth stacks; per-query shared thresholds.
+// different banks; per-warp op windows; per-warp depth stacks; per-query shared bounds.
 // Each warp pulls chunks of the op program and runs the delta recurrence with lanes =
 // queries: one table row read per changed subspace for the old and the new centroid.
+//
+// Candidates: a node whose distance is below the query's current bound is APPENDED to that
+// (warp, query)'s buffer in global scratch (one store); when a buffer fills, the whole warp
+// compacts it to its kp smallest keys (rank by counting through shuffles) and tightens the
+// bound, which is shared through shared memory (CTA) and global memory (other slices).
+
+// Warp-cooperative compaction of one buffer: keeps the min(n, kp) smallest of its n keys,
+// sorted ascending, and returns the kept count (uniform).  *kth = distance part of the
+// kp-th smallest key when n >= kp.
+template <int MAXPER>
+__device__ __forceinline__ int compact_buffer_t(uint64_t* buf, int n, int kp, int lane, uint32_t* kth) {
+    __syncwarp();
+    const int per = (n + 31) >> 5;
+    uint64_t mine[MAXPER];
+    int rank[MAXPER];
+#pragma unroll
+    for (int t = 0; t < MAXPER; ++t) {
+        mine[t] = ~0ull;
+        rank[t] = 0;
+        if (t < per) {
+            int i = t * 32 + lane;
+            if (i < n) mine[t] = buf[i];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXPER; ++u) {
+        if (u < per) {
+            for (int j = 0; j < 32; ++j) {
+                uint64_t o = __shfl_sync(0xffffffffu, mine[u], j);
+#pragma unroll
+                for (int t = 0; t < MAXPER; ++t)
+                    if (t < per) rank[t] += o < mine[t];
+            }
+        }
+    }
+    __syncwarp();
+    const int keep = n < kp ? n : kp;
+    uint32_t kd = 0;
+#pragma unroll
+    for (int t = 0; t < MAXPER; ++t) {
+        if (t < per) {
+            int i = t * 32 + lane;
+            if (i < n && rank[t] < keep) buf[rank[t]] = mine[t];  // keys are unique
+            if (i < n && rank[t] == kp - 1) kd = (uint32_t)(mine[t] >> 32);
+        }
+    }
+    for (int o = 16; o; o >>= 1) kd |= __shfl_xor_sync(0xffffffffu, kd, o);
+    *kth = kd;
+    __syncwarp();
+    return keep;
+}
+
+__device__ __noinline__ int compact_buffer_big(uint64_t* buf, int n, int kp, int lane, uint32_t* kth) {
+    return compact_buffer_t<16>(buf, n, kp, lane, kth);  // buffers hold at most 512 keys
+}
+__device__ __forceinline__ int compact_buffer(uint64_t* buf, int n, int kp, int lane, uint32_t* kth) {
+    if (n <= 32) return compact_buffer_t<1>(buf, n, kp, lane, kth);
+    return compact_buffer_big(buf, n, kp, lane, kth);
+}
+
+// Lock-free insert of distance v into a CTA-shared ascending array A[0..n) that keeps the n
+// smallest distances any warp of the CTA has seen for one query.  Each step is one
+// atomicMin that leaves min(old, carry) in the slot and carries max(old, carry) on: the
+// multiset {slots} + {carried values} is preserved and the array stays sorted under any
+// interleaving, so A[n-1] is always a valid bound once no slot holds the initial ~0.
+__device__ __forceinline__ void shared_topk_insert(uint32_t* A, int n, uint32_t v) {
+    int p = n - 1;
+    if (v >= A[p]) return;
+    while (p > 0 && A[p - 1] > v) --p;  // slots before p are <= v and only ever decrease
+    uint32_t c = v;
+    for (int i = p; i < n && c != 0xFFFFFFFFu; ++i) {
+        const uint32_t old = atomicMin(&A[i], c);
+        c = old > c ? old : c;
+    }
+}
+
 template <int PACK>
-struct Lists {
-    uint64_t* base;  // this warp's lists: [kp][32*PACK]
-    int kp;
+struct CandCtx {  // per-thread constants of the candidate slow path (lives in local memory)
+    uint64_t* bufs;   // this warp's buffers [32*PACK][bcap]
+    uint32_t* s_thr;  // CTA-shared exclusive bounds [32*PACK]
+    uint32_t* gthr;   // global exclusive bounds
+    int kp, bcap, lane;
+    int qidx[PACK];
+    bool valid[PACK];
+    uint32_t livemask;
+};
+template <int PACK>
+struct CandState {  // per-thread mutable state, kept in registers
+    int cnt[PACK];
+    uint32_t own[PACK];  // own exclusive bound (kp-th distance + 1 after a compaction)
 };
 
-// Sorted insert into one lane's candidate list (global scratch).  Returns new count.
-__device__ __forceinline__ int list_insert(uint64_t* L, int stride, int kp, int n, uint64_t key) {
-    if (n == kp) {
-        if (key >= L[(size_t)(kp - 1) * stride]) return n;
+// warp-uniform: compact the buffer of (lane l, half h), publish the tightened bound
+template <int PACK>
+__device__ __forceinline__ void cand_compact(const CandCtx<PACK>* cx, CandState<PACK>& st, int l, int h) {
+    int n = __shfl_sync(0xffffffffu, st.cnt[h], l);
+    uint32_t kth = 0;
+    int keep = compact_buffer(cx->bufs + (size_t)(l + 32 * h) * cx->bcap, n, cx->kp, cx->lane, &kth);
+    if (cx->lane == l) {
+        st.cnt[h] = keep;
+        if (n >= cx->kp) {
+            st.own[h] = kth + 1u;
+            atomicMin(&cx->s_thr[cx->lane + 32 * h], kth + 1u);
+            atomicMin(&cx->gthr[cx->qidx[h]], kth + 1u);
+        }
     }
-    int i = n < kp ? n : kp - 1;
-    while (i > 0) {
-        uint64_t prev = L[(size_t)(i - 1) * stride];
-        if (prev <= key) break;
-        L[(size_t)i * stride] = prev;
-        --i;
+}
+
+// Window-boundary maintenance (whole warp, out of line): compact every buffer that could
+// overflow during the next op window (at most `room` appends), then refresh the bounds.
+template <int PACK>
+__device__ __noinline__ CandState<PACK> cand_maintain(const CandCtx<PACK>* cx, CandState<PACK> st, int room) {
+#pragma unroll
+    for (int h = 0; h < PACK; ++h) {
+        uint32_t full = __ballot_sync(0xffffffffu, st.cnt[h] + room > cx->bcap);
+        while (full) {
+            int l = __ffs(full) - 1;
+            full &= full - 1;
+            cand_compact(cx, st, l, h);
+        }
     }
-    L[(size_t)i * stride] = key;
-    return n < kp ? n + 1 : n;
+    return st;
+}
+
+template <int PACK>
+__device__ __noinline__ CandState<PACK> cand_finish(const CandCtx<PACK>* cx, CandState<PACK> st) {
+#pragma unroll
+    for (int h = 0; h < PACK; ++h) {
+        uint32_t todo = __ballot_sync(0xffffffffu, st.cnt[h] > 0);
+        while (todo) {
+            int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            cand_compact(cx, st, l, h);
+        }
+    }
+    return st;
 }
 
 template <int RB, int PACK>
@@ -179,15 +299,16 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const ScanGeom& g = a.g;
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* s_stack = s_lut + (size_t)g.qgl * ROWS;       // [n_warps][LEVELS][32]
-    uint32_t* s_thr = s_stack + (size_t)g.n_warps * LEVELS * 32;  // [LW]
-    int* s_next = reinterpret_cast<int*>(s_thr + LW);
+    uint4* s_ring = reinterpret_cast<uint4*>(s_lut + (size_t)g.qgl * ROWS);  // [n_warps][32]
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(s_ring + (size_t)g.n_warps * 32);  // [n_warps][LEVELS][32]
+    uint32_t* s_thr = s_stack + (size_t)g.n_warps * LEVELS * 32;                        // [LW]
+    uint32_t* s_top = s_thr + LW;  // [LW][kps]: CTA-shared kps smallest distances per query
+    int* s_next = reinterpret_cast<int*>(s_top + (size_t)LW * g.kps);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_next + 2);
 
     const int item = blockIdx.x;
     const int slice = item / g.n_groups, grp = item % g.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // this slice's chunk range
     const int c_lo = (int)((int64_t)a.n_chunks * slice / g.n_slices);
     const int c_hi = (int)((int64_t)a.n_chunks * (slice + 1) / g.n_slices);
 
@@ -196,7 +317,6 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
         *s_next = c_lo;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < LW; i += blockDim.x) s_thr[i] = XINF;
     __syncthreads();
     if (threadIdx.x == 0) {  // TMA bulk copy of the group's table: qgl regions of ROWS*4 bytes
         const uint32_t bytes = (uint32_t)g.qgl * ROWS * 4u;
@@ -204,68 +324,114 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.qlut) + (size_t)grp * bytes;
         for (uint32_t o = 0; o < bytes; o += ROWS * 4u) bulk_g2s(smem + o, src + o, ROWS * 4u, s_bar);
     }
-    mbar_wait(s_bar, 0);
 
     const int ql = lane < g.qgl ? lane : g.qgl - 1;  // idle lanes alias the last region
     // a (lane, half) is valid when it maps to a real query of this group
     bool valid[PACK];
+    int qidx[PACK];
     uint32_t livemask = 0;
 #pragma unroll
     for (int h = 0; h < PACK; ++h) {
-        valid[h] = lane < g.qgl && grp * g.qpg + h * g.qgl + lane < a.Q;
+        qidx[h] = grp * g.qpg + h * g.qgl + lane;
+        valid[h] = lane < g.qgl && qidx[h] < a.Q;
         if (valid[h]) livemask |= PACK == 1 ? 1u : (0x8000u << (16 * h));
     }
     const bool live = livemask != 0;
+    if (warp == 0) {  // seed the CTA-shared bounds from the global ones (other slices)
+#pragma unroll
+        for (int h = 0; h < PACK; ++h) s_thr[lane + 32 * h] = valid[h] ? a.gthr[qidx[h]] : XINF;
+    }
+    for (int i = threadIdx.x; i < LW * g.kps; i += blockDim.x) s_top[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    mbar_wait(s_bar, 0);
+
     const uint32_t Lx = ((uint32_t)ql << (RB + 2)) | ((uint32_t)ql << 2);
     const unsigned char* lutb = smem;
     uint32_t* stack = s_stack + (size_t)warp * LEVELS * 32 + lane;
+    uint4* ring = s_ring + warp * 32;
 #define DPQ_LUT(off) (*reinterpret_cast<const uint32_t*>(lutb + (off)))
 
-    // candidate lists of this warp
-    uint64_t* lists = a.cand + ((size_t)item * g.n_warps + warp) * (size_t)g.kp * LW;
-    const int kp = g.kp;
-    int cnt[PACK];
-    uint32_t own[PACK];  // own exclusive bound (kp-th distance + 1 once the list is full)
+    // candidate buffers of this warp: [LW][bcap]
+    CandCtx<PACK> cx;
+    cx.bufs = a.cand + ((size_t)item * g.n_warps + warp) * (size_t)LW * g.bcap;
+    cx.s_thr = s_thr;
+    cx.gthr = a.gthr;
+    cx.kp = g.kp;
+    cx.bcap = g.bcap;
+    cx.lane = lane;
+    cx.livemask = livemask;
+    CandState<PACK> st;
+    uint64_t* bp[PACK];  // this lane's buffer per half
+    uint32_t xb[PACK];   // exclusive distance bound per half (0 = reject everything)
 #pragma unroll
     for (int h = 0; h < PACK; ++h) {
-        cnt[h] = 0;
-        own[h] = XINF;
+        cx.qidx[h] = qidx[h];
+        cx.valid[h] = valid[h];
+        st.cnt[h] = 0;
+        st.own[h] = XINF;
+        bp[h] = cx.bufs + (size_t)(lane + 32 * h) * g.bcap;
+        xb[h] = 0;
     }
     uint32_t thr = 0;  // PACK 1: exclusive bound; PACK 2: packed ((X-1)|0x8000) per half
-
-    auto refresh = [&]() {
-        if (PACK == 1) {
-            thr = live ? min(own[0], s_thr[lane]) : 0u;  // bound 0 rejects everything
-        } else {
-            uint32_t x0 = min(own[0], s_thr[lane]);
-            uint32_t x1 = min(own[PACK - 1], s_thr[lane + 32 * (PACK - 1)]);
-            thr = ((x0 - 1u) | 0x8000u) | (((x1 - 1u) | 0x8000u) << 16);
-        }
-    };
-    // slow path: at least one lane has a candidate for node `pos` with packed distance d
-    auto offer = [&](uint32_t d, uint32_t pos) {
-        if (live) {
+    constexpr int WIN_ROOM = 16 + 1;  // appends between two maintenance points (16 quads + the root)
+    const int bcap = g.bcap;
+    const int kps = g.kps;
+    uint32_t gb[PACK];    // last global bound seen / published
+    uint32_t* topq[PACK]; // this lane's shared top-kps array per half
 #pragma unroll
-            for (int h = 0; h < PACK; ++h) {
-                uint32_t dh = PACK == 1 ? d : ((d >> (16 * h)) & 0xFFFFu);
-                uint32_t x = min(own[h], s_thr[lane + 32 * h]);
-                if (dh < x && valid[h]) {
-                    uint64_t key = ((uint64_t)dh << 32) | pos;
-                    cnt[h] = list_insert(lists + lane + 32 * h, LW, kp, cnt[h], key);
-                    if (cnt[h] == kp) {
-                        uint32_t kth = (uint32_t)(lists[(size_t)(kp - 1) * LW + lane + 32 * h] >> 32);
-                        own[h] = kth + 1u;
-                        atomicMin(&s_thr[lane + 32 * h], kth + 1u);
-                    }
-                }
-            }
-        }
-        refresh();
-    };
-    auto is_cand = [&](uint32_t d) -> bool {
-        if (PACK == 1) return d < thr;
-        return ((thr - d) & livemask) != 0u;
-    };
+    for (int h = 0; h < PACK; ++h) {
+        gb[h] = XINF;
+        topq[h] = s_top + (size_t)(lane + 32 * h) * kps;
+    }
+
+#define DPQ_IS_CAND(d) (PACK == 1 ? ((d) < thr) : (((thr - (d)) & livemask) != 0u))
+    // inline append (no call in the hot loop): one store + counter bump per accepted half
+#define DPQ_APPEND(d, p)                                                              \
+    {                                                                                 \
+        _Pragma("unroll") for (int h = 0; h < PACK; ++h) {                            \
+            const uint32_t dh = PACK == 1 ? (d) : (((d) >> (16 * h)) & 0xFFFFu);      \
+            if (dh < xb[h]) {                                                         \
+                bp[h][st.cnt[h]] = ((uint64_t)dh << 32) | (p);                        \
+                ++st.cnt[h];                                                          \
+                if (kps) shared_topk_insert(topq[h], kps, dh);                        \
+            }                                                                         \
+        }                                                                             \
+    }
+    // window boundary: make room for WIN_ROOM appends, then reload the shared bounds
+#define DPQ_WINDOW_BOUNDARY()                                                         \
+    {                                                                                 \
+        bool tight = false;                                                           \
+        _Pragma("unroll") for (int h = 0; h < PACK; ++h) tight |= st.cnt[h] + WIN_ROOM > bcap; \
+        if (__any_sync(0xffffffffu, tight)) st = cand_maintain(&cx, st, WIN_ROOM);    \
+        _Pragma("unroll") for (int h = 0; h < PACK; ++h) {                            \
+            uint32_t x = min(st.own[h], s_thr[lane + 32 * h]);                        \
+            if (kps) {                                                                \
+                const uint32_t t = topq[h][kps - 1];                                  \
+                if (t < x) x = t + 1u; /* ties stay candidates */                     \
+            }                                                                         \
+            if (valid[h] && x < gb[h]) { /* publish to the other slices */            \
+                atomicMin(&a.gthr[qidx[h]], x);                                       \
+                gb[h] = x;                                                            \
+            }                                                                         \
+            xb[h] = valid[h] ? x : 0u;                                                \
+        }                                                                             \
+        if (PACK == 1) {                                                              \
+            thr = xb[0];                                                              \
+        } else {                                                                      \
+            const uint32_t x0 = valid[0] ? xb[0] : 1u, x1 = valid[PACK - 1] ? xb[PACK - 1] : 1u; \
+            thr = ((x0 - 1u) | 0x8000u) | (((x1 - 1u) | 0x8000u) << 16);              \
+        }                                                                             \
+    }
+
+    // 8 table reads of one quad -> signed sum of (new - old) over its 4 ops (zero ops cancel)
+#define DPQ_QUAD_DELTA(Q, OUT)                                                        \
+    {                                                                                 \
+        const uint32_t f0 = DPQ_LUT(((Q).x & FMASK) ^ Lx), t0 = DPQ_LUT((((Q).x >> TSH) & FMASK) ^ Lx); \
+        const uint32_t f1 = DPQ_LUT(((Q).y & FMASK) ^ Lx), t1 = DPQ_LUT((((Q).y >> TSH) & FMASK) ^ Lx); \
+        const uint32_t f2 = DPQ_LUT(((Q).z & FMASK) ^ Lx), t2 = DPQ_LUT((((Q).z >> TSH) & FMASK) ^ Lx); \
+        const uint32_t f3 = DPQ_LUT(((Q).w & FMASK) ^ Lx), t3 = DPQ_LUT((((Q).w >> TSH) & FMASK) ^ Lx); \
+        OUT = (t0 - f0 + t1) + (t2 - f1 - f2) + (t3 - f3);                            \
+    }
 
     for (;;) {
         int c = 0;
@@ -274,7 +440,22 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
         if (c >= c_hi) break;
         const ChunkDesc cd = a.chunks[c];
         const int n_anc = (int)(cd.n_anc_flags & 0xFFu);
-        refresh();
+        const uint4* qp = a.ops + cd.quad_begin;
+        const int n_quads = (int)cd.n_quads;
+        // op ring: 32 quads in two halves of 16; the whole ring is filled up front, then the
+        // half the consumer has left is refilled from `pre` (loaded one half ahead)
+        uint4 pre = make_uint4(0, 0, 0, 0);
+        if (lane < n_quads) pre = __ldg(qp + lane);
+#pragma unroll
+        for (int h = 0; h < PACK; ++h)
+            if (valid[h]) {  // bounds published by other slices of this query group
+                const uint32_t gx = __ldcg(&a.gthr[qidx[h]]);
+                if (gx < gb[h]) {
+                    gb[h] = gx;
+                    atomicMin(&s_thr[lane + 32 * h], gx);
+                }
+            }
+        DPQ_WINDOW_BOUNDARY()
         // chunk prologue: full M-term sums for the ancestors of the first node
         uint32_t par = 0;
         {
@@ -288,53 +469,65 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
                 stack[lev * 32] = d;
                 par = d;
                 if (lev == 0 && (cd.n_anc_flags & CHUNK_EMIT_ROOT)) {
-                    if (__any_sync(0xffffffffu, is_cand(d))) offer(d, 0u);
+                    if (__any_sync(0xffffffffu, DPQ_IS_CAND(d))) DPQ_APPEND(d, 0u)
                 }
             }
         }
-        uint32_t acc = par;
+        __syncwarp();  // every lane is done with the previous chunk's ring
+        ring[lane] = pre;
+        __syncwarp();
+        int filled = 32;
+        if (lane < 16 && filled + lane < n_quads) pre = __ldg(qp + filled + lane);
         uint32_t pos = cd.first_pos;
-        const uint4* qp = a.ops + cd.quad_begin;
-        const uint4* qe = qp + cd.n_quads;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (qp < qe) nxt = __ldg(qp);
-        while (qp < qe) {
-            const uint4 cur = nxt;
-            ++qp;
-            if (qp < qe) nxt = __ldg(qp);
-#define DPQ_OP(w)                                                                     \
-    {                                                                                 \
-        const uint32_t fo = ((w) & FMASK) ^ Lx;                                       \
-        const uint32_t to = (((w) >> TSH) & FMASK) ^ Lx;                              \
-        acc = acc + DPQ_LUT(to) - DPQ_LUT(fo);                                        \
-        if ((int)(w) < 0) {                                                           \
-            const uint32_t d = acc;                                                   \
-            if (__any_sync(0xffffffffu, is_cand(d))) offer(d, pos);                   \
-            if ((w) & (OP_CHILD | OP_AUX)) {                                          \
-                const uint32_t lev = RB == 11 ? (((w) >> 26) & 7u)                    \
-                                              : (((w) & 3u) | ((((w) >> 14) & 3u) << 2)); \
-                if ((w) & OP_CHILD) {                                                 \
-                    par = d;                                                          \
-                    if ((w) & OP_AUX) stack[lev * 32] = d;                            \
-                } else {                                                              \
-                    par = stack[lev * 32];                                            \
-                }                                                                     \
-            }                                                                         \
-            acc = par;                                                                \
-            ++pos;                                                                    \
-        }                                                                             \
-    }
-            DPQ_OP(cur.x)
-            DPQ_OP(cur.y)
-            DPQ_OP(cur.z)
-            DPQ_OP(cur.w)
-#undef DPQ_OP
+        int p = 0;
+        uint4 A = ring[0];
+        while (p < n_quads) {
+            if (p >= filled - 16 && filled < n_quads) {  // left a half behind: refill it
+                DPQ_WINDOW_BOUNDARY()
+                __syncwarp();
+                if (lane < 16) ring[(filled & 31) + lane] = pre;
+                __syncwarp();
+                filled += 16;
+                if (lane < 16 && filled + lane < n_quads) pre = __ldg(qp + filled + lane);
+            }
+            const uint32_t w0 = A.x;
+            const int nq = (int)(w0 >> 30) + 1;
+            const int pn = p + nq;
+            const uint4 An = ring[pn & 31];  // next record's first quad, requested early
+            uint32_t delta;
+            DPQ_QUAD_DELTA(A, delta)
+            for (int e = 1; e < nq; ++e) {
+                const uint4 B = ring[(p + e) & 31];
+                uint32_t dB;
+                DPQ_QUAD_DELTA(B, dB)
+                delta += dB;
+            }
+            const uint32_t d = par + delta;
+            if (__any_sync(0xffffffffu, DPQ_IS_CAND(d))) DPQ_APPEND(d, pos)
+            if (w0 & (OP_CHILD | OP_AUX)) {
+                const uint32_t lev = (w0 & 3u) | ((w0 >> RB) & 0xCu);
+                if (w0 & OP_CHILD) {
+                    par = d;
+                    if (w0 & OP_AUX) stack[lev * 32] = d;
+                } else {
+                    par = stack[lev * 32];
+                }
+            }
+            ++pos;
+            p = pn;
+            A = An;
         }
     }
+#undef DPQ_QUAD_DELTA
 #undef DPQ_LUT
+#undef DPQ_IS_CAND
+#undef DPQ_APPEND
+#undef DPQ_WINDOW_BOUNDARY
+    // final compaction: every buffer becomes a sorted list of at most kp keys
+    st = cand_finish(&cx, st);
 #pragma unroll
     for (int h = 0; h < PACK; ++h)
-        a.cand_cnt[((size_t)item * g.n_warps + warp) * LW + lane + 32 * h] = live ? (uint32_t)cnt[h] : 0u;
+        a.cand_cnt[((size_t)item * g.n_warps + warp) * LW + lane + 32 * h] = (uint32_t)st.cnt[h];
 }
 
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st) {
@@ -379,7 +572,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
     auto list_base = [&](int id) -> const uint64_t* {
         int s = id / g.n_warps, ww = id % g.n_warps;
         size_t item = (size_t)s * g.n_groups + grp;
-        return a.cand + ((item * g.n_warps + ww) * (size_t)kp) * LW + sl;
+        return a.cand + ((item * g.n_warps + ww) * (size_t)LW + sl) * g.bcap;
     };
     for (int j = 0; j < my; ++j) {
         int id = lane + 32 * j;
@@ -394,7 +587,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
         int bj = -1;
         for (int j = 0; j < my; ++j)
             if (cur[j] < len[j]) {
-                uint64_t k = list_base(lane + 32 * j)[(size_t)cur[j] * LW];
+                uint64_t k = list_base(lane + 32 * j)[cur[j]];
                 if (k < best) {
                     best = k;
                     bj = j;

@@ -19,6 +19,8 @@ struct ScanGeom {
     int n_slices;      // tree slices (chunk ranges) per group
     int n_warps;       // warps per CTA
     int kp;            // candidates kept per (warp, query): topk + slack, <= 256
+    int kps;           // CTA-shared top-distance array length per query (kp, or 0 = disabled)
+    int bcap;          // candidate buffer capacity per (warp, query): multiple of 32, >= 2*kp, <= 512
     int levels;        // depth stack levels
     size_t smem_bytes;
 };
@@ -30,15 +32,16 @@ struct ScanArgs {
     const uint8_t* anc;
     int n_chunks;
     const uint32_t* qlut;   // [n_groups][qgl][rows]   (swizzled, see lut kernel)
-    uint64_t* cand;         // [n_items][n_warps][kp][32*pack]
+    uint64_t* cand;         // [n_items][n_warps][32*pack][bcap]
+    uint32_t* gthr;         // [n_groups*qpg] exclusive distance bounds shared across slices
     uint32_t* cand_cnt;     // [n_items][n_warps][32*pack]
     int Q;
 };
 
 // ADC tables: exact float table [Q][M*K] + per-query scale + quantised swizzled table.
 void launch_lut(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q,
-                float* d_lutf, double* d_scale, uint32_t* d_qlut, const ScanGeom& g,
-                cudaStream_t st);
+                float* d_lutf, double* d_scale, uint32_t* d_qlut, uint32_t* d_gthr,
+                const ScanGeom& g, cudaStream_t st);
 // plain float tables only (dpq_adc_tables)
 void launch_lut_plain(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q,
                       float* d_lutf, cudaStream_t st);

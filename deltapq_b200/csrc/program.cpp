@@ -21,9 +21,9 @@ struct Emitter {
     bool open = false;
     int nodes_in_chunk = 0;
     size_t chunk_op_begin = 0;
-    long prev_last = -1;  // op index of the previous node's LAST op (this chunk), or -1
+    long prev_last = -1;  // index of the previous node's header word (this chunk), or -1
     int prev_depth = 0;
-    std::vector<long> level_idx;  // op index of LAST op of the in-chunk node at each depth
+    std::vector<long> level_idx;  // header word index of the in-chunk node at each depth
 
     void begin(uint32_t first_pos, int depth, const uint8_t* stack, bool emit_root) {
         ChunkDesc c;
@@ -43,13 +43,12 @@ struct Emitter {
     }
     void end() {
         if (!open) return;
-        while (p->ops.size() % 4) p->ops.push_back(0u);  // no-op: row 0 minus row 0, not LAST
         p->chunks.back().n_quads = (uint32_t)((p->ops.size() - chunk_op_begin) / 4);
         open = false;
     }
     // node at `depth` whose parent code is `par`, own code `cur`
     void node(int depth, const uint8_t* par, const uint8_t* cur) {
-        if (prev_last >= 0) {  // now the previous node's successor is known: patch its KIND
+        if (prev_last >= 0) {  // now the previous node's successor is known: patch its header
             uint32_t& w = p->ops[(size_t)prev_last];
             if (depth == prev_depth + 1) {
                 w |= OP_CHILD;
@@ -61,6 +60,7 @@ struct Emitter {
                     p->ops[(size_t)owner] |= OP_AUX | fmt.level_bits((uint32_t)lev);
             }
         }
+        const size_t first = p->ops.size();
         int n = 0;
         for (int m = 0; m < M; ++m)
             if (par[m] != cur[m]) {
@@ -69,9 +69,10 @@ struct Emitter {
                 p->ops.push_back(fr | (to << fmt.tshift()));
                 ++n;
             }
-        if (n == 0) p->ops.push_back(0u);
-        p->ops.back() |= OP_LAST;
-        prev_last = (long)p->ops.size() - 1;
+        const int nq = n == 0 ? 1 : (n + 3) / 4;
+        p->ops.resize(first + (size_t)nq * 4, 0u);  // zero ops: table row 0 minus row 0
+        p->ops[first] |= (uint32_t)(nq - 1) << 30;
+        prev_last = (long)first;  // header lives in the record's first word
         prev_depth = depth;
         level_idx[(size_t)depth] = prev_last;
         ++nodes_in_chunk;

@@ -25,7 +25,7 @@ def assert_topk_equal(pos_a, dist_a, pos_b, dist_b, node_dist=None, rel=REL_TOL)
 
 
 def interpret_program(prog, table_q):
-    """Runs the op program for ONE query on the CPU.  table_q: integer or float table
+    """Runs the record program for ONE query on the CPU.  table_q: integer or float table
     [M*K].  Returns (positions, distances) of every node the program emits, in order."""
     rb = prog["rb"]
     fmask = ((1 << rb) - 1) << 2
@@ -46,26 +46,25 @@ def interpret_program(prog, table_q):
             if lev == 0 and emit_root:
                 out_pos.append(0)
                 out_d.append(d)
-        acc, pos = par, first_pos
-        for w in ops[qb * 4:(qb + nq) * 4]:
-            w = int(w)
-            fr = (w & fmask) >> 2
-            to = ((w >> tsh) & fmask) >> 2
-            acc = acc + table_q[to] - table_q[fr]
-            if w & 0x80000000:
-                d = acc
-                out_pos.append(pos)
-                out_d.append(d)
-                if rb == 11:
-                    lev = (w >> 26) & 7
-                else:
-                    lev = (w & 3) | (((w >> 14) & 3) << 2)
-                if w & 0x40000000:
-                    par = d
-                    if w & 0x20000000:
-                        stack[lev] = d
-                elif w & 0x20000000:
-                    par = stack[lev]
-                acc = par
-                pos += 1
+        pos = first_pos
+        p, end = qb * 4, (qb + nq) * 4
+        while p < end:
+            w0 = int(ops[p])
+            rq = (w0 >> 30) + 1
+            d = par
+            for w in ops[p:p + 4 * rq]:
+                w = int(w)
+                d = d + table_q[((w >> tsh) & fmask) >> 2] - table_q[(w & fmask) >> 2]
+            out_pos.append(pos)
+            out_d.append(d)
+            lev = (w0 & 3) | ((w0 >> rb) & 0xC)
+            if w0 & (1 << 29):
+                par = d
+                if w0 & (1 << 28):
+                    stack[lev] = d
+            elif w0 & (1 << 28):
+                par = stack[lev]
+            pos += 1
+            p += 4 * rq
+        assert p == end
     return np.array(out_pos, np.int64), np.array(out_d)
