@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of the DeltaPQ query hot path (ADC tables -> DeltaTree scan ->
+top-k) on B200, through libdpq.so's C ABI (include/dpq.h).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): SIFT1M-shaped synthetic, 1M x 128-d, M=8 K=256 h=1,
+10K queries, top-10.  One step = one pass of the hot path over one batch of 10K queries.
+The tree is produced by the product's own pipeline (GPU encode, GPU edge search, host DFS
+layout + stream writer); only the cpu_baseline leg / --impl reference touch oracle/.
+
+N > 1 (torchrun, one rank per GPU): the SAME 1M-code tree is sharded by whole depth-1
+subtrees, every rank scans its shard for all queries, the per-rank top-k key
+lists are all-gathered over NCCL and merged on the device: strong scaling.
+PyTorch is plumbing here (device buffers, stream, events, torch.distributed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # datagen: synthetic data + file formats (tooling)
+
+METRIC = "queries/sec @top10 on 1M-code DeltaTree (SIFT1M-shaped synthetic, M=8 K=256)"
+UNIT = "queries/s"
+N_CODES, N_QUERIES, DIM, PQ_M, PQ_K, TOPK = 1_000_000, 10_000, 128, 8, 256, 10
+
+
+def synth(n_codes, n_queries):
+    import datagen as dg
+    base = dg.sift_like(n_codes, DIM, seed=1)
+    learn = dg.sift_like(20000, DIM, seed=3)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(learn, PQ_M, PQ_K, iters=6))
+    queries = dg.sift_like(n_queries, DIM, seed=2)
+    return base, cw, queries
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = samples at or above the median power draw
+        med_p = float(np.median(power))
+        load = [s for s, p in zip(sm, power) if p >= med_p] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ------------------------------------------------------------------------ reference arm --
+def _ref_worker(args):
+    """One process = one single-threaded reference scanner (its globals are not thread safe)."""
+    payload, n_codes, cw, queries, topk = args
+    from oracle import pyoracle as po
+    if po.have_ref():
+        _, _, secs = po.ref_scan(payload, n_codes, cw, queries, topk)
+        return secs
+    t = time.perf_counter()
+    for q in queries:
+        po.scan(payload, n_codes, cw, q, topk)
+    return time.perf_counter() - t
+
+
+def cpu_reference_tree(base, cw):
+    """CPU-only tree for the reference arm (oracle/ builder; same seeds => same tree)."""
+    from oracle import pyoracle as po
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    parts = np.array_split(base, max(1, cores))
+    with mp.get_context("fork").Pool(cores) as pool:
+        codes = np.concatenate(pool.starmap(po.encode, [(cw, p) for p in parts]))
+    _, _, lay, payload = po.build_tree(codes, cw)
+    return payload
+
+
+def time_reference(payload, n_codes, cw, queries, topk, procs, per_proc):
+    """procs single-threaded reference scanners side by side, per_proc queries each."""
+    import multiprocessing as mp
+    jobs = [(payload, n_codes, cw, queries[i * per_proc:(i + 1) * per_proc], topk) for i in range(procs)]
+    t = time.perf_counter()
+    if procs == 1:
+        _ref_worker(jobs[0])
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_ref_worker, jobs)
+    return time.perf_counter() - t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import pyoracle as po
+    base, cw, queries = synth(args.n_codes, args.queries)
+    payload = cpu_reference_tree(base, cw)
+    cores = len(os.sched_getaffinity(0))
+    per_proc = args.ref_queries_per_proc
+    kind = "reference" if po.have_ref() else "port"
+    # fork the pool once per step (the harness process is short lived by design: the reference
+    # leaks per query); pool start-up is inside the timed region and is small
+    # against per_proc * ~20 ms of scanning
+    for _ in range(args.warmup):
+        time_reference(payload, args.n_codes, cw, queries, TOPK, cores, per_proc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_reference(payload, args.n_codes, cw, queries, TOPK, cores, per_proc)
+    dt = time.perf_counter() - t0
+    nq = cores * per_proc * args.steps
+    qps = nq / dt
+    sample = (f"{cores * per_proc} of the {args.queries} queries per step ({per_proc} per process, {cores} "
+              f"single-threaded reference scanners side by side: DCAT.h:3731 in-memory scan via oracle/_ref)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, top-10", "n_codes": args.n_codes,
+                   "queries_per_step": cores * per_proc, "topk": TOPK, "n_bytes": int(len(payload))},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+    return 0
+
+
+# ------------------------------------------------------------------------ GPU arm -------
+def run_gpu(args):
+    import torch
+    import deltapq_b200 as dpq
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(dpq.LIB_PATH):
+        raise SystemExit("libdpq.so is missing: run __graft_entry__.build() (no CPU fallback exists)")
+    if dpq.device_count() < 1 or not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libdpq has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dpq.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: product pipeline only (encode -> approx_tree -> index) -----------------
+    t_setup = time.perf_counter()
+    base, cw, queries = synth(args.n_codes, args.queries)
+    codes = dpq.encode(cw, base)
+    tree = dpq.tree_build(codes, cw, h=1, method=1)
+    payload = tree["payload"]
+    del base
+    ix = dpq.DeltaTreeIndex(payload, args.n_codes, PQ_M, PQ_K, pos2id=tree["vec_id"], rank=rank, n_ranks=world)
+    ix.set_codebook(cw)
+    for kv in (args.opts.split(",") if args.opts else []):
+        k, v = kv.split("=")
+        ix.set_option(k, int(v))
+    stream = torch.cuda.current_stream()
+    ix.set_stream(stream.cuda_stream)
+    t_setup = time.perf_counter() - t_setup
+
+    Q, k = args.queries, TOPK
+    d_q = torch.from_numpy(queries).to(dev)
+    d_key = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    d_all = torch.empty((world, Q, k), dtype=torch.int64, device=dev) if world > 1 else None
+    d_out = torch.empty((Q, k), dtype=torch.int64, device=dev) if world > 1 else d_key
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        ix.search_device(d_q.data_ptr(), Q, k, d_key.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all.view(-1), d_key.view(-1))
+            ix.merge_device(d_all.data_ptr(), world, Q, k, d_out.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    barrier()
+
+    # ---- timed: K steps, device time per step (L2 flushed before each, outside the events) --
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ix.set_option("timing_reset", 1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        step_device()
+        b.record(stream)
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    scan_ns = ix.stat("sum_scan_ns")
+    lut_ns = ix.stat("sum_lut_ns")
+    calls = ix.stat("timed_calls")
+    fallback = ix.stat("last_fallback")
+    launches_per_step = ix.stat("last_launches") + (1 if world > 1 else 0)  # + merge kernel
+
+    # ---- e2e: host buffers in, host buffers out; H2D + D2H inside the timed region.  N = 1 goes
+    # through the reference-facing C-ABI call dpq_index_search (pinned staging inside libdpq);
+    # N > 1 adds the NCCL gather + merge between the same copies.
+    barrier()
+    h_q = torch.from_numpy(queries).pin_memory()
+    h_out = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+    pos, ids, dst = ix.search(queries, k)  # warm the pinned staging
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if world == 1:
+            pos, ids, dst = ix.search(queries, k)
+        else:
+            d_q.copy_(h_q, non_blocking=True)
+            step_device()
+            h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s, scan_ns / 1e6], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, scan_ms_max = (float(x) for x in t.tolist())
+    else:
+        scan_ms_max = scan_ns / 1e6
+
+    # ---- check: merged result equals the unsharded result (cheap sanity, outside timing) ---
+    out_keys = d_out.cpu().numpy().view(np.uint64)
+    out_pos, out_dist = dpq.unpack_keys(out_keys)
+    assert np.all(np.diff(out_dist.astype(np.float64), axis=1) >= 0), "top-k not ascending"
+
+    n_local_bytes = ix.stat("n_bytes")
+    n_bytes_total = ix.stat("n_bytes_total")
+    n_diffs = ix.stat("n_diffs")
+    n_local = ix.stat("n_local")
+    peak, peak_src = measured_peak()
+    # algorithmic bytes of one scan launch: Q queries x (stream bytes of this
+    # shard + 4 D query floats + 8 k result bytes)
+    alg_bytes = Q * (n_local_bytes + 4 * DIM + 8 * k)
+    scan_s = (scan_ns / 1e9) / max(calls, 1)
+    achieved = alg_bytes / scan_s / 1e9
+    qps = Q * args.steps / (total_ms / 1e3)
+    e2e_qps = Q * args.steps / e2e_s
+
+    line = None
+    if rank == 0:
+        cpu_base = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_base = cpu_baseline(payload, args.n_codes, cw, queries, args.cpu_baseline_queries)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u16 fixed-point filter + f64 exact re-score",
+            "data": "synthetic",
+            "config": {"workload": "SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, 10K queries, top-10 (BASELINE configs[1])",
+                       "n_codes": args.n_codes, "queries_per_step": Q, "topk": k, "n_bytes": n_bytes_total,
+                       "mean_diffs_per_node": round((n_bytes_total - 8 - (3 * (args.n_codes - 1) + 1) // 2) / (args.n_codes - 1), 3),
+                       "sharding": "whole tree on one GPU" if world == 1 else f"depth-1 subtrees over {world} GPUs + NCCL all-gather of top-k keys + device merge",
+                       "l2": "256 MiB buffer written before every timed step (L2 flush, outside the events)",
+                       "tree": "built by libdpq (GPU encode + GPU edge search + host DFS layout)",
+                       "setup_s": round(t_setup, 1), "opts": args.opts or "default"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "scan_kernel",
+                         "algorithmic_bytes_per_launch": alg_bytes, "scan_ms_per_launch": scan_s * 1e3,
+                         "peak_source": peak_src,
+                         "note": "effective bandwidth: every query batch re-reads the L2-resident tree (SURVEY 8d)"},
+            "cpu_baseline": cpu_base,
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4, "d2h_bytes_per_step": Q * k * 8},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "breakdown_ms_per_step": {"lut": lut_ns / 1e6 / max(calls, 1), "scan": scan_s * 1e3,
+                                      "scan_max_over_ranks": scan_ms_max / max(calls, 1), "exact_fallback_queries": fallback},
+            "shard": {"n_local": n_local, "n_bytes_local": n_local_bytes, "n_diffs_local": n_diffs},
+        }
+        print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(payload, n_codes, cw, queries, n_q):
+    """The reference's own CPU scan (oracle/_ref when it was built, else the oracle port) on a
+    bounded sample of the same workload, one thread (the reference query path is single
+    threaded by design)."""
+    from oracle import pyoracle as po
+    kind = "reference" if po.have_ref() else "port"
+    qs = np.ascontiguousarray(queries[:n_q])
+    t = time.perf_counter()
+    if kind == "reference":
+        _, _, secs = po.ref_scan(payload, n_codes, cw, qs, TOPK)
+    else:
+        for q in qs:
+            po.scan(payload, n_codes, cw, q, TOPK)
+        secs = time.perf_counter() - t
+    return {"value": n_q / secs, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"first {n_q} of the {len(queries)} queries on the same 1M-code tree, in-memory scan "
+                      f"(DCAT.h:3731), 1 thread, {secs:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dpq", choices=["dpq", "reference"])
+    ap.add_argument("--n-codes", type=int, default=N_CODES)
+    ap.add_argument("--queries", type=int, default=N_QUERIES)
+    ap.add_argument("--opts", default="", help="libdpq tuning options, e.g. pack=2,warps=16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-queries", type=int, default=600)
+    ap.add_argument("--ref-queries-per-proc", type=int, default=20)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -16,12 +16,14 @@ LIB_PATH = os.path.join(HERE, "libdpq.so")
 SYMBOLS = [
     "dpq_version", "dpq_last_error", "dpq_device_count", "dpq_set_device",
     "dpq_index_open", "dpq_index_open_file", "dpq_index_set_codebook", "dpq_index_set_option",
+    "dpq_index_set_stream",
     "dpq_index_search", "dpq_index_search_device", "dpq_index_sync", "dpq_merge_topk_device",
     "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",
     "dpq_free_host", "dpq_index_stat", "dpq_index_close", "dpq_adc_tables", "dpq_encode",
     "dpq_find_edges", "dpq_edge_diffs", "dpq_groundtruth_begin", "dpq_groundtruth_chunk",
     "dpq_groundtruth_finish", "dpq_program_compile", "dpq_program_size", "dpq_program_copy",
-    "dpq_program_free",
+    "dpq_program_free", "dpq_tree_build", "dpq_tree_from_edges", "dpq_tree_size", "dpq_tree_copy",
+    "dpq_tree_free",
 ]
 
 
@@ -52,6 +54,7 @@ def lib():
     L.dpq_index_open_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(vp)]
     L.dpq_index_set_codebook.argtypes = [vp, vp, i32]
     L.dpq_index_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.dpq_index_set_stream.argtypes = [vp, vp]
     L.dpq_index_search.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.dpq_index_search_device.argtypes = [vp, vp, i32, i32, vp]
     L.dpq_index_sync.argtypes = [vp]
@@ -79,6 +82,13 @@ def lib():
     L.dpq_program_copy.argtypes = [vp, C.c_char_p, vp]
     L.dpq_program_free.argtypes = [vp]
     L.dpq_program_free.restype = None
+    L.dpq_tree_build.argtypes = [vp, i64, i32, i32, vp, i32, i32, i32, C.POINTER(vp)]
+    L.dpq_tree_from_edges.argtypes = [vp, i64, i32, i32, vp, i32, vp, C.c_uint32, C.POINTER(vp)]
+    L.dpq_tree_size.restype = i64
+    L.dpq_tree_size.argtypes = [vp, C.c_char_p]
+    L.dpq_tree_copy.argtypes = [vp, C.c_char_p, vp]
+    L.dpq_tree_free.argtypes = [vp]
+    L.dpq_tree_free.restype = None
     _lib = L
     return L
 
@@ -169,6 +179,10 @@ class DeltaTreeIndex:
     def set_option(self, name, value):
         _check(lib().dpq_index_set_option(self._h, name.encode(), int(value)))
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(lib().dpq_index_set_stream(self._h, C.c_void_p(cuda_stream)))
+
     def stat(self, name):
         return int(lib().dpq_index_stat(self._h, name.encode()))
 
@@ -238,6 +252,53 @@ def edge_diffs(codes, edges):
     _check(lib().dpq_edge_diffs(_ptr(codes), codes.shape[0], codes.shape[1], _ptr(edges), edges.shape[0],
                                 _ptr(bm), C.byref(nd)))
     return bm, int(nd.value)
+
+
+_TREE_ARRAYS = (("edges", np.uint32), ("vec_id", np.uint32), ("parent_pos", np.uint32), ("child_num", np.uint32),
+                ("depth", np.uint8), ("max_dist", np.float32), ("max_dist2p", np.float32),
+                ("codes_by_pos", np.uint8), ("payload", np.uint8), ("qnodes", np.uint8))
+
+
+def _tree_out(h, M):
+    try:
+        out = {}
+        for name, dt in _TREE_ARRAYS:
+            nb = lib().dpq_tree_size(h, name.encode())
+            if nb < 0:
+                continue
+            arr = np.empty(nb // np.dtype(dt).itemsize, dt)
+            if nb:
+                _check(lib().dpq_tree_copy(h, name.encode(), _ptr(arr)))
+            out[name] = arr
+        for name in ("root_id", "n_diffs", "n_codes"):
+            out[name] = int(lib().dpq_tree_size(h, name.encode()))
+        out["edges"] = out["edges"].reshape(-1, 2)
+        out["codes_by_pos"] = out["codes_by_pos"].reshape(-1, M)
+        return out
+    finally:
+        lib().dpq_tree_free(h)
+
+
+def tree_build(codes, cw, h=1, method=1):
+    """`deltapq -task approx_tree` (DCAT.h:970): GPU edge search + host layout + stream."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    cw = np.ascontiguousarray(cw, np.float32)
+    n, M = codes.shape
+    t = C.c_void_p()
+    _check(lib().dpq_tree_build(_ptr(codes), n, M, cw.shape[1], _ptr(cw), cw.shape[2], h, method, C.byref(t)))
+    return _tree_out(t, M)
+
+
+def tree_from_edges(codes, cw, edges, root_id):
+    """Host half of the build only (layout + stream), no GPU needed."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    cw = np.ascontiguousarray(cw, np.float32)
+    edges = np.ascontiguousarray(edges, np.uint32)
+    n, M = codes.shape
+    t = C.c_void_p()
+    _check(lib().dpq_tree_from_edges(_ptr(codes), n, M, cw.shape[1], _ptr(cw), cw.shape[2], _ptr(edges),
+                                     int(root_id), C.byref(t)))
+    return _tree_out(t, M)
 
 
 def groundtruth(base, queries, topk, chunk=100000):

@@ -63,7 +63,12 @@ struct DevBuf {
 struct dpq_index {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // total begin, scan begin, scan end, total end
+    bool own_stream = true;
+    // per search call: total begin, scan begin, scan end, total end.  Calls since the last
+    // "timing_reset" keep their own events so a bench loop can time K steps without syncing.
+    std::vector<cudaEvent_t> evs;
+    int timed_calls = 0;
+    cudaEvent_t* ev = nullptr;  // the last call's four events
     dpq::ScanProgram prog;  // host copy (ops/codes released after upload)
     int Ds = 0;
     // device-resident tree
@@ -73,7 +78,7 @@ struct dpq_index {
     bool has_pos2id = false;
     std::vector<uint32_t> pos2id_host;  // local slice
     // options
-    int opt_slices = 0, opt_pack = 1, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
+    int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
     int chunk_nodes = 512;
     // scratch
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_fbuf,
@@ -136,7 +141,6 @@ int finish_open(dpq_index* ix, const uint32_t* pos2id) {
     dpq::ScanProgram& P = ix->prog;
     CU(cudaSetDevice(ix->device));
     CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    for (auto& e : ix->ev) CU(cudaEventCreate(&e));
     int rc;
     if ((rc = upload(ix->d_ops, P.ops.data(), P.ops.size() * 4, ix->stream))) return rc;
     if ((rc = upload(ix->d_chunks, P.chunks.data(), P.chunks.size() * sizeof(dpq::ChunkDesc), ix->stream)))
@@ -272,6 +276,16 @@ int dpq_index_set_codebook(dpq_index* ix, const float* cw, int Ds) {
     return DPQ_OK;
 }
 
+int dpq_index_set_stream(dpq_index* ix, void* cuda_stream) {
+    if (!ix) return fail(DPQ_ERR_ARG, "dpq_index_set_stream: null");
+    CU(cudaSetDevice(ix->device));
+    CU(cudaStreamSynchronize(ix->stream));
+    if (ix->own_stream && ix->stream) CU(cudaStreamDestroy(ix->stream));
+    ix->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ix->own_stream = false;
+    return DPQ_OK;
+}
+
 int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     if (!ix || !name) return fail(DPQ_ERR_ARG, "dpq_index_set_option: null argument");
     std::string n(name);
@@ -280,6 +294,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "warps") ix->opt_warps = (int)v;
     else if (n == "slack") ix->opt_slack = (int)v;
     else if (n == "force_fallback") ix->opt_force_fallback = (int)v;
+    else if (n == "timing_reset") ix->timed_calls = 0;
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
 }
@@ -313,6 +328,16 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_fcnt.ensure((size_t)max_flagged * 4))) return rc;
     cudaStream_t st = ix->stream;
     uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();  // [0] n_flagged, [1] overflow
+    {
+        const int slot = std::min(ix->timed_calls, 4095);
+        while ((int)ix->evs.size() < 4 * (slot + 1)) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            ix->evs.push_back(e);
+        }
+        ix->ev = ix->evs.data() + 4 * slot;
+        ix->timed_calls = slot + 1;
+    }
     CU(cudaEventRecord(ix->ev[0], st));
     CU(cudaMemsetAsync(ctrl, 0, 64, st));
     CU(cudaMemsetAsync(ix->d_fcnt.p, 0, (size_t)max_flagged * 4, st));
@@ -486,15 +511,25 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
         size_t d = (size_t)atoi(n.c_str() + 11);
         return d < P.depth_hist.size() ? P.depth_hist[d] : 0;
     }
-    if (n == "last_scan_us" || n == "last_total_us" || n == "last_lut_us") {
-        if (!ix->timing_valid) return -1;
+    if (n == "timed_calls") return ix->timed_calls;
+    const bool last = n == "last_scan_us" || n == "last_total_us" || n == "last_lut_us";
+    const bool sum = n == "sum_scan_ns" || n == "sum_total_ns" || n == "sum_lut_ns";
+    if (last || sum) {  // "last_*": the last search; "sum_*": all searches since "timing_reset"
+        if (!ix->timing_valid || !ix->ev) return -1;
         cudaSetDevice(ix->device);
         if (cudaEventSynchronize(ix->ev[3]) != cudaSuccess) return -1;
-        float ms = 0;
-        cudaEvent_t a = n == "last_scan_us" ? ix->ev[1] : ix->ev[0];
-        cudaEvent_t b = n == "last_scan_us" ? ix->ev[2] : (n == "last_lut_us" ? ix->ev[1] : ix->ev[3]);
-        if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return -1;
-        return (int64_t)(ms * 1000.0f + 0.5f);
+        const int which = n.find("scan") != std::string::npos ? 0 : (n.find("lut") != std::string::npos ? 1 : 2);
+        double total_ms = 0;
+        const int first = last ? ix->timed_calls - 1 : 0;
+        for (int c = first; c < ix->timed_calls; ++c) {
+            cudaEvent_t* e = ix->evs.data() + 4 * c;
+            float ms = 0;
+            cudaEvent_t a = which == 0 ? e[1] : e[0];
+            cudaEvent_t b = which == 0 ? e[2] : (which == 1 ? e[1] : e[3]);
+            if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return -1;
+            total_ms += ms;
+        }
+        return last ? (int64_t)(total_ms * 1e3 + 0.5) : (int64_t)(total_ms * 1e6 + 0.5);
     }
     return -1;
 }
@@ -509,9 +544,9 @@ void dpq_index_close(dpq_index* ix) {
                       &ix->d_gthr})
         b->release();
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
-    for (auto& e : ix->ev)
+    for (auto& e : ix->evs)
         if (e) cudaEventDestroy(e);
-    if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->stream && ix->own_stream) cudaStreamDestroy(ix->stream);
     (void)cudaGetLastError();
     delete ix;
 }

@@ -55,6 +55,12 @@ int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, in
 /* Codebook [M][K][Ds] as PQ::ReadCodewords returns it (pq.cpp:288-312). */
 int dpq_index_set_codebook(dpq_index* idx, const float* codewords, int Ds);
 
+/* Run this handle's work on the caller's CUDA stream (a cudaStream_t; NULL = the legacy
+ * default stream) instead of the handle's own, so that a host that already owns streams
+ * and events (bench.py: torch.cuda.current_stream()) can order and time the searches and
+ * the NCCL gather on one stream.  The handle does not take ownership. */
+int dpq_index_set_stream(dpq_index* idx, void* cuda_stream);
+
 /* Tuning knobs (optional): "slices", "chunk_nodes", "pack" (1 = 32-bit, 2 = 2x16-bit
  * filter), "warps", "slack" (extra candidates re-scored exactly). */
 int dpq_index_set_option(dpq_index* idx, const char* name, int64_t value);
@@ -95,7 +101,8 @@ int dpq_free_host(void* hptr);
  * "n_local" (nodes scanned by this rank), "n_diffs", "n_chunks", "ops_bytes",
  * "last_launches" (kernels launched by the last search), "last_fallback" (queries that
  * took the exact fallback in the last search), "last_scan_us" (scan kernel time of the
- * last search, CUDA events), "last_total_us". */
+ * last search, CUDA events), "last_total_us"; "sum_scan_ns" / "sum_lut_ns" / "sum_total_ns" /
+ * "timed_calls": the same summed over every search since set_option("timing_reset"). */
 int64_t dpq_index_stat(dpq_index* idx, const char* name);
 
 void dpq_index_close(dpq_index* idx);
@@ -125,6 +132,27 @@ int dpq_encode(const float* codewords, int M, int K, int Ds, const float* x, int
  * edges[n_codes-1][2] = (parent id, child id) in emission order, *root_id. */
 int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_height_folds,
                    int method, uint32_t* edges, uint32_t* root_id);
+
+/* create_approx_tree (DCAT.h:970-1065), the whole `deltapq -task approx_tree` computation:
+ * edge search on the GPU (dpq_find_edges), then on the host the DFS layout
+ * edges_to_tree_index_approx_dfs_layout (DCAT.h:1334-1487) and the stream writer
+ * qnodes_to_compressed_codes_opt (DCAT.h:1730-1845).  codewords [M][K][Ds] feed the K x K
+ * centroid tables (dmain:101-118) that order the children.  dpq_tree_from_edges is the host
+ * half alone (no GPU needed).  Arrays are fetched by name with dpq_tree_size / dpq_tree_copy:
+ *   "edges" uint32[n-1][2] (the ..._Approx_Edges file body), "root_id",
+ *   per DFS position: "vec_id" "parent_pos" "child_num" (uint32), "depth" (uint8),
+ *   "max_dist" "max_dist2p" (float), "codes_by_pos" uint8[n][M];
+ *   "qnodes": the (n+1) x 60-byte ..._Approx_TreeNodesDFS file body (M == 8 only);
+ *   "payload": the ..._Approx_compressed_codes_opt stream without its 16-byte header
+ *   (M > 8: extension format, ceil(M/8) bitmap bytes); scalars "n_diffs", "n_codes". */
+typedef struct dpq_tree dpq_tree;
+int dpq_tree_build(const uint8_t* codes, int64_t n_codes, int M, int K, const float* codewords, int Ds,
+                   int max_height_folds, int method, dpq_tree** out);
+int dpq_tree_from_edges(const uint8_t* codes, int64_t n_codes, int M, int K, const float* codewords,
+                        int Ds, const uint32_t* edges, uint32_t root_id, dpq_tree** out);
+int64_t dpq_tree_size(dpq_tree* t, const char* what); /* bytes for arrays, value for scalars */
+int dpq_tree_copy(dpq_tree* t, const char* what, void* dst);
+void dpq_tree_free(dpq_tree* t);
 
 /* check_num_diffs / dfs_node_layout diff extraction (DCAT.h:196-238, 1156-1183): for each
  * edge the changed-subspace bitmap (bit m set <=> codes differ in subspace m);
