@@ -5,7 +5,9 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,13 +74,14 @@ struct dpq_index {
     dpq::ScanProgram prog;  // host copy (ops/codes released after upload)
     int Ds = 0;
     // device-resident tree
-    DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw;
+    DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_recs, d_chunks2, d_ovf;
     int n_chunks = 0;
     size_t ops_bytes = 0;
     bool has_pos2id = false;
     std::vector<uint32_t> pos2id_host;  // local slice
     // options
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
+    int opt_epoch = 32, opt_trigger = 0, opt_ramp = 1;
     int chunk_nodes = 512;
     // scratch
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_fbuf,
@@ -130,6 +133,49 @@ int choose_geometry(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     return DPQ_OK;
 }
 
+// v2: 56 queries per group; pick the number of tree slices so that (a) the items fill whole
+// waves of 148 one-CTA SMs and (b) an item is a whole number of rounds (16 warps x 4 strands
+// x chunk_nodes nodes) as nearly as possible.
+int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
+    const dpq::ScanProgram& P = ix->prog;
+    g->M = P.M;
+    g->K = P.K;
+    g->rb = 11;
+    g->pack = 2;
+    g->levels = 0;
+    g->n_warps = 16;
+    int slack = ix->opt_slack >= 0 ? ix->opt_slack : std::max(6, topk / 4);
+    g->kp = topk + slack;
+    if (g->kp > 128) return fail(DPQ_ERR_ARG, "topk + slack must be <= 128 for the v2 scan (set DPQ_ENGINE=1)");
+    g->kps = 0;
+    g->bcap = g->kp <= 64 ? 256 : 512;
+    g->qgl = dpq::V2_LPG;
+    g->qpg = dpq::V2_QB;
+    g->n_groups = (Q + dpq::V2_QB - 1) / dpq::V2_QB;
+    int n_slices = ix->opt_slices;
+    if (n_slices <= 0) {
+        const int chunks_per_round = g->n_warps * 4;
+        double best = -1.0;
+        n_slices = 1;
+        for (int s = 1; s <= 64 && s <= std::max(1, ix->n_chunks / chunks_per_round); ++s) {
+            const int64_t items = (int64_t)g->n_groups * s;
+            const int64_t waves = (items + 147) / 148;
+            const double eff_wave = (double)items / (double)(waves * 148);
+            const double cpi = (double)ix->n_chunks / s;
+            const double rounds = std::ceil(cpi / chunks_per_round);
+            const double eff = eff_wave * (cpi / chunks_per_round) / rounds;
+            if (eff > best + 1e-9) {
+                best = eff;
+                n_slices = s;
+            }
+        }
+    }
+    n_slices = std::max(1, std::min(n_slices, std::max(1, ix->n_chunks)));
+    g->n_slices = n_slices;
+    g->smem_bytes = 0;
+    return DPQ_OK;
+}
+
 int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
     int rc = b.ensure(std::max<size_t>(bytes, 16));
     if (rc) return rc;
@@ -149,6 +195,13 @@ int finish_open(dpq_index* ix, const uint32_t* pos2id) {
     if ((rc = upload(ix->d_codes, P.codes.data(), P.codes.size(), ix->stream))) return rc;
     ix->n_chunks = (int)P.chunks.size();
     ix->ops_bytes = P.ops.size() * 4;
+    if (P.v2) {
+        if ((rc = upload(ix->d_recs, P.recs.data(), P.recs.size() * 4, ix->stream))) return rc;
+        if ((rc = upload(ix->d_chunks2, P.chunks2.data(), P.chunks2.size() * sizeof(dpq::ChunkDesc2), ix->stream)))
+            return rc;
+        ix->n_chunks = (int)P.chunks2.size();
+        ix->ops_bytes = P.recs.size() * 4;
+    }
     if (pos2id) {
         ix->has_pos2id = true;
         ix->pos2id_host.assign(pos2id + P.base_pos, pos2id + P.base_pos + P.n_local);
@@ -159,6 +212,8 @@ int finish_open(dpq_index* ix, const uint32_t* pos2id) {
     std::vector<uint8_t>().swap(P.codes);
     std::vector<uint8_t>().swap(P.anc);
     std::vector<dpq::ChunkDesc>().swap(P.chunks);
+    std::vector<uint32_t>().swap(P.recs);
+    std::vector<dpq::ChunkDesc2>().swap(P.chunks2);
     return DPQ_OK;
 }
 
@@ -211,8 +266,10 @@ int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int
     if (rc) return rc;
     dpq_index* ix = new dpq_index();
     ix->device = g_device;
+    // DPQ_ENGINE=1 in the environment keeps the first-generation op program / kernel
+    const char* eng = getenv("DPQ_ENGINE");
     std::string err = dpq::compile_program(payload, n_bytes, n_codes, M, K, rank, n_ranks,
-                                           ix->chunk_nodes, &ix->prog);
+                                           ix->chunk_nodes, &ix->prog, eng && eng[0] == '1' ? 1 : 0);
     if (!err.empty()) {
         delete ix;
         return fail(DPQ_ERR_FORMAT, "dpq_index_open: " + err);
@@ -295,6 +352,9 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "slack") ix->opt_slack = (int)v;
     else if (n == "force_fallback") ix->opt_force_fallback = (int)v;
     else if (n == "timing_reset") ix->timed_calls = 0;
+    else if (n == "epoch") ix->opt_epoch = (int)v;
+    else if (n == "trigger") ix->opt_trigger = (int)v;
+    else if (n == "ramp") ix->opt_ramp = (int)v;
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
 }
@@ -306,9 +366,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if (ix->Ds < 1) return fail(DPQ_ERR_ARG, "dpq_index_search: codebook not set");
     CU(cudaSetDevice(ix->device));
     dpq::ScanGeom g;
-    int rc = choose_geometry(ix, Q, topk, &g);
-    if (rc) return rc;
     const dpq::ScanProgram& P = ix->prog;
+    int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g) : choose_geometry(ix, Q, topk, &g);
+    if (rc) return rc;
     const size_t MK = (size_t)P.M * P.K;
     const size_t rows = (size_t)1 << g.rb;
     const size_t LW = 32 * (size_t)g.pack;
@@ -318,9 +378,16 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_lutf.ensure((size_t)Q * MK * 4))) return rc;
     if ((rc = ix->d_scale.ensure((size_t)g.n_groups * g.qpg * 8))) return rc;
     if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * g.qgl * rows * 4))) return rc;
-    if ((rc = ix->d_cand.ensure(n_items * g.n_warps * g.bcap * LW * 8))) return rc;
+    if (P.v2) {
+        if ((rc = ix->d_cand.ensure(n_items * dpq::V2_QB * g.bcap * 8))) return rc;
+        if ((rc = ix->d_cnt.ensure(n_items * dpq::V2_QB * 4))) return rc;
+        if ((rc = ix->d_ovf.ensure((size_t)g.n_groups * g.qpg * 4))) return rc;
+        if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * 2048 * dpq::V2_ROW_BYTES))) return rc;
+    } else {
+        if ((rc = ix->d_cand.ensure(n_items * g.n_warps * g.bcap * LW * 8))) return rc;
+        if ((rc = ix->d_cnt.ensure(n_items * g.n_warps * LW * 4))) return rc;
+    }
     if ((rc = ix->d_gthr.ensure((size_t)g.n_groups * g.qpg * 4))) return rc;
-    if ((rc = ix->d_cnt.ensure(n_items * g.n_warps * LW * 4))) return rc;
     if ((rc = ix->d_flagged.ensure((size_t)max_flagged * 4))) return rc;
     if ((rc = ix->d_ctrl.ensure(64))) return rc;
     if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
@@ -341,8 +408,13 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaEventRecord(ix->ev[0], st));
     CU(cudaMemsetAsync(ctrl, 0, 64, st));
     CU(cudaMemsetAsync(ix->d_fcnt.p, 0, (size_t)max_flagged * 4, st));
-    dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
-                    ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);
+    if (P.v2)
+        dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
+                         ix->d_scale.as<double>(), ix->d_qlut.as<uint16_t>(), ix->d_gthr.as<uint32_t>(),
+                         ix->d_ovf.as<uint32_t>(), g.n_groups, st);
+    else
+        dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
+                        ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);
     dpq::ScanArgs sa;
     sa.g = g;
     sa.ops = ix->d_ops.as<uint4>();
@@ -355,10 +427,35 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     sa.gthr = ix->d_gthr.as<uint32_t>();
     sa.Q = Q;
     CU(cudaEventRecord(ix->ev[1], st));
-    CU(dpq::launch_scan(sa, st));
+    if (P.v2) {
+        dpq::Scan2Args s2;
+        s2.recs = ix->d_recs.as<uint4>();
+        s2.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
+        s2.n_chunks = ix->n_chunks;
+        s2.chunk_nodes = P.v2_chunk_nodes;
+        s2.qlut = ix->d_qlut.as<uint16_t>();
+        s2.cand = sa.cand;
+        s2.cand_cnt = sa.cand_cnt;
+        s2.gthr = sa.gthr;
+        s2.ovf = ix->d_ovf.as<uint32_t>();
+        s2.Q = Q;
+        s2.n_groups = g.n_groups;
+        s2.n_slices = g.n_slices;
+        s2.n_warps = g.n_warps;
+        s2.kp = g.kp;
+        s2.bcap = g.bcap;
+        s2.trigger = ix->opt_trigger > 0 ? std::min(ix->opt_trigger, g.bcap / 2) : std::min(3 * g.kp, g.bcap / 2);
+        s2.epoch = std::max(1, ix->opt_epoch);
+        s2.ramp = ix->opt_ramp;
+        CU(dpq::launch_scan2(s2, st));
+    } else {
+        CU(dpq::launch_scan(sa, st));
+    }
     CU(cudaEventRecord(ix->ev[2], st));
     dpq::SelectArgs se;
     se.g = g;
+    se.v2 = P.v2 ? 1 : 0;
+    se.ovf = ix->d_ovf.as<uint32_t>();
     se.cand = sa.cand;
     se.cand_cnt = sa.cand_cnt;
     se.lutf = ix->d_lutf.as<float>();
@@ -395,7 +492,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     dpq::launch_fallback(fa, st);
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
-    ix->last_launches = 5;  // lut, scan, select, fallback collect, fallback finish
+    ix->last_launches = P.v2 ? 6 : 5;  // lut (+ pack), scan, select, fallback collect, fallback finish
     ix->timing_valid = true;
     return DPQ_OK;
 }
@@ -506,6 +603,8 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
     if (n == "n_chunks") return ix->n_chunks;
     if (n == "ops_bytes") return (int64_t)ix->ops_bytes;
     if (n == "last_launches") return ix->last_launches;
+    if (n == "engine") return P.v2 ? 2 : 1;
+    if (n == "v2_delta_nodes") return P.v2_delta_nodes;
     if (n == "last_fallback") return ix->last_fallback;
     if (n.rfind("depth_hist_", 0) == 0) {
         size_t d = (size_t)atoi(n.c_str() + 11);
@@ -538,7 +637,7 @@ void dpq_index_close(dpq_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+    for (DevBuf* b : {&ix->d_recs, &ix->d_chunks2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
                       &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_fbuf, &ix->d_fcnt, &ix->d_key,
                       &ix->d_gthr})

@@ -52,8 +52,45 @@ struct ChunkDesc {
 };
 constexpr uint32_t CHUNK_EMIT_ROOT = 1u << 8;
 
+// ---------------------------------------------------------------------------------------
+// Second-generation layout ("v2", used when M <= 8 and the table has <= 2048 rows): ONE
+// fixed 16-byte record per node, eight 16-bit table-row fields, executed by a quarter-warp
+// ("strand") that serves 56 queries with 128-bit table loads.
+//
+//   field  = row * 7            row = m*K + centroid; the table row is 7 x 16 bytes
+//   x = plus0 | plus1 << 16     y = plus2 | plus3 << 16
+//   z = minus0 | minus1 << 16   w = minus2 | minus3 << 16
+//   x bit 14 (ABS)   : 1: dist = sum of all eight rows (full M-term lookup, rows of m = 0..7;
+//                         unused fields point at the all-zero row M*K)
+//                      0: dist = parent + (plus rows) - (minus rows): one (new, old) pair per
+//                         changed subspace, at most four, unused pairs are (row 0, row 0)
+//   x bit 15 (CHILD) : the strand's parent register takes this node's distance
+//
+// A node is delta-encoded when its edge changes <= 4 subspaces AND its parent's distance is
+// in the parent register (the node is the first child of the previous node, or a later child
+// with only leaves in between); otherwise it gets the full M-term record, which costs the
+// same eight table reads and needs no depth stack.  Chunks are v2_chunk_nodes consecutive
+// positions, each starting with a full record, so chunks are independent.
+constexpr uint32_t V2_ABS = 1u << 14;
+constexpr uint32_t V2_CHILD = 1u << 15;
+constexpr int V2_LPG = 7;            // 16-byte lanes per table row = 56 queries per CTA
+constexpr int V2_ROW_BYTES = V2_LPG * 16;
+constexpr int V2_QB = V2_LPG * 8;
+
+struct ChunkDesc2 {
+    uint32_t rec_begin;  // first record of this chunk
+    uint32_t n_nodes;    // records in the chunk (== v2_chunk_nodes except the last)
+    uint32_t first_pos;  // global DFS position of the first record
+    uint32_t pad;
+};
+
 struct ScanProgram {
     int M = 0, K = 0;
+    bool v2 = false;
+    int v2_chunk_nodes = 64;
+    std::vector<uint32_t> recs;        // v2 records, 4 words each
+    std::vector<ChunkDesc2> chunks2;
+    int64_t v2_delta_nodes = 0;        // nodes that got a delta record
     OpFormat fmt{11};
     int64_t n_codes = 0;       // nodes in the whole tree
     int64_t n_bytes = 0;       // stream bytes of the whole tree
@@ -71,6 +108,8 @@ struct ScanProgram {
 // Decodes `payload` and builds the program for shard `rank` of `n_ranks`.
 // Returns empty string on success, else an error message.
 std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
-                            int rank, int n_ranks, int chunk_nodes, ScanProgram* out);
+                            int rank, int n_ranks, int chunk_nodes, ScanProgram* out, int engine = 0);
+// engine: 0 = v2 when the shape allows it, 1 = always the first-generation op program
+inline bool v2_shape_ok(int M, int K) { return M <= 8 && (M * K < 2048 || (M == 8 && M * K == 2048)); }
 
 }  // namespace dpq

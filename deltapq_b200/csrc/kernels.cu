@@ -56,19 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 
 // ------------------------------------------------------------------------ ADC tables ---
-// One CTA per (virtual) query; thread = centroid.  acc follows the reference exactly:
-// float accumulator, each term the double square of the float difference, rounded back to
-// float after every add (DCAT.h:3754-3757: `m_sub_distances[i][j] += pow(float, 2)`).
-__device__ __forceinline__ float adc_entry(const float* __restrict__ c, const float* q, int Ds) {
-    float acc = 0.0f;
-    for (int d = 0; d < Ds; ++d) {
-        float diff = __fsub_rn(c[d], q[d]);
-        double t = __dmul_rn((double)diff, (double)diff);
-        acc = (float)__dadd_rn((double)acc, t);
-    }
-    return acc;
-}
-
+// One CTA per (virtual) query; thread = centroid (adc_entry: kernels.cuh).
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ cw, int M, int K, int Ds,
                                                   const float* __restrict__ queries, int Q,
                                                   float* __restrict__ lutf, double* __restrict__ scale,
@@ -559,10 +547,11 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * SEL_WARPS + w;
     if (q >= a.Q) return;
-    const int LW = 32 * g.pack;
+    const int LW = a.v2 ? V2_QB : 32 * g.pack;
     const int grp = q / g.qpg, sub = q % g.qpg;
-    const int sl = (sub % g.qgl) + 32 * (sub / g.qgl);
-    const int n_lists = g.n_slices * g.n_warps;
+    const int sl = a.v2 ? sub : (sub % g.qgl) + 32 * (sub / g.qgl);
+    const int lists_per_item = a.v2 ? 1 : g.n_warps;  // v2: one CTA-wide list per (slice, query)
+    const int n_lists = g.n_slices * lists_per_item;
     const int kp = g.kp;
 
     // cursors over this lane's lists (list id = lane + 32*j)
@@ -570,15 +559,15 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
     uint16_t len[SEL_MAXLISTS_PER_LANE];
     const int my = (n_lists - lane + 31) / 32;
     auto list_base = [&](int id) -> const uint64_t* {
-        int s = id / g.n_warps, ww = id % g.n_warps;
+        int s = id / lists_per_item, ww = id % lists_per_item;
         size_t item = (size_t)s * g.n_groups + grp;
-        return a.cand + ((item * g.n_warps + ww) * (size_t)LW + sl) * g.bcap;
+        return a.cand + ((item * lists_per_item + ww) * (size_t)LW + sl) * g.bcap;
     };
     for (int j = 0; j < my; ++j) {
         int id = lane + 32 * j;
-        int s = id / g.n_warps, ww = id % g.n_warps;
+        int s = id / lists_per_item, ww = id % lists_per_item;
         size_t item = (size_t)s * g.n_groups + grp;
-        len[j] = (uint16_t)a.cand_cnt[(item * g.n_warps + ww) * LW + sl];
+        len[j] = (uint16_t)a.cand_cnt[(item * lists_per_item + ww) * LW + sl];
         cur[j] = 0;
     }
     int n_sel = 0;
@@ -641,6 +630,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
             if (!((double)bound * a.scale[q] + E < G)) flag = 1;
         }
         if (a.force_fallback) flag = 1;
+        if (a.v2 && a.ovf[(size_t)grp * V2_QB + sub]) flag = 1;  // dropped candidates: redo exactly
         a.bound[q] = bound;
         if (flag) {
             uint32_t slot = atomicAdd(a.n_flagged, 1u);

@@ -48,8 +48,40 @@ void launch_lut_plain(const float* d_cw, int M, int K, int Ds, const float* d_qu
 
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
 
+// ---- second-generation scan (scan2.cu) --------------------------------------------------
+struct Scan2Args {
+    const uint4* recs;            // one 16-byte record per node
+    const ChunkDesc2* chunks;
+    int n_chunks, chunk_nodes;
+    const uint16_t* qlut;         // [n_groups][2048][56] fixed-point tables
+    uint64_t* cand;               // [n_items][56][bcap] candidate keys (dist << 32 | pos)
+    uint32_t* cand_cnt;           // [n_items][56]
+    uint32_t* gthr;               // [n_groups*56] exclusive bounds shared across tree slices
+    uint32_t* ovf;                // [n_groups*56] a candidate buffer overflowed: query needs the exact fallback
+    int Q, n_groups, n_slices, n_warps;
+    int kp, bcap, trigger, epoch, ramp;
+};
+void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
+                 double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
+                 cudaStream_t st);
+cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
+
+// One ADC table entry in the reference's arithmetic (DCAT.h:3754-3757): float accumulator,
+// each term the double square of the float difference, rounded back to float after every add.
+__device__ __forceinline__ float adc_entry(const float* __restrict__ c, const float* q, int Ds) {
+    float acc = 0.0f;
+    for (int d = 0; d < Ds; ++d) {
+        float diff = __fsub_rn(c[d], q[d]);
+        double t = __dmul_rn((double)diff, (double)diff);
+        acc = (float)__dadd_rn((double)acc, t);
+    }
+    return acc;
+}
+
 struct SelectArgs {
     ScanGeom g;
+    int v2;                  // 1: lists are per (slice) with 56 queries per group (scan2.cu)
+    const uint32_t* ovf;     // v2: per-query overflow flags
     const uint64_t* cand;
     const uint32_t* cand_cnt;
     const float* lutf;       // [Q][M*K]

@@ -79,10 +79,75 @@ struct Emitter {
     }
 };
 
+// v2 emitter: one fixed record per node (see dpq_internal.h)
+struct Emitter2 {
+    ScanProgram* p;
+    int M, K;
+    int chunk_nodes;
+    bool open = false;
+    int in_chunk = 0;
+    long prev_rec = -1;     // word index of the previous record in this chunk, or -1
+    int prev_depth = 0;
+    long reg_owner_depth = -1;  // depth of the node whose distance the parent register holds, -1: none
+    // the register holds dist(node at depth reg_owner_depth on the current path) iff that
+    // node is still on the path, i.e. no shallower-or-equal node was emitted since
+    void begin(uint32_t first_pos) {
+        ChunkDesc2 c;
+        c.rec_begin = (uint32_t)(p->recs.size() / 4);
+        c.n_nodes = 0;
+        c.first_pos = first_pos;
+        c.pad = 0;
+        p->chunks2.push_back(c);
+        open = true;
+        in_chunk = 0;
+        prev_rec = -1;
+        reg_owner_depth = -1;
+    }
+    void end() {
+        if (!open) return;
+        p->chunks2.back().n_nodes = (uint32_t)in_chunk;
+        open = false;
+    }
+    void node(int depth, const uint8_t* par, const uint8_t* cur) {
+        if (prev_rec >= 0 && depth == prev_depth + 1) {  // previous node is this node's parent
+            p->recs[(size_t)prev_rec] |= V2_CHILD;
+            reg_owner_depth = prev_depth;
+        } else if (reg_owner_depth >= depth) {
+            reg_owner_depth = -1;  // the register's node left the path
+        }
+        int nd = 0;
+        for (int m = 0; m < M; ++m) nd += par[m] != cur[m];
+        uint32_t f[8];
+        bool abs = !(reg_owner_depth >= 0 && reg_owner_depth == depth - 1 && nd <= 4);
+        if (!abs) {
+            for (int i = 0; i < 8; ++i) f[i] = 0;
+            int j = 0;
+            for (int m = 0; m < M; ++m)
+                if (par[m] != cur[m]) {
+                    f[j] = (uint32_t)(m * K + cur[m]) * V2_LPG;      // plus: new centroid
+                    f[4 + j] = (uint32_t)(m * K + par[m]) * V2_LPG;  // minus: old centroid
+                    ++j;
+                }
+            p->v2_delta_nodes++;
+        } else {
+            const uint32_t zero_row = (uint32_t)(M * K) * V2_LPG;
+            for (int i = 0; i < 8; ++i) f[i] = i < M ? (uint32_t)(i * K + cur[i]) * V2_LPG : zero_row;
+        }
+        const size_t at = p->recs.size();
+        p->recs.push_back(f[0] | (abs ? V2_ABS : 0u) | (f[1] << 16));
+        p->recs.push_back(f[2] | (f[3] << 16));
+        p->recs.push_back(f[4] | (f[5] << 16));
+        p->recs.push_back(f[6] | (f[7] << 16));
+        prev_rec = (long)at;
+        prev_depth = depth;
+        ++in_chunk;
+    }
+};
+
 }  // namespace
 
 std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
-                            int rank, int n_ranks, int chunk_nodes, ScanProgram* out) {
+                            int rank, int n_ranks, int chunk_nodes, ScanProgram* out, int engine) {
     if (M < 1 || M > 16 || K < 1 || K > 256) return "unsupported M/K (need 1<=M<=16, 1<=K<=256)";
     if (n_codes < 1) return "empty tree";
     if (n_codes >= 0x7FFFFFFFLL) return "n_codes must be < 2^31-1 (DCAT.h:982)";
@@ -101,6 +166,12 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
     const int dmask = M > 8 ? 15 : 7;  // DCAT.h:3794 masks nibbles with &7
     P.depth_hist.assign((size_t)levels + 1, 0);
     if (chunk_nodes < 4) chunk_nodes = 4;
+    P.v2 = engine == 0 && v2_shape_ok(M, K);
+    Emitter2 E2;
+    E2.p = &P;
+    E2.M = M;
+    E2.K = K;
+    E2.chunk_nodes = P.v2_chunk_nodes;
 
     std::vector<uint8_t> stack((size_t)(levels + 1) * M, 0);
     int64_t off = 0;
@@ -124,6 +195,10 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
         P.n_local = 1;
         P.local_bytes = M;
         P.depth_hist[0] = 1;
+        if (P.v2) {  // the root is an ordinary full record at position 0
+            E2.begin(0u);
+            E2.node(0, payload, payload);
+        }
     }
     int cur_rank = 0;
     int depths = 0;
@@ -163,18 +238,29 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
         }
         if (cur_rank != rank) {
             if (E.open) E.end();
+            if (E2.open) E2.end();
             continue;
         }
         if (!have_base) {
             P.base_pos = i;
             have_base = true;
         }
-        if (!E.open || E.nodes_in_chunk >= chunk_nodes) {
-            E.end();
-            E.begin((uint32_t)i, d, stack.data(), pending_root);
-            pending_root = false;
+        if (P.v2) {
+            // positions of one shard are contiguous except that rank 0 also holds the root
+            const bool gap = E2.open && P.chunks2.back().first_pos + (uint32_t)E2.in_chunk != (uint32_t)i;
+            if (!E2.open || E2.in_chunk >= E2.chunk_nodes || gap) {
+                E2.end();
+                E2.begin((uint32_t)i);
+            }
+            E2.node(d, par, cur);
+        } else {
+            if (!E.open || E.nodes_in_chunk >= chunk_nodes) {
+                E.end();
+                E.begin((uint32_t)i, d, stack.data(), pending_root);
+                pending_root = false;
+            }
+            E.node(d, par, cur);
         }
-        E.node(d, par, cur);
         P.codes.insert(P.codes.end(), cur, cur + M);
         P.n_local++;
         P.n_diffs += nd;
@@ -183,9 +269,10 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
         P.depth_hist[(size_t)d]++;
     }
     E.end();
+    E2.end();
     if (off != n_bytes) return "stream has trailing or missing bytes (n_bytes mismatch)";
     P.local_bytes += (local_nodes_records + 1) / 2;  // depth nibbles
-    if (pending_root) {  // root only (n_codes == 1, or rank 0 owns no subtree)
+    if (pending_root && !P.v2) {  // root only (n_codes == 1, or rank 0 owns no subtree)
         E.begin(1u, 1, stack.data(), true);
         E.end();
     }

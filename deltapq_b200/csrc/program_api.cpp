@@ -17,9 +17,12 @@ extern "C" {
 
 int dpq_program_compile(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K, int rank,
                         int n_ranks, int chunk_nodes, dpq_program** out) {
+    // chunk_nodes < 0 selects the first-generation op program with |chunk_nodes| nodes per chunk
+    const int engine = chunk_nodes < 0 ? 1 : 0;
+    if (chunk_nodes < 0) chunk_nodes = -chunk_nodes;
     if (!payload || !out) return dpq::api_fail(DPQ_ERR_ARG, "dpq_program_compile: null argument");
     dpq_program* h = new dpq_program();
-    std::string err = dpq::compile_program(payload, n_bytes, n_codes, M, K, rank, n_ranks, chunk_nodes, &h->p);
+    std::string err = dpq::compile_program(payload, n_bytes, n_codes, M, K, rank, n_ranks, chunk_nodes, &h->p, engine);
     if (!err.empty()) {
         delete h;
         *out = nullptr;
@@ -37,6 +40,10 @@ int64_t dpq_program_size(dpq_program* h, const char* what) {
     if (w == "chunks") return (int64_t)p.chunks.size() * (int64_t)sizeof(dpq::ChunkDesc);
     if (w == "anc") return (int64_t)p.anc.size();
     if (w == "codes") return (int64_t)p.codes.size();
+    if (w == "recs") return (int64_t)p.recs.size() * 4;
+    if (w == "chunks2") return (int64_t)p.chunks2.size() * (int64_t)sizeof(dpq::ChunkDesc2);
+    if (w == "v2") return p.v2 ? 1 : 0;
+    if (w == "v2_delta_nodes") return p.v2_delta_nodes;
     if (w == "n_ops") return (int64_t)p.ops.size();
     if (w == "n_chunks") return (int64_t)p.chunks.size();
     if (w == "n_local") return p.n_local;
@@ -53,6 +60,8 @@ int dpq_program_copy(dpq_program* h, const char* what, void* dst) {
     std::string w(what);
     const dpq::ScanProgram& p = h->p;
     if (w == "ops") memcpy(dst, p.ops.data(), p.ops.size() * 4);
+    else if (w == "recs") memcpy(dst, p.recs.data(), p.recs.size() * 4);
+    else if (w == "chunks2") memcpy(dst, p.chunks2.data(), p.chunks2.size() * sizeof(dpq::ChunkDesc2));
     else if (w == "chunks") memcpy(dst, p.chunks.data(), p.chunks.size() * sizeof(dpq::ChunkDesc));
     else if (w == "anc") memcpy(dst, p.anc.data(), p.anc.size());
     else if (w == "codes") memcpy(dst, p.codes.data(), p.codes.size());

@@ -1,0 +1,372 @@
+// Second-generation DeltaTree scan for sm_100a (M <= 8, table <= 2048 rows).
+//
+// What the first-generation kernel's ncu capture showed (profiles/scan_r1_gen1.md): the scan
+// is bound by instruction issue, not by shared-memory wavefronts or HBM: 136 warp
+// instructions per node for 48 queries, most of it per-node control (variable-length
+// records, depth stack, ring refills) and address arithmetic for one 32-bit table read per
+// (lane, lookup).  This kernel removes that overhead structurally:
+//
+//   * one fixed 16-byte record per node (dpq_internal.h "v2"): a delta record (parent +
+//     new rows - old rows, edges that change <= 4 subspaces) or a full M-term record; both
+//     are exactly eight table reads, no variable length, no depth stack;
+//   * the warp is four quarter-warp STRANDS, each walking its own chunk of the tree, so one
+//     instruction advances four nodes;
+//   * the fixed-point ADC table is laid out [row][56 queries] (112-byte rows) and read with
+//     128-bit loads: lane j of a strand gets queries 8j..8j+7 of the row in one LDS.128, the
+//     eight lanes of a strand cover one contiguous row = one conflict-free wavefront;
+//   * all arithmetic is packed 2 x 15-bit in 32-bit integer adds (exact, see kernels.cu);
+//   * top-k: CTA-wide candidate buffers (one per query, in global scratch) appended with one
+//     shared-memory atomic + one store; at epoch boundaries (every 32 iterations = 2048
+//     nodes per CTA, ramping up from 1) a CTA barrier lets the owner warp of a query compact
+//     its buffer to the k' best and tighten the bound, which is shared through shared
+//     memory (CTA) and global memory (the other tree slices of the same query group).
+//
+// The table for 56 queries fills shared memory (229,376 of 232,448 bytes); the tree records
+// stream from L2/HBM through L1 with one 16-byte load per strand per node.
+#include "kernels.cuh"
+
+#include <cfloat>
+
+namespace dpq {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
+constexpr int ROWS2 = 2048;
+constexpr int LUT2_BYTES = ROWS2 * V2_ROW_BYTES;  // 229,376
+
+}  // namespace
+
+// ------------------------------------------------------------------------ ADC tables ---
+// Exact float tables [Q][M*K] (reference arithmetic, adc_entry) + per-query fixed-point scale.
+__global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw, int M, int K, int Ds,
+                                                   const float* __restrict__ queries, int Q,
+                                                   float* __restrict__ lutf, double* __restrict__ scale) {
+    extern __shared__ float s_q[];  // M*Ds
+    __shared__ int s_max[16];
+    const int q = blockIdx.x;
+    const int k = threadIdx.x;
+    for (int i = k; i < M * Ds; i += blockDim.x) s_q[i] = queries[(size_t)q * M * Ds + i];
+    if (k < 16) s_max[k] = 0;
+    __syncthreads();
+    float* out = lutf + (size_t)q * M * K;
+    for (int m = 0; m < M; ++m) {
+        float v = 0.0f;
+        if (k < K) {
+            v = adc_entry(cw + ((size_t)m * K + k) * Ds, s_q + m * Ds, Ds);
+            out[m * K + k] = v;
+        }
+        int vi = __float_as_int(v);  // v >= 0: integer order == float order
+        for (int o = 16; o; o >>= 1) vi = max(vi, __shfl_xor_sync(0xffffffffu, vi, o));
+        if ((k & 31) == 0) atomicMax(&s_max[m], vi);
+    }
+    __syncthreads();
+    if (k == 0) {
+        double sum = 0.0;
+        for (int m = 0; m < M; ++m) sum += (double)__int_as_float(s_max[m]);
+        scale[q] = sum > 0.0 ? (double)(32767 - 16) / sum : 1.0;
+    }
+}
+
+// Quantise + transpose into the scan layout [group][row][56] u16; rows >= M*K and queries >= Q
+// are zero.  Block = 64 rows of one group; reads and writes are both coalesced.
+__global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lutf, const double* __restrict__ scale,
+                                                    int MK, int Q, uint16_t* __restrict__ qlut,
+                                                    uint32_t* __restrict__ gthr, uint32_t* __restrict__ ovf) {
+    __shared__ uint16_t tile[64][V2_QB];
+    const int grp = blockIdx.x, row0 = blockIdx.y * 64;
+    for (int i = threadIdx.x; i < 64 * V2_QB; i += blockDim.x) {
+        const int ql = i >> 6, r = i & 63;
+        const int q = grp * V2_QB + ql, row = row0 + r;
+        uint16_t v = 0;
+        if (q < Q && row < MK) v = (uint16_t)__double2ll_rn((double)lutf[(size_t)q * MK + row] * scale[q]);
+        tile[r][ql] = v;
+    }
+    __syncthreads();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(qlut + ((size_t)grp * ROWS2 + row0) * V2_QB);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&tile[0][0]);
+    for (int i = threadIdx.x; i < 64 * V2_QB / 2; i += blockDim.x) dst[i] = src[i];
+    if (blockIdx.y == 0 && threadIdx.x < V2_QB) {
+        gthr[grp * V2_QB + threadIdx.x] = 0x8000u;  // exclusive bound: accept everything
+        ovf[grp * V2_QB + threadIdx.x] = 0u;
+    }
+}
+
+void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
+                 double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
+                 cudaStream_t st) {
+    lut2_kernel<<<Q, 256, (size_t)M * Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf, d_scale);
+    pack2_kernel<<<dim3((unsigned)n_groups, ROWS2 / 64), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, d_qlut, d_gthr, d_ovf);
+}
+
+// ------------------------------------------------------------------------ scan ---------
+// warp-cooperative: keep the min(n, kp) smallest of buf[0..n), sorted ascending (keys unique)
+template <int MAXPER>
+__device__ __forceinline__ int compact2_t(uint64_t* buf, int n, int kp, int lane, uint32_t* kth) {
+    const int per = (n + 31) >> 5;
+    uint64_t mine[MAXPER];
+    int rank[MAXPER];
+#pragma unroll
+    for (int t = 0; t < MAXPER; ++t) {
+        mine[t] = ~0ull;
+        rank[t] = 0;
+        if (t < per) {
+            int i = t * 32 + lane;
+            if (i < n) mine[t] = __ldcg(buf + i);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXPER; ++u) {
+        if (u < per) {
+            for (int j = 0; j < 32; ++j) {
+                uint64_t o = __shfl_sync(0xffffffffu, mine[u], j);
+#pragma unroll
+                for (int t = 0; t < MAXPER; ++t)
+                    if (t < per) rank[t] += o < mine[t];
+            }
+        }
+    }
+    __syncwarp();
+    const int keep = n < kp ? n : kp;
+    uint32_t kd = 0;
+#pragma unroll
+    for (int t = 0; t < MAXPER; ++t) {
+        if (t < per) {
+            int i = t * 32 + lane;
+            if (i < n && rank[t] < keep) __stcg(buf + rank[t], mine[t]);
+            if (i < n && rank[t] == kp - 1) kd = (uint32_t)(mine[t] >> 32);
+        }
+    }
+    for (int o = 16; o; o >>= 1) kd |= __shfl_xor_sync(0xffffffffu, kd, o);
+    *kth = kd;
+    __syncwarp();
+    return keep;
+}
+__device__ __noinline__ int compact2(uint64_t* buf, int n, int kp, int lane, uint32_t* kth) {
+    if (n <= 64) return compact2_t<2>(buf, n, kp, lane, kth);
+    if (n <= 256) return compact2_t<8>(buf, n, kp, lane, kth);
+    return compact2_t<16>(buf, n, kp, lane, kth);
+}
+
+struct Own2 {  // what an owner warp needs to compact one query's buffer
+    uint64_t* cand;    // this item's buffers [56][bcap]
+    uint32_t* s_cnt;
+    uint32_t* s_thr;
+    uint32_t* gthr;    // this group's global bounds [56]
+    int kp, bcap, lane;
+};
+__device__ __noinline__ void own_compact(const Own2* o, int ql, int trigger) {
+    int n = (int)o->s_cnt[ql];
+    if (n > o->bcap) n = o->bcap;
+    if (n < trigger || n == 0) return;
+    __threadfence_block();
+    uint32_t kth = 0;
+    const int keep = compact2(o->cand + (size_t)ql * o->bcap, n, o->kp, o->lane, &kth);
+    if (o->lane == 0) {
+        o->s_cnt[ql] = (uint32_t)keep;
+        if (n >= o->kp) {
+            atomicMin(&o->s_thr[ql], kth + 1u);
+            atomicMin(&o->gthr[ql], kth + 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + LUT2_BYTES);  // [64] exclusive bounds
+    uint32_t* s_cnt = s_thr + 64;                                      // [64] candidates per query
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cnt + 64);
+
+    const int item = blockIdx.x;
+    const int slice = item / a.n_groups, grp = item % a.n_groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strand = lane >> 3, j = lane & 7;
+    const int jj = j < V2_LPG ? j : V2_LPG - 1;  // the idle eighth lane aliases lane 6
+    const int c_lo = (int)((int64_t)a.n_chunks * slice / a.n_slices);
+    const int c_hi = (int)((int64_t)a.n_chunks * (slice + 1) / a.n_slices);
+    uint32_t* gthr = a.gthr + (size_t)grp * V2_QB;
+
+    if (threadIdx.x == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // TMA bulk copy of the group's table
+        mbar_expect_tx(s_bar, (uint32_t)LUT2_BYTES);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.qlut) + (size_t)grp * LUT2_BYTES;
+        for (uint32_t o = 0; o < (uint32_t)LUT2_BYTES; o += 32768u) bulk_g2s(smem + o, src + o, 32768u, s_bar);
+    }
+    if (threadIdx.x < 64) {
+        const int q = grp * V2_QB + threadIdx.x;
+        s_thr[threadIdx.x] = (threadIdx.x < V2_QB && q < a.Q) ? __ldcg(&gthr[threadIdx.x]) : 1u;
+        s_cnt[threadIdx.x] = 0u;
+    }
+    __syncthreads();
+    mbar_wait(s_bar, 0);
+
+    // my 8 queries: ql = jj*8 + 2k + h (word k, half h).  A dead half (idle eighth lane, or a
+    // query beyond Q in the last group) gets the bound word 0x7FFF: thr - d never has bit 15.
+    uint32_t lut_base = smem_u32(smem) + (uint32_t)jj * 16u;
+    asm volatile("" : "+r"(lut_base));  // keep it one register: address = lut_base + (field << 4)
+    uint64_t* my_cand = a.cand + (size_t)item * V2_QB * a.bcap;
+    Own2 own{my_cand, s_cnt, s_thr, gthr, a.kp, a.bcap, lane};
+    const int trigger = a.trigger;
+    const int n_live = j < V2_LPG ? min(8, max(0, a.Q - (grp * V2_QB + jj * 8))) : 0;  // my live queries
+
+    uint32_t thr[4];
+    auto reload_thr = [&]() {
+        const uint4 t0 = *reinterpret_cast<const uint4*>(s_thr + jj * 8);
+        const uint4 t1 = *reinterpret_cast<const uint4*>(s_thr + jj * 8 + 4);
+        const uint32_t x[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo = 2 * k < n_live ? ((x[2 * k] - 1u) | 0x8000u) : 0x7FFFu;
+            const uint32_t hi = 2 * k + 1 < n_live ? ((x[2 * k + 1] - 1u) | 0x8000u) : 0x7FFFu;
+            thr[k] = lo | (hi << 16);
+        }
+    };
+    reload_thr();
+
+    const int n_batches = (c_hi - c_lo + 3) >> 2;
+    const int n_rounds = (n_batches + a.n_warps - 1) / a.n_warps;
+    const int C = a.chunk_nodes;
+    int since = 0, epoch_len = a.ramp ? 1 : a.epoch;
+    uint32_t parp[4] = {1u, 1u, 1u, 1u};
+
+    for (int round = 0; round < n_rounds; ++round) {
+        const int c = c_lo + ((round * a.n_warps + warp) << 2) + strand;
+        int n_nodes = 0;
+        uint32_t pos = 0;
+        const uint4* recp = a.recs;
+        if (c < c_hi) {
+            const ChunkDesc2 cd = a.chunks[c];
+            n_nodes = (int)cd.n_nodes;
+            pos = cd.first_pos;
+            recp = a.recs + cd.rec_begin;
+        }
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (n_nodes > 0) rec = __ldg(recp);
+        for (int it = 0; it < C; ++it) {
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (it + 1 < n_nodes) nxt = __ldg(recp + it + 1);
+            // eight 128-bit table reads: rows of the record's fields, this lane's 8 queries
+            const uint4 P0 = lds128(lut_base + ((rec.x & 0x3FFFu) << 4));
+            const uint4 P1 = lds128(lut_base + ((rec.x >> 16) << 4));
+            const uint4 P2 = lds128(lut_base + ((rec.y & 0xFFFFu) << 4));
+            const uint4 P3 = lds128(lut_base + ((rec.y >> 16) << 4));
+            const uint4 M0 = lds128(lut_base + ((rec.z & 0xFFFFu) << 4));
+            const uint4 M1 = lds128(lut_base + ((rec.z >> 16) << 4));
+            const uint4 M2 = lds128(lut_base + ((rec.w & 0xFFFFu) << 4));
+            const uint4 M3 = lds128(lut_base + ((rec.w >> 16) << 4));
+            // ABS: d = sum of all eight; delta: d = parent + plus - minus  (parp = parent + 1,
+            // -x = ~x + 1: one 32-bit subtraction of the packed sums)
+            const uint32_t dm = (rec.x & V2_ABS) ? 0u : 0xFFFFFFFFu;
+            uint32_t d[4];
+            d[0] = (P0.x + P1.x + P2.x) + (P3.x + (parp[0] & dm)) + ((M0.x + M1.x + M2.x + M3.x) ^ dm);
+            d[1] = (P0.y + P1.y + P2.y) + (P3.y + (parp[1] & dm)) + ((M0.y + M1.y + M2.y + M3.y) ^ dm);
+            d[2] = (P0.z + P1.z + P2.z) + (P3.z + (parp[2] & dm)) + ((M0.z + M1.z + M2.z + M3.z) ^ dm);
+            d[3] = (P0.w + P1.w + P2.w) + (P3.w + (parp[3] & dm)) + ((M0.w + M1.w + M2.w + M3.w) ^ dm);
+            // candidate test: bit 15 / 31 of (thr - d) survives iff d < bound, per packed half
+            const uint32_t am = it < n_nodes ? 0x80008000u : 0u;
+            const uint32_t h0 = thr[0] - d[0], h1 = thr[1] - d[1], h2 = thr[2] - d[2], h3 = thr[3] - d[3];
+            const uint32_t hit = (h0 | h1 | h2 | h3) & am;
+            if (__any_sync(0xffffffffu, hit != 0u)) {
+                if (hit) {
+                    const uint32_t hh[4] = {h0, h1, h2, h3};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (hh[k] & am & (0x8000u << (16 * h))) {
+                                const int ql = jj * 8 + 2 * k + h;
+                                const uint32_t dist = (d[k] >> (16 * h)) & 0xFFFFu;
+                                const uint32_t slot = atomicAdd(&s_cnt[ql], 1u);
+                                if (slot < (uint32_t)a.bcap)
+                                    __stcg(my_cand + (size_t)ql * a.bcap + slot, ((uint64_t)dist << 32) | pos);
+                                else
+                                    a.ovf[(size_t)grp * V2_QB + ql] = 1u;  // exact fallback will redo this query
+                            }
+                        }
+                    }
+                }
+            }
+            if (rec.x & V2_CHILD) {
+                parp[0] = d[0] + 1u;
+                parp[1] = d[1] + 1u;
+                parp[2] = d[2] + 1u;
+                parp[3] = d[3] + 1u;
+            }
+            rec = nxt;
+            ++pos;
+            if (++since == epoch_len) {  // epoch boundary (uniform over the CTA)
+                since = 0;
+                if (epoch_len < a.epoch) epoch_len <<= 1;
+                bool need = false;
+                if (lane < 4) {
+                    const int ql = warp + a.n_warps * lane;
+                    if (ql < V2_QB && (int)s_cnt[ql] >= trigger) need = true;
+                }
+                const int any_need = __syncthreads_or(need);
+                if (warp == 0) {  // bounds published by the other slices of this query group
+                    for (int ql = lane; ql < V2_QB; ql += 32)
+                        if (grp * V2_QB + ql < a.Q) atomicMin(&s_thr[ql], __ldcg(&gthr[ql]));
+                }
+                if (any_need) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int ql = warp + a.n_warps * i;
+                        if (ql < V2_QB) own_compact(&own, ql, trigger);
+                    }
+                    __syncthreads();
+                }
+                reload_thr();
+            }
+        }
+    }
+    // final compaction: every buffer becomes a sorted list of at most kp keys
+    __syncthreads();
+    for (int ql = warp; ql < V2_QB; ql += a.n_warps) {
+        own_compact(&own, ql, 1);
+        if (lane == 0) a.cand_cnt[(size_t)item * V2_QB + ql] = min(s_cnt[ql], (uint32_t)a.kp);
+    }
+}
+
+cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st) {
+    const size_t smem = (size_t)LUT2_BYTES + 64 * 4 * 2 + 16;
+    cudaError_t e = cudaFuncSetAttribute(scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    scan2_kernel<<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace dpq

@@ -24,6 +24,39 @@ def assert_topk_equal(pos_a, dist_a, pos_b, dist_b, node_dist=None, rel=REL_TOL)
             np.testing.assert_allclose(nd[pos_a[q]], dist_a[q], rtol=rel)
 
 
+def interpret_program2(prog, table_q):
+    """Second-generation fixed records (dpq_internal.h "v2", scan2.cu) for ONE query on the
+    CPU.  Returns (positions, distances, n_delta_records)."""
+    M, K = prog["M"], prog["K"]
+    tab = np.concatenate([np.asarray(table_q), np.zeros(1, np.asarray(table_q).dtype)])  # + the all-zero row M*K
+    out_pos, out_d, n_delta = [], [], 0
+    for rec_begin, n_nodes, first_pos, _ in prog["chunks2"]:
+        par = None
+        for i in range(int(n_nodes)):
+            x, y, z, w = (int(v) for v in prog["recs"][int(rec_begin) + i])
+            f = [x & 0x3FFF, x >> 16, y & 0xFFFF, y >> 16, z & 0xFFFF, z >> 16, w & 0xFFFF, w >> 16]
+            assert all(v % 7 == 0 and v // 7 <= M * K for v in f)
+            rows = [v // 7 for v in f]
+            if x & (1 << 14):
+                d = sum(tab[r] for r in rows)
+            else:
+                assert par is not None, "delta record without a parent in the register"
+                d = par + sum(tab[r] for r in rows[:4]) - sum(tab[r] for r in rows[4:])
+                n_delta += 1
+            if x & (1 << 15):
+                par = d
+            out_pos.append(int(first_pos) + i)
+            out_d.append(d)
+    return np.array(out_pos, np.int64), np.array(out_d), n_delta
+
+
+def interpret_any(prog, table_q):
+    if prog.get("v2"):
+        pos, d, _ = interpret_program2(prog, table_q)
+        return pos, d
+    return interpret_program(prog, table_q)
+
+
 def interpret_program(prog, table_q):
     """Runs the record program for ONE query on the CPU.  table_q: integer or float table
     [M*K].  Returns (positions, distances) of every node the program emits, in order."""

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import deltapq_b200 as dpq
-from helpers import interpret_program
+from helpers import interpret_any, interpret_program, interpret_program2
 from oracle import pyoracle as po
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -50,26 +50,51 @@ def test_rejects_malformed_stream(golden1501):
         dpq.compile_program(g["payload"], n, 33, 256)
 
 
+@pytest.mark.parametrize("engine", [0, 1])
 @pytest.mark.parametrize("chunk_nodes", [4, 37, 256, 100000])
-def test_program_reproduces_every_node_distance(golden4000, chunk_nodes):
+def test_program_reproduces_every_node_distance(golden4000, chunk_nodes, engine):
     """The compiled op program, interpreted on the CPU with an integer table, reproduces the
     oracle's per-node sums exactly, for any chunking."""
     g = golden4000
     n = int(g["n"])
-    prog = dpq.compile_program(g["payload"], n, 8, 256, chunk_nodes=chunk_nodes)
+    prog = dpq.compile_program(g["payload"], n, 8, 256, chunk_nodes=chunk_nodes, engine=engine)
+    assert prog["v2"] == (engine == 0)
     assert prog["n_local"] == n and prog["base_pos"] == 0
     assert prog["n_bytes"] == len(g["payload"])
     assert np.array_equal(prog["codes"], g["codes"][g["vec_id"]])
     rng = np.random.default_rng(3)
     table = rng.integers(0, 1 << 20, 8 * 256).astype(np.int64)
-    pos, d = interpret_program(prog, table)
+    pos, d = interpret_any(prog, table)
     assert np.array_equal(np.sort(pos), np.arange(n))
     want = table.reshape(8, 256)[np.arange(8)[None, :], prog["codes"]].sum(1)
     assert np.array_equal(d[np.argsort(pos)], want)
 
 
+def test_v2_program_keeps_the_delta_recurrence(golden4000):
+    """Edges that change <= 4 subspaces and whose parent distance is in the strand's register
+    are delta records (parent + new rows - old rows); everything else is a full M-term record."""
+    g = golden4000
+    n = int(g["n"])
+    prog = dpq.compile_program(g["payload"], n, 8, 256)
+    table = np.random.default_rng(9).integers(0, 1 << 20, 8 * 256).astype(np.int64)
+    pos, d, n_delta = interpret_program2(prog, table)
+    assert n_delta == prog["v2_delta_nodes"] > 0
+    codes, depth, parent = po.decode(g["payload"], n, 8)
+    nd = (codes[1:] != codes[parent[1:]]).sum(1)
+    assert n_delta <= int((nd <= 4).sum())
+    # a first child with <= 4 changed subspaces is always delta encoded (within a chunk)
+    first_child = np.flatnonzero((parent[1:] == np.arange(n - 1)) & (nd <= 4)) + 1
+    recs = prog["recs"]
+    in_chunk_start = set(int(c[2]) for c in prog["chunks2"])
+    for p_ in first_child[:200]:
+        if int(p_) in in_chunk_start:
+            continue
+        assert not (int(recs[p_][0]) & (1 << 14)), p_
+
+
+@pytest.mark.parametrize("engine", [0, 1])
 @pytest.mark.parametrize("n_ranks", [2, 3, 8])
-def test_shards_partition_the_tree(golden4000, n_ranks):
+def test_shards_partition_the_tree(golden4000, n_ranks, engine):
     g = golden4000
     n = int(g["n"])
     codes_dfs = g["codes"][g["vec_id"]]
@@ -79,13 +104,13 @@ def test_shards_partition_the_tree(golden4000, n_ranks):
     total_bytes = 0
     next_base = 0
     for r in range(n_ranks):
-        prog = dpq.compile_program(g["payload"], n, 8, 256, rank=r, n_ranks=n_ranks, chunk_nodes=64)
+        prog = dpq.compile_program(g["payload"], n, 8, 256, rank=r, n_ranks=n_ranks, chunk_nodes=64, engine=engine)
         if prog["n_local"] == 0:
             continue
         assert prog["base_pos"] == next_base  # contiguous position ranges
         next_base = prog["base_pos"] + prog["n_local"]
         assert np.array_equal(prog["codes"], codes_dfs[prog["base_pos"]:next_base])
-        pos, d = interpret_program(prog, table)
+        pos, d = interpret_any(prog, table)
         seen[pos] += 1
         assert np.array_equal(d, want[pos])
         total_bytes += prog["n_bytes"]
@@ -109,5 +134,5 @@ def test_m16_program(golden_m16):
 def test_single_node_tree():
     payload = np.arange(8, dtype=np.uint8)
     prog = dpq.compile_program(payload, 1, 8, 256)
-    pos, d = interpret_program(prog, np.arange(2048, dtype=np.int64))
+    pos, d = interpret_any(prog, np.arange(2048, dtype=np.int64))
     assert list(pos) == [0] and d[0] == sum(m * 256 + m for m in range(8))

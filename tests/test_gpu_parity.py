@@ -12,6 +12,18 @@ from oracle import pyoracle as po
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["v2", "gen1"], autouse=True)
+def engine(request, monkeypatch):
+    """Every test runs on both scan engines: the second-generation fixed-record kernel
+    (scan2.cu, default for M <= 8) and the first-generation op-program kernel (kernels.cu,
+    DPQ_ENGINE=1; also what M = 16 uses)."""
+    if request.param == "gen1":
+        monkeypatch.setenv("DPQ_ENGINE", "1")
+    else:
+        monkeypatch.delenv("DPQ_ENGINE", raising=False)
+    return request.param
+
+
 def _open(g, **opts):
     ix = dpq.DeltaTreeIndex(g["payload"], int(g["n"]), int(g["M"]), int(g["K"]), pos2id=g["vec_id"])
     ix.set_codebook(g["cw"])
@@ -57,6 +69,51 @@ def test_search_vs_oracle_all_nodes(golden4000, pack, slices, warps):
         assert np.array_equal(dist[i], odist)
         assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
         assert len(set(pos[i])) == k
+    ix.close()
+
+
+def test_engine_selection(golden4000, golden_m16, engine):
+    ix = _open(golden4000)
+    assert ix.stat("engine") == (2 if engine == "v2" else 1)
+    ix.close()
+
+
+@pytest.mark.parametrize("opts", [dict(slices=1), dict(slices=7), dict(epoch=4, trigger=20), dict(epoch=1),
+                                  dict(ramp=0), dict(ramp=0, epoch=256)])
+def test_v2_options_and_overflow_path(golden4000, engine, opts):
+    """Epoch / trigger / slice settings change how candidates are collected, never the result;
+    ramp=0 floods the candidate buffers in the first epoch, which must divert the affected
+    queries to the exact fallback instead of losing candidates."""
+    if engine != "v2":
+        pytest.skip("v2 options")
+    g = golden4000
+    n = int(g["n"])
+    ix = _open(g, **opts)
+    for k in (10, 100):
+        pos, _, dist = ix.search(g["queries"], k)
+        for i, q in enumerate(g["queries"]):
+            opos, odist, nd = po.scan(g["payload"], n, g["cw"], q, k, want_node_dist=True)
+            assert np.array_equal(dist[i], odist)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+    if opts.get("ramp") == 0:
+        assert ix.stat("last_fallback") > 0
+    ix.close()
+
+
+def test_many_queries_ragged_groups(golden4000, engine):
+    """Q not a multiple of the group size (56 / 48..52): padding lanes must stay silent."""
+    g = golden4000
+    n = int(g["n"])
+    rng = np.random.default_rng(17)
+    base_q = g["queries"]
+    queries = np.clip(base_q[rng.integers(0, len(base_q), 300)] + rng.integers(-9, 10, (300, 128)), 0, 255).astype(np.float32)
+    ix = _open(g)
+    for Q in (1, 55, 57, 113, 300):
+        pos, _, dist = ix.search(queries[:Q], 10)
+        for i in range(0, Q, max(1, Q // 9)):
+            opos, odist, nd = po.scan(g["payload"], n, g["cw"], queries[i], 10, want_node_dist=True)
+            assert np.array_equal(dist[i], odist)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
     ix.close()
 
 
