@@ -81,7 +81,7 @@ struct dpq_index {
     std::vector<uint32_t> pos2id_host;  // local slice
     // options
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
-    int opt_epoch = 32, opt_trigger = 0, opt_ramp = 1;
+    int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
     int chunk_nodes = 512;
     // scratch
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_fbuf,
@@ -444,7 +444,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s2.n_warps = g.n_warps;
         s2.kp = g.kp;
         s2.bcap = g.bcap;
-        s2.trigger = ix->opt_trigger > 0 ? std::min(ix->opt_trigger, g.bcap / 2) : std::min(3 * g.kp, g.bcap / 2);
+        s2.trigger = ix->opt_trigger > 0 ? std::min(ix->opt_trigger, g.bcap / 2) : std::min(2 * g.kp, g.bcap / 2);
         s2.epoch = std::max(1, ix->opt_epoch);
         s2.ramp = ix->opt_ramp;
         CU(dpq::launch_scan2(s2, st));

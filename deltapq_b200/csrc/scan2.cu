@@ -63,6 +63,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     return v;
 }
 
+// table address of a record field: base + field * 16 (one IMAD)
+__device__ __forceinline__ uint32_t fld(uint32_t base, uint32_t field) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(r) : "r"(field), "r"(base));
+    return r;
+}
+
 constexpr int ROWS2 = 2048;
 constexpr int LUT2_BYTES = ROWS2 * V2_ROW_BYTES;  // 229,376
 
@@ -277,18 +284,19 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
         }
         uint4 rec = make_uint4(0, 0, 0, 0);
         if (n_nodes > 0) rec = __ldg(recp);
+#pragma unroll 2
         for (int it = 0; it < C; ++it) {
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (it + 1 < n_nodes) nxt = __ldg(recp + it + 1);
             // eight 128-bit table reads: rows of the record's fields, this lane's 8 queries
-            const uint4 P0 = lds128(lut_base + ((rec.x & 0x3FFFu) << 4));
-            const uint4 P1 = lds128(lut_base + ((rec.x >> 16) << 4));
-            const uint4 P2 = lds128(lut_base + ((rec.y & 0xFFFFu) << 4));
-            const uint4 P3 = lds128(lut_base + ((rec.y >> 16) << 4));
-            const uint4 M0 = lds128(lut_base + ((rec.z & 0xFFFFu) << 4));
-            const uint4 M1 = lds128(lut_base + ((rec.z >> 16) << 4));
-            const uint4 M2 = lds128(lut_base + ((rec.w & 0xFFFFu) << 4));
-            const uint4 M3 = lds128(lut_base + ((rec.w >> 16) << 4));
+            const uint4 P0 = lds128(fld(lut_base, rec.x & 0x3FFFu));
+            const uint4 P1 = lds128(fld(lut_base, rec.x >> 16));
+            const uint4 P2 = lds128(fld(lut_base, rec.y & 0xFFFFu));
+            const uint4 P3 = lds128(fld(lut_base, rec.y >> 16));
+            const uint4 M0 = lds128(fld(lut_base, rec.z & 0xFFFFu));
+            const uint4 M1 = lds128(fld(lut_base, rec.z >> 16));
+            const uint4 M2 = lds128(fld(lut_base, rec.w & 0xFFFFu));
+            const uint4 M3 = lds128(fld(lut_base, rec.w >> 16));
             // ABS: d = sum of all eight; delta: d = parent + plus - minus  (parp = parent + 1,
             // -x = ~x + 1: one 32-bit subtraction of the packed sums)
             const uint32_t dm = (rec.x & V2_ABS) ? 0u : 0xFFFFFFFFu;
