@@ -330,7 +330,7 @@ def run_gpu(args):
                        "tree": "built by libdpq (GPU encode + GPU edge search + host DFS layout)",
                        "setup_s": round(t_setup, 1), "opts": args.opts or "default"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "scan_kernel",
+                         "traffic": traffic, "kernel": "scan2_kernel" if ix.stat("engine") == 2 else "scan_kernel",
                          "algorithmic_bytes_per_launch": alg_bytes, "scan_ms_per_launch": scan_s * 1e3,
                          "peak_source": peak_src,
                          "note": "effective bandwidth: every query batch re-reads the L2-resident tree (SURVEY 8d)"},
