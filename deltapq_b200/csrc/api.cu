@@ -82,6 +82,7 @@ struct dpq_index {
     // options
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
+    int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
     // scratch
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_fbuf,
@@ -355,6 +356,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "epoch") ix->opt_epoch = (int)v;
     else if (n == "trigger") ix->opt_trigger = (int)v;
     else if (n == "ramp") ix->opt_ramp = (int)v;
+    else if (n == "dbg_bound") ix->opt_dbg_bound = (int)v;
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
 }
@@ -411,7 +413,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if (P.v2)
         dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                          ix->d_scale.as<double>(), ix->d_qlut.as<uint16_t>(), ix->d_gthr.as<uint32_t>(),
-                         ix->d_ovf.as<uint32_t>(), g.n_groups, st);
+                         ix->d_ovf.as<uint32_t>(), g.n_groups, (uint32_t)ix->opt_dbg_bound, st);
     else
         dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                         ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);

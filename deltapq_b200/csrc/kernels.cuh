@@ -63,7 +63,7 @@ struct Scan2Args {
 };
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
-                 cudaStream_t st);
+                 uint32_t bound0, cudaStream_t st);
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
 
 // One ADC table entry in the reference's arithmetic (DCAT.h:3754-3757): float accumulator,

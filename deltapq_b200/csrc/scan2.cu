@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
 // are zero.  Block = 64 rows of one group; reads and writes are both coalesced.
 __global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lutf, const double* __restrict__ scale,
                                                     int MK, int Q, uint16_t* __restrict__ qlut,
-                                                    uint32_t* __restrict__ gthr, uint32_t* __restrict__ ovf) {
+                                                    uint32_t* __restrict__ gthr, uint32_t* __restrict__ ovf,
+                                                    uint32_t bound0) {
     __shared__ uint16_t tile[64][V2_QB];
     const int grp = blockIdx.x, row0 = blockIdx.y * 64;
     for (int i = threadIdx.x; i < 64 * V2_QB; i += blockDim.x) {
@@ -125,16 +126,16 @@ __global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lu
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&tile[0][0]);
     for (int i = threadIdx.x; i < 64 * V2_QB / 2; i += blockDim.x) dst[i] = src[i];
     if (blockIdx.y == 0 && threadIdx.x < V2_QB) {
-        gthr[grp * V2_QB + threadIdx.x] = 0x8000u;  // exclusive bound: accept everything
+        gthr[grp * V2_QB + threadIdx.x] = bound0;  // exclusive bound; 0x8000 = accept everything
         ovf[grp * V2_QB + threadIdx.x] = 0u;
     }
 }
 
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
-                 cudaStream_t st) {
+                 uint32_t bound0, cudaStream_t st) {
     lut2_kernel<<<Q, 256, (size_t)M * Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf, d_scale);
-    pack2_kernel<<<dim3((unsigned)n_groups, ROWS2 / 64), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, d_qlut, d_gthr, d_ovf);
+    pack2_kernel<<<dim3((unsigned)n_groups, ROWS2 / 64), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, d_qlut, d_gthr, d_ovf, bound0);
 }
 
 // ------------------------------------------------------------------------ scan ---------
