@@ -9,9 +9,12 @@ Workload (BASELINE.json configs[1]): SIFT1M-shaped synthetic, 1M x 128-d, M=8 K=
 The tree is produced by the product's own pipeline (GPU encode, GPU edge search, host DFS
 layout + stream writer); only the cpu_baseline leg / --impl reference touch oracle/.
 
-N > 1 (torchrun, one rank per GPU): the SAME 1M-code tree is sharded by whole depth-1
-subtrees, every rank scans its shard for all queries, the per-rank top-k key
-lists are all-gathered over NCCL and merged on the device: strong scaling.
+N > 1 (torchrun, one rank per GPU).  Primary number: the 16 MB tree is replicated and the
+QUERIES are the sharded units (10K per GPU per step, weak scaling), result keys all-gathered
+over NCCL.  Secondary block "tree_sharded": the same tree sharded by whole depth-1 subtrees
+(the 1B-code design), every rank scans its shard for the same 10K queries, the
+per-rank top-k key lists are all-gathered over NCCL and merged on the device (strong scaling);
+its merged result is checked against the unsharded one in the same run.
 PyTorch is plumbing here (device buffers, stream, events, torch.distributed).
 """
 import argparse
@@ -179,6 +182,20 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------ GPU arm -------
+def timed_steps(torch, stream, flush, steps, step_fn, barrier):
+    """K steps, device time per step; a 256 MiB write before every step flushes L2 (outside
+    the events).  Returns the summed device milliseconds."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        step_fn()
+        b.record(stream)
+    barrier()
+    return float(sum(a.elapsed_time(b) for a, b in ev))
+
+
 def run_gpu(args):
     import torch
     import deltapq_b200 as dpq
@@ -198,114 +215,134 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(*vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
     # ---- workload: product pipeline only (encode -> approx_tree -> index) -----------------
     t_setup = time.perf_counter()
-    base, cw, queries = synth(args.n_codes, args.queries)
+    base, cw, queries0 = synth(args.n_codes, args.queries)
     codes = dpq.encode(cw, base)
     tree = dpq.tree_build(codes, cw, h=1, method=1)
     payload = tree["payload"]
     del base
-    ix = dpq.DeltaTreeIndex(payload, args.n_codes, PQ_M, PQ_K, pos2id=tree["vec_id"], rank=rank, n_ranks=world)
-    ix.set_codebook(cw)
-    for kv in (args.opts.split(",") if args.opts else []):
-        k, v = kv.split("=")
-        ix.set_option(k, int(v))
-    stream = torch.cuda.current_stream()
-    ix.set_stream(stream.cuda_stream)
-    t_setup = time.perf_counter() - t_setup
-
     Q, k = args.queries, TOPK
+    stream = torch.cuda.current_stream()
+
+    def open_index(r, n):
+        ix_ = dpq.DeltaTreeIndex(payload, args.n_codes, PQ_M, PQ_K, pos2id=tree["vec_id"], rank=r, n_ranks=n)
+        ix_.set_codebook(cw)
+        for kv in (args.opts.split(",") if args.opts else []):
+            kk, v = kv.split("=")
+            ix_.set_option(kk, int(v))
+        ix_.set_stream(stream.cuda_stream)
+        return ix_
+
+    # Primary mode.  The 1M-code tree is 16 MB on the device: every GPU holds the whole tree
+    # and answers ITS OWN batch of 10K queries (the units of work are queries: weak scaling,
+    # per-GPU batch fixed); the per-rank result keys are all-gathered so every rank ends with
+    # all N x 10K answers.  N = 1 is the plain single-GPU run.
+    ix = open_index(0, 1)
+    t_setup = time.perf_counter() - t_setup
+    if world > 1:
+        import datagen as dg
+        queries = dg.sift_like(Q, DIM, seed=2 + 1000 * rank)  # a different batch per rank
+    else:
+        queries = queries0
     d_q = torch.from_numpy(queries).to(dev)
     d_key = torch.empty((Q, k), dtype=torch.int64, device=dev)
     d_all = torch.empty((world, Q, k), dtype=torch.int64, device=dev) if world > 1 else None
-    d_out = torch.empty((Q, k), dtype=torch.int64, device=dev) if world > 1 else d_key
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_device():
         ix.search_device(d_q.data_ptr(), Q, k, d_key.data_ptr())
         if world > 1:
             dist.all_gather_into_tensor(d_all.view(-1), d_key.view(-1))
-            ix.merge_device(d_all.data_ptr(), world, Q, k, d_out.data_ptr())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
     barrier()
-
-    # ---- timed: K steps, device time per step (L2 flushed before each, outside the events) --
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ix.set_option("timing_reset", 1)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for a, b in ev:
-        flush.zero_()
-        a.record(stream)
-        step_device()
-        b.record(stream)
-    barrier()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
+    total_ms = timed_steps(torch, stream, flush, args.steps, step_device, barrier)
     scan_ns = ix.stat("sum_scan_ns")
     lut_ns = ix.stat("sum_lut_ns")
     calls = ix.stat("timed_calls")
     fallback = ix.stat("last_fallback")
-    launches_per_step = ix.stat("last_launches") + (1 if world > 1 else 0)  # + merge kernel
+    launches_per_step = ix.stat("last_launches")
 
-    # ---- e2e: host buffers in, host buffers out; H2D + D2H inside the timed region.  N = 1 goes
-    # through the reference-facing C-ABI call dpq_index_search (pinned staging inside libdpq);
-    # N > 1 adds the NCCL gather + merge between the same copies.
-    barrier()
-    h_q = torch.from_numpy(queries).pin_memory()
-    h_out = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+    # ---- e2e: the reference-facing C-ABI call dpq_index_search with HOST buffers (pinned staging
+    # inside libdpq, H2D of the queries + D2H of the results inside the timed region)
     pos, ids, dst = ix.search(queries, k)  # warm the pinned staging
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        if world == 1:
-            pos, ids, dst = ix.search(queries, k)
-        else:
-            d_q.copy_(h_q, non_blocking=True)
-            step_device()
-            h_out.copy_(d_out, non_blocking=True)
-            torch.cuda.synchronize()
+        pos, ids, dst = ix.search(queries, k)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+    total_ms, e2e_s, scan_ms_max = max_over_ranks(total_ms, e2e_s, scan_ns / 1e6)
 
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_s, scan_ns / 1e6], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, scan_ms_max = (float(x) for x in t.tolist())
-    else:
-        scan_ms_max = scan_ns / 1e6
-
-    # ---- check: merged result equals the unsharded result (cheap sanity, outside timing) ---
-    out_keys = d_out.cpu().numpy().view(np.uint64)
-    out_pos, out_dist = dpq.unpack_keys(out_keys)
+    out_pos, out_dist = dpq.unpack_keys(d_key.cpu().numpy().view(np.uint64))
     assert np.all(np.diff(out_dist.astype(np.float64), axis=1) >= 0), "top-k not ascending"
+    assert np.array_equal(out_dist, dst) and np.array_equal(out_pos, pos), "device and host paths disagree"
 
-    n_local_bytes = ix.stat("n_bytes")
+    # ---- secondary mode at N > 1: the SAME tree sharded by depth-1 subtrees over the ranks
+    # (the 1B-code design): every rank scans its shard for the same 10K queries, one
+    # NCCL all-gather of the local top-k keys, device merge.  Strong scaling on a 16 MB tree.
+    tree_sharded = None
+    if world > 1:
+        sh = open_index(rank, world)
+        d_q0 = torch.from_numpy(queries0).to(dev)
+        d_loc = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        d_mrg = torch.empty((Q, k), dtype=torch.int64, device=dev)
+
+        def step_sharded():
+            sh.search_device(d_q0.data_ptr(), Q, k, d_loc.data_ptr())
+            dist.all_gather_into_tensor(d_all.view(-1), d_loc.view(-1))
+            sh.merge_device(d_all.data_ptr(), world, Q, k, d_mrg.data_ptr())
+
+        for _ in range(args.warmup):
+            flush.zero_()
+            step_sharded()
+        barrier()
+        sh.set_option("timing_reset", 1)
+        ms = timed_steps(torch, stream, flush, args.steps, step_sharded, barrier)
+        sh_scan = sh.stat("sum_scan_ns") / 1e6 / max(sh.stat("timed_calls"), 1)
+        ms, sh_scan = max_over_ranks(ms, sh_scan)
+        # the merged result must equal the unsharded search of the same queries
+        ix.search_device(d_q0.data_ptr(), Q, k, d_key.data_ptr())
+        torch.cuda.synchronize()
+        same = bool(torch.equal(d_key, d_mrg))
+        tree_sharded = {"value": Q * args.steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / args.steps,
+                        "scan_ms_max_over_ranks": sh_scan, "scaling": "strong", "equals_unsharded": same,
+                        "n_local_nodes": sh.stat("n_local"),
+                        "what": f"1M-code tree sharded by depth-1 subtrees over {world} GPUs, same 10K queries, "
+                                f"NCCL all-gather of {Q * k * 8} B/rank + device merge"}
+        assert same, "sharded + merged top-k differs from the unsharded result"
+        sh.close()
+
     n_bytes_total = ix.stat("n_bytes_total")
-    n_diffs = ix.stat("n_diffs")
-    n_local = ix.stat("n_local")
     peak, peak_src = measured_peak()
-    # algorithmic bytes of one scan launch: Q queries x (stream bytes of this
-    # shard + 4 D query floats + 8 k result bytes)
-    alg_bytes = Q * (n_local_bytes + 4 * DIM + 8 * k)
+    # algorithmic bytes of one scan launch: Q queries x (stream bytes + 4 D query
+    # floats + 8 k result bytes)
+    alg_bytes = Q * (ix.stat("n_bytes") + 4 * DIM + 8 * k)
     scan_s = (scan_ns / 1e9) / max(calls, 1)
     achieved = alg_bytes / scan_s / 1e9
-    qps = Q * args.steps / (total_ms / 1e3)
-    e2e_qps = Q * args.steps / e2e_s
+    qps = world * Q * args.steps / (total_ms / 1e3)
+    e2e_qps = world * Q * args.steps / e2e_s
 
-    line = None
     if rank == 0:
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
@@ -320,12 +357,13 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u16 fixed-point filter + f64 exact re-score",
+            "scaling": "weak", "vs_baseline": None, "dtype": "u16 fixed-point filter + f64 exact re-score",
             "data": "synthetic",
-            "config": {"workload": "SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, 10K queries, top-10 (BASELINE configs[1])",
-                       "n_codes": args.n_codes, "queries_per_step": Q, "topk": k, "n_bytes": n_bytes_total,
+            "config": {"workload": "SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, 10K queries per GPU per step, top-10 (BASELINE configs[1])",
+                       "n_codes": args.n_codes, "queries_per_step": world * Q, "topk": k, "n_bytes": n_bytes_total,
                        "mean_diffs_per_node": round((n_bytes_total - 8 - (3 * (args.n_codes - 1) + 1) // 2) / (args.n_codes - 1), 3),
-                       "sharding": "whole tree on one GPU" if world == 1 else f"depth-1 subtrees over {world} GPUs + NCCL all-gather of top-k keys + device merge",
+                       "sharding": "whole tree on one GPU" if world == 1 else
+                                   f"queries sharded: {world} replicas of the tree, {Q} queries per GPU per step, NCCL all-gather of the result keys",
                        "l2": "256 MiB buffer written before every timed step (L2 flush, outside the events)",
                        "tree": "built by libdpq (GPU encode + GPU edge search + host DFS layout)",
                        "setup_s": round(t_setup, 1), "opts": args.opts or "default"},
@@ -333,14 +371,16 @@ def run_gpu(args):
                          "traffic": traffic, "kernel": "scan2_kernel" if ix.stat("engine") == 2 else "scan_kernel",
                          "algorithmic_bytes_per_launch": alg_bytes, "scan_ms_per_launch": scan_s * 1e3,
                          "peak_source": peak_src,
-                         "note": "effective bandwidth: every query batch re-reads the L2-resident tree (SURVEY 8d)"},
+                         "note": "per GPU; effective bandwidth: one pass over the L2-resident tree serves 56 queries (SURVEY 8d); "
+                                 "traffic = physical DRAM bytes per launch from the committed ncu capture"},
             "cpu_baseline": cpu_base,
-            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4, "d2h_bytes_per_step": Q * k * 8},
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": world * Q * DIM * 4,
+                    "d2h_bytes_per_step": world * Q * k * 8},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "breakdown_ms_per_step": {"lut": lut_ns / 1e6 / max(calls, 1), "scan": scan_s * 1e3,
                                       "scan_max_over_ranks": scan_ms_max / max(calls, 1), "exact_fallback_queries": fallback},
-            "shard": {"n_local": n_local, "n_bytes_local": n_local_bytes, "n_diffs_local": n_diffs},
+            "tree_sharded": tree_sharded,
         }
         print(json.dumps(line))
     ix.close()

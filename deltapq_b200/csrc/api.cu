@@ -144,7 +144,7 @@ int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     g->rb = 11;
     g->pack = 2;
     g->levels = 0;
-    g->n_warps = 16;
+    g->n_warps = std::max(2, std::min(16, ix->opt_warps));
     int slack = ix->opt_slack >= 0 ? ix->opt_slack : std::max(6, topk / 4);
     g->kp = topk + slack;
     if (g->kp > 128) return fail(DPQ_ERR_ARG, "topk + slack must be <= 128 for the v2 scan (set DPQ_ENGINE=1)");
@@ -435,6 +435,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s2.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
         s2.n_chunks = ix->n_chunks;
         s2.chunk_nodes = P.v2_chunk_nodes;
+        s2.rec_stride = P.v2_rec_stride;
         s2.qlut = ix->d_qlut.as<uint16_t>();
         s2.cand = sa.cand;
         s2.cand_cnt = sa.cand_cnt;

@@ -78,7 +78,8 @@ constexpr int V2_ROW_BYTES = V2_LPG * 16;
 constexpr int V2_QB = V2_LPG * 8;
 
 struct ChunkDesc2 {
-    uint32_t rec_begin;  // first record of this chunk
+    uint32_t rec_begin;  // slot of this chunk's first record; record i is at rec_begin + stride*i
+                         // (stride 4 when the four chunks of a batch are interleaved, program.cpp)
     uint32_t n_nodes;    // records in the chunk (== v2_chunk_nodes except the last)
     uint32_t first_pos;  // global DFS position of the first record
     uint32_t pad;
@@ -88,6 +89,7 @@ struct ScanProgram {
     int M = 0, K = 0;
     bool v2 = false;
     int v2_chunk_nodes = 64;
+    int v2_rec_stride = 1;             // 1: chunk records contiguous; 4: batches of four chunks interleaved
     std::vector<uint32_t> recs;        // v2 records, 4 words each
     std::vector<ChunkDesc2> chunks2;
     int64_t v2_delta_nodes = 0;        // nodes that got a delta record

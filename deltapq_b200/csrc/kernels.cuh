@@ -52,7 +52,7 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
 struct Scan2Args {
     const uint4* recs;            // one 16-byte record per node
     const ChunkDesc2* chunks;
-    int n_chunks, chunk_nodes;
+    int n_chunks, chunk_nodes, rec_stride;
     const uint16_t* qlut;         // [n_groups][2048][56] fixed-point tables
     uint64_t* cand;               // [n_items][56][bcap] candidate keys (dist << 32 | pos)
     uint32_t* cand_cnt;           // [n_items][56]

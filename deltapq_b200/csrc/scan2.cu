@@ -76,33 +76,53 @@ constexpr int LUT2_BYTES = ROWS2 * V2_ROW_BYTES;  // 229,376
 }  // namespace
 
 // ------------------------------------------------------------------------ ADC tables ---
-// Exact float tables [Q][M*K] (reference arithmetic, adc_entry) + per-query fixed-point scale.
+// Exact float tables [Q][M*K] (reference arithmetic, DCAT.h:3754-3757, same expression as
+// adc_entry) + per-query fixed-point scale.  Block = 8 queries x one thread per centroid: every
+// codebook value is loaded once and feeds eight independent accumulation chains (the chain is
+// a dependent float -> double -> float sequence, so the eight queries are the ILP).
+constexpr int LUT2_QPB = 8;
 __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw, int M, int K, int Ds,
                                                    const float* __restrict__ queries, int Q,
                                                    float* __restrict__ lutf, double* __restrict__ scale) {
-    extern __shared__ float s_q[];  // M*Ds
-    __shared__ int s_max[16];
-    const int q = blockIdx.x;
+    extern __shared__ float s_q[];  // [LUT2_QPB][M*Ds]
+    __shared__ int s_max[LUT2_QPB][16];
+    const int q0 = blockIdx.x * LUT2_QPB;
     const int k = threadIdx.x;
-    for (int i = k; i < M * Ds; i += blockDim.x) s_q[i] = queries[(size_t)q * M * Ds + i];
-    if (k < 16) s_max[k] = 0;
+    const int D = M * Ds;
+    for (int i = k; i < LUT2_QPB * D; i += blockDim.x) {
+        const int q = q0 + i / D;
+        s_q[i] = q < Q ? queries[(size_t)q * D + i % D] : 0.0f;
+    }
+    if (k < LUT2_QPB * 16) s_max[k / 16][k % 16] = 0;
     __syncthreads();
-    float* out = lutf + (size_t)q * M * K;
     for (int m = 0; m < M; ++m) {
-        float v = 0.0f;
+        float acc[LUT2_QPB];
+#pragma unroll
+        for (int j = 0; j < LUT2_QPB; ++j) acc[j] = 0.0f;
         if (k < K) {
-            v = adc_entry(cw + ((size_t)m * K + k) * Ds, s_q + m * Ds, Ds);
-            out[m * K + k] = v;
+            const float* c = cw + ((size_t)m * K + k) * Ds;
+            for (int d = 0; d < Ds; ++d) {
+                const float cv = c[d];
+#pragma unroll
+                for (int j = 0; j < LUT2_QPB; ++j) {
+                    const float diff = __fsub_rn(cv, s_q[j * D + m * Ds + d]);
+                    acc[j] = (float)__dadd_rn((double)acc[j], __dmul_rn((double)diff, (double)diff));
+                }
+            }
         }
-        int vi = __float_as_int(v);  // v >= 0: integer order == float order
-        for (int o = 16; o; o >>= 1) vi = max(vi, __shfl_xor_sync(0xffffffffu, vi, o));
-        if ((k & 31) == 0) atomicMax(&s_max[m], vi);
+#pragma unroll
+        for (int j = 0; j < LUT2_QPB; ++j) {
+            if (k < K && q0 + j < Q) lutf[(size_t)(q0 + j) * M * K + m * K + k] = acc[j];
+            int vi = __float_as_int(acc[j]);  // >= 0: integer order == float order
+            for (int o = 16; o; o >>= 1) vi = max(vi, __shfl_xor_sync(0xffffffffu, vi, o));
+            if ((k & 31) == 0) atomicMax(&s_max[j][m], vi);
+        }
     }
     __syncthreads();
-    if (k == 0) {
+    if (k < LUT2_QPB && q0 + k < Q) {
         double sum = 0.0;
-        for (int m = 0; m < M; ++m) sum += (double)__int_as_float(s_max[m]);
-        scale[q] = sum > 0.0 ? (double)(32767 - 16) / sum : 1.0;
+        for (int m = 0; m < M; ++m) sum += (double)__int_as_float(s_max[k][m]);
+        scale[q0 + k] = sum > 0.0 ? (double)(32767 - 16) / sum : 1.0;
     }
 }
 
@@ -134,7 +154,8 @@ __global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lu
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  uint32_t bound0, cudaStream_t st) {
-    lut2_kernel<<<Q, 256, (size_t)M * Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf, d_scale);
+    lut2_kernel<<<(Q + LUT2_QPB - 1) / LUT2_QPB, 256, (size_t)LUT2_QPB * M * Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, Q,
+                                                                                                   d_lutf, d_scale);
     pack2_kernel<<<dim3((unsigned)n_groups, ROWS2 / 64), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, d_qlut, d_gthr, d_ovf, bound0);
 }
 
@@ -221,8 +242,10 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strand = lane >> 3, j = lane & 7;
     const int jj = j < V2_LPG ? j : V2_LPG - 1;  // the idle eighth lane aliases lane 6
-    const int c_lo = (int)((int64_t)a.n_chunks * slice / a.n_slices);
-    const int c_hi = (int)((int64_t)a.n_chunks * (slice + 1) / a.n_slices);
+    // slices are whole batches of four chunks (the record interleaving unit)
+    const int n_bt = (a.n_chunks + 3) >> 2;
+    const int c_lo = (int)((int64_t)n_bt * slice / a.n_slices) << 2;
+    const int c_hi = min(a.n_chunks, (int)((int64_t)n_bt * (slice + 1) / a.n_slices) << 2);
     uint32_t* gthr = a.gthr + (size_t)grp * V2_QB;
 
     if (threadIdx.x == 0) {
@@ -269,6 +292,7 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     const int n_batches = (c_hi - c_lo + 3) >> 2;
     const int n_rounds = (n_batches + a.n_warps - 1) / a.n_warps;
     const int C = a.chunk_nodes;
+    const int rs = a.rec_stride;
     int since = 0, epoch_len = a.ramp ? 1 : a.epoch;
     uint32_t parp[4] = {1u, 1u, 1u, 1u};
 
@@ -276,19 +300,20 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
         const int c = c_lo + ((round * a.n_warps + warp) << 2) + strand;
         int n_nodes = 0;
         uint32_t pos = 0;
-        const uint4* recp = a.recs;
+        uint32_t rix = 0;  // record slot (32-bit index off the uniform base pointer)
         if (c < c_hi) {
             const ChunkDesc2 cd = a.chunks[c];
             n_nodes = (int)cd.n_nodes;
             pos = cd.first_pos;
-            recp = a.recs + cd.rec_begin;
+            rix = cd.rec_begin;
         }
         uint4 rec = make_uint4(0, 0, 0, 0);
-        if (n_nodes > 0) rec = __ldg(recp);
-#pragma unroll 2
+        if (n_nodes > 0) rec = __ldg(a.recs + rix);
+#pragma unroll 1
         for (int it = 0; it < C; ++it) {
             uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (it + 1 < n_nodes) nxt = __ldg(recp + it + 1);
+            rix += (uint32_t)rs;
+            if (it + 1 < n_nodes) nxt = __ldg(a.recs + rix);
             // eight 128-bit table reads: rows of the record's fields, this lane's 8 queries
             const uint4 P0 = lds128(fld(lut_base, rec.x & 0x3FFFu));
             const uint4 P1 = lds128(fld(lut_base, rec.x >> 16));
@@ -311,23 +336,23 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
             const uint32_t h0 = thr[0] - d[0], h1 = thr[1] - d[1], h2 = thr[2] - d[2], h3 = thr[3] - d[3];
             const uint32_t hit = (h0 | h1 | h2 | h3) & am;
             if (__any_sync(0xffffffffu, hit != 0u)) {
-                if (hit) {
-                    const uint32_t hh[4] = {h0, h1, h2, h3};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (hh[k] & am & (0x8000u << (16 * h))) {
-                                const int ql = jj * 8 + 2 * k + h;
-                                const uint32_t dist = (d[k] >> (16 * h)) & 0xFFFFu;
-                                const uint32_t slot = atomicAdd(&s_cnt[ql], 1u);
-                                if (slot < (uint32_t)a.bcap)
-                                    __stcg(my_cand + (size_t)ql * a.bcap + slot, ((uint64_t)dist << 32) | pos);
-                                else
-                                    a.ovf[(size_t)grp * V2_QB + ql] = 1u;  // exact fallback will redo this query
-                            }
-                        }
-                    }
+                // rare path: one bit per (word, half) that is below its bound
+                uint32_t bits = 0;
+                bits |= ((h0 & am) >> 15 & 1u) | ((h0 & am) >> 30 & 2u);
+                bits |= (((h1 & am) >> 15 & 1u) | ((h1 & am) >> 30 & 2u)) << 2;
+                bits |= (((h2 & am) >> 15 & 1u) | ((h2 & am) >> 30 & 2u)) << 4;
+                bits |= (((h3 & am) >> 15 & 1u) | ((h3 & am) >> 30 & 2u)) << 6;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t dw = b < 4 ? (b < 2 ? d[0] : d[1]) : (b < 6 ? d[2] : d[3]);
+                    const uint32_t dist = (dw >> (16 * (b & 1))) & 0xFFFFu;
+                    const int ql = jj * 8 + b;
+                    const uint32_t slot = atomicAdd(&s_cnt[ql], 1u);
+                    if (slot < (uint32_t)a.bcap)
+                        __stcg(my_cand + (size_t)ql * a.bcap + slot, ((uint64_t)dist << 32) | pos);
+                    else
+                        a.ovf[(size_t)grp * V2_QB + ql] = 1u;  // exact fallback will redo this query
                 }
             }
             if (rec.x & V2_CHILD) {
@@ -342,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
                 since = 0;
                 if (epoch_len < a.epoch) epoch_len <<= 1;
                 bool need = false;
-                if (lane < 4) {
+                {  // warp w owns queries w, w + n_warps, ...
                     const int ql = warp + a.n_warps * lane;
                     if (ql < V2_QB && (int)s_cnt[ql] >= trigger) need = true;
                 }
@@ -352,10 +377,7 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
                         if (grp * V2_QB + ql < a.Q) atomicMin(&s_thr[ql], __ldcg(&gthr[ql]));
                 }
                 if (any_need) {
-                    for (int i = 0; i < 4; ++i) {
-                        const int ql = warp + a.n_warps * i;
-                        if (ql < V2_QB) own_compact(&own, ql, trigger);
-                    }
+                    for (int ql = warp; ql < V2_QB; ql += a.n_warps) own_compact(&own, ql, trigger);
                     __syncthreads();
                 }
                 reload_thr();

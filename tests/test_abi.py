@@ -85,11 +85,14 @@ def test_v2_program_keeps_the_delta_recurrence(golden4000):
     # a first child with <= 4 changed subspaces is always delta encoded (within a chunk)
     first_child = np.flatnonzero((parent[1:] == np.arange(n - 1)) & (nd <= 4)) + 1
     recs = prog["recs"]
-    in_chunk_start = set(int(c[2]) for c in prog["chunks2"])
+    C = 64
+    starts = {int(c[2]): ci for ci, c in enumerate(prog["chunks2"])}
     for p_ in first_child[:200]:
-        if int(p_) in in_chunk_start:
+        if int(p_) in starts:
             continue
-        assert not (int(recs[p_][0]) & (1 << 14)), p_
+        ci = max(c for s_, c in starts.items() if s_ <= int(p_))
+        slot = int(prog["chunks2"][ci][0]) + (int(p_) - int(prog["chunks2"][ci][2]))
+        assert not (int(recs[slot][0]) & (1 << 14)), p_
 
 
 @pytest.mark.parametrize("engine", [0, 1])
