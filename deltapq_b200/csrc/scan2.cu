@@ -314,7 +314,11 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
             uint4 nxt = make_uint4(0, 0, 0, 0);
             rix += (uint32_t)rs;
             if (it + 1 < n_nodes) nxt = __ldg(a.recs + rix);
-            // eight 128-bit table reads: rows of the record's fields, this lane's 8 queries
+            // ABS: d = sum of all eight; delta: d = parent + plus - minus  (parp = parent + 1,
+            // -x = ~x + 1: one 32-bit subtraction of the packed sums)
+            const uint32_t dm = (rec.x & V2_ABS) ? 0u : 0xFFFFFFFFu;
+            uint32_t d[4];
+            // eight 128-bit table reads in flight: rows of the record's fields, this lane's 8 queries
             const uint4 P0 = lds128(fld(lut_base, rec.x & 0x3FFFu));
             const uint4 P1 = lds128(fld(lut_base, rec.x >> 16));
             const uint4 P2 = lds128(fld(lut_base, rec.y & 0xFFFFu));
@@ -323,10 +327,6 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
             const uint4 M1 = lds128(fld(lut_base, rec.z >> 16));
             const uint4 M2 = lds128(fld(lut_base, rec.w & 0xFFFFu));
             const uint4 M3 = lds128(fld(lut_base, rec.w >> 16));
-            // ABS: d = sum of all eight; delta: d = parent + plus - minus  (parp = parent + 1,
-            // -x = ~x + 1: one 32-bit subtraction of the packed sums)
-            const uint32_t dm = (rec.x & V2_ABS) ? 0u : 0xFFFFFFFFu;
-            uint32_t d[4];
             d[0] = (P0.x + P1.x + P2.x) + (P3.x + (parp[0] & dm)) + ((M0.x + M1.x + M2.x + M3.x) ^ dm);
             d[1] = (P0.y + P1.y + P2.y) + (P3.y + (parp[1] & dm)) + ((M0.y + M1.y + M2.y + M3.y) ^ dm);
             d[2] = (P0.z + P1.z + P2.z) + (P3.z + (parp[2] & dm)) + ((M0.z + M1.z + M2.z + M3.z) ^ dm);
@@ -394,9 +394,10 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
 
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st) {
     const size_t smem = (size_t)LUT2_BYTES + 64 * 4 * 2 + 16;
-    cudaError_t e = cudaFuncSetAttribute(scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*k)(const Scan2Args) = scan2_kernel;  // 16 warps x 128 registers: more warps spill and ran 2x slower
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    scan2_kernel<<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);
+    k<<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);
     return cudaGetLastError();
 }
 
