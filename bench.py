@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -267,13 +267,14 @@ def run_gpu(args):
         if world > 1:
             dist.all_gather_into_tensor(d_all.view(-1), d_key.view(-1))
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)  # nvidia-smi start-up: the first sample must not land after the timed region
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ix.set_option("timing_reset", 1)
     total_ms = timed_steps(torch, stream, flush, args.steps, step_device, barrier)
     scan_ns = ix.stat("sum_scan_ns")
