@@ -1,0 +1,66 @@
+"""Secondary kernels vs the UNMODIFIED reference on the same box (developer measurement, not
+bench.py): encode, approx_tree, groundtruth at BASELINE configs[1] shape.  Prints one JSON line
+per stage.  The reference legs run the binaries in oracle/_ref (all host threads, OpenMP)."""
+import json, os, subprocess, sys, tempfile, time, shutil
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import datagen as dg
+import deltapq_b200 as dpq
+from oracle import pyoracle as po
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+NQ = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+M = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+run_ref = os.path.exists(os.path.join(po.REF_DIR, "pqtree")) and "--no-ref" not in sys.argv
+d = tempfile.mkdtemp(prefix="dpq_sec_")
+try:
+    base, queries, cw = dg.make_dataset(d, N, NQ, M=M, K=256, d=128, seed=0, n_learn=20000)
+    os.makedirs(d + "/groundtruth")
+    BIN = os.path.join(ROOT, "deltapq_b200", "bin")
+    common = ["-dataset", d, "-m", str(M), "-k", "256", "-N", str(N), "-ext", "fvecs"]
+
+    def timed(cmd):
+        t = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        dt = time.perf_counter() - t
+        if r.returncode != 0:
+            raise RuntimeError(f"{cmd}: rc={r.returncode}\n{r.stdout[-1500:]}\n{r.stderr[-1500:]}")
+        return dt
+
+    # in-process kernel-level times (host buffers in, host buffers out)
+    dpq.encode(cw, base[:1000])
+    t = time.perf_counter(); codes = dpq.encode(cw, base); t_enc = time.perf_counter() - t
+    t = time.perf_counter(); tree = dpq.tree_build(codes, cw); t_tree = time.perf_counter() - t
+    t = time.perf_counter(); ge, gr = dpq.find_edges(codes, 256, 1, 1); t_edges = time.perf_counter() - t
+    t = time.perf_counter(); gid, gd = dpq.groundtruth(base, queries, 10); t_gt = time.perf_counter() - t
+    out = dict(N=N, M=M, encode_s=round(t_enc, 3), encode_vec_per_s=round(N / t_enc),
+               find_edges_s=round(t_edges, 3), tree_build_s=round(t_tree, 3),
+               groundtruth_s=round(t_gt, 3), groundtruth_ms_per_query=round(t_gt / NQ * 1e3, 2),
+               n_bytes=int(len(tree["payload"])), n_diffs=tree["n_diffs"])
+    # CLI wall times (file I/O included, like the reference's own timers)
+    out["cli_encode_s"] = round(timed([BIN + "/pqtree", "-task", "encode"] + common), 2)
+    out["cli_approx_tree_s"] = round(timed([BIN + "/deltapq", "-task", "approx_tree", "-h", "1", "-diff", str(M)] + common), 2)
+    out["cli_groundtruth_s"] = round(timed([BIN + "/pqtree", "-task", "groundtruth", "-query_size", str(NQ), "-topk", "10"] + common), 2)
+    if run_ref:
+        r = tempfile.mkdtemp(prefix="dpq_secref_")
+        try:
+            for f in ("base.fvecs", "query.fvecs", f"M{M}K256codewords.txt"):
+                os.symlink(os.path.join(d, f), os.path.join(r, f))
+            os.makedirs(r + "/groundtruth")
+            rc = ["-dataset", r] + common[2:]
+            out["ref_encode_s"] = round(timed([po.REF_DIR + "/pqtree", "-task", "encode"] + rc), 2)
+            if M == 8:
+                out["ref_approx_tree_s"] = round(timed([po.REF_DIR + "/deltapq_canon", "-task", "approx_tree", "-h", "1", "-diff", "8"] + rc), 2)
+            out["ref_groundtruth_s"] = round(timed([po.REF_DIR + "/pqtree", "-task", "groundtruth", "-query_size", str(NQ), "-topk", "10"] + rc), 2)
+            out["ref_threads"] = len(os.sched_getaffinity(0))
+            same = np.array_equal(np.fromfile(f"{d}/codes.bin.plain.M{M}K256N{N}", np.uint8), np.fromfile(f"{r}/codes.bin.plain.M{M}K256N{N}", np.uint8))
+            out["codes_identical"] = bool(same)
+            if M == 8:
+                nm = f"M8K256_Approx_compressed_codes_opt_N{N}"
+                out["tree_identical"] = bool(np.array_equal(np.fromfile(f"{d}/{nm}", np.uint8), np.fromfile(f"{r}/{nm}", np.uint8)))
+        finally:
+            shutil.rmtree(r, ignore_errors=True)
+    print(json.dumps(out))
+finally:
+    shutil.rmtree(d, ignore_errors=True)
