@@ -333,11 +333,11 @@ def compile_program(payload, n_codes, M, K, rank=0, n_ranks=1, chunk_nodes=256, 
                 _check(lib().dpq_program_copy(h, name.encode(), _ptr(arr)))
             out[name] = arr
         for name in ("n_local", "base_pos", "rb", "levels", "n_bytes", "n_diffs", "n_chunks", "v2",
-                     "v2_delta_nodes"):
+                     "v2_delta_nodes", "v2_nf", "v2_lpg"):
             out[name] = int(lib().dpq_program_size(h, name.encode()))
         out["chunks"] = out["chunks"].reshape(-1, 4)
         out["chunks2"] = out["chunks2"].reshape(-1, 4)
-        out["recs"] = out["recs"].reshape(-1, 4)
+        out["recs"] = out["recs"].reshape(-1, max(out["v2_nf"], 8) // 2)
         out["codes"] = out["codes"].reshape(-1, M)
         out["anc"] = out["anc"].reshape(-1, out["levels"], M)
         out["M"], out["K"] = M, K

@@ -141,7 +141,8 @@ int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     const dpq::ScanProgram& P = ix->prog;
     g->M = P.M;
     g->K = P.K;
-    g->rb = 11;
+    const dpq::V2Shape sh = P.shape;
+    g->rb = sh.rows == 2048 ? 11 : 12;
     g->pack = 2;
     g->levels = 0;
     g->n_warps = std::max(2, std::min(16, ix->opt_warps));
@@ -150,12 +151,12 @@ int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     if (g->kp > 128) return fail(DPQ_ERR_ARG, "topk + slack must be <= 128 for the v2 scan (set DPQ_ENGINE=1)");
     g->kps = 0;
     g->bcap = g->kp <= 64 ? 256 : 512;
-    g->qgl = dpq::V2_LPG;
-    g->qpg = dpq::V2_QB;
-    g->n_groups = (Q + dpq::V2_QB - 1) / dpq::V2_QB;
+    g->qgl = sh.lpg;
+    g->qpg = sh.qb();
+    g->n_groups = (Q + sh.qb() - 1) / sh.qb();
     int n_slices = ix->opt_slices;
     if (n_slices <= 0) {
-        const int chunks_per_round = g->n_warps * 4;
+        const int chunks_per_round = g->n_warps * sh.spw();
         double best = -1.0;
         n_slices = 1;
         for (int s = 1; s <= 64 && s <= std::max(1, ix->n_chunks / chunks_per_round); ++s) {
@@ -381,10 +382,10 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_scale.ensure((size_t)g.n_groups * g.qpg * 8))) return rc;
     if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * g.qgl * rows * 4))) return rc;
     if (P.v2) {
-        if ((rc = ix->d_cand.ensure(n_items * dpq::V2_QB * g.bcap * 8))) return rc;
-        if ((rc = ix->d_cnt.ensure(n_items * dpq::V2_QB * 4))) return rc;
+        if ((rc = ix->d_cand.ensure(n_items * g.qpg * g.bcap * 8))) return rc;
+        if ((rc = ix->d_cnt.ensure(n_items * g.qpg * 4))) return rc;
         if ((rc = ix->d_ovf.ensure((size_t)g.n_groups * g.qpg * 4))) return rc;
-        if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * 2048 * dpq::V2_ROW_BYTES))) return rc;
+        if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * P.shape.lut_bytes()))) return rc;
     } else {
         if ((rc = ix->d_cand.ensure(n_items * g.n_warps * g.bcap * LW * 8))) return rc;
         if ((rc = ix->d_cnt.ensure(n_items * g.n_warps * LW * 4))) return rc;
@@ -413,7 +414,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if (P.v2)
         dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                          ix->d_scale.as<double>(), ix->d_qlut.as<uint16_t>(), ix->d_gthr.as<uint32_t>(),
-                         ix->d_ovf.as<uint32_t>(), g.n_groups, (uint32_t)ix->opt_dbg_bound, st);
+                         ix->d_ovf.as<uint32_t>(), g.n_groups, P.shape, (uint32_t)ix->opt_dbg_bound, st);
     else
         dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                         ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);
@@ -431,6 +432,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaEventRecord(ix->ev[1], st));
     if (P.v2) {
         dpq::Scan2Args s2;
+        s2.shape = P.shape;
         s2.recs = ix->d_recs.as<uint4>();
         s2.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
         s2.n_chunks = ix->n_chunks;

@@ -71,11 +71,31 @@ constexpr uint32_t CHUNK_EMIT_ROOT = 1u << 8;
 // with only leaves in between); otherwise it gets the full M-term record, which costs the
 // same eight table reads and needs no depth stack.  Chunks are v2_chunk_nodes consecutive
 // positions, each starting with a full record, so chunks are independent.
+//
+// Two shapes share this design:
+//   narrow (M <= 8,  M*K <= 2048): 8 fields = 16-byte record, 7 x 16-byte table rows (56 queries
+//           per CTA), a strand is a quarter warp (8 lanes, 7 active): 4 nodes per warp step;
+//   wide   (M <= 16, M*K <= 4096): 16 fields = 32-byte record (plus fields first, minus fields
+//           second, <= 8 changed subspaces for a delta record), 3 x 16-byte rows (24 queries per
+//           CTA), a strand is 4 lanes (3 active): 8 nodes per warp step.
+// In both the table fills shared memory: 2048 x 112 B = 229,376 B, 4096 x 48 B = 196,608 B.
 constexpr uint32_t V2_ABS = 1u << 14;
 constexpr uint32_t V2_CHILD = 1u << 15;
-constexpr int V2_LPG = 7;            // 16-byte lanes per table row = 56 queries per CTA
-constexpr int V2_ROW_BYTES = V2_LPG * 16;
-constexpr int V2_QB = V2_LPG * 8;
+struct V2Shape {
+    int nf;         // fields per record (8 or 16); record = 2*nf bytes
+    int lpg;        // active 16-byte lanes per strand = table row bytes / 16
+    int sw;         // lanes per strand (8 or 4)
+    int rows;       // table rows allocated (2048 or 4096)
+    int qb() const { return lpg * 8; }            // queries per CTA
+    int row_bytes() const { return lpg * 16; }
+    int lut_bytes() const { return rows * row_bytes(); }
+    int spw() const { return 32 / sw; }           // strands (= chunks in flight) per warp
+    int rec_words() const { return nf / 2; }
+};
+inline V2Shape v2_shape(int M, int K) {
+    if (M <= 8 && M * K <= 2048) return V2Shape{8, 7, 8, 2048};
+    return V2Shape{16, 3, 4, 4096};
+}
 
 struct ChunkDesc2 {
     uint32_t rec_begin;  // slot of this chunk's first record; record i is at rec_begin + stride*i
@@ -90,7 +110,8 @@ struct ScanProgram {
     bool v2 = false;
     int v2_chunk_nodes = 64;
     int v2_rec_stride = 1;             // 1: chunk records contiguous; 4: batches of four chunks interleaved
-    std::vector<uint32_t> recs;        // v2 records, 4 words each
+    V2Shape shape{8, 7, 8, 2048};
+    std::vector<uint32_t> recs;        // v2 records, shape.rec_words() words each
     std::vector<ChunkDesc2> chunks2;
     int64_t v2_delta_nodes = 0;        // nodes that got a delta record
     OpFormat fmt{11};
@@ -112,6 +133,11 @@ struct ScanProgram {
 std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
                             int rank, int n_ranks, int chunk_nodes, ScanProgram* out, int engine = 0);
 // engine: 0 = v2 when the shape allows it, 1 = always the first-generation op program
-inline bool v2_shape_ok(int M, int K) { return M <= 8 && (M * K < 2048 || (M == 8 && M * K == 2048)); }
+// a full record needs either all nf fields used (M == nf) or a spare all-zero table row M*K
+inline bool v2_shape_ok(int M, int K) {
+    if (M > 16 || M * K > 4096) return false;
+    const V2Shape sh = v2_shape(M, K);
+    return M == sh.nf || M * K < sh.rows;
+}
 
 }  // namespace dpq

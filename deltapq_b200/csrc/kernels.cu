@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * SEL_WARPS + w;
     if (q >= a.Q) return;
-    const int LW = a.v2 ? V2_QB : 32 * g.pack;
+    const int LW = a.v2 ? g.qpg : 32 * g.pack;
     const int grp = q / g.qpg, sub = q % g.qpg;
     const int sl = a.v2 ? sub : (sub % g.qgl) + 32 * (sub / g.qgl);
     const int lists_per_item = a.v2 ? 1 : g.n_warps;  // v2: one CTA-wide list per (slice, query)
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
             if (!((double)bound * a.scale[q] + E < G)) flag = 1;
         }
         if (a.force_fallback) flag = 1;
-        if (a.v2 && a.ovf[(size_t)grp * V2_QB + sub]) flag = 1;  // dropped candidates: redo exactly
+        if (a.v2 && a.ovf[(size_t)grp * g.qpg + sub]) flag = 1;  // dropped candidates: redo exactly
         a.bound[q] = bound;
         if (flag) {
             uint32_t slot = atomicAdd(a.n_flagged, 1u);

@@ -50,7 +50,8 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
 
 // ---- second-generation scan (scan2.cu) --------------------------------------------------
 struct Scan2Args {
-    const uint4* recs;            // one 16-byte record per node
+    V2Shape shape;
+    const uint4* recs;            // one 16- or 32-byte record per node
     const ChunkDesc2* chunks;
     int n_chunks, chunk_nodes, rec_stride;
     const uint16_t* qlut;         // [n_groups][2048][56] fixed-point tables
@@ -63,7 +64,7 @@ struct Scan2Args {
 };
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
-                 uint32_t bound0, cudaStream_t st);
+                 const V2Shape& sh, uint32_t bound0, cudaStream_t st);
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
 
 // One ADC table entry in the reference's arithmetic (DCAT.h:3754-3757): float accumulator,

@@ -84,6 +84,7 @@ struct Emitter {
 struct Emitter2 {
     ScanProgram* p;
     int M, K;
+    V2Shape sh;
     int chunk_nodes;
     bool open = false;
     int in_chunk = 0;
@@ -94,7 +95,7 @@ struct Emitter2 {
     // node is still on the path, i.e. no shallower-or-equal node was emitted since
     void begin(uint32_t first_pos) {
         ChunkDesc2 c;
-        c.rec_begin = (uint32_t)(p->recs.size() / 4);
+        c.rec_begin = (uint32_t)(p->recs.size() / (size_t)sh.rec_words());
         c.n_nodes = 0;
         c.first_pos = first_pos;
         c.pad = 0;
@@ -116,29 +117,28 @@ struct Emitter2 {
         } else if (reg_owner_depth >= depth) {
             reg_owner_depth = -1;  // the register's node left the path
         }
+        const int nf = sh.nf, half = sh.nf / 2;
         int nd = 0;
         for (int m = 0; m < M; ++m) nd += par[m] != cur[m];
-        uint32_t f[8];
-        bool abs = !(reg_owner_depth >= 0 && reg_owner_depth == depth - 1 && nd <= 4);
+        uint32_t f[16];
+        const bool abs = !(reg_owner_depth >= 0 && reg_owner_depth == depth - 1 && nd <= half);
         if (!abs) {
-            for (int i = 0; i < 8; ++i) f[i] = 0;
+            for (int i = 0; i < nf; ++i) f[i] = 0;
             int j = 0;
             for (int m = 0; m < M; ++m)
                 if (par[m] != cur[m]) {
-                    f[j] = (uint32_t)(m * K + cur[m]) * V2_LPG;      // plus: new centroid
-                    f[4 + j] = (uint32_t)(m * K + par[m]) * V2_LPG;  // minus: old centroid
+                    f[j] = (uint32_t)(m * K + cur[m]) * (uint32_t)sh.lpg;         // plus: new centroid
+                    f[half + j] = (uint32_t)(m * K + par[m]) * (uint32_t)sh.lpg;  // minus: old centroid
                     ++j;
                 }
             p->v2_delta_nodes++;
         } else {
-            const uint32_t zero_row = (uint32_t)(M * K) * V2_LPG;
-            for (int i = 0; i < 8; ++i) f[i] = i < M ? (uint32_t)(i * K + cur[i]) * V2_LPG : zero_row;
+            const uint32_t zero_row = (uint32_t)(M * K) * (uint32_t)sh.lpg;
+            for (int i = 0; i < nf; ++i) f[i] = i < M ? (uint32_t)(i * K + cur[i]) * (uint32_t)sh.lpg : zero_row;
         }
         const size_t at = p->recs.size();
-        p->recs.push_back(f[0] | (abs ? V2_ABS : 0u) | (f[1] << 16));
-        p->recs.push_back(f[2] | (f[3] << 16));
-        p->recs.push_back(f[4] | (f[5] << 16));
-        p->recs.push_back(f[6] | (f[7] << 16));
+        for (int w = 0; w < half; ++w) p->recs.push_back(f[2 * w] | (f[2 * w + 1] << 16));
+        if (abs) p->recs[at] |= V2_ABS;
         prev_rec = (long)at;
         prev_depth = depth;
         ++in_chunk;
@@ -168,11 +168,13 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
     P.depth_hist.assign((size_t)levels + 1, 0);
     if (chunk_nodes < 4) chunk_nodes = 4;
     P.v2 = engine == 0 && v2_shape_ok(M, K);
-    if (const char* e = getenv("DPQ_V2_STRIDE")) P.v2_rec_stride = atoi(e) == 4 ? 4 : 1;  // developer knob
+    if (const char* e = getenv("DPQ_V2_STRIDE")) P.v2_rec_stride = (atoi(e) == 4 && M <= 8) ? 4 : 1;  // developer knob (narrow shape only)
+    if (P.v2) P.shape = v2_shape(M, K);
     Emitter2 E2;
     E2.p = &P;
     E2.M = M;
     E2.K = K;
+    E2.sh = P.shape;
     E2.chunk_nodes = P.v2_chunk_nodes;
 
     std::vector<uint8_t> stack((size_t)(levels + 1) * M, 0);
@@ -277,13 +279,13 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
         // 4b+g lives at slot (b*C + i)*4 + g, so the four strands of a warp (one chunk each,
         // iterating in lockstep) read one contiguous 64-byte piece per step.  Short chunks are
         // padded with zero records (a delta record of row 0 - row 0; never emitted).
-        const size_t C = (size_t)P.v2_chunk_nodes;
+        const size_t C = (size_t)P.v2_chunk_nodes, W = (size_t)P.shape.rec_words();
         const size_t n_batches = (P.chunks2.size() + 3) / 4;
-        std::vector<uint32_t> il(n_batches * C * 16, 0u);
+        std::vector<uint32_t> il(n_batches * C * 4 * W, 0u);
         for (size_t c = 0; c < P.chunks2.size(); ++c) {
             const ChunkDesc2& cd = P.chunks2[c];
             for (size_t i = 0; i < cd.n_nodes; ++i)
-                memcpy(&il[(((c >> 2) * C + i) * 4 + (c & 3)) * 4], &P.recs[((size_t)cd.rec_begin + i) * 4], 16);
+                memcpy(&il[(((c >> 2) * C + i) * 4 + (c & 3)) * W], &P.recs[((size_t)cd.rec_begin + i) * W], W * 4);
         }
         P.recs.swap(il);
         for (size_t c = 0; c < P.chunks2.size(); ++c) P.chunks2[c].rec_begin = (uint32_t)((c >> 2) * C * 4 + (c & 3));

@@ -43,6 +43,8 @@ int64_t dpq_program_size(dpq_program* h, const char* what) {
     if (w == "recs") return (int64_t)p.recs.size() * 4;
     if (w == "chunks2") return (int64_t)p.chunks2.size() * (int64_t)sizeof(dpq::ChunkDesc2);
     if (w == "v2") return p.v2 ? 1 : 0;
+    if (w == "v2_nf") return p.shape.nf;
+    if (w == "v2_lpg") return p.shape.lpg;
     if (w == "v2_delta_nodes") return p.v2_delta_nodes;
     if (w == "n_ops") return (int64_t)p.ops.size();
     if (w == "n_chunks") return (int64_t)p.chunks.size();

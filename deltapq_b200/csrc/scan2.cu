@@ -70,8 +70,7 @@ __device__ __forceinline__ uint32_t fld(uint32_t base, uint32_t field) {
     return r;
 }
 
-constexpr int ROWS2 = 2048;
-constexpr int LUT2_BYTES = ROWS2 * V2_ROW_BYTES;  // 229,376
+constexpr int MAXQB = 64;  // s_thr / s_cnt slots (56 or 24 used)
 
 }  // namespace
 
@@ -126,37 +125,39 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
     }
 }
 
-// Quantise + transpose into the scan layout [group][row][56] u16; rows >= M*K and queries >= Q
+// Quantise + transpose into the scan layout [group][row][QB] u16; rows >= M*K and queries >= Q
 // are zero.  Block = 64 rows of one group; reads and writes are both coalesced.
 __global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lutf, const double* __restrict__ scale,
-                                                    int MK, int Q, uint16_t* __restrict__ qlut,
+                                                    int MK, int Q, int QB, int rows, uint16_t* __restrict__ qlut,
                                                     uint32_t* __restrict__ gthr, uint32_t* __restrict__ ovf,
                                                     uint32_t bound0) {
-    __shared__ uint16_t tile[64][V2_QB];
+    __shared__ uint16_t tile[64 * MAXQB];
     const int grp = blockIdx.x, row0 = blockIdx.y * 64;
-    for (int i = threadIdx.x; i < 64 * V2_QB; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 64 * QB; i += blockDim.x) {
         const int ql = i >> 6, r = i & 63;
-        const int q = grp * V2_QB + ql, row = row0 + r;
+        const int q = grp * QB + ql, row = row0 + r;
         uint16_t v = 0;
         if (q < Q && row < MK) v = (uint16_t)__double2ll_rn((double)lutf[(size_t)q * MK + row] * scale[q]);
-        tile[r][ql] = v;
+        tile[r * QB + ql] = v;
     }
     __syncthreads();
-    uint32_t* dst = reinterpret_cast<uint32_t*>(qlut + ((size_t)grp * ROWS2 + row0) * V2_QB);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&tile[0][0]);
-    for (int i = threadIdx.x; i < 64 * V2_QB / 2; i += blockDim.x) dst[i] = src[i];
-    if (blockIdx.y == 0 && threadIdx.x < V2_QB) {
-        gthr[grp * V2_QB + threadIdx.x] = bound0;  // exclusive bound; 0x8000 = accept everything
-        ovf[grp * V2_QB + threadIdx.x] = 0u;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(qlut + ((size_t)grp * rows + row0) * QB);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
+    for (int i = threadIdx.x; i < 64 * QB / 2; i += blockDim.x) dst[i] = src[i];
+    if (blockIdx.y == 0 && threadIdx.x < QB) {
+        gthr[grp * QB + threadIdx.x] = bound0;  // exclusive bound; 0x8000 = accept everything
+        ovf[grp * QB + threadIdx.x] = 0u;
     }
 }
 
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
-                 uint32_t bound0, cudaStream_t st) {
-    lut2_kernel<<<(Q + LUT2_QPB - 1) / LUT2_QPB, 256, (size_t)LUT2_QPB * M * Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, Q,
-                                                                                                   d_lutf, d_scale);
-    pack2_kernel<<<dim3((unsigned)n_groups, ROWS2 / 64), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, d_qlut, d_gthr, d_ovf, bound0);
+                 const V2Shape& sh, uint32_t bound0, cudaStream_t st) {
+    const size_t lsm = (size_t)LUT2_QPB * M * Ds * sizeof(float);
+    if (lsm > 48 * 1024) cudaFuncSetAttribute(lut2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+    lut2_kernel<<<(Q + LUT2_QPB - 1) / LUT2_QPB, 256, lsm, st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf, d_scale);
+    pack2_kernel<<<dim3((unsigned)n_groups, (unsigned)(sh.rows / 64)), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, sh.qb(), sh.rows,
+                                                                                    d_qlut, d_gthr, d_ovf, bound0);
 }
 
 // ------------------------------------------------------------------------ scan ---------
@@ -231,22 +232,29 @@ __device__ __noinline__ void own_compact(const Own2* o, int ql, int trigger) {
     }
 }
 
+// NF fields per record, LPG active 16-byte lanes per strand, SW lanes per strand.
+template <int NF, int LPG, int SW>
 __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
+    constexpr int QB = LPG * 8;                  // queries per CTA
+    constexpr int ROWS = NF == 8 ? 2048 : 4096;
+    constexpr int LUT_BYTES = ROWS * LPG * 16;
+    constexpr int SPW = 32 / SW;                 // strands per warp = chunks in flight per warp
+    constexpr int RW = NF / 8;                   // uint4 words per record
     extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + LUT2_BYTES);  // [64] exclusive bounds
-    uint32_t* s_cnt = s_thr + 64;                                      // [64] candidates per query
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cnt + 64);
+    uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + LUT_BYTES);  // [64] exclusive bounds
+    uint32_t* s_cnt = s_thr + MAXQB;                                  // [64] candidates per query
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cnt + MAXQB);
 
     const int item = blockIdx.x;
     const int slice = item / a.n_groups, grp = item % a.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strand = lane >> 3, j = lane & 7;
-    const int jj = j < V2_LPG ? j : V2_LPG - 1;  // the idle eighth lane aliases lane 6
-    // slices are whole batches of four chunks (the record interleaving unit)
-    const int n_bt = (a.n_chunks + 3) >> 2;
-    const int c_lo = (int)((int64_t)n_bt * slice / a.n_slices) << 2;
-    const int c_hi = min(a.n_chunks, (int)((int64_t)n_bt * (slice + 1) / a.n_slices) << 2);
-    uint32_t* gthr = a.gthr + (size_t)grp * V2_QB;
+    const int strand = lane / SW, j = lane % SW;
+    const int jj = j < LPG ? j : LPG - 1;  // the idle last lane of a strand aliases its neighbour
+    // slices are whole batches of SPW chunks
+    const int n_bt = (a.n_chunks + SPW - 1) / SPW;
+    const int c_lo = (int)((int64_t)n_bt * slice / a.n_slices) * SPW;
+    const int c_hi = min(a.n_chunks, (int)((int64_t)n_bt * (slice + 1) / a.n_slices) * SPW);
+    uint32_t* gthr = a.gthr + (size_t)grp * QB;
 
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
@@ -254,26 +262,26 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {  // TMA bulk copy of the group's table
-        mbar_expect_tx(s_bar, (uint32_t)LUT2_BYTES);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.qlut) + (size_t)grp * LUT2_BYTES;
-        for (uint32_t o = 0; o < (uint32_t)LUT2_BYTES; o += 32768u) bulk_g2s(smem + o, src + o, 32768u, s_bar);
+        mbar_expect_tx(s_bar, (uint32_t)LUT_BYTES);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.qlut) + (size_t)grp * LUT_BYTES;
+        for (uint32_t o = 0; o < (uint32_t)LUT_BYTES; o += 32768u) bulk_g2s(smem + o, src + o, 32768u, s_bar);
     }
-    if (threadIdx.x < 64) {
-        const int q = grp * V2_QB + threadIdx.x;
-        s_thr[threadIdx.x] = (threadIdx.x < V2_QB && q < a.Q) ? __ldcg(&gthr[threadIdx.x]) : 1u;
+    if (threadIdx.x < MAXQB) {
+        const int q = grp * QB + threadIdx.x;
+        s_thr[threadIdx.x] = (threadIdx.x < QB && q < a.Q) ? __ldcg(&gthr[threadIdx.x]) : 1u;
         s_cnt[threadIdx.x] = 0u;
     }
     __syncthreads();
     mbar_wait(s_bar, 0);
 
-    // my 8 queries: ql = jj*8 + 2k + h (word k, half h).  A dead half (idle eighth lane, or a
-    // query beyond Q in the last group) gets the bound word 0x7FFF: thr - d never has bit 15.
+    // my 8 queries: ql = jj*8 + 2k + h (word k, half h).  A dead half (idle lane, or a query
+    // beyond Q in the last group) gets the bound word 0x7FFF: thr - d never has bit 15.
     uint32_t lut_base = smem_u32(smem) + (uint32_t)jj * 16u;
-    asm volatile("" : "+r"(lut_base));  // keep it one register: address = lut_base + (field << 4)
-    uint64_t* my_cand = a.cand + (size_t)item * V2_QB * a.bcap;
+    asm volatile("" : "+r"(lut_base));  // keep it one register: address = lut_base + field * 16
+    uint64_t* my_cand = a.cand + (size_t)item * QB * a.bcap;
     Own2 own{my_cand, s_cnt, s_thr, gthr, a.kp, a.bcap, lane};
     const int trigger = a.trigger;
-    const int n_live = j < V2_LPG ? min(8, max(0, a.Q - (grp * V2_QB + jj * 8))) : 0;  // my live queries
+    const int n_live = j < LPG ? min(8, max(0, a.Q - (grp * QB + jj * 8))) : 0;  // my live queries
 
     uint32_t thr[4];
     auto reload_thr = [&]() {
@@ -289,48 +297,83 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     };
     reload_thr();
 
-    const int n_batches = (c_hi - c_lo + 3) >> 2;
+    const int n_batches = (c_hi - c_lo + SPW - 1) / SPW;
     const int n_rounds = (n_batches + a.n_warps - 1) / a.n_warps;
     const int C = a.chunk_nodes;
-    const int rs = a.rec_stride;
+    const int rs = a.rec_stride * RW;
     int since = 0, epoch_len = a.ramp ? 1 : a.epoch;
     uint32_t parp[4] = {1u, 1u, 1u, 1u};
 
     for (int round = 0; round < n_rounds; ++round) {
-        const int c = c_lo + ((round * a.n_warps + warp) << 2) + strand;
+        const int c = c_lo + (round * a.n_warps + warp) * SPW + strand;
         int n_nodes = 0;
         uint32_t pos = 0;
-        uint32_t rix = 0;  // record slot (32-bit index off the uniform base pointer)
+        uint32_t rix = 0;  // record slot (32-bit index off the uniform base pointer), in uint4 units
         if (c < c_hi) {
             const ChunkDesc2 cd = a.chunks[c];
             n_nodes = (int)cd.n_nodes;
             pos = cd.first_pos;
-            rix = cd.rec_begin;
+            rix = cd.rec_begin * RW;
         }
-        uint4 rec = make_uint4(0, 0, 0, 0);
-        if (n_nodes > 0) rec = __ldg(a.recs + rix);
+        uint4 rec[RW], nxt[RW];
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            rec[w] = make_uint4(0, 0, 0, 0);
+            if (n_nodes > 0) rec[w] = __ldg(a.recs + rix + w);
+        }
 #pragma unroll 1
         for (int it = 0; it < C; ++it) {
-            uint4 nxt = make_uint4(0, 0, 0, 0);
             rix += (uint32_t)rs;
-            if (it + 1 < n_nodes) nxt = __ldg(a.recs + rix);
-            // ABS: d = sum of all eight; delta: d = parent + plus - minus  (parp = parent + 1,
+#pragma unroll
+            for (int w = 0; w < RW; ++w) {
+                nxt[w] = make_uint4(0, 0, 0, 0);
+                if (it + 1 < n_nodes) nxt[w] = __ldg(a.recs + rix + w);
+            }
+            // ABS: d = sum of all NF rows; delta: d = parent + plus - minus  (parp = parent + 1,
             // -x = ~x + 1: one 32-bit subtraction of the packed sums)
-            const uint32_t dm = (rec.x & V2_ABS) ? 0u : 0xFFFFFFFFu;
+            const uint32_t dm = (rec[0].x & V2_ABS) ? 0u : 0xFFFFFFFFu;
             uint32_t d[4];
-            // eight 128-bit table reads in flight: rows of the record's fields, this lane's 8 queries
-            const uint4 P0 = lds128(fld(lut_base, rec.x & 0x3FFFu));
-            const uint4 P1 = lds128(fld(lut_base, rec.x >> 16));
-            const uint4 P2 = lds128(fld(lut_base, rec.y & 0xFFFFu));
-            const uint4 P3 = lds128(fld(lut_base, rec.y >> 16));
-            const uint4 M0 = lds128(fld(lut_base, rec.z & 0xFFFFu));
-            const uint4 M1 = lds128(fld(lut_base, rec.z >> 16));
-            const uint4 M2 = lds128(fld(lut_base, rec.w & 0xFFFFu));
-            const uint4 M3 = lds128(fld(lut_base, rec.w >> 16));
-            d[0] = (P0.x + P1.x + P2.x) + (P3.x + (parp[0] & dm)) + ((M0.x + M1.x + M2.x + M3.x) ^ dm);
-            d[1] = (P0.y + P1.y + P2.y) + (P3.y + (parp[1] & dm)) + ((M0.y + M1.y + M2.y + M3.y) ^ dm);
-            d[2] = (P0.z + P1.z + P2.z) + (P3.z + (parp[2] & dm)) + ((M0.z + M1.z + M2.z + M3.z) ^ dm);
-            d[3] = (P0.w + P1.w + P2.w) + (P3.w + (parp[3] & dm)) + ((M0.w + M1.w + M2.w + M3.w) ^ dm);
+            if (NF == 8) {
+                // eight 128-bit table reads in flight: rows of the record's fields, this lane's 8 queries
+                const uint4 P0 = lds128(fld(lut_base, rec[0].x & 0x3FFFu));
+                const uint4 P1 = lds128(fld(lut_base, rec[0].x >> 16));
+                const uint4 P2 = lds128(fld(lut_base, rec[0].y & 0xFFFFu));
+                const uint4 P3 = lds128(fld(lut_base, rec[0].y >> 16));
+                const uint4 M0 = lds128(fld(lut_base, rec[0].z & 0xFFFFu));
+                const uint4 M1 = lds128(fld(lut_base, rec[0].z >> 16));
+                const uint4 M2 = lds128(fld(lut_base, rec[0].w & 0xFFFFu));
+                const uint4 M3 = lds128(fld(lut_base, rec[0].w >> 16));
+                d[0] = (P0.x + P1.x + P2.x) + (P3.x + (parp[0] & dm)) + ((M0.x + M1.x + M2.x + M3.x) ^ dm);
+                d[1] = (P0.y + P1.y + P2.y) + (P3.y + (parp[1] & dm)) + ((M0.y + M1.y + M2.y + M3.y) ^ dm);
+                d[2] = (P0.z + P1.z + P2.z) + (P3.z + (parp[2] & dm)) + ((M0.z + M1.z + M2.z + M3.z) ^ dm);
+                d[3] = (P0.w + P1.w + P2.w) + (P3.w + (parp[3] & dm)) + ((M0.w + M1.w + M2.w + M3.w) ^ dm);
+            } else {
+                // sixteen reads: plus fields = first record word, minus fields = second
+                const uint4 rp = rec[0], rm = rec[RW - 1];
+                uint32_t sp[4], sm[4];
+                {
+                    const uint4 A0 = lds128(fld(lut_base, rp.x & 0x3FFFu)), A1 = lds128(fld(lut_base, rp.x >> 16));
+                    const uint4 A2 = lds128(fld(lut_base, rp.y & 0xFFFFu)), A3 = lds128(fld(lut_base, rp.y >> 16));
+                    const uint4 A4 = lds128(fld(lut_base, rp.z & 0xFFFFu)), A5 = lds128(fld(lut_base, rp.z >> 16));
+                    const uint4 A6 = lds128(fld(lut_base, rp.w & 0xFFFFu)), A7 = lds128(fld(lut_base, rp.w >> 16));
+                    sp[0] = (A0.x + A1.x + A2.x) + (A3.x + A4.x + A5.x) + (A6.x + A7.x);
+                    sp[1] = (A0.y + A1.y + A2.y) + (A3.y + A4.y + A5.y) + (A6.y + A7.y);
+                    sp[2] = (A0.z + A1.z + A2.z) + (A3.z + A4.z + A5.z) + (A6.z + A7.z);
+                    sp[3] = (A0.w + A1.w + A2.w) + (A3.w + A4.w + A5.w) + (A6.w + A7.w);
+                }
+                {
+                    const uint4 B0 = lds128(fld(lut_base, rm.x & 0xFFFFu)), B1 = lds128(fld(lut_base, rm.x >> 16));
+                    const uint4 B2 = lds128(fld(lut_base, rm.y & 0xFFFFu)), B3 = lds128(fld(lut_base, rm.y >> 16));
+                    const uint4 B4 = lds128(fld(lut_base, rm.z & 0xFFFFu)), B5 = lds128(fld(lut_base, rm.z >> 16));
+                    const uint4 B6 = lds128(fld(lut_base, rm.w & 0xFFFFu)), B7 = lds128(fld(lut_base, rm.w >> 16));
+                    sm[0] = (B0.x + B1.x + B2.x) + (B3.x + B4.x + B5.x) + (B6.x + B7.x);
+                    sm[1] = (B0.y + B1.y + B2.y) + (B3.y + B4.y + B5.y) + (B6.y + B7.y);
+                    sm[2] = (B0.z + B1.z + B2.z) + (B3.z + B4.z + B5.z) + (B6.z + B7.z);
+                    sm[3] = (B0.w + B1.w + B2.w) + (B3.w + B4.w + B5.w) + (B6.w + B7.w);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = sp[k] + (parp[k] & dm) + (sm[k] ^ dm);
+            }
             // candidate test: bit 15 / 31 of (thr - d) survives iff d < bound, per packed half
             const uint32_t am = it < n_nodes ? 0x80008000u : 0u;
             const uint32_t h0 = thr[0] - d[0], h1 = thr[1] - d[1], h2 = thr[2] - d[2], h3 = thr[3] - d[3];
@@ -352,16 +395,17 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
                     if (slot < (uint32_t)a.bcap)
                         __stcg(my_cand + (size_t)ql * a.bcap + slot, ((uint64_t)dist << 32) | pos);
                     else
-                        a.ovf[(size_t)grp * V2_QB + ql] = 1u;  // exact fallback will redo this query
+                        a.ovf[(size_t)grp * QB + ql] = 1u;  // exact fallback will redo this query
                 }
             }
-            if (rec.x & V2_CHILD) {
+            if (rec[0].x & V2_CHILD) {
                 parp[0] = d[0] + 1u;
                 parp[1] = d[1] + 1u;
                 parp[2] = d[2] + 1u;
                 parp[3] = d[3] + 1u;
             }
-            rec = nxt;
+#pragma unroll
+            for (int w = 0; w < RW; ++w) rec[w] = nxt[w];
             ++pos;
             if (++since == epoch_len) {  // epoch boundary (uniform over the CTA)
                 since = 0;
@@ -369,15 +413,15 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
                 bool need = false;
                 {  // warp w owns queries w, w + n_warps, ...
                     const int ql = warp + a.n_warps * lane;
-                    if (ql < V2_QB && (int)s_cnt[ql] >= trigger) need = true;
+                    if (ql < QB && (int)s_cnt[ql] >= trigger) need = true;
                 }
                 const int any_need = __syncthreads_or(need);
                 if (warp == 0) {  // bounds published by the other slices of this query group
-                    for (int ql = lane; ql < V2_QB; ql += 32)
-                        if (grp * V2_QB + ql < a.Q) atomicMin(&s_thr[ql], __ldcg(&gthr[ql]));
+                    for (int ql = lane; ql < QB; ql += 32)
+                        if (grp * QB + ql < a.Q) atomicMin(&s_thr[ql], __ldcg(&gthr[ql]));
                 }
                 if (any_need) {
-                    for (int ql = warp; ql < V2_QB; ql += a.n_warps) own_compact(&own, ql, trigger);
+                    for (int ql = warp; ql < QB; ql += a.n_warps) own_compact(&own, ql, trigger);
                     __syncthreads();
                 }
                 reload_thr();
@@ -386,15 +430,16 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     }
     // final compaction: every buffer becomes a sorted list of at most kp keys
     __syncthreads();
-    for (int ql = warp; ql < V2_QB; ql += a.n_warps) {
+    for (int ql = warp; ql < QB; ql += a.n_warps) {
         own_compact(&own, ql, 1);
-        if (lane == 0) a.cand_cnt[(size_t)item * V2_QB + ql] = min(s_cnt[ql], (uint32_t)a.kp);
+        if (lane == 0) a.cand_cnt[(size_t)item * QB + ql] = min(s_cnt[ql], (uint32_t)a.kp);
     }
 }
 
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st) {
-    const size_t smem = (size_t)LUT2_BYTES + 64 * 4 * 2 + 16;
-    void (*k)(const Scan2Args) = scan2_kernel;  // 16 warps x 128 registers: more warps spill and ran 2x slower
+    const size_t smem = (size_t)a.shape.lut_bytes() + MAXQB * 4 * 2 + 16;
+    // 16 warps x 128 registers: more warps spill and ran 2x slower (gpurun_out/probe12.log)
+    void (*k)(const Scan2Args) = a.shape.nf == 8 ? scan2_kernel<8, 7, 8> : scan2_kernel<16, 3, 4>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);

@@ -26,24 +26,29 @@ def assert_topk_equal(pos_a, dist_a, pos_b, dist_b, node_dist=None, rel=REL_TOL)
 
 def interpret_program2(prog, table_q):
     """Second-generation fixed records (dpq_internal.h "v2", scan2.cu) for ONE query on the
-    CPU.  Returns (positions, distances, n_delta_records)."""
+    CPU: nf 16-bit fields per record (8: narrow, 16: wide), field = row * lpg, plus fields
+    first, minus fields second.  Returns (positions, distances, n_delta_records)."""
     M, K = prog["M"], prog["K"]
+    nf, lpg = prog["v2_nf"], prog["v2_lpg"]
     tab = np.concatenate([np.asarray(table_q), np.zeros(1, np.asarray(table_q).dtype)])  # + the all-zero row M*K
     out_pos, out_d, n_delta = [], [], 0
     for rec_begin, n_nodes, first_pos, _ in prog["chunks2"]:
         par = None
         for i in range(int(n_nodes)):
-            x, y, z, w = (int(v) for v in prog["recs"][int(rec_begin) + i])
-            f = [x & 0x3FFF, x >> 16, y & 0xFFFF, y >> 16, z & 0xFFFF, z >> 16, w & 0xFFFF, w >> 16]
-            assert all(v % 7 == 0 and v // 7 <= M * K for v in f)
-            rows = [v // 7 for v in f]
-            if x & (1 << 14):
+            words = [int(v) for v in prog["recs"][int(rec_begin) + i]]
+            f = []
+            for w in words:
+                f += [w & 0xFFFF, w >> 16]
+            flags, f[0] = f[0] >> 14, f[0] & 0x3FFF
+            assert len(f) == nf and all(v % lpg == 0 and v // lpg <= M * K for v in f)
+            rows = [v // lpg for v in f]
+            if flags & 1:
                 d = sum(tab[r] for r in rows)
             else:
                 assert par is not None, "delta record without a parent in the register"
-                d = par + sum(tab[r] for r in rows[:4]) - sum(tab[r] for r in rows[4:])
+                d = par + sum(tab[r] for r in rows[:nf // 2]) - sum(tab[r] for r in rows[nf // 2:])
                 n_delta += 1
-            if x & (1 << 15):
+            if flags & 2:
                 par = d
             out_pos.append(int(first_pos) + i)
             out_d.append(d)

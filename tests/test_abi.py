@@ -126,12 +126,33 @@ def test_m16_program(golden_m16):
     g = golden_m16
     codes, cw = g["codes"], g["cw"]
     _, _, lay, payload = po.build_tree(codes, cw)
-    prog = dpq.compile_program(payload, len(codes), 16, 256, chunk_nodes=50)
-    assert prog["rb"] == 12 and prog["levels"] == 16
     table = np.random.default_rng(5).integers(0, 1 << 18, 16 * 256).astype(np.int64)
-    pos, d = interpret_program(prog, table)
     want = table.reshape(16, 256)[np.arange(16)[None, :], codes[lay["vec_id"]]].sum(1)
+    prog = dpq.compile_program(payload, len(codes), 16, 256, chunk_nodes=50, engine=1)
+    assert prog["rb"] == 12 and prog["levels"] == 16 and not prog["v2"]
+    pos, d = interpret_program(prog, table)
     assert np.array_equal(d[np.argsort(pos)], want)
+    # wide second-generation records: 16 fields, 3 x 16-byte table rows
+    prog = dpq.compile_program(payload, len(codes), 16, 256)
+    assert prog["v2"] and prog["v2_nf"] == 16 and prog["v2_lpg"] == 3 and prog["recs"].shape[1] == 8
+    pos, d, n_delta = interpret_program2(prog, table)
+    assert np.array_equal(d[np.argsort(pos)], want) and n_delta == prog["v2_delta_nodes"]
+
+
+@pytest.mark.parametrize("M,K", [(4, 256), (8, 100), (3, 16), (12, 256), (16, 200), (9, 64)])
+def test_v2_program_other_shapes(M, K):
+    """M < 8 / M < 16 full records pad with the all-zero table row M*K."""
+    rng = np.random.default_rng(M * 1000 + K)
+    n = 700
+    codes = rng.integers(0, min(K, 5), (n, M)).astype(np.uint8)
+    cw = rng.random((M, K, 2)).astype(np.float32)
+    _, _, lay, payload = po.build_tree(codes, cw)
+    prog = dpq.compile_program(payload, n, M, K)
+    assert prog["v2"] and prog["v2_nf"] == (8 if M <= 8 else 16)
+    table = rng.integers(0, 1 << 16, M * K).astype(np.int64)
+    pos, d, _ = interpret_program2(prog, table)
+    want = table.reshape(M, K)[np.arange(M)[None, :], codes[lay["vec_id"]]].sum(1)
+    assert np.array_equal(np.sort(pos), np.arange(n)) and np.array_equal(d[np.argsort(pos)], want)
 
 
 def test_single_node_tree():

@@ -220,6 +220,29 @@ def test_m16_extension_search(golden_m16):
     ix.close()
 
 
+@pytest.mark.parametrize("M,K,Ds", [(4, 256, 4), (8, 100, 3), (3, 16, 5), (12, 256, 2), (16, 200, 2), (9, 64, 4)])
+def test_search_other_shapes(M, K, Ds, engine):
+    """M < 8 (narrow records padded with the zero row), 8 < M <= 16 (wide records), K < 256."""
+    rng = np.random.default_rng(M * 131 + K)
+    n, k = 2500, 12
+    cw = dg.roundtrip_codebook((rng.random((M, K, Ds)) * 40).astype(np.float32))
+    base = (rng.random((n, M * Ds)) * 40).astype(np.float32)
+    codes = po.encode(cw, base)
+    codes[rng.random(n) < 0.2] = codes[0]  # duplicates
+    _, _, lay, payload = po.build_tree(codes, cw)
+    ix = dpq.DeltaTreeIndex(payload, n, M, K, pos2id=lay["vec_id"])
+    ix.set_codebook(cw)
+    assert ix.stat("engine") == (2 if engine == "v2" else 1)
+    queries = (rng.random((70, M * Ds)) * 40).astype(np.float32)
+    pos, ids, dist = ix.search(queries, k)
+    for i in range(0, 70, 6):
+        opos, odist, nd = po.scan(payload, n, cw, queries[i], k, want_node_dist=True)
+        np.testing.assert_allclose(dist[i], odist, rtol=REL_TOL)
+        assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+        assert np.array_equal(ids[i], lay["vec_id"][pos[i]])
+    ix.close()
+
+
 def test_encode_bit_exact(golden4000, golden_m16):
     for g in (golden4000, golden_m16):
         assert np.array_equal(dpq.encode(g["cw"], g["base_head"]), g["codes"][:256])

@@ -1,0 +1,25 @@
+"""Developer probe: BASELINE configs[2] shape (SIFT1M-shaped, M=16 K=256, top-100).
+Usage: python tools/perf_probe_m16.py N Q"""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import datagen as dg
+import deltapq_b200 as dpq
+from oracle import pyoracle as po
+N = int(sys.argv[1]); Q = int(sys.argv[2]); M = 16; K = 256; topk = 100
+base = dg.sift_like(N, 128, seed=1)
+cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(20000, 128, seed=3), M, K, iters=6))
+queries = dg.sift_like(Q, 128, seed=2)
+t = time.time(); codes = dpq.encode(cw, base); print("encode %.2fs" % (time.time() - t), flush=True)
+t = time.time(); tree = dpq.tree_build(codes, cw); print("tree build %.2fs" % (time.time() - t), "n_bytes", len(tree["payload"]), "n_diffs", tree["n_diffs"], flush=True)
+payload = tree["payload"]
+ix = dpq.DeltaTreeIndex(payload, N, M, K, pos2id=tree["vec_id"]); ix.set_codebook(cw)
+print("engine", ix.stat("engine"), "prog_bytes", ix.stat("ops_bytes"), flush=True)
+for it in range(3):
+    pos, ids, dist = ix.search(queries, topk)
+    print(json.dumps(dict(scan_ms=ix.stat("last_scan_us") / 1e3, lut_ms=ix.stat("last_lut_us") / 1e3, total_ms=ix.stat("last_total_us") / 1e3,
+                          qps=round(Q / (ix.stat("last_total_us") * 1e-6)), fallback=ix.stat("last_fallback"))), flush=True)
+for i in (0, Q // 2):
+    opos, odist = po.scan(payload, N, cw, queries[i], topk)
+    print("q", i, "dist allclose", bool(np.allclose(odist, dist[i], rtol=1e-5)), "exact", bool(np.array_equal(odist, dist[i])))
