@@ -146,11 +146,13 @@ int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     g->pack = 2;
     g->levels = 0;
     g->n_warps = std::max(2, std::min(16, ix->opt_warps));
-    int slack = ix->opt_slack >= 0 ? ix->opt_slack : std::max(6, topk / 4);
-    g->kp = topk + slack;
-    if (g->kp > 128) return fail(DPQ_ERR_ARG, "topk + slack must be <= 128 for the v2 scan (set DPQ_ENGINE=1)");
+    // slack: extra candidates re-scored exactly so that the rounding-bound proof in select_kernel
+    // succeeds; deeper lists are denser in distance, so the slack grows with topk
+    int slack = ix->opt_slack >= 0 ? ix->opt_slack : (topk <= 32 ? std::max(6, topk / 4) : topk / 2);
+    g->kp = std::min(256, topk + slack);
+    if (topk > 256) return fail(DPQ_ERR_ARG, "topk must be <= 256");
     g->kps = 0;
-    g->bcap = g->kp <= 64 ? 256 : 512;
+    g->bcap = g->kp <= 64 ? 256 : (g->kp <= 128 ? 512 : 1024);
     g->qgl = sh.lpg;
     g->qpg = sh.qb();
     g->n_groups = (Q + sh.qb() - 1) / sh.qb();

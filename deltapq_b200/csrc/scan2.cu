@@ -206,7 +206,8 @@ __device__ __forceinline__ int compact2_t(uint64_t* buf, int n, int kp, int lane
 __device__ __noinline__ int compact2(uint64_t* buf, int n, int kp, int lane, uint32_t* kth) {
     if (n <= 64) return compact2_t<2>(buf, n, kp, lane, kth);
     if (n <= 256) return compact2_t<8>(buf, n, kp, lane, kth);
-    return compact2_t<16>(buf, n, kp, lane, kth);
+    if (n <= 512) return compact2_t<16>(buf, n, kp, lane, kth);
+    return compact2_t<32>(buf, n, kp, lane, kth);  // bcap <= 1024
 }
 
 struct Own2 {  // what an owner warp needs to compact one query's buffer
