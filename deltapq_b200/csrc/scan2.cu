@@ -70,6 +70,10 @@ __device__ __forceinline__ uint32_t fld(uint32_t base, uint32_t field) {
     return r;
 }
 
+// hint: pull the line three lines ahead of the record cursor into L2 (hides HBM latency when the
+// tree does not fit L2; the 16M-code probe ran 3.4x off the shared-memory bound without it)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr int MAXQB = 64;  // s_thr / s_cnt slots (56 or 24 used)
 
 }  // namespace
@@ -204,10 +208,25 @@ __device__ __forceinline__ int compact2_t(uint64_t* buf, int n, int kp, int lane
     return keep;
 }
 __device__ __noinline__ int compact2(uint64_t* buf, int n, int kp, int lane, uint32_t* kth) {
+    // more than 512 keys (bcap = 1024, kp <= 256): reduce the first 512 to their kp best, slide the
+    // tail down behind them, repeat.  Keeps the register footprint of this (called) function small:
+    // a 1024-key variant made the scan loop of the calling kernel spill.
+    while (n > 512) {
+        uint32_t dummy;
+        const int keep = compact2_t<16>(buf, 512, kp, lane, &dummy);
+        const int tail = n - 512;
+        for (int i = 0; i < tail; i += 32) {  // destination is always below every unread key
+            uint64_t v = 0;
+            if (i + lane < tail) v = __ldcg(buf + 512 + i + lane);
+            __syncwarp();
+            if (i + lane < tail) __stcg(buf + keep + i + lane, v);
+            __syncwarp();
+        }
+        n = keep + tail;
+    }
     if (n <= 64) return compact2_t<2>(buf, n, kp, lane, kth);
     if (n <= 256) return compact2_t<8>(buf, n, kp, lane, kth);
-    if (n <= 512) return compact2_t<16>(buf, n, kp, lane, kth);
-    return compact2_t<32>(buf, n, kp, lane, kth);  // bcap <= 1024
+    return compact2_t<16>(buf, n, kp, lane, kth);
 }
 
 struct Own2 {  // what an owner warp needs to compact one query's buffer
@@ -325,6 +344,7 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
 #pragma unroll 1
         for (int it = 0; it < C; ++it) {
             rix += (uint32_t)rs;
+            if ((it & 7) == 0 && it + 25 < n_nodes) prefetch_l2(a.recs + rix + 24 * rs);
 #pragma unroll
             for (int w = 0; w < RW; ++w) {
                 nxt[w] = make_uint4(0, 0, 0, 0);
