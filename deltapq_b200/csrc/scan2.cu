@@ -73,6 +73,7 @@ __device__ __forceinline__ uint32_t fld(uint32_t base, uint32_t field) {
 // hint: pull the line three lines ahead of the record cursor into L2 (hides HBM latency when the
 // tree does not fit L2; the 16M-code probe ran 3.4x off the shared-memory bound without it)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 constexpr int MAXQB = 64;  // s_thr / s_cnt slots (56 or 24 used)
 
@@ -344,7 +345,10 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
 #pragma unroll 1
         for (int it = 0; it < C; ++it) {
             rix += (uint32_t)rs;
-            if ((it & 7) == 0 && it + 25 < n_nodes) prefetch_l2(a.recs + rix + 24 * rs);
+            if ((it & 7) == 0 && it + 25 < n_nodes) {
+                prefetch_l2(a.recs + rix + 24 * rs);
+                prefetch_l1(a.recs + rix + 8 * rs);
+            }
 #pragma unroll
             for (int w = 0; w < RW; ++w) {
                 nxt[w] = make_uint4(0, 0, 0, 0);
