@@ -75,6 +75,8 @@ struct dpq_index {
     int Ds = 0;
     // device-resident tree
     DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_recs, d_chunks2, d_ovf;
+    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_fcnt2;
+    int last_coarse = 0;
     int n_chunks = 0;
     size_t ops_bytes = 0;
     bool has_pos2id = false;
@@ -82,6 +84,10 @@ struct dpq_index {
     // options
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
+    int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
+    int opt_sample = 16;       // the sample pass walks every opt_sample-th batch
+    int opt_bcap8 = 512, opt_warps8 = 16;
+    int64_t opt_coarse_min = 262144;  // nodes in the shard from which the coarse search pays
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
     // scratch
@@ -137,7 +143,7 @@ int choose_geometry(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
 // v2: 56 queries per group; pick the number of tree slices so that (a) the items fill whole
 // waves of 148 one-CTA SMs and (b) an item is a whole number of rounds (16 warps x 4 strands
 // x chunk_nodes nodes) as nearly as possible.
-int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
+int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g, int n_chunks_eff = -1) {
     const dpq::ScanProgram& P = ix->prog;
     g->M = P.M;
     g->K = P.K;
@@ -156,16 +162,17 @@ int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
     g->qgl = sh.lpg;
     g->qpg = sh.qb();
     g->n_groups = (Q + sh.qb() - 1) / sh.qb();
-    int n_slices = ix->opt_slices;
+    const int n_chunks = n_chunks_eff > 0 ? n_chunks_eff : ix->n_chunks;
+    int n_slices = n_chunks_eff > 0 ? 0 : ix->opt_slices;
     if (n_slices <= 0) {
         const int chunks_per_round = g->n_warps * sh.spw();
         double best = -1.0;
         n_slices = 1;
-        for (int s = 1; s <= 64 && s <= std::max(1, ix->n_chunks / chunks_per_round); ++s) {
+        for (int s = 1; s <= 64 && s <= std::max(1, n_chunks / chunks_per_round); ++s) {
             const int64_t items = (int64_t)g->n_groups * s;
             const int64_t waves = (items + 147) / 148;
             const double eff_wave = (double)items / (double)(waves * 148);
-            const double cpi = (double)ix->n_chunks / s;
+            const double cpi = (double)n_chunks / s;
             const double rounds = std::ceil(cpi / chunks_per_round);
             const double eff = eff_wave * (cpi / chunks_per_round) / rounds;
             if (eff > best + 1e-9) {
@@ -174,7 +181,7 @@ int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g) {
             }
         }
     }
-    n_slices = std::max(1, std::min(n_slices, std::max(1, ix->n_chunks)));
+    n_slices = std::max(1, std::min(n_slices, std::max(1, n_chunks)));
     g->n_slices = n_slices;
     g->smem_bytes = 0;
     return DPQ_OK;
@@ -360,6 +367,11 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "trigger") ix->opt_trigger = (int)v;
     else if (n == "ramp") ix->opt_ramp = (int)v;
     else if (n == "dbg_bound") ix->opt_dbg_bound = (int)v;
+    else if (n == "coarse") ix->opt_coarse = (int)v;
+    else if (n == "sample") ix->opt_sample = std::max(1, (int)v);
+    else if (n == "bcap8") ix->opt_bcap8 = std::max(32, (int)v);
+    else if (n == "warps8") ix->opt_warps8 = std::max(2, std::min(24, (int)v));
+    else if (n == "coarse_min") ix->opt_coarse_min = v;
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
 }
@@ -372,8 +384,38 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaSetDevice(ix->device));
     dpq::ScanGeom g;
     const dpq::ScanProgram& P = ix->prog;
-    int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g) : choose_geometry(ix, Q, topk, &g);
+    // coarse search (scan8.cu): 15-bit scan over a 1/S sample -> cap per query -> 8-bit scan of
+    // the whole tree -> exact re-score.  Narrow shape, moderate k, trees large enough to pay.
+    const bool coarse = P.v2 && P.shape.nf == 8 && P.v2_rec_stride == 1 && topk <= 64 && ix->opt_coarse != 0 &&
+                        (ix->opt_coarse == 1 || P.n_local >= ix->opt_coarse_min);
+    const int S = coarse ? ix->opt_sample : 1;
+    const int n_chunks_sample = (((ix->n_chunks + 3) / 4 + S - 1) / S) * 4;  // chunks the sample pass walks
+    int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
     if (rc) return rc;
+    ix->last_coarse = coarse ? 1 : 0;
+    // geometry of the coarse pass: 112-query groups, slices by the same wave/round rule
+    int g8_groups = 0, g8_slices = 1;
+    const int warps8 = ix->opt_warps8, bcap8 = ix->opt_bcap8;
+    if (coarse) {
+        g8_groups = (Q + dpq::C8_QB - 1) / dpq::C8_QB;
+        g8_slices = ix->opt_slices;
+        if (g8_slices <= 0) {
+            const int cpr = warps8 * 4;
+            double best = -1.0;
+            g8_slices = 1;
+            for (int s = 1; s <= 96 && s <= std::max(1, ix->n_chunks / cpr); ++s) {
+                const int64_t items = (int64_t)g8_groups * s;
+                const int64_t waves = (items + 147) / 148;
+                const double cpi = (double)ix->n_chunks / s;
+                const double eff = (double)items / (double)(waves * 148) * (cpi / cpr) / std::ceil(cpi / cpr);
+                if (eff > best + 1e-9) {
+                    best = eff;
+                    g8_slices = s;
+                }
+            }
+        }
+        g8_slices = std::max(1, std::min(g8_slices, std::max(1, ix->n_chunks)));
+    }
     const size_t MK = (size_t)P.M * P.K;
     const size_t rows = (size_t)1 << g.rb;
     const size_t LW = 32 * (size_t)g.pack;
@@ -398,6 +440,15 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
     if ((rc = ix->d_fbuf.ensure((size_t)max_flagged * fcap * 8))) return rc;
     if ((rc = ix->d_fcnt.ensure((size_t)max_flagged * 4))) return rc;
+    if (coarse) {
+        const size_t items8 = (size_t)g8_groups * g8_slices;
+        if ((rc = ix->d_qlut8.ensure((size_t)g8_groups * 2048 * dpq::C8_ROW_BYTES))) return rc;
+        if ((rc = ix->d_cand8.ensure(items8 * dpq::C8_QB * bcap8 * 4))) return rc;
+        if ((rc = ix->d_cnt8.ensure(items8 * dpq::C8_QB * 4))) return rc;
+        if ((rc = ix->d_ovf8.ensure((size_t)g8_groups * dpq::C8_QB * 4))) return rc;
+        if ((rc = ix->d_flagged2.ensure((size_t)max_flagged * 4))) return rc;
+        if ((rc = ix->d_fcnt2.ensure((size_t)max_flagged * 4))) return rc;
+    }
     cudaStream_t st = ix->stream;
     uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();  // [0] n_flagged, [1] overflow
     {
@@ -413,6 +464,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaEventRecord(ix->ev[0], st));
     CU(cudaMemsetAsync(ctrl, 0, 64, st));
     CU(cudaMemsetAsync(ix->d_fcnt.p, 0, (size_t)max_flagged * 4, st));
+    if (coarse) CU(cudaMemsetAsync(ix->d_fcnt2.p, 0, (size_t)max_flagged * 4, st));
     if (P.v2)
         dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                          ix->d_scale.as<double>(), ix->d_qlut.as<uint16_t>(), ix->d_gthr.as<uint32_t>(),
@@ -440,6 +492,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s2.n_chunks = ix->n_chunks;
         s2.chunk_nodes = P.v2_chunk_nodes;
         s2.rec_stride = P.v2_rec_stride;
+        s2.bt_stride = S;
         s2.qlut = ix->d_qlut.as<uint16_t>();
         s2.cand = sa.cand;
         s2.cand_cnt = sa.cand_cnt;
@@ -458,7 +511,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     } else {
         CU(dpq::launch_scan(sa, st));
     }
-    CU(cudaEventRecord(ix->ev[2], st));
+    if (!coarse) CU(cudaEventRecord(ix->ev[2], st));
     dpq::SelectArgs se;
     se.g = g;
     se.v2 = P.v2 ? 1 : 0;
@@ -497,9 +550,56 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     fa.out_key = d_out_key;
     fa.overflow = ctrl + 1;
     dpq::launch_fallback(fa, st);
+    if (coarse) {
+        // d_out_key now holds the exact top-k of the SAMPLE: its k-th distance caps the coarse tables
+        dpq::launch_pack8(se.lutf, d_out_key, topk, (int)MK, Q, ix->d_qlut8.as<uint8_t>(), ix->d_ovf8.as<uint32_t>(),
+                          g8_groups, st);
+        dpq::Scan8Args s8;
+        s8.recs = ix->d_recs.as<uint4>();
+        s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
+        s8.n_chunks = ix->n_chunks;
+        s8.chunk_nodes = P.v2_chunk_nodes;
+        s8.qlut8 = ix->d_qlut8.as<uint8_t>();
+        s8.cand = ix->d_cand8.as<uint32_t>();
+        s8.cand_cnt = ix->d_cnt8.as<uint32_t>();
+        s8.ovf = ix->d_ovf8.as<uint32_t>();
+        s8.Q = Q;
+        s8.n_groups = g8_groups;
+        s8.n_slices = g8_slices;
+        s8.n_warps = warps8;
+        s8.bcap = bcap8;
+        CU(dpq::launch_scan8(s8, st));
+        dpq::Rescore8Args r8;
+        r8.cand = s8.cand;
+        r8.cand_cnt = s8.cand_cnt;
+        r8.ovf = s8.ovf;
+        r8.n_groups = g8_groups;
+        r8.n_slices = g8_slices;
+        r8.bcap = bcap8;
+        r8.lutf = se.lutf;
+        r8.codes = se.codes;
+        r8.base_pos = P.base_pos;
+        r8.M = P.M;
+        r8.K = P.K;
+        r8.Q = Q;
+        r8.topk = topk;
+        r8.out_key = d_out_key;
+        r8.flagged = ix->d_flagged2.as<uint32_t>();
+        r8.n_flagged = ctrl + 2;
+        r8.max_flagged = max_flagged;
+        r8.bound = se.bound;
+        dpq::launch_rescore8(r8, st);
+        CU(cudaEventRecord(ix->ev[2], st));
+        dpq::FallbackArgs fb = fa;
+        fb.flagged = r8.flagged;
+        fb.n_flagged = ctrl + 2;
+        fb.buf_cnt = ix->d_fcnt2.as<uint32_t>();
+        dpq::launch_fallback(fb, st);
+    }
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
-    ix->last_launches = P.v2 ? 6 : 5;  // lut (+ pack), scan, select, fallback collect, fallback finish
+    // lut (+ pack), scan, select, fallback collect/finish (+ pack8, scan8, rescore8, fallback x2)
+    ix->last_launches = coarse ? 11 : (P.v2 ? 6 : 5);
     ix->timing_valid = true;
     return DPQ_OK;
 }
@@ -509,9 +609,9 @@ int dpq_index_sync(dpq_index* ix) {
     CU(cudaSetDevice(ix->device));
     CU(cudaStreamSynchronize(ix->stream));
     if (ix->d_ctrl.p) {
-        uint32_t ctrl[2] = {0, 0};
-        CU(cudaMemcpy(ctrl, ix->d_ctrl.p, 8, cudaMemcpyDeviceToHost));
-        ix->last_fallback = ctrl[0];
+        uint32_t ctrl[4] = {0, 0, 0, 0};
+        CU(cudaMemcpy(ctrl, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost));
+        ix->last_fallback = (int64_t)ctrl[0] + ctrl[2];
         if (ctrl[1]) return fail(DPQ_ERR_NOMEM, "exact fallback overflowed its buffers (massive ties)");
     }
     return DPQ_OK;
@@ -611,6 +711,7 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
     if (n == "ops_bytes") return (int64_t)ix->ops_bytes;
     if (n == "last_launches") return ix->last_launches;
     if (n == "engine") return P.v2 ? 2 : 1;
+    if (n == "last_coarse") return ix->last_coarse;
     if (n == "v2_delta_nodes") return P.v2_delta_nodes;
     if (n == "last_fallback") return ix->last_fallback;
     if (n.rfind("depth_hist_", 0) == 0) {
@@ -644,7 +745,7 @@ void dpq_index_close(dpq_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->d_recs, &ix->d_chunks2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+    for (DevBuf* b : {&ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_fcnt2, &ix->d_recs, &ix->d_chunks2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
                       &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_fbuf, &ix->d_fcnt, &ix->d_key,
                       &ix->d_gthr})

@@ -10,6 +10,51 @@ namespace dpq {
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in per CTA on sm_100
 constexpr uint32_t kInf31 = 0x7FFFFFFFu;
 
+// ------------------------------------------------------------------------ PTX helpers --
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+// table address of a record field: base + field * 16 (one IMAD)
+__device__ __forceinline__ uint32_t fld(uint32_t base, uint32_t field) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(r) : "r"(field), "r"(base));
+    return r;
+}
+// hints: pull the line three lines ahead of the record cursor into L2 (hides HBM latency when the
+// tree does not fit L2; a 16M-code tree ran 3.4x off the shared-memory bound without it), and the
+// next line into L1
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct ScanGeom {
     int M, K, rb;      // rows = 1 << rb words per query-lane
     int pack;          // 1: one 31-bit query per lane; 2: two 15-bit queries per lane
@@ -54,6 +99,7 @@ struct Scan2Args {
     const uint4* recs;            // one 16- or 32-byte record per node
     const ChunkDesc2* chunks;
     int n_chunks, chunk_nodes, rec_stride;
+    int bt_stride;                // 1: every batch; S: every S-th batch (sample pass)
     const uint16_t* qlut;         // [n_groups][2048][56] fixed-point tables
     uint64_t* cand;               // [n_items][56][bcap] candidate keys (dist << 32 | pos)
     uint32_t* cand_cnt;           // [n_items][56]
@@ -66,6 +112,43 @@ void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  const V2Shape& sh, uint32_t bound0, cudaStream_t st);
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
+
+// ---- coarse search (scan8.cu): 8-bit packed filter over the whole tree + exact re-score ----
+constexpr int C8_QB = 112;          // queries per CTA: 7 lanes x 16 queries, one byte each
+constexpr int C8_ROW_BYTES = 112;
+constexpr int C8_LEVELS = 31;       // table entries 0..31 (8 x 31 <= 255: byte sums never carry)
+constexpr int C8_THRESH = 36;       // a node within the cap has coarse sum <= 31 + 8 * 0.5 (+1 safety)
+struct Scan8Args {
+    const uint4* recs;
+    const ChunkDesc2* chunks;
+    int n_chunks, chunk_nodes;
+    const uint8_t* qlut8;         // [n_groups][2048][112] coarse tables
+    uint32_t* cand;               // [n_items][112][bcap] candidate positions
+    uint32_t* cand_cnt;           // [n_items][112]
+    uint32_t* ovf;                // [n_groups*112]
+    int Q, n_groups, n_slices, n_warps, bcap;
+};
+// coarse tables: entry = min(31, rint(lut / unit)), unit = cap / 31, cap = the query's exact k-th
+// distance over the sample (out_key[q][topk-1]); transposed to [group][row][112] u8
+void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, uint8_t* d_qlut8,
+                  uint32_t* d_ovf, int n_groups, cudaStream_t st);
+cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st);
+struct Rescore8Args {
+    const uint32_t* cand;
+    const uint32_t* cand_cnt;
+    const uint32_t* ovf;
+    int n_groups, n_slices, bcap;
+    const float* lutf;            // [Q][M*K]
+    const uint8_t* codes;         // [n_local][M]
+    int64_t base_pos;
+    int M, K, Q, topk;
+    uint64_t* out_key;            // [Q][topk]
+    uint32_t* flagged;            // queries whose candidate buffer overflowed -> exact fallback
+    uint32_t* n_flagged;
+    int max_flagged;
+    float* bound;                 // [Q] exact distance bound for the fallback
+};
+void launch_rescore8(const Rescore8Args& a, cudaStream_t st);
 
 // One ADC table entry in the reference's arithmetic (DCAT.h:3754-3757): float accumulator,
 // each term the double square of the float difference, rounded back to float after every add.

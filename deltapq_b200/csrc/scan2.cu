@@ -31,50 +31,6 @@ namespace dpq {
 
 namespace {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
-    }
-}
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-    return v;
-}
-
-// table address of a record field: base + field * 16 (one IMAD)
-__device__ __forceinline__ uint32_t fld(uint32_t base, uint32_t field) {
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(r) : "r"(field), "r"(base));
-    return r;
-}
-
-// hint: pull the line three lines ahead of the record cursor into L2 (hides HBM latency when the
-// tree does not fit L2; the 16M-code probe ran 3.4x off the shared-memory bound without it)
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 constexpr int MAXQB = 64;  // s_thr / s_cnt slots (56 or 24 used)
 
 }  // namespace
@@ -271,10 +227,11 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strand = lane / SW, j = lane % SW;
     const int jj = j < LPG ? j : LPG - 1;  // the idle last lane of a strand aliases its neighbour
-    // slices are whole batches of SPW chunks
-    const int n_bt = (a.n_chunks + SPW - 1) / SPW;
-    const int c_lo = (int)((int64_t)n_bt * slice / a.n_slices) * SPW;
-    const int c_hi = min(a.n_chunks, (int)((int64_t)n_bt * (slice + 1) / a.n_slices) * SPW);
+    // slices are whole batches of SPW chunks; bt_stride > 1 walks every bt_stride-th batch only
+    // (the sample pass of the coarse search)
+    const int n_bt = ((a.n_chunks + SPW - 1) / SPW + a.bt_stride - 1) / a.bt_stride;
+    const int b_lo = (int)((int64_t)n_bt * slice / a.n_slices);
+    const int b_hi = (int)((int64_t)n_bt * (slice + 1) / a.n_slices);
     uint32_t* gthr = a.gthr + (size_t)grp * QB;
 
     if (threadIdx.x == 0) {
@@ -318,19 +275,19 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     };
     reload_thr();
 
-    const int n_batches = (c_hi - c_lo + SPW - 1) / SPW;
-    const int n_rounds = (n_batches + a.n_warps - 1) / a.n_warps;
+    const int n_rounds = (b_hi - b_lo + a.n_warps - 1) / a.n_warps;
     const int C = a.chunk_nodes;
     const int rs = a.rec_stride * RW;
     int since = 0, epoch_len = a.ramp ? 1 : a.epoch;
     uint32_t parp[4] = {1u, 1u, 1u, 1u};
 
     for (int round = 0; round < n_rounds; ++round) {
-        const int c = c_lo + (round * a.n_warps + warp) * SPW + strand;
+        const int bt = b_lo + round * a.n_warps + warp;
+        const int c = bt * a.bt_stride * SPW + strand;
         int n_nodes = 0;
         uint32_t pos = 0;
         uint32_t rix = 0;  // record slot (32-bit index off the uniform base pointer), in uint4 units
-        if (c < c_hi) {
+        if (bt < b_hi && c < a.n_chunks) {
             const ChunkDesc2 cd = a.chunks[c];
             n_nodes = (int)cd.n_nodes;
             pos = cd.first_pos;

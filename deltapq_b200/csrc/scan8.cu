@@ -1,0 +1,290 @@
+// Coarse search for the narrow shape (M <= 8): the whole tree is scanned with a 5-bit table in
+// packed 8-bit arithmetic -- four queries per 32-bit word, sixteen per 128-bit table read, 112
+// queries per CTA, i.e. HALF the shared-memory wavefronts per (node, query) of the 15-bit scan
+// (scan2.cu), which is bound by exactly those wavefronts (profiles/r1_summary.md).
+//
+// Why it is exact.  Before this pass the 15-bit scan runs over a 1/16 sample of the tree and
+// select_kernel / the exact fallback give cap_q = the exact k-th distance over the sample, an
+// upper bound of the true k-th distance T_q.  Coarse entry = min(31, rint(lut / unit)) with
+// unit = cap_q / 31.  A node with distance d <= T_q <= cap_q has every table entry <= cap_q (no
+// entry saturates) and its coarse sum is <= d / unit + 8 * 0.5 <= 31 + 4: EVERY true top-k node
+// passes the test "sum < 36".  The survivors (a few hundred per query) are re-scored exactly
+// (float tables, double sum, reference arithmetic) by rescore8_kernel, which keeps the k best
+// by (distance, position).  A candidate buffer that overflows flags its query for the exact
+// fallback.  No result ever depends on the coarse values.
+//
+// The kernel is scan2's strand design (one 16-byte record per node, four nodes per warp step,
+// eight 128-bit reads per node) with the candidate machinery reduced to an append: the bound is
+// the constant 36 for every query, so there are no epochs, barriers or compactions.
+#include "kernels.cuh"
+
+#include <cfloat>
+
+namespace dpq {
+
+namespace {
+constexpr int ROWS8 = 2048;
+constexpr int LUT8_BYTES = ROWS8 * C8_ROW_BYTES;  // 229,376
+}  // namespace
+
+__global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lutf,
+                                                    const uint64_t* __restrict__ sample_key, int topk, int MK, int Q,
+                                                    uint8_t* __restrict__ qlut8, uint32_t* __restrict__ ovf) {
+    __shared__ uint8_t tile[64 * C8_QB];
+    __shared__ double s_inv[C8_QB];
+    const int grp = blockIdx.x, row0 = blockIdx.y * 64;
+    if (threadIdx.x < C8_QB) {
+        const int q = grp * C8_QB + threadIdx.x;
+        double inv = 0.0;
+        if (q < Q) {
+            const float cap = __uint_as_float((uint32_t)(sample_key[(size_t)q * topk + topk - 1] >> 32));
+            // cap == FLT_MAX: the sample held fewer than k nodes; every entry quantises to 0 and
+            // every node becomes a candidate (correct, merely slow: tiny trees only)
+            inv = cap > 0.0f ? (double)C8_LEVELS / (double)cap : 0.0;
+            if (cap == 0.0f) inv = 1e30;  // k exact matches: only zero entries stay below the bound
+        }
+        s_inv[threadIdx.x] = inv;
+        if (blockIdx.y == 0) ovf[grp * C8_QB + threadIdx.x] = 0u;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * C8_QB; i += blockDim.x) {
+        const int ql = i >> 6, r = i & 63;
+        const int q = grp * C8_QB + ql, row = row0 + r;
+        uint8_t v = 0;
+        if (q < Q && row < MK) {
+            const double x = (double)lutf[(size_t)q * MK + row] * s_inv[ql];
+            v = x >= (double)C8_LEVELS ? (uint8_t)C8_LEVELS : (uint8_t)__double2int_rn(x);
+        }
+        tile[r * C8_QB + ql] = v;
+    }
+    __syncthreads();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(qlut8 + ((size_t)grp * ROWS8 + row0) * C8_QB);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
+    for (int i = threadIdx.x; i < 64 * C8_QB / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, uint8_t* d_qlut8,
+                  uint32_t* d_ovf, int n_groups, cudaStream_t st) {
+    pack8_kernel<<<dim3((unsigned)n_groups, ROWS8 / 64), 256, 0, st>>>(d_lutf, d_sample_key, topk, MK, Q, d_qlut8, d_ovf);
+}
+
+__global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + LUT8_BYTES);  // [128] candidates per query
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cnt + 128);
+
+    const int item = blockIdx.x;
+    const int slice = item / a.n_groups, grp = item % a.n_groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strand = lane >> 3, j = lane & 7;
+    const int jj = j < 7 ? j : 6;
+    const int n_bt = (a.n_chunks + 3) >> 2;
+    const int b_lo = (int)((int64_t)n_bt * slice / a.n_slices);
+    const int b_hi = (int)((int64_t)n_bt * (slice + 1) / a.n_slices);
+
+    if (threadIdx.x == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // TMA bulk copy of the group's coarse table
+        mbar_expect_tx(s_bar, (uint32_t)LUT8_BYTES);
+        const unsigned char* src = a.qlut8 + (size_t)grp * LUT8_BYTES;
+        for (uint32_t o = 0; o < (uint32_t)LUT8_BYTES; o += 32768u) bulk_g2s(smem + o, src + o, 32768u, s_bar);
+    }
+    if (threadIdx.x < 128) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    mbar_wait(s_bar, 0);
+
+    // my 16 queries: ql = jj*16 + 4k + b (word k, byte b).  Per byte: hit iff sum < C8_THRESH,
+    // tested as bit 7 of (0x80 + C8_THRESH - 1 - low7(sum)) with bit 7 of the sum clear; a dead
+    // byte (idle lane / query beyond Q) gets the constant 0x7F, which never sets bit 7.
+    uint32_t lut_base = smem_u32(smem) + (uint32_t)jj * 16u;
+    asm volatile("" : "+r"(lut_base));
+    const int n_live = j < 7 ? min(16, max(0, a.Q - (grp * C8_QB + jj * 16))) : 0;
+    uint32_t cmpc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cmpc[k] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cmpc[k] |= (4 * k + b < n_live ? (0x80u + C8_THRESH - 1u) : 0x7Fu) << (8 * b);
+    }
+    uint32_t* my_cand = a.cand + (size_t)item * C8_QB * a.bcap;
+    const int n_rounds = (b_hi - b_lo + a.n_warps - 1) / a.n_warps;
+    const int C = a.chunk_nodes;
+    uint32_t parp[4] = {1u, 1u, 1u, 1u};
+
+    for (int round = 0; round < n_rounds; ++round) {
+        const int bt = b_lo + round * a.n_warps + warp;
+        const int c = bt * 4 + strand;
+        int n_nodes = 0;
+        uint32_t pos = 0, rix = 0;
+        if (bt < b_hi && c < a.n_chunks) {
+            const ChunkDesc2 cd = a.chunks[c];
+            n_nodes = (int)cd.n_nodes;
+            pos = cd.first_pos;
+            rix = cd.rec_begin;
+        }
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (n_nodes > 0) rec = __ldg(a.recs + rix);
+#pragma unroll 1
+        for (int it = 0; it < C; ++it) {
+            ++rix;
+            if ((it & 7) == 0 && it + 25 < n_nodes) {
+                prefetch_l2(a.recs + rix + 24);
+                prefetch_l1(a.recs + rix + 8);
+            }
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (it + 1 < n_nodes) nxt = __ldg(a.recs + rix);
+            const uint32_t dm = (rec.x & V2_ABS) ? 0u : 0xFFFFFFFFu;
+            const uint4 P0 = lds128(fld(lut_base, rec.x & 0x3FFFu));
+            const uint4 P1 = lds128(fld(lut_base, rec.x >> 16));
+            const uint4 P2 = lds128(fld(lut_base, rec.y & 0xFFFFu));
+            const uint4 P3 = lds128(fld(lut_base, rec.y >> 16));
+            const uint4 M0 = lds128(fld(lut_base, rec.z & 0xFFFFu));
+            const uint4 M1 = lds128(fld(lut_base, rec.z >> 16));
+            const uint4 M2 = lds128(fld(lut_base, rec.w & 0xFFFFu));
+            const uint4 M3 = lds128(fld(lut_base, rec.w >> 16));
+            uint32_t d[4];
+            d[0] = (P0.x + P1.x + P2.x) + (P3.x + (parp[0] & dm)) + ((M0.x + M1.x + M2.x + M3.x) ^ dm);
+            d[1] = (P0.y + P1.y + P2.y) + (P3.y + (parp[1] & dm)) + ((M0.y + M1.y + M2.y + M3.y) ^ dm);
+            d[2] = (P0.z + P1.z + P2.z) + (P3.z + (parp[2] & dm)) + ((M0.z + M1.z + M2.z + M3.z) ^ dm);
+            d[3] = (P0.w + P1.w + P2.w) + (P3.w + (parp[3] & dm)) + ((M0.w + M1.w + M2.w + M3.w) ^ dm);
+            const uint32_t am = it < n_nodes ? 0x80808080u : 0u;
+            const uint32_t h0 = (cmpc[0] - (d[0] & 0x7F7F7F7Fu)) & ~d[0];
+            const uint32_t h1 = (cmpc[1] - (d[1] & 0x7F7F7F7Fu)) & ~d[1];
+            const uint32_t h2 = (cmpc[2] - (d[2] & 0x7F7F7F7Fu)) & ~d[2];
+            const uint32_t h3 = (cmpc[3] - (d[3] & 0x7F7F7F7Fu)) & ~d[3];
+            const uint32_t hit = (h0 | h1 | h2 | h3) & am;
+            if (__any_sync(0xffffffffu, hit != 0u)) {
+                // rare path: one bit per byte below the bound -> append the position
+                const uint32_t hh[4] = {h0 & am, h1 & am, h2 & am, h3 & am};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t m = hh[k];
+                    while (m) {
+                        const int b = (__ffs(m) - 1) >> 3;
+                        m &= m - 1;
+                        const int ql = jj * 16 + 4 * k + b;
+                        const uint32_t slot = atomicAdd(&s_cnt[ql], 1u);
+                        if (slot < (uint32_t)a.bcap) __stcg(my_cand + (size_t)ql * a.bcap + slot, pos);
+                        else a.ovf[(size_t)grp * C8_QB + ql] = 1u;
+                    }
+                }
+            }
+            if (rec.x & V2_CHILD) {
+                parp[0] = d[0] + 1u;
+                parp[1] = d[1] + 1u;
+                parp[2] = d[2] + 1u;
+                parp[3] = d[3] + 1u;
+            }
+            rec = nxt;
+            ++pos;
+        }
+    }
+    __syncthreads();
+    for (int ql = threadIdx.x; ql < C8_QB; ql += blockDim.x)
+        a.cand_cnt[(size_t)item * C8_QB + ql] = min(s_cnt[ql], (uint32_t)a.bcap);
+}
+
+cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st) {
+    const size_t smem = (size_t)LUT8_BYTES + 128 * 4 + 16;
+    cudaError_t e = cudaFuncSetAttribute(scan8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    scan8_kernel<<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------ exact re-score --
+// One warp per query: every coarse survivor is scored exactly (float tables, double sum of the
+// node's M entries = what the reference's double accumulation rounds to) and the k best keys
+// (distance bits << 32 | position) are kept in a small shared-memory buffer that is reduced by
+// rank counting whenever it fills.
+constexpr int R8_WARPS = 4;
+constexpr int R8_BUF = 512;
+
+__device__ __forceinline__ int r8_compact(uint64_t* buf, int n, int k, int lane) {
+    // keep the min(n, k) smallest of buf[0..n) sorted ascending (keys unique); n <= R8_BUF
+    uint64_t mine[R8_BUF / 32];
+    int rank[R8_BUF / 32];
+    const int per = (n + 31) >> 5;
+#pragma unroll
+    for (int t = 0; t < R8_BUF / 32; ++t) {
+        mine[t] = ~0ull;
+        rank[t] = 0;
+        if (t < per && t * 32 + lane < n) mine[t] = buf[t * 32 + lane];
+    }
+    __syncwarp();
+    for (int i = 0; i < n; ++i) {
+        const uint64_t o = buf[i];  // broadcast read
+#pragma unroll
+        for (int t = 0; t < R8_BUF / 32; ++t) rank[t] += o < mine[t];
+    }
+    __syncwarp();
+    const int keep = n < k ? n : k;
+#pragma unroll
+    for (int t = 0; t < R8_BUF / 32; ++t)
+        if (t < per && t * 32 + lane < n && rank[t] < keep) buf[rank[t]] = mine[t];
+    __syncwarp();
+    return keep;
+}
+
+__global__ void __launch_bounds__(R8_WARPS * 32) rescore8_kernel(const Rescore8Args a) {
+    __shared__ uint64_t s_buf[R8_WARPS][R8_BUF];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x * R8_WARPS + w;
+    if (q >= a.Q) return;
+    const int grp = q / C8_QB, ql = q % C8_QB;
+    const float* lut = a.lutf + (size_t)q * a.M * a.K;
+    uint64_t* buf = s_buf[w];
+    int n = 0;
+    uint64_t bound = ~0ull;  // k-th best key so far (exclusive)
+    const int k = a.topk;
+    for (int s = 0; s < a.n_slices; ++s) {
+        const size_t item = (size_t)s * a.n_groups + grp;
+        const int cnt = (int)a.cand_cnt[item * C8_QB + ql];
+        const uint32_t* list = a.cand + (item * C8_QB + ql) * (size_t)a.bcap;
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            uint64_t key = ~0ull;
+            if (i0 + lane < cnt) {
+                const uint32_t pos = __ldcg(list + i0 + lane);
+                const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.M;
+                double d = 0.0;
+                for (int m = 0; m < a.M; ++m) d += (double)lut[m * a.K + code[m]];
+                key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
+            }
+            const bool take = key < bound;
+            const uint32_t mk = __ballot_sync(0xffffffffu, take);
+            if (mk) {
+                if (n + 32 > R8_BUF) {  // make room: reduce to the k best, tighten the bound
+                    n = r8_compact(buf, n, k, lane);
+                    if (n == k) bound = buf[k - 1];
+                    __syncwarp();
+                }
+                const bool still = take && key < bound;
+                const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
+                if (still) buf[n + __popc(mk2 & ((1u << lane) - 1u))] = key;
+                n += __popc(mk2);
+                __syncwarp();
+            }
+        }
+    }
+    n = r8_compact(buf, n, k, lane);
+    for (int i = lane; i < k; i += 32)
+        a.out_key[(size_t)q * k + i] = i < n ? buf[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+    if (lane == 0) {
+        // a dropped candidate (buffer overflow) may hide a true top-k node: exact fallback, bounded
+        // by the best k found so far
+        a.bound[q] = n >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
+        if (a.ovf[(size_t)grp * C8_QB + ql]) {
+            const uint32_t slot = atomicAdd(a.n_flagged, 1u);
+            if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;
+        }
+    }
+}
+
+void launch_rescore8(const Rescore8Args& a, cudaStream_t st) {
+    rescore8_kernel<<<(a.Q + R8_WARPS - 1) / R8_WARPS, R8_WARPS * 32, 0, st>>>(a);
+}
+
+}  // namespace dpq

@@ -100,6 +100,56 @@ def test_v2_options_and_overflow_path(golden4000, engine, opts):
     ix.close()
 
 
+@pytest.mark.parametrize("opts", [dict(coarse=1), dict(coarse=1, sample=4), dict(coarse=1, sample=1),
+                                  dict(coarse=1, bcap8=32), dict(coarse=1, slices=3, warps8=24)])
+def test_coarse_search_is_exact(golden4000, engine, opts):
+    """Three-phase search (sample scan -> 8-bit coarse scan -> exact re-score, scan8.cu) gives
+    the same answers as the oracle; a tiny candidate buffer (bcap8=32) overflows and must divert
+    the query to the exact fallback instead of losing candidates."""
+    if engine != "v2":
+        pytest.skip("coarse search belongs to the v2 engine")
+    g = golden4000
+    n = int(g["n"])
+    rng = np.random.default_rng(23)
+    queries = np.clip(g["queries"][rng.integers(0, len(g["queries"]), 130)] + rng.integers(-12, 13, (130, 128)), 0, 255).astype(np.float32)
+    ix = _open(g, **opts)
+    for k in (1, 10, 40):
+        pos, ids, dist = ix.search(queries, k)
+        assert ix.stat("last_coarse") == 1
+        for i in range(0, 130, 7):
+            opos, odist, nd = po.scan(g["payload"], n, g["cw"], queries[i], k, want_node_dist=True)
+            assert np.array_equal(dist[i], odist)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+            assert np.array_equal(ids[i], g["vec_id"][pos[i]])
+    if opts.get("bcap8") == 32:
+        assert ix.stat("last_fallback") > 0
+    ix.close()
+
+
+def test_coarse_search_duplicates_and_exact_matches(engine):
+    """Queries that ARE database vectors (k-th distance 0 for duplicates) and heavy ties."""
+    if engine != "v2":
+        pytest.skip("coarse search belongs to the v2 engine")
+    rng = np.random.default_rng(71)
+    M, K, n = 8, 256, 6000
+    cw = dg.roundtrip_codebook((rng.random((M, K, 4)) * 50).astype(np.float32))
+    uniq = rng.integers(0, K, (300, M)).astype(np.uint8)
+    codes = uniq[rng.integers(0, 300, n)]
+    _, _, lay, payload = po.build_tree(codes, cw)
+    ix = dpq.DeltaTreeIndex(payload, n, M, K)
+    ix.set_codebook(cw)
+    ix.set_option("coarse", 1)
+    # queries = exact reconstructions of some codes: distance 0 to ~20 duplicates each
+    queries = np.stack([np.concatenate([cw[m, uniq[i, m]] for m in range(M)]) for i in range(40)]).astype(np.float32)
+    for k in (5, 30):
+        pos, _, dist = ix.search(queries, k)
+        for i in range(0, 40, 3):
+            opos, odist, nd = po.scan(payload, n, cw, queries[i], k, want_node_dist=True)
+            assert np.array_equal(dist[i], odist)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+    ix.close()
+
+
 def test_many_queries_ragged_groups(golden4000, engine):
     """Q not a multiple of the group size (56 / 48..52): padding lanes must stay silent."""
     g = golden4000
@@ -291,6 +341,7 @@ def test_medium_tree_end_to_end():
     queries = dg.sift_like(64, 128, seed=23)
     for pack in (1, 2):
         ix.set_option("pack", pack)
+        ix.set_option("coarse", pack - 1)  # second round: the three-phase coarse search
         pos, ids, dist = ix.search(queries, 10)
         assert ix.stat("last_fallback") <= 2
         for i in range(0, 64, 7):
