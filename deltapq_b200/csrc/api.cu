@@ -66,7 +66,8 @@ struct dpq_index {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
-    // per search call: total begin, scan begin, scan end, total end.  Calls since the last
+    // per search call: total begin, scan begin, scan end, total end, coarse-scan kernel begin / end.
+    // Calls since the last
     // "timing_reset" keep their own events so a bench loop can time K steps without syncing.
     std::vector<cudaEvent_t> evs;
     int timed_calls = 0;
@@ -77,6 +78,7 @@ struct dpq_index {
     DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_recs, d_chunks2, d_ovf;
     DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_fcnt2;
     int last_coarse = 0;
+    int64_t last_items8 = 0;
     int n_chunks = 0;
     size_t ops_bytes = 0;
     bool has_pos2id = false;
@@ -86,7 +88,7 @@ struct dpq_index {
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
     int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
     int opt_sample = 16;       // the sample pass walks every opt_sample-th batch
-    int opt_bcap8 = 512, opt_warps8 = 16;
+    int opt_bcap8 = 512, opt_warps8 = 24, opt_levels8 = 80;
     int64_t opt_coarse_min = 262144;  // nodes in the shard from which the coarse search pays
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
@@ -372,6 +374,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "bcap8") ix->opt_bcap8 = std::max(32, (int)v);
     else if (n == "warps8") ix->opt_warps8 = std::max(2, std::min(24, (int)v));
     else if (n == "coarse_min") ix->opt_coarse_min = v;
+    else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
 }
@@ -403,7 +406,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             const int cpr = warps8 * 4;
             double best = -1.0;
             g8_slices = 1;
-            for (int s = 1; s <= 96 && s <= std::max(1, ix->n_chunks / cpr); ++s) {
+            for (int s = 1; s <= 96 && s <= std::max(1, ix->n_chunks / cpr); ++s) {  // <= R8_MAXSL
                 const int64_t items = (int64_t)g8_groups * s;
                 const int64_t waves = (items + 147) / 148;
                 const double cpi = (double)ix->n_chunks / s;
@@ -414,7 +417,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
                 }
             }
         }
-        g8_slices = std::max(1, std::min(g8_slices, std::max(1, ix->n_chunks)));
+        g8_slices = std::max(1, std::min(std::min(g8_slices, 128), std::max(1, ix->n_chunks)));
     }
     const size_t MK = (size_t)P.M * P.K;
     const size_t rows = (size_t)1 << g.rb;
@@ -442,6 +445,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_fcnt.ensure((size_t)max_flagged * 4))) return rc;
     if (coarse) {
         const size_t items8 = (size_t)g8_groups * g8_slices;
+        ix->last_items8 = (int64_t)items8;
         if ((rc = ix->d_qlut8.ensure((size_t)g8_groups * 2048 * dpq::C8_ROW_BYTES))) return rc;
         if ((rc = ix->d_cand8.ensure(items8 * dpq::C8_QB * bcap8 * 4))) return rc;
         if ((rc = ix->d_cnt8.ensure(items8 * dpq::C8_QB * 4))) return rc;
@@ -453,12 +457,12 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();  // [0] n_flagged, [1] overflow
     {
         const int slot = std::min(ix->timed_calls, 4095);
-        while ((int)ix->evs.size() < 4 * (slot + 1)) {
+        while ((int)ix->evs.size() < 6 * (slot + 1)) {
             cudaEvent_t e;
             CU(cudaEventCreate(&e));
             ix->evs.push_back(e);
         }
-        ix->ev = ix->evs.data() + 4 * slot;
+        ix->ev = ix->evs.data() + 6 * slot;
         ix->timed_calls = slot + 1;
     }
     CU(cudaEventRecord(ix->ev[0], st));
@@ -552,8 +556,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     dpq::launch_fallback(fa, st);
     if (coarse) {
         // d_out_key now holds the exact top-k of the SAMPLE: its k-th distance caps the coarse tables
-        dpq::launch_pack8(se.lutf, d_out_key, topk, (int)MK, Q, ix->d_qlut8.as<uint8_t>(), ix->d_ovf8.as<uint32_t>(),
-                          g8_groups, st);
+        dpq::launch_pack8(se.lutf, d_out_key, topk, (int)MK, Q, ix->opt_levels8, ix->d_qlut8.as<uint8_t>(),
+                          ix->d_ovf8.as<uint32_t>(), g8_groups, st);
         dpq::Scan8Args s8;
         s8.recs = ix->d_recs.as<uint4>();
         s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
@@ -568,7 +572,10 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s8.n_slices = g8_slices;
         s8.n_warps = warps8;
         s8.bcap = bcap8;
+        s8.thresh = ix->opt_levels8 + 5;
+        CU(cudaEventRecord(ix->ev[4], st));
         CU(dpq::launch_scan8(s8, st));
+        CU(cudaEventRecord(ix->ev[5], st));
         dpq::Rescore8Args r8;
         r8.cand = s8.cand;
         r8.cand_cnt = s8.cand_cnt;
@@ -712,6 +719,16 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
     if (n == "last_launches") return ix->last_launches;
     if (n == "engine") return P.v2 ? 2 : 1;
     if (n == "last_coarse") return ix->last_coarse;
+    if (n == "cand8_total") {  // developer statistic: coarse survivors of the last search
+        if (!ix->last_coarse || !ix->d_cnt8.p) return -1;
+        cudaSetDevice(ix->device);
+        std::vector<uint32_t> c(ix->d_cnt8.cap / 4);
+        if (cudaStreamSynchronize(ix->stream) != cudaSuccess) return -1;
+        if (cudaMemcpy(c.data(), ix->d_cnt8.p, c.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t t = 0;
+        for (size_t i = 0; i < (size_t)ix->last_items8 * dpq::C8_QB && i < c.size(); ++i) t += c[i];
+        return t;
+    }
     if (n == "v2_delta_nodes") return P.v2_delta_nodes;
     if (n == "last_fallback") return ix->last_fallback;
     if (n.rfind("depth_hist_", 0) == 0) {
@@ -719,20 +736,21 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
         return d < P.depth_hist.size() ? P.depth_hist[d] : 0;
     }
     if (n == "timed_calls") return ix->timed_calls;
-    const bool last = n == "last_scan_us" || n == "last_total_us" || n == "last_lut_us";
-    const bool sum = n == "sum_scan_ns" || n == "sum_total_ns" || n == "sum_lut_ns";
+    const bool last = n == "last_scan_us" || n == "last_total_us" || n == "last_lut_us" || n == "last_scan8_us";
+    const bool sum = n == "sum_scan_ns" || n == "sum_total_ns" || n == "sum_lut_ns" || n == "sum_scan8_ns";
     if (last || sum) {  // "last_*": the last search; "sum_*": all searches since "timing_reset"
         if (!ix->timing_valid || !ix->ev) return -1;
         cudaSetDevice(ix->device);
         if (cudaEventSynchronize(ix->ev[3]) != cudaSuccess) return -1;
-        const int which = n.find("scan") != std::string::npos ? 0 : (n.find("lut") != std::string::npos ? 1 : 2);
+        const int which = n.find("scan8") != std::string::npos ? 3 : (n.find("scan") != std::string::npos ? 0 : (n.find("lut") != std::string::npos ? 1 : 2));
+        if (which == 3 && !ix->last_coarse) return -1;
         double total_ms = 0;
         const int first = last ? ix->timed_calls - 1 : 0;
         for (int c = first; c < ix->timed_calls; ++c) {
-            cudaEvent_t* e = ix->evs.data() + 4 * c;
+            cudaEvent_t* e = ix->evs.data() + 6 * c;
             float ms = 0;
-            cudaEvent_t a = which == 0 ? e[1] : e[0];
-            cudaEvent_t b = which == 0 ? e[2] : (which == 1 ? e[1] : e[3]);
+            cudaEvent_t a = which == 3 ? e[4] : (which == 0 ? e[1] : e[0]);
+            cudaEvent_t b = which == 3 ? e[5] : (which == 0 ? e[2] : (which == 1 ? e[1] : e[3]));
             if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return -1;
             total_ms += ms;
         }

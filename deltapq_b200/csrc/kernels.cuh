@@ -116,8 +116,11 @@ cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
 // ---- coarse search (scan8.cu): 8-bit packed filter over the whole tree + exact re-score ----
 constexpr int C8_QB = 112;          // queries per CTA: 7 lanes x 16 queries, one byte each
 constexpr int C8_ROW_BYTES = 112;
-constexpr int C8_LEVELS = 31;       // table entries 0..31 (8 x 31 <= 255: byte sums never carry)
-constexpr int C8_THRESH = 36;       // a node within the cap has coarse sum <= 31 + 8 * 0.5 (+1 safety)
+constexpr int C8_SAT = 31;          // table entries saturate at 31 (8 x 31 <= 255: byte sums never carry)
+// The unit is cap / L with L > 31 ("levels", default 80): finer than the saturation point, so a
+// large entry saturates.  Saturation only lowers a coarse sum (more false positives, never a
+// false negative); a node within the cap has coarse sum <= L + 8 * 0.5, so the test is
+// "sum < L + 5".  On the 1M SIFT-shaped tree L = 80 leaves 4.5x fewer survivors than L = 31.
 struct Scan8Args {
     const uint4* recs;
     const ChunkDesc2* chunks;
@@ -127,11 +130,12 @@ struct Scan8Args {
     uint32_t* cand_cnt;           // [n_items][112]
     uint32_t* ovf;                // [n_groups*112]
     int Q, n_groups, n_slices, n_warps, bcap;
+    int thresh;                   // hit iff coarse sum < thresh (= levels + 5 <= 128)
 };
-// coarse tables: entry = min(31, rint(lut / unit)), unit = cap / 31, cap = the query's exact k-th
+// coarse tables: entry = min(31, rint(lut / unit)), unit = cap / levels, cap = the query's exact k-th
 // distance over the sample (out_key[q][topk-1]); transposed to [group][row][112] u8
-void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, uint8_t* d_qlut8,
-                  uint32_t* d_ovf, int n_groups, cudaStream_t st);
+void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, int levels,
+                  uint8_t* d_qlut8, uint32_t* d_ovf, int n_groups, cudaStream_t st);
 cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st);
 struct Rescore8Args {
     const uint32_t* cand;

@@ -6,9 +6,10 @@
 // Why it is exact.  Before this pass the 15-bit scan runs over a 1/16 sample of the tree and
 // select_kernel / the exact fallback give cap_q = the exact k-th distance over the sample, an
 // upper bound of the true k-th distance T_q.  Coarse entry = min(31, rint(lut / unit)) with
-// unit = cap_q / 31.  A node with distance d <= T_q <= cap_q has every table entry <= cap_q (no
-// entry saturates) and its coarse sum is <= d / unit + 8 * 0.5 <= 31 + 4: EVERY true top-k node
-// passes the test "sum < 36".  The survivors (a few hundred per query) are re-scored exactly
+// unit = cap_q / L (L = 80 levels; entries saturate at 31 so that eight of them never carry out
+// of a byte).  Saturation only lowers a sum, and rounding adds at most 0.5 per entry, so a node
+// with distance d <= T_q <= cap_q has coarse sum <= d / unit + 4 <= L + 4: EVERY true top-k node
+// passes the test "sum < L + 5".  The survivors (a few hundred per query) are re-scored exactly
 // (float tables, double sum, reference arithmetic) by rescore8_kernel, which keeps the k best
 // by (distance, position).  A candidate buffer that overflows flags its query for the exact
 // fallback.  No result ever depends on the coarse values.
@@ -29,7 +30,7 @@ constexpr int LUT8_BYTES = ROWS8 * C8_ROW_BYTES;  // 229,376
 
 __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lutf,
                                                     const uint64_t* __restrict__ sample_key, int topk, int MK, int Q,
-                                                    uint8_t* __restrict__ qlut8, uint32_t* __restrict__ ovf) {
+                                                    int levels, uint8_t* __restrict__ qlut8, uint32_t* __restrict__ ovf) {
     __shared__ uint8_t tile[64 * C8_QB];
     __shared__ double s_inv[C8_QB];
     const int grp = blockIdx.x, row0 = blockIdx.y * 64;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lu
             const float cap = __uint_as_float((uint32_t)(sample_key[(size_t)q * topk + topk - 1] >> 32));
             // cap == FLT_MAX: the sample held fewer than k nodes; every entry quantises to 0 and
             // every node becomes a candidate (correct, merely slow: tiny trees only)
-            inv = cap > 0.0f ? (double)C8_LEVELS / (double)cap : 0.0;
+            inv = cap > 0.0f ? (double)levels / (double)cap : 0.0;
             if (cap == 0.0f) inv = 1e30;  // k exact matches: only zero entries stay below the bound
         }
         s_inv[threadIdx.x] = inv;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lu
         uint8_t v = 0;
         if (q < Q && row < MK) {
             const double x = (double)lutf[(size_t)q * MK + row] * s_inv[ql];
-            v = x >= (double)C8_LEVELS ? (uint8_t)C8_LEVELS : (uint8_t)__double2int_rn(x);
+            v = x >= (double)C8_SAT ? (uint8_t)C8_SAT : (uint8_t)__double2int_rn(x);
         }
         tile[r * C8_QB + ql] = v;
     }
@@ -63,9 +64,10 @@ __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lu
     for (int i = threadIdx.x; i < 64 * C8_QB / 4; i += blockDim.x) dst[i] = src[i];
 }
 
-void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, uint8_t* d_qlut8,
-                  uint32_t* d_ovf, int n_groups, cudaStream_t st) {
-    pack8_kernel<<<dim3((unsigned)n_groups, ROWS8 / 64), 256, 0, st>>>(d_lutf, d_sample_key, topk, MK, Q, d_qlut8, d_ovf);
+void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, int levels,
+                  uint8_t* d_qlut8, uint32_t* d_ovf, int n_groups, cudaStream_t st) {
+    pack8_kernel<<<dim3((unsigned)n_groups, ROWS8 / 64), 256, 0, st>>>(d_lutf, d_sample_key, topk, MK, Q, levels, d_qlut8,
+                                                                      d_ovf);
 }
 
 __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
     __syncthreads();
     mbar_wait(s_bar, 0);
 
-    // my 16 queries: ql = jj*16 + 4k + b (word k, byte b).  Per byte: hit iff sum < C8_THRESH,
-    // tested as bit 7 of (0x80 + C8_THRESH - 1 - low7(sum)) with bit 7 of the sum clear; a dead
+    // my 16 queries: ql = jj*16 + 4k + b (word k, byte b).  Per byte: hit iff sum < thresh (<= 128),
+    // tested as bit 7 of (0x80 + thresh - 1 - low7(sum)) with bit 7 of the sum clear; a dead
     // byte (idle lane / query beyond Q) gets the constant 0x7F, which never sets bit 7.
     uint32_t lut_base = smem_u32(smem) + (uint32_t)jj * 16u;
     asm volatile("" : "+r"(lut_base));
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
     for (int k = 0; k < 4; ++k) {
         cmpc[k] = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) cmpc[k] |= (4 * k + b < n_live ? (0x80u + C8_THRESH - 1u) : 0x7Fu) << (8 * b);
+        for (int b = 0; b < 4; ++b) cmpc[k] |= (4 * k + b < n_live ? (0x80u + (uint32_t)a.thresh - 1u) : 0x7Fu) << (8 * b);
     }
     uint32_t* my_cand = a.cand + (size_t)item * C8_QB * a.bcap;
     const int n_rounds = (b_hi - b_lo + a.n_warps - 1) / a.n_warps;
@@ -201,7 +203,7 @@ cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st) {
 // (distance bits << 32 | position) are kept in a small shared-memory buffer that is reduced by
 // rank counting whenever it fills.
 constexpr int R8_WARPS = 4;
-constexpr int R8_BUF = 512;
+constexpr int R8_BUF = 128;  // >= topk + 32 (coarse search serves topk <= 64); rank counting is O(n^2 / 32)
 
 __device__ __forceinline__ int r8_compact(uint64_t* buf, int n, int k, int lane) {
     // keep the min(n, k) smallest of buf[0..n) sorted ascending (keys unique); n <= R8_BUF
@@ -229,44 +231,69 @@ __device__ __forceinline__ int r8_compact(uint64_t* buf, int n, int k, int lane)
     return keep;
 }
 
+constexpr int R8_MAXSL = 128;  // slices per group the flattened candidate index can address
+
 __global__ void __launch_bounds__(R8_WARPS * 32) rescore8_kernel(const Rescore8Args a) {
     __shared__ uint64_t s_buf[R8_WARPS][R8_BUF];
+    __shared__ uint32_t s_off[R8_WARPS][R8_MAXSL + 1];  // exclusive prefix of the per-slice counts
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.x * R8_WARPS + w;
     if (q >= a.Q) return;
     const int grp = q / C8_QB, ql = q % C8_QB;
     const float* lut = a.lutf + (size_t)q * a.M * a.K;
     uint64_t* buf = s_buf[w];
+    uint32_t* off = s_off[w];
+    // all slices' counts at once (one load per lane), then one flat candidate index space so
+    // that every step scores 32 candidates no matter how they are spread over the slices
+    uint32_t run = 0;
+    for (int s0 = 0; s0 < a.n_slices; s0 += 32) {
+        const int s = s0 + lane;
+        uint32_t c = 0;
+        if (s < a.n_slices) c = a.cand_cnt[((size_t)s * a.n_groups + grp) * C8_QB + ql];
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (s < a.n_slices) off[s] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) off[a.n_slices] = run;
+    __syncwarp();
+    const int total = (int)run;
     int n = 0;
     uint64_t bound = ~0ull;  // k-th best key so far (exclusive)
     const int k = a.topk;
-    for (int s = 0; s < a.n_slices; ++s) {
-        const size_t item = (size_t)s * a.n_groups + grp;
-        const int cnt = (int)a.cand_cnt[item * C8_QB + ql];
-        const uint32_t* list = a.cand + (item * C8_QB + ql) * (size_t)a.bcap;
-        for (int i0 = 0; i0 < cnt; i0 += 32) {
-            uint64_t key = ~0ull;
-            if (i0 + lane < cnt) {
-                const uint32_t pos = __ldcg(list + i0 + lane);
-                const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.M;
-                double d = 0.0;
-                for (int m = 0; m < a.M; ++m) d += (double)lut[m * a.K + code[m]];
-                key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        uint64_t key = ~0ull;
+        const int i = i0 + lane;
+        if (i < total) {
+            int lo = 0, hi = a.n_slices;  // slice s with off[s] <= i < off[s+1]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (off[mid] <= (uint32_t)i) lo = mid;
+                else hi = mid;
             }
-            const bool take = key < bound;
-            const uint32_t mk = __ballot_sync(0xffffffffu, take);
-            if (mk) {
-                if (n + 32 > R8_BUF) {  // make room: reduce to the k best, tighten the bound
-                    n = r8_compact(buf, n, k, lane);
-                    if (n == k) bound = buf[k - 1];
-                    __syncwarp();
-                }
-                const bool still = take && key < bound;
-                const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
-                if (still) buf[n + __popc(mk2 & ((1u << lane) - 1u))] = key;
-                n += __popc(mk2);
+            const size_t item = (size_t)lo * a.n_groups + grp;
+            const uint32_t pos = __ldcg(a.cand + (item * C8_QB + ql) * (size_t)a.bcap + ((uint32_t)i - off[lo]));
+            const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.M;
+            double d = 0.0;
+            for (int m = 0; m < a.M; ++m) d += (double)lut[m * a.K + code[m]];
+            key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
+        }
+        const bool take = key < bound;
+        const uint32_t mk = __ballot_sync(0xffffffffu, take);
+        if (mk) {
+            if (n + 32 > R8_BUF) {  // make room: reduce to the k best, tighten the bound
+                n = r8_compact(buf, n, k, lane);
+                if (n == k) bound = buf[k - 1];
                 __syncwarp();
             }
+            const bool still = take && key < bound;
+            const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
+            if (still) buf[n + __popc(mk2 & ((1u << lane) - 1u))] = key;
+            n += __popc(mk2);
+            __syncwarp();
         }
     }
     n = r8_compact(buf, n, k, lane);
@@ -275,7 +302,9 @@ __global__ void __launch_bounds__(R8_WARPS * 32) rescore8_kernel(const Rescore8A
     if (lane == 0) {
         // a dropped candidate (buffer overflow) may hide a true top-k node: exact fallback, bounded
         // by the best k found so far
-        a.bound[q] = n >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
+        // (never looser than the sample's exact k-th distance, which select_kernel left in bound[q])
+        const float mine = n >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
+        a.bound[q] = fminf(a.bound[q], mine);
         if (a.ovf[(size_t)grp * C8_QB + ql]) {
             const uint32_t slot = atomicAdd(a.n_flagged, 1u);
             if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;

@@ -61,8 +61,10 @@ int dpq_index_set_codebook(dpq_index* idx, const float* codewords, int Ds);
  * the NCCL gather on one stream.  The handle does not take ownership. */
 int dpq_index_set_stream(dpq_index* idx, void* cuda_stream);
 
-/* Tuning knobs (optional): "slices", "chunk_nodes", "pack" (1 = 32-bit, 2 = 2x16-bit
- * filter), "warps", "slack" (extra candidates re-scored exactly). */
+/* Tuning knobs (optional): "slices", "warps", "slack" (extra candidates re-scored exactly),
+ * "epoch", "trigger", "ramp" (candidate collection of the 15-bit scan); "coarse" (-1 auto, 0 off,
+ * 1 on), "sample", "levels8", "bcap8", "warps8", "coarse_min" (coarse search); first-generation
+ * engine only: "pack" (1 = 31-bit, 2 = 2x15-bit filter). */
 int dpq_index_set_option(dpq_index* idx, const char* name, int64_t value);
 
 /* Replaces the per-query loop dmain:328-344 calling
@@ -102,7 +104,9 @@ int dpq_free_host(void* hptr);
  * "last_launches" (kernels launched by the last search), "last_fallback" (queries that
  * took the exact fallback in the last search), "last_scan_us" (scan kernel time of the
  * last search, CUDA events), "last_total_us"; "sum_scan_ns" / "sum_lut_ns" / "sum_total_ns" /
- * "timed_calls": the same summed over every search since set_option("timing_reset"). */
+ * "timed_calls": the same summed over every search since set_option("timing_reset");
+ * "last_coarse" (1 when the last search used the sample -> 8-bit coarse scan -> exact re-score
+ * path), "last_scan8_us" / "sum_scan8_ns" (the coarse scan kernel alone), "engine". */
 int64_t dpq_index_stat(dpq_index* idx, const char* name);
 
 void dpq_index_close(dpq_index* idx);

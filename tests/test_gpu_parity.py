@@ -343,7 +343,9 @@ def test_medium_tree_end_to_end():
         ix.set_option("pack", pack)
         ix.set_option("coarse", pack - 1)  # second round: the three-phase coarse search
         pos, ids, dist = ix.search(queries, 10)
-        assert ix.stat("last_fallback") <= 2
+        # (forcing the coarse search on a 50K tree gives a loose cap from a 3K-node sample: a few
+        # candidate buffers may overflow into the exact fallback; results are checked either way)
+        assert ix.stat("last_fallback") <= (2 if pack == 1 else 16)
         for i in range(0, 64, 7):
             opos, odist, nd = po.scan(payload, len(codes), cw, queries[i], 10, want_node_dist=True)
             assert np.array_equal(dist[i], odist)
