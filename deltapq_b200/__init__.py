@@ -136,6 +136,22 @@ class DeviceBuffer:
             self.ptr = C.c_void_p()
 
 
+def pinned_array(shape, dtype):
+    """numpy array over page-locked host memory from dpq_malloc_host (kept alive by the array);
+    dpq_index_search copies from such a buffer without staging."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _check(lib().dpq_malloc_host(C.byref(p), max(n, 16)))
+    buf = (C.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED.append((arr, p))  # never freed before process exit: the array may outlive any scope
+    return arr
+
+
+_PINNED = []
+
+
 def unpack_keys(keys):
     """uint64 keys (float bits << 32 | pos) -> (pos uint32, dist float32)."""
     keys = np.asarray(keys, np.uint64)

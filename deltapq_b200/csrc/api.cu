@@ -631,33 +631,46 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     CU(cudaSetDevice(ix->device));
     const size_t D = (size_t)ix->prog.M * ix->Ds;
     const size_t qbytes = (size_t)Q * D * 4, kbytes = (size_t)Q * topk * 8;
-    if (ix->h_stage_cap < qbytes + kbytes) {
+    // pinned staging: [queries][keys][ctrl words]; a caller buffer that is already page-locked
+    // (dpq_malloc_host, cudaHostRegister) is copied from directly
+    if (ix->h_stage_cap < qbytes + kbytes + 64) {
         if (ix->h_stage) cudaFreeHost(ix->h_stage);
         ix->h_stage = nullptr;
         ix->h_stage_cap = 0;
-        CU(cudaMallocHost(&ix->h_stage, qbytes + kbytes));
-        ix->h_stage_cap = qbytes + kbytes;
+        CU(cudaMallocHost(&ix->h_stage, qbytes + kbytes + 64));
+        ix->h_stage_cap = qbytes + kbytes + 64;
     }
     int rc;
     if ((rc = ix->d_queries.ensure(qbytes))) return rc;
     if ((rc = ix->d_key.ensure(kbytes))) return rc;
     float* hq = reinterpret_cast<float*>(ix->h_stage);
     uint64_t* hk = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes);
-    memcpy(hq, queries, qbytes);
-    CU(cudaMemcpyAsync(ix->d_queries.p, hq, qbytes, cudaMemcpyHostToDevice, ix->stream));
+    uint32_t* hc = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes + kbytes);
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, queries) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    const float* src = queries;
+    if (!pinned) {
+        memcpy(hq, queries, qbytes);
+        src = hq;
+    }
+    CU(cudaMemcpyAsync(ix->d_queries.p, src, qbytes, cudaMemcpyHostToDevice, ix->stream));
     if ((rc = dpq_index_search_device(ix, ix->d_queries.as<float>(), Q, topk, ix->d_key.as<uint64_t>())))
         return rc;
     CU(cudaMemcpyAsync(hk, ix->d_key.p, kbytes, cudaMemcpyDeviceToHost, ix->stream));
-    if ((rc = dpq_index_sync(ix))) return rc;
+    CU(cudaMemcpyAsync(hc, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));  // the one host sync of the call
+    ix->last_fallback = (int64_t)hc[0] + hc[2];
+    if (hc[1]) return fail(DPQ_ERR_NOMEM, "exact fallback overflowed its buffers (massive ties)");
     const int64_t base = ix->prog.base_pos;
+    const bool map = ix->has_pos2id;
+    const uint32_t* p2i = ix->pos2id_host.data();
     for (size_t i = 0; i < (size_t)Q * topk; ++i) {
-        uint32_t pos = (uint32_t)hk[i];
-        uint32_t bits = (uint32_t)(hk[i] >> 32);
-        float d;
-        memcpy(&d, &bits, 4);
+        const uint32_t pos = (uint32_t)hk[i];
+        const uint32_t bits = (uint32_t)(hk[i] >> 32);
         if (out_pos) out_pos[i] = pos;
-        if (out_dist) out_dist[i] = d;
-        if (out_id) out_id[i] = (ix->has_pos2id && pos != 0xFFFFFFFFu) ? ix->pos2id_host[(size_t)(pos - base)] : pos;
+        if (out_dist) memcpy(&out_dist[i], &bits, 4);
+        if (out_id) out_id[i] = (map && pos != 0xFFFFFFFFu) ? p2i[(size_t)(pos - base)] : pos;
     }
     return DPQ_OK;
 }
