@@ -421,6 +421,22 @@ def cpu_baseline(payload, n_codes, cw, queries, n_q):
                       f"(DCAT.h:3731), 1 thread, {secs:.1f} s"}
 
 
+class StdoutToStderr:
+    """Everything libraries print on fd 1 while the bench runs (e.g. NCCL's version banner) goes
+    to stderr; stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,9 +452,22 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_gpu(args)
+    holder = []
+    real_print = print
+
+    def capture(*a, **k):  # run_* print their JSON line last; emit it after fd 1 is restored
+        holder.append(" ".join(str(x) for x in a))
+
+    with StdoutToStderr():
+        import builtins
+        builtins.print = capture
+        try:
+            rc = run_reference(args) if args.impl == "reference" else run_gpu(args)
+        finally:
+            builtins.print = real_print
+    for line in holder:
+        real_print(line, flush=True)
+    return rc
 
 
 if __name__ == "__main__":
