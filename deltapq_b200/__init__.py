@@ -23,7 +23,8 @@ SYMBOLS = [
     "dpq_find_edges", "dpq_edge_diffs", "dpq_groundtruth_begin", "dpq_groundtruth_chunk",
     "dpq_groundtruth_finish", "dpq_program_compile", "dpq_program_size", "dpq_program_copy",
     "dpq_program_free", "dpq_tree_build", "dpq_tree_from_edges", "dpq_tree_size", "dpq_tree_copy",
-    "dpq_tree_free",
+    "dpq_tree_free", "dpq_multi_open_file", "dpq_multi_set_codebook", "dpq_multi_search", "dpq_multi_stat",
+    "dpq_multi_close",
 ]
 
 

@@ -91,6 +91,20 @@ int dpq_index_sync(dpq_index* idx);
 int dpq_merge_topk_device(dpq_index* idx, const uint64_t* d_keys, int n_lists, int Q, int topk,
                           uint64_t* d_out_key);
 
+/* ---- multi-GPU search, one process ------------------------------------------ */
+/* One shard per GPU (devices 0..n_gpus-1, whole depth-1 subtrees balanced by stream bytes),
+ * local top-k with global positions on every GPU, ONE collective (NCCL all-gather of the
+ * Q x k keys over NVLink, libnccl.so.2 bound at run time) and the k-way merge kernel.  Used by
+ * `deltapq -task query -gpus N`.  Same argument meaning as dpq_index_open_file / _search. */
+typedef struct dpq_multi dpq_multi;
+int dpq_multi_open_file(const char* tree_path, const char* qnode_path, int M, int K, int n_gpus,
+                        dpq_multi** out);
+int dpq_multi_set_codebook(dpq_multi* m, const float* codewords, int Ds);
+int dpq_multi_search(dpq_multi* m, const float* queries, int Q, int topk, uint32_t* out_pos,
+                     uint32_t* out_id, float* out_dist);
+int64_t dpq_multi_stat(dpq_multi* m, int rank, const char* name); /* dpq_index_stat of one shard */
+void dpq_multi_close(dpq_multi* m);
+
 /* Raw device allocation helpers for hosts without a CUDA binding (ctypes, cgo, JNI). */
 int dpq_malloc(void** dptr, size_t bytes);
 int dpq_free(void* dptr);

@@ -122,3 +122,27 @@ def test_cli_groundtruth_and_learn(tmp_path):
     assert r.returncode == 0, r.stderr
     cw = dg.read_codebook(d + "/M8K16codewords.txt")
     assert cw.shape == (8, 16, 16) and np.isfinite(cw).all() and len(np.unique(cw[0], axis=0)) == 16
+
+
+@pytest.mark.gpu
+def test_cli_query_multi_gpu_matches_single_gpu(tmp_path):
+    """`deltapq -task query -gpus 2`: one shard per GPU, NCCL all-gather of the top-k keys, merge
+    kernel (dpq_multi_*).  Result file identical to the single-GPU run.  Needs 2 GPUs."""
+    import deltapq_b200 as dpq
+    if dpq.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    n, nq, M, K, k = 60000, 500, 8, 256, 10
+    d = str(tmp_path)
+    dg.make_dataset(d, n, nq, M=M, K=K, d=128, seed=51)
+    common = ["-dataset", d, "-m", str(M), "-k", str(K), "-N", str(n), "-ext", "fvecs"]
+    for cmd in ([BIN + "/pqtree", "-task", "encode"], [BIN + "/deltapq", "-task", "approx_tree", "-h", "1", "-diff", "8"]):
+        r = run(cmd + common)
+        assert r.returncode == 0, r.stderr
+    outs = []
+    for g in (1, 2):
+        out = f"{d}/res{g}.txt"
+        r = run([BIN + "/deltapq", "-task", "query", "-query_size", str(nq), "-topk", str(k), "-gpus", str(g),
+                 "-results", out] + common)
+        assert r.returncode == 0, r.stderr
+        outs.append(open(out).read())
+    assert outs[0] == outs[1]
