@@ -76,7 +76,7 @@ struct dpq_index {
     int Ds = 0;
     // device-resident tree
     DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_recs, d_chunks2, d_ovf;
-    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_fcnt2;
+    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_fcnt2, d_cap0, d_cap1;
     int last_coarse = 0;
     int64_t last_items8 = 0;
     int n_chunks = 0;
@@ -88,6 +88,8 @@ struct dpq_index {
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
     int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
     int opt_sample = 16;       // the sample pass walks every opt_sample-th batch
+    int opt_seed = 1;          // 1: presample -> sampled coarse scan gives the cap; 0: sampled 15-bit scan
+    int opt_presample = 2048;  // nodes scored exactly per query to seed the sample pass
     int opt_bcap8 = 512, opt_warps8 = 24, opt_levels8 = 80;
     int64_t opt_coarse_min = 262144;  // nodes in the shard from which the coarse search pays
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
@@ -374,6 +376,8 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "bcap8") ix->opt_bcap8 = std::max(32, (int)v);
     else if (n == "warps8") ix->opt_warps8 = std::max(2, std::min(24, (int)v));
     else if (n == "coarse_min") ix->opt_coarse_min = v;
+    else if (n == "seed") ix->opt_seed = (int)v;
+    else if (n == "presample") ix->opt_presample = std::max(64, std::min(2048, (int)v));
     else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
@@ -419,6 +423,23 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         }
         g8_slices = std::max(1, std::min(std::min(g8_slices, 128), std::max(1, ix->n_chunks)));
     }
+    // slices of the SAMPLED coarse pass (seed = 1): same rule on the reduced chunk count
+    int g8_slices_s = 1;
+    if (coarse && ix->opt_seed == 1) {
+        const int cpr = warps8 * 4;
+        double best = -1.0;
+        for (int s = 1; s <= 96 && s <= std::max(1, n_chunks_sample / cpr); ++s) {
+            const int64_t items = (int64_t)g8_groups * s;
+            const int64_t waves = (items + 147) / 148;
+            const double cpi = (double)n_chunks_sample / s;
+            const double eff = (double)items / (double)(waves * 148) * (cpi / cpr) / std::ceil(cpi / cpr);
+            if (eff > best + 1e-9) {
+                best = eff;
+                g8_slices_s = s;
+            }
+        }
+    }
+    const bool seeded = coarse && ix->opt_seed == 1;
     const size_t MK = (size_t)P.M * P.K;
     const size_t rows = (size_t)1 << g.rb;
     const size_t LW = 32 * (size_t)g.pack;
@@ -444,8 +465,10 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_fbuf.ensure((size_t)max_flagged * fcap * 8))) return rc;
     if ((rc = ix->d_fcnt.ensure((size_t)max_flagged * 4))) return rc;
     if (coarse) {
-        const size_t items8 = (size_t)g8_groups * g8_slices;
-        ix->last_items8 = (int64_t)items8;
+        const size_t items8 = (size_t)g8_groups * std::max(g8_slices, g8_slices_s);
+        ix->last_items8 = (int64_t)g8_groups * g8_slices;
+        if ((rc = ix->d_cap0.ensure((size_t)Q * 4))) return rc;
+        if ((rc = ix->d_cap1.ensure((size_t)Q * 4))) return rc;
         if ((rc = ix->d_qlut8.ensure((size_t)g8_groups * 2048 * dpq::C8_ROW_BYTES))) return rc;
         if ((rc = ix->d_cand8.ensure(items8 * dpq::C8_QB * bcap8 * 4))) return rc;
         if ((rc = ix->d_cnt8.ensure(items8 * dpq::C8_QB * 4))) return rc;
@@ -471,8 +494,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if (coarse) CU(cudaMemsetAsync(ix->d_fcnt2.p, 0, (size_t)max_flagged * 4, st));
     if (P.v2)
         dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
-                         ix->d_scale.as<double>(), ix->d_qlut.as<uint16_t>(), ix->d_gthr.as<uint32_t>(),
-                         ix->d_ovf.as<uint32_t>(), g.n_groups, P.shape, (uint32_t)ix->opt_dbg_bound, st);
+                         ix->d_scale.as<double>(), seeded ? nullptr : ix->d_qlut.as<uint16_t>(),
+                         ix->d_gthr.as<uint32_t>(), ix->d_ovf.as<uint32_t>(), g.n_groups, P.shape,
+                         (uint32_t)ix->opt_dbg_bound, st);
     else
         dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                         ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);
@@ -488,7 +512,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     sa.gthr = ix->d_gthr.as<uint32_t>();
     sa.Q = Q;
     CU(cudaEventRecord(ix->ev[1], st));
-    if (P.v2) {
+    if (P.v2 && !seeded) {
         dpq::Scan2Args s2;
         s2.shape = P.shape;
         s2.recs = ix->d_recs.as<uint4>();
@@ -512,7 +536,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s2.epoch = std::max(1, ix->opt_epoch);
         s2.ramp = ix->opt_ramp;
         CU(dpq::launch_scan2(s2, st));
-    } else {
+    } else if (!seeded) {
         CU(dpq::launch_scan(sa, st));
     }
     if (!coarse) CU(cudaEventRecord(ix->ev[2], st));
@@ -535,7 +559,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     se.max_flagged = max_flagged;
     se.bound = ix->d_bound.as<float>();
     se.force_fallback = ix->opt_force_fallback;
-    dpq::launch_select(se, st);
+    if (!seeded) dpq::launch_select(se, st);
     dpq::FallbackArgs fa;
     fa.flagged = se.flagged;
     fa.n_flagged = ctrl;
@@ -553,16 +577,66 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     fa.cap = fcap;
     fa.out_key = d_out_key;
     fa.overflow = ctrl + 1;
-    dpq::launch_fallback(fa, st);
+    if (!seeded) dpq::launch_fallback(fa, st);
     if (coarse) {
-        // d_out_key now holds the exact top-k of the SAMPLE: its k-th distance caps the coarse tables
-        dpq::launch_pack8(se.lutf, d_out_key, topk, (int)MK, Q, ix->opt_levels8, ix->d_qlut8.as<uint8_t>(),
-                          ix->d_ovf8.as<uint32_t>(), g8_groups, st);
+        float* cap0 = ix->d_cap0.as<float>();
+        float* cap1 = ix->d_cap1.as<float>();
         dpq::Scan8Args s8;
+        dpq::Rescore8Args r8;
+        if (!seeded) {
+            // d_out_key holds the exact top-k of the 15-bit SAMPLE pass: its k-th distance is the cap
+            dpq::launch_cap_from_keys(d_out_key, topk, Q, cap1, st);
+        } else {
+            // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the
+            // sample (every S-th batch) -> exact re-score -> cap1 = the sample's k-th distance
+            dpq::launch_presample(se.lutf, se.codes, P.n_local, P.M, P.K, Q, topk, ix->opt_presample, cap0, st);
+            dpq::launch_pack8(se.lutf, cap0, (int)MK, Q, ix->opt_levels8, ix->d_qlut8.as<uint8_t>(),
+                              ix->d_ovf8.as<uint32_t>(), g8_groups, st);
+            s8.recs = ix->d_recs.as<uint4>();
+            s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
+            s8.n_chunks = ix->n_chunks;
+            s8.chunk_nodes = P.v2_chunk_nodes;
+            s8.bt_stride = S;
+            s8.qlut8 = ix->d_qlut8.as<uint8_t>();
+            s8.cand = ix->d_cand8.as<uint32_t>();
+            s8.cand_cnt = ix->d_cnt8.as<uint32_t>();
+            s8.ovf = ix->d_ovf8.as<uint32_t>();
+            s8.Q = Q;
+            s8.n_groups = g8_groups;
+            s8.n_slices = g8_slices_s;
+            s8.n_warps = warps8;
+            s8.bcap = bcap8;
+            s8.thresh = ix->opt_levels8 + 5;
+            CU(dpq::launch_scan8(s8, st));
+            r8.cand = s8.cand;
+            r8.cand_cnt = s8.cand_cnt;
+            r8.ovf = s8.ovf;
+            r8.n_groups = g8_groups;
+            r8.n_slices = g8_slices_s;
+            r8.bcap = bcap8;
+            r8.lutf = se.lutf;
+            r8.codes = se.codes;
+            r8.base_pos = P.base_pos;
+            r8.M = P.M;
+            r8.K = P.K;
+            r8.Q = Q;
+            r8.topk = topk;
+            r8.out_key = nullptr;
+            r8.cap_in = cap0;
+            r8.cap_out = cap1;
+            r8.flagged = nullptr;
+            r8.n_flagged = nullptr;
+            r8.max_flagged = 0;
+            r8.bound = nullptr;
+            dpq::launch_rescore8(r8, st);
+        }
+        dpq::launch_pack8(se.lutf, cap1, (int)MK, Q, ix->opt_levels8, ix->d_qlut8.as<uint8_t>(),
+                          ix->d_ovf8.as<uint32_t>(), g8_groups, st);
         s8.recs = ix->d_recs.as<uint4>();
         s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
         s8.n_chunks = ix->n_chunks;
         s8.chunk_nodes = P.v2_chunk_nodes;
+        s8.bt_stride = 1;
         s8.qlut8 = ix->d_qlut8.as<uint8_t>();
         s8.cand = ix->d_cand8.as<uint32_t>();
         s8.cand_cnt = ix->d_cnt8.as<uint32_t>();
@@ -576,7 +650,6 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         CU(cudaEventRecord(ix->ev[4], st));
         CU(dpq::launch_scan8(s8, st));
         CU(cudaEventRecord(ix->ev[5], st));
-        dpq::Rescore8Args r8;
         r8.cand = s8.cand;
         r8.cand_cnt = s8.cand_cnt;
         r8.ovf = s8.ovf;
@@ -591,6 +664,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         r8.Q = Q;
         r8.topk = topk;
         r8.out_key = d_out_key;
+        r8.cap_in = cap1;
+        r8.cap_out = nullptr;
         r8.flagged = ix->d_flagged2.as<uint32_t>();
         r8.n_flagged = ctrl + 2;
         r8.max_flagged = max_flagged;
@@ -606,7 +681,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
     // lut (+ pack), scan, select, fallback collect/finish (+ pack8, scan8, rescore8, fallback x2)
-    ix->last_launches = coarse ? 11 : (P.v2 ? 6 : 5);
+    ix->last_launches = coarse ? (seeded ? 10 : 12) : (P.v2 ? 6 : 5);
     ix->timing_valid = true;
     return DPQ_OK;
 }
@@ -776,7 +851,7 @@ void dpq_index_close(dpq_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_fcnt2, &ix->d_recs, &ix->d_chunks2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_fcnt2, &ix->d_recs, &ix->d_chunks2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
                       &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_fbuf, &ix->d_fcnt, &ix->d_key,
                       &ix->d_gthr})

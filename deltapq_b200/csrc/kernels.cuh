@@ -108,6 +108,7 @@ struct Scan2Args {
     int Q, n_groups, n_slices, n_warps;
     int kp, bcap, trigger, epoch, ramp;
 };
+// d_qlut == nullptr: float tables only (the coarse pipeline quantises them itself)
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  const V2Shape& sh, uint32_t bound0, cudaStream_t st);
@@ -125,6 +126,7 @@ struct Scan8Args {
     const uint4* recs;
     const ChunkDesc2* chunks;
     int n_chunks, chunk_nodes;
+    int bt_stride;                // 1: every batch; S: every S-th batch (sample pass)
     const uint8_t* qlut8;         // [n_groups][2048][112] coarse tables
     uint32_t* cand;               // [n_items][112][bcap] candidate positions
     uint32_t* cand_cnt;           // [n_items][112]
@@ -134,8 +136,14 @@ struct Scan8Args {
 };
 // coarse tables: entry = min(31, rint(lut / unit)), unit = cap / levels, cap = the query's exact k-th
 // distance over the sample (out_key[q][topk-1]); transposed to [group][row][112] u8
-void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, int levels,
-                  uint8_t* d_qlut8, uint32_t* d_ovf, int n_groups, cudaStream_t st);
+void launch_pack8(const float* d_lutf, const float* d_cap, int MK, int Q, int levels, uint8_t* d_qlut8,
+                  uint32_t* d_ovf, int n_groups, cudaStream_t st);
+// cap of every query from the key lists of a finished search: cap[q] = distance of out_key[q][topk-1]
+void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap, cudaStream_t st);
+// cap0[q] = exact k-th smallest distance over R evenly strided nodes (float tables, reference
+// arithmetic): a valid, loose upper bound of the true k-th distance that seeds the sample pass
+void launch_presample(const float* d_lutf, const uint8_t* d_codes, int64_t n_local, int M, int K, int Q, int topk,
+                      int R, float* d_cap, cudaStream_t st);
 cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st);
 struct Rescore8Args {
     const uint32_t* cand;
@@ -146,8 +154,10 @@ struct Rescore8Args {
     const uint8_t* codes;         // [n_local][M]
     int64_t base_pos;
     int M, K, Q, topk;
-    uint64_t* out_key;            // [Q][topk]
-    uint32_t* flagged;            // queries whose candidate buffer overflowed -> exact fallback
+    uint64_t* out_key;            // [Q][topk] (may be null for the sample pass)
+    const float* cap_in;          // [Q] a valid upper bound of the k-th distance known beforehand (may be null)
+    float* cap_out;               // [Q] min(cap_in, k-th exact distance found), may be null
+    uint32_t* flagged;            // queries whose candidate buffer overflowed -> exact fallback (may be null)
     uint32_t* n_flagged;
     int max_flagged;
     float* bound;                 // [Q] exact distance bound for the fallback

@@ -117,6 +117,7 @@ void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries
     const size_t lsm = (size_t)LUT2_QPB * M * Ds * sizeof(float);
     if (lsm > 48 * 1024) cudaFuncSetAttribute(lut2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
     lut2_kernel<<<(Q + LUT2_QPB - 1) / LUT2_QPB, 256, lsm, st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf, d_scale);
+    if (!d_qlut) return;
     pack2_kernel<<<dim3((unsigned)n_groups, (unsigned)(sh.rows / 64)), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, sh.qb(), sh.rows,
                                                                                     d_qlut, d_gthr, d_ovf, bound0);
 }

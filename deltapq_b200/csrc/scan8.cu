@@ -28,9 +28,70 @@ constexpr int ROWS8 = 2048;
 constexpr int LUT8_BYTES = ROWS8 * C8_ROW_BYTES;  // 229,376
 }  // namespace
 
-__global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lutf,
-                                                    const uint64_t* __restrict__ sample_key, int topk, int MK, int Q,
-                                                    int levels, uint8_t* __restrict__ qlut8, uint32_t* __restrict__ ovf) {
+__global__ void cap_from_keys_kernel(const uint64_t* __restrict__ keys, int topk, int Q, float* __restrict__ cap) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q) cap[q] = __uint_as_float((uint32_t)(keys[(size_t)q * topk + topk - 1] >> 32));
+}
+void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap, cudaStream_t st) {
+    cap_from_keys_kernel<<<(Q + 255) / 256, 256, 0, st>>>(d_keys, topk, Q, d_cap);
+}
+
+// One block per query: exact distances of R evenly strided nodes (the query's float table in
+// shared memory), then the k-th smallest by bisection on the float bit patterns (distances are
+// non-negative, so the integer order of the bits is the float order).
+constexpr int PS_T = 128;
+__global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict__ lutf, const uint8_t* __restrict__ codes,
+                                                         int64_t n_local, int M, int K, int topk, int R,
+                                                         float* __restrict__ cap) {
+    extern __shared__ float s_lut[];  // M*K
+    __shared__ int s_cnt[PS_T / 32];
+    const int q = blockIdx.x;
+    const int MK = M * K;
+    for (int i = threadIdx.x; i < MK; i += PS_T) s_lut[i] = lutf[(size_t)q * MK + i];
+    __syncthreads();
+    constexpr int PER = 16;  // R <= PS_T * PER
+    uint32_t v[PER];
+    const int64_t stride = n_local / R > 0 ? n_local / R : 1;
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+        const int i = t * PS_T + threadIdx.x;
+        v[t] = 0x7F800000u;  // +inf: never counted
+        if (i < R && (int64_t)i * stride < n_local) {
+            const uint8_t* c = codes + (size_t)((int64_t)i * stride) * M;
+            double d = 0.0;
+            for (int m = 0; m < M; ++m) d += (double)s_lut[m * K + c[m]];
+            v[t] = __float_as_uint((float)d);
+        }
+    }
+    // smallest x with count(v <= x) >= topk
+    uint32_t lo = 0, hi = 0x7F7FFFFFu;  // FLT_MAX
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < PER; ++t) c += v[t] <= mid;
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < PS_T / 32; ++w) tot += s_cnt[w];
+        __syncthreads();
+        if (tot >= topk) hi = mid;
+        else lo = mid + 1;
+    }
+    if (threadIdx.x == 0) cap[q] = __uint_as_float(lo);  // FLT_MAX when the sample holds fewer than k nodes
+}
+void launch_presample(const float* d_lutf, const uint8_t* d_codes, int64_t n_local, int M, int K, int Q, int topk,
+                      int R, float* d_cap, cudaStream_t st) {
+    if (R > PS_T * 16) R = PS_T * 16;
+    const size_t sm = (size_t)M * K * sizeof(float);
+    presample_kernel<<<Q, PS_T, sm, st>>>(d_lutf, d_codes, n_local, M, K, topk, R, d_cap);
+}
+
+__global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lutf, const float* __restrict__ capv,
+                                                    int MK, int Q, int levels, uint8_t* __restrict__ qlut8,
+                                                    uint32_t* __restrict__ ovf) {
     __shared__ uint8_t tile[64 * C8_QB];
     __shared__ double s_inv[C8_QB];
     const int grp = blockIdx.x, row0 = blockIdx.y * 64;
@@ -38,7 +99,7 @@ __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lu
         const int q = grp * C8_QB + threadIdx.x;
         double inv = 0.0;
         if (q < Q) {
-            const float cap = __uint_as_float((uint32_t)(sample_key[(size_t)q * topk + topk - 1] >> 32));
+            const float cap = capv[q];
             // cap == FLT_MAX: the sample held fewer than k nodes; every entry quantises to 0 and
             // every node becomes a candidate (correct, merely slow: tiny trees only)
             inv = cap > 0.0f ? (double)levels / (double)cap : 0.0;
@@ -64,10 +125,9 @@ __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lu
     for (int i = threadIdx.x; i < 64 * C8_QB / 4; i += blockDim.x) dst[i] = src[i];
 }
 
-void launch_pack8(const float* d_lutf, const uint64_t* d_sample_key, int topk, int MK, int Q, int levels,
-                  uint8_t* d_qlut8, uint32_t* d_ovf, int n_groups, cudaStream_t st) {
-    pack8_kernel<<<dim3((unsigned)n_groups, ROWS8 / 64), 256, 0, st>>>(d_lutf, d_sample_key, topk, MK, Q, levels, d_qlut8,
-                                                                      d_ovf);
+void launch_pack8(const float* d_lutf, const float* d_cap, int MK, int Q, int levels, uint8_t* d_qlut8,
+                  uint32_t* d_ovf, int n_groups, cudaStream_t st) {
+    pack8_kernel<<<dim3((unsigned)n_groups, ROWS8 / 64), 256, 0, st>>>(d_lutf, d_cap, MK, Q, levels, d_qlut8, d_ovf);
 }
 
 __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
@@ -80,7 +140,7 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strand = lane >> 3, j = lane & 7;
     const int jj = j < 7 ? j : 6;
-    const int n_bt = (a.n_chunks + 3) >> 2;
+    const int n_bt = (((a.n_chunks + 3) >> 2) + a.bt_stride - 1) / a.bt_stride;  // batches this launch walks
     const int b_lo = (int)((int64_t)n_bt * slice / a.n_slices);
     const int b_hi = (int)((int64_t)n_bt * (slice + 1) / a.n_slices);
 
@@ -118,7 +178,7 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
 
     for (int round = 0; round < n_rounds; ++round) {
         const int bt = b_lo + round * a.n_warps + warp;
-        const int c = bt * 4 + strand;
+        const int c = bt * a.bt_stride * 4 + strand;
         int n_nodes = 0;
         uint32_t pos = 0, rix = 0;
         if (bt < b_hi && c < a.n_chunks) {
@@ -297,14 +357,18 @@ __global__ void __launch_bounds__(R8_WARPS * 32) rescore8_kernel(const Rescore8A
         }
     }
     n = r8_compact(buf, n, k, lane);
-    for (int i = lane; i < k; i += 32)
-        a.out_key[(size_t)q * k + i] = i < n ? buf[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
-    if (lane == 0) {
+    if (a.out_key)
+        for (int i = lane; i < k; i += 32)
+            a.out_key[(size_t)q * k + i] = i < n ? buf[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+    // the k best found are real nodes: their k-th distance bounds the true k-th from above even
+    // when candidates were dropped
+    const float found = n >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
+    const float known = a.cap_in ? a.cap_in[q] : FLT_MAX;
+    if (lane == 0 && a.cap_out) a.cap_out[q] = fminf(found, known);
+    if (lane == 0 && a.flagged) {
         // a dropped candidate (buffer overflow) may hide a true top-k node: exact fallback, bounded
         // by the best k found so far
-        // (never looser than the sample's exact k-th distance, which select_kernel left in bound[q])
-        const float mine = n >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
-        a.bound[q] = fminf(a.bound[q], mine);
+        a.bound[q] = fminf(found, known);
         if (a.ovf[(size_t)grp * C8_QB + ql]) {
             const uint32_t slot = atomicAdd(a.n_flagged, 1u);
             if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;
