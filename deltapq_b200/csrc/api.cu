@@ -88,7 +88,8 @@ struct dpq_index {
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
     int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
     int opt_sample = 16;       // the sample pass walks every opt_sample-th batch
-    int opt_seed = 1;          // 1: presample -> sampled coarse scan gives the cap; 0: sampled 15-bit scan
+    int opt_seed = 0;          // 0: sampled 15-bit scan gives the cap (default, 0.90 ms at C2);
+                               // 1: exact presample -> sampled coarse scan -> re-score (1.18 ms at C2)
     int opt_presample = 2048;  // nodes scored exactly per query to seed the sample pass
     int opt_bcap8 = 512, opt_warps8 = 24, opt_levels8 = 80;
     int64_t opt_coarse_min = 262144;  // nodes in the shard from which the coarse search pays

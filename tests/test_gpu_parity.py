@@ -101,7 +101,9 @@ def test_v2_options_and_overflow_path(golden4000, engine, opts):
 
 
 @pytest.mark.parametrize("opts", [dict(coarse=1), dict(coarse=1, sample=4), dict(coarse=1, sample=1),
-                                  dict(coarse=1, bcap8=32), dict(coarse=1, slices=3, warps8=24)])
+                                  dict(coarse=1, bcap8=32), dict(coarse=1, slices=3, warps8=24),
+                                  dict(coarse=1, seed=1), dict(coarse=1, seed=1, presample=64, levels8=40),
+                                  dict(coarse=1, seed=1, bcap8=32)])
 def test_coarse_search_is_exact(golden4000, engine, opts):
     """Three-phase search (sample scan -> 8-bit coarse scan -> exact re-score, scan8.cu) gives
     the same answers as the oracle; a tiny candidate buffer (bcap8=32) overflows and must divert
