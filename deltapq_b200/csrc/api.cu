@@ -88,6 +88,7 @@ struct dpq_index {
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
     int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
     int opt_sample = 16;       // the sample pass walks every opt_sample-th batch
+    int opt_slices_s = 0;      // slices of the sample pass (0 = auto)
     int opt_seed = 0;          // 0: sampled 15-bit scan gives the cap (default, 0.90 ms at C2);
                                // 1: exact presample -> sampled coarse scan -> re-score (1.18 ms at C2)
     int opt_presample = 2048;  // nodes scored exactly per query to seed the sample pass
@@ -168,7 +169,7 @@ int choose_geometry2(const dpq_index* ix, int Q, int topk, dpq::ScanGeom* g, int
     g->qpg = sh.qb();
     g->n_groups = (Q + sh.qb() - 1) / sh.qb();
     const int n_chunks = n_chunks_eff > 0 ? n_chunks_eff : ix->n_chunks;
-    int n_slices = n_chunks_eff > 0 ? 0 : ix->opt_slices;
+    int n_slices = n_chunks_eff > 0 ? ix->opt_slices_s : ix->opt_slices;
     if (n_slices <= 0) {
         const int chunks_per_round = g->n_warps * sh.spw();
         double best = -1.0;
@@ -378,6 +379,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "warps8") ix->opt_warps8 = std::max(2, std::min(24, (int)v));
     else if (n == "coarse_min") ix->opt_coarse_min = v;
     else if (n == "seed") ix->opt_seed = (int)v;
+    else if (n == "slices_s") ix->opt_slices_s = (int)v;
     else if (n == "presample") ix->opt_presample = std::max(64, std::min(2048, (int)v));
     else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
     else return fail(DPQ_ERR_ARG, "unknown option " + n);

@@ -1,5 +1,6 @@
-"""Developer probe: BASELINE configs[2] shape (SIFT1M-shaped, M=16 K=256, top-100).
-Usage: python tools/perf_probe_m16.py N Q"""
+"""Developer probe: BASELINE configs[2] shape (SIFT1M-shaped, M=16 K=256, top-100) or, with a
+third argument "gist", configs[3] shape (GIST-shaped 960-d floats in [0,1), M=16 K=256).
+Usage: python tools/perf_probe_m16.py N Q [gist]"""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -8,9 +9,13 @@ import datagen as dg
 import deltapq_b200 as dpq
 from oracle import pyoracle as po
 N = int(sys.argv[1]); Q = int(sys.argv[2]); M = 16; K = 256; topk = 100
-base = dg.sift_like(N, 128, seed=1)
-cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(20000, 128, seed=3), M, K, iters=6))
-queries = dg.sift_like(Q, 128, seed=2)
+gist = len(sys.argv) > 3 and sys.argv[3] == "gist"
+gen, D = (dg.gist_like, 960) if gist else (dg.sift_like, 128)
+base = gen(N, D, seed=1)
+cw = dg.roundtrip_codebook(dg.kmeans_codebook(gen(8000 if gist else 20000, D, seed=3), M, K, iters=4 if gist else 6))
+queries = gen(Q, D, seed=2)
+if gist:
+    assert np.array_equal(dpq.encode(cw, base[:3000]), po.encode(cw, base[:3000])), "GIST-shaped encode not bit-exact"
 t = time.time(); codes = dpq.encode(cw, base); print("encode %.2fs" % (time.time() - t), flush=True)
 t = time.time(); tree = dpq.tree_build(codes, cw); print("tree build %.2fs" % (time.time() - t), "n_bytes", len(tree["payload"]), "n_diffs", tree["n_diffs"], flush=True)
 payload = tree["payload"]
