@@ -708,6 +708,20 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     if (Q < 1 || topk < 1) return fail(DPQ_ERR_ARG, "dpq_index_search: Q and topk must be >= 1");
     CU(cudaSetDevice(ix->device));
     const size_t D = (size_t)ix->prog.M * ix->Ds;
+    constexpr int kMaxBatch = 32768;  // bounds the per-search scratch (float tables: 8 KB per query at M = 8)
+    if (Q > kMaxBatch) {
+        int64_t fb = 0;
+        for (int q0 = 0; q0 < Q; q0 += kMaxBatch) {
+            const int n = std::min(kMaxBatch, Q - q0);
+            const size_t o = (size_t)q0 * topk;
+            int rc = dpq_index_search(ix, queries + (size_t)q0 * D, n, topk, out_pos ? out_pos + o : nullptr,
+                                      out_id ? out_id + o : nullptr, out_dist ? out_dist + o : nullptr);
+            if (rc) return rc;
+            fb += ix->last_fallback;
+        }
+        ix->last_fallback = fb;
+        return DPQ_OK;
+    }
     const size_t qbytes = (size_t)Q * D * 4, kbytes = (size_t)Q * topk * 8;
     // pinned staging: [queries][keys][ctrl words]; a caller buffer that is already page-locked
     // (dpq_malloc_host, cudaHostRegister) is copied from directly

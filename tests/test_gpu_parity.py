@@ -152,6 +152,20 @@ def test_coarse_search_duplicates_and_exact_matches(engine):
     ix.close()
 
 
+def test_large_batch_is_split(golden1501, engine):
+    """More than 32768 queries in one dpq_index_search call are processed in sub-batches."""
+    g = golden1501
+    rng = np.random.default_rng(3)
+    Q = 40000
+    queries = np.clip(g["queries"][rng.integers(0, len(g["queries"]), Q)] + rng.integers(-20, 21, (Q, 128)), 0, 255).astype(np.float32)
+    ix = _open(g)
+    pos, ids, dist = ix.search(queries, 5)
+    for i in (0, 32767, 32768, 39999):
+        opos, odist = po.scan(g["payload"], int(g["n"]), g["cw"], queries[i], 5)
+        assert np.array_equal(dist[i], odist)
+    ix.close()
+
+
 def test_many_queries_ragged_groups(golden4000, engine):
     """Q not a multiple of the group size (56 / 48..52): padding lanes must stay silent."""
     g = golden4000
