@@ -34,7 +34,7 @@ class DpqError(RuntimeError):
 
 def build(verbose=False):
     """Compile libdpq.so in tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=not verbose, text=True)
+    r = subprocess.run(["make", "-j8", "-C", os.path.join(HERE, "csrc")], capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise DpqError("building libdpq.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
 
