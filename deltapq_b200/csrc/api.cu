@@ -87,13 +87,13 @@ struct dpq_index {
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
     int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
-    int opt_sample = 16;       // the sample pass walks every opt_sample-th batch
+    int opt_sample = 0;        // the sample pass walks every opt_sample-th batch (0 = auto: 16, or 8 below 400K nodes)
     int opt_slices_s = 0;      // slices of the sample pass (0 = auto)
     int opt_seed = 0;          // 0: sampled 15-bit scan gives the cap (default, 0.90 ms at C2);
                                // 1: exact presample -> sampled coarse scan -> re-score (1.18 ms at C2)
     int opt_presample = 2048;  // nodes scored exactly per query to seed the sample pass
     int opt_bcap8 = 512, opt_warps8 = 24, opt_levels8 = 80;
-    int64_t opt_coarse_min = 262144;  // nodes in the shard from which the coarse search pays
+    int64_t opt_coarse_min = 100000;  // nodes in the shard from which the coarse search pays (gpurun_out/probe22.log)
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
     // scratch
@@ -374,7 +374,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "ramp") ix->opt_ramp = (int)v;
     else if (n == "dbg_bound") ix->opt_dbg_bound = (int)v;
     else if (n == "coarse") ix->opt_coarse = (int)v;
-    else if (n == "sample") ix->opt_sample = std::max(1, (int)v);
+    else if (n == "sample") ix->opt_sample = std::max(0, (int)v);
     else if (n == "bcap8") ix->opt_bcap8 = std::max(32, (int)v);
     else if (n == "warps8") ix->opt_warps8 = std::max(2, std::min(24, (int)v));
     else if (n == "coarse_min") ix->opt_coarse_min = v;
@@ -398,7 +398,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     // the whole tree -> exact re-score.  Narrow shape, moderate k, trees large enough to pay.
     const bool coarse = P.v2 && P.shape.nf == 8 && P.v2_rec_stride == 1 && topk <= 64 && ix->opt_coarse != 0 &&
                         (ix->opt_coarse == 1 || P.n_local >= ix->opt_coarse_min);
-    const int S = coarse ? ix->opt_sample : 1;
+    const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : (P.n_local >= 400000 ? 16 : 8));
     const int n_chunks_sample = (((ix->n_chunks + 3) / 4 + S - 1) / S) * 4;  // chunks the sample pass walks
     int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
     if (rc) return rc;
