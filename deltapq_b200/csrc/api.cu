@@ -396,7 +396,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     const dpq::ScanProgram& P = ix->prog;
     // coarse search (scan8.cu): 15-bit scan over a 1/S sample -> cap per query -> 8-bit scan of
     // the whole tree -> exact re-score.  Narrow shape, moderate k, trees large enough to pay.
-    const bool coarse = P.v2 && P.shape.nf == 8 && P.v2_rec_stride == 1 && topk <= 64 && ix->opt_coarse != 0 &&
+    const bool coarse = P.v2 && P.shape.nf == 8 && topk <= 64 && ix->opt_coarse != 0 &&
                         (ix->opt_coarse == 1 || P.n_local >= ix->opt_coarse_min);
     const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : (P.n_local >= 400000 ? 16 : 8));
     const int n_chunks_sample = (((ix->n_chunks + 3) / 4 + S - 1) / S) * 4;  // chunks the sample pass walks
@@ -522,7 +522,6 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s2.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
         s2.n_chunks = ix->n_chunks;
         s2.chunk_nodes = P.v2_chunk_nodes;
-        s2.rec_stride = P.v2_rec_stride;
         s2.bt_stride = S;
         s2.qlut = ix->d_qlut.as<uint16_t>();
         s2.cand = sa.cand;

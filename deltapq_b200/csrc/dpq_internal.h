@@ -98,8 +98,7 @@ inline V2Shape v2_shape(int M, int K) {
 }
 
 struct ChunkDesc2 {
-    uint32_t rec_begin;  // slot of this chunk's first record; record i is at rec_begin + stride*i
-                         // (stride 4 when the four chunks of a batch are interleaved, program.cpp)
+    uint32_t rec_begin;  // first record of this chunk (records of a chunk are contiguous)
     uint32_t n_nodes;    // records in the chunk (== v2_chunk_nodes except the last)
     uint32_t first_pos;  // global DFS position of the first record
     uint32_t pad;
@@ -109,7 +108,6 @@ struct ScanProgram {
     int M = 0, K = 0;
     bool v2 = false;
     int v2_chunk_nodes = 64;
-    int v2_rec_stride = 1;             // 1: chunk records contiguous; 4: batches of four chunks interleaved
     V2Shape shape{8, 7, 8, 2048};
     std::vector<uint32_t> recs;        // v2 records, shape.rec_words() words each
     std::vector<ChunkDesc2> chunks2;

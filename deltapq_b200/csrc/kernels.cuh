@@ -98,7 +98,7 @@ struct Scan2Args {
     V2Shape shape;
     const uint4* recs;            // one 16- or 32-byte record per node
     const ChunkDesc2* chunks;
-    int n_chunks, chunk_nodes, rec_stride;
+    int n_chunks, chunk_nodes;
     int bt_stride;                // 1: every batch; S: every S-th batch (sample pass)
     const uint16_t* qlut;         // [n_groups][2048][56] fixed-point tables
     uint64_t* cand;               // [n_items][56][bcap] candidate keys (dist << 32 | pos)

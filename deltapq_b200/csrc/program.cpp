@@ -168,7 +168,6 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
     P.depth_hist.assign((size_t)levels + 1, 0);
     if (chunk_nodes < 4) chunk_nodes = 4;
     P.v2 = engine == 0 && v2_shape_ok(M, K);
-    if (const char* e = getenv("DPQ_V2_STRIDE")) P.v2_rec_stride = (atoi(e) == 4 && M <= 8) ? 4 : 1;  // developer knob (narrow shape only)
     if (P.v2) P.shape = v2_shape(M, K);
     Emitter2 E2;
     E2.p = &P;
@@ -274,22 +273,6 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
     }
     E.end();
     E2.end();
-    if (P.v2 && P.v2_rec_stride == 4) {
-        // Interleave the records of each batch of four consecutive chunks: record i of chunk
-        // 4b+g lives at slot (b*C + i)*4 + g, so the four strands of a warp (one chunk each,
-        // iterating in lockstep) read one contiguous 64-byte piece per step.  Short chunks are
-        // padded with zero records (a delta record of row 0 - row 0; never emitted).
-        const size_t C = (size_t)P.v2_chunk_nodes, W = (size_t)P.shape.rec_words();
-        const size_t n_batches = (P.chunks2.size() + 3) / 4;
-        std::vector<uint32_t> il(n_batches * C * 4 * W, 0u);
-        for (size_t c = 0; c < P.chunks2.size(); ++c) {
-            const ChunkDesc2& cd = P.chunks2[c];
-            for (size_t i = 0; i < cd.n_nodes; ++i)
-                memcpy(&il[(((c >> 2) * C + i) * 4 + (c & 3)) * W], &P.recs[((size_t)cd.rec_begin + i) * W], W * 4);
-        }
-        P.recs.swap(il);
-        for (size_t c = 0; c < P.chunks2.size(); ++c) P.chunks2[c].rec_begin = (uint32_t)((c >> 2) * C * 4 + (c & 3));
-    }
     if (off != n_bytes) return "stream has trailing or missing bytes (n_bytes mismatch)";
     P.local_bytes += (local_nodes_records + 1) / 2;  // depth nibbles
     if (pending_root && !P.v2) {  // root only (n_codes == 1, or rank 0 owns no subtree)

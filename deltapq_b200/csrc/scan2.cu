@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
 
     const int n_rounds = (b_hi - b_lo + a.n_warps - 1) / a.n_warps;
     const int C = a.chunk_nodes;
-    const int rs = a.rec_stride * RW;
+    constexpr int rs = RW;  // records of a chunk are contiguous
     int since = 0, epoch_len = a.ramp ? 1 : a.epoch;
     uint32_t parp[4] = {1u, 1u, 1u, 1u};
 
