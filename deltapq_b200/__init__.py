@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libdpq.so")
 # every symbol include/dpq.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "dpq_version", "dpq_last_error", "dpq_device_count", "dpq_set_device",
-    "dpq_index_open", "dpq_index_open_file", "dpq_index_set_codebook", "dpq_index_set_option",
+    "dpq_index_open", "dpq_index_open_part", "dpq_index_open_file", "dpq_index_set_codebook", "dpq_index_set_option",
     "dpq_index_set_stream",
     "dpq_index_search", "dpq_index_search_device", "dpq_index_sync", "dpq_merge_topk_device",
     "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",
@@ -52,6 +52,7 @@ def lib():
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     L.dpq_last_error.restype = C.c_char_p
     L.dpq_index_open.argtypes = [vp, i64, i64, i32, i32, vp, i32, i32, C.POINTER(vp)]
+    L.dpq_index_open_part.argtypes = [vp, i64, i64, i32, i32, vp, i64, C.POINTER(vp)]
     L.dpq_index_open_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(vp)]
     L.dpq_index_set_codebook.argtypes = [vp, vp, i32]
     L.dpq_index_set_option.argtypes = [vp, C.c_char_p, i64]
@@ -165,7 +166,9 @@ class DeltaTreeIndex:
     """Host mirror of the reference's query entry points (DCAT.h:2805 / :3731): open a
     compressed DeltaTree, set the codebook, search batches of queries."""
 
-    def __init__(self, payload, n_codes, M, K, pos2id=None, rank=0, n_ranks=1):
+    def __init__(self, payload, n_codes, M, K, pos2id=None, rank=0, n_ranks=1, first_pos=None):
+        """first_pos: open the tree as one part of a forest (dpq_index_open_part): the whole
+        tree, positions reported as first_pos + DFS position."""
         payload = np.ascontiguousarray(payload, np.uint8)
         self.M, self.K = M, K
         self._h = C.c_void_p()
@@ -173,8 +176,12 @@ class DeltaTreeIndex:
         if pos2id is not None:
             self._p2i = np.ascontiguousarray(pos2id, np.uint32)
             p2i = _ptr(self._p2i)
-        _check(lib().dpq_index_open(_ptr(payload), payload.nbytes, n_codes, M, K, p2i, rank, n_ranks,
-                                    C.byref(self._h)))
+        if first_pos is not None:
+            _check(lib().dpq_index_open_part(_ptr(payload), payload.nbytes, n_codes, M, K, p2i, int(first_pos),
+                                             C.byref(self._h)))
+        else:
+            _check(lib().dpq_index_open(_ptr(payload), payload.nbytes, n_codes, M, K, p2i, rank, n_ranks,
+                                        C.byref(self._h)))
         self.Ds = None
 
     @classmethod
@@ -276,10 +283,12 @@ _TREE_ARRAYS = (("edges", np.uint32), ("vec_id", np.uint32), ("parent_pos", np.u
                 ("codes_by_pos", np.uint8), ("payload", np.uint8), ("qnodes", np.uint8))
 
 
-def _tree_out(h, M):
+def _tree_out(h, M, want=None):
     try:
         out = {}
         for name, dt in _TREE_ARRAYS:
+            if want is not None and name not in want:
+                continue
             nb = lib().dpq_tree_size(h, name.encode())
             if nb < 0:
                 continue
@@ -287,23 +296,34 @@ def _tree_out(h, M):
             if nb:
                 _check(lib().dpq_tree_copy(h, name.encode(), _ptr(arr)))
             out[name] = arr
-        for name in ("root_id", "n_diffs", "n_codes"):
+        for name in ("root_id", "n_diffs", "n_codes", "edge_us", "layout_us"):
             out[name] = int(lib().dpq_tree_size(h, name.encode()))
-        out["edges"] = out["edges"].reshape(-1, 2)
-        out["codes_by_pos"] = out["codes_by_pos"].reshape(-1, M)
+        if "edges" in out:
+            out["edges"] = out["edges"].reshape(-1, 2)
+        if "codes_by_pos" in out:
+            out["codes_by_pos"] = out["codes_by_pos"].reshape(-1, M)
         return out
     finally:
         lib().dpq_tree_free(h)
 
 
-def tree_build(codes, cw, h=1, method=1):
-    """`deltapq -task approx_tree` (DCAT.h:970): GPU edge search + host layout + stream."""
+def tree_build(codes, cw, h=1, method=1, want=None):
+    """`deltapq -task approx_tree` (DCAT.h:970): GPU edge search + GPU layout + stream.
+    want: names of the arrays to fetch (default all; at 10^8 nodes the QNode file body alone
+    is 6 GB)."""
     codes = np.ascontiguousarray(codes, np.uint8)
     cw = np.ascontiguousarray(cw, np.float32)
     n, M = codes.shape
     t = C.c_void_p()
     _check(lib().dpq_tree_build(_ptr(codes), n, M, cw.shape[1], _ptr(cw), cw.shape[2], h, method, C.byref(t)))
-    return _tree_out(t, M)
+    return _tree_out(t, M, want)
+
+
+def encode_device(cw, d_x_ptr, n, D, d_codes_ptr):
+    """dpq_encode with DEVICE buffers x [n][D] float32 -> codes [n][M] (raw pointers)."""
+    cw = np.ascontiguousarray(cw, np.float32)
+    M, K, Ds = cw.shape
+    _check(lib().dpq_encode(_ptr(cw), M, K, Ds, C.c_void_p(d_x_ptr), n, D, C.c_void_p(d_codes_ptr)))
 
 
 def tree_from_edges(codes, cw, edges, root_id):

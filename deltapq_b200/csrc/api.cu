@@ -83,6 +83,7 @@ struct dpq_index {
     size_t ops_bytes = 0;
     bool has_pos2id = false;
     std::vector<uint32_t> pos2id_host;  // local slice
+    int64_t pos_shift = 0;              // dpq_index_open_part: added to every reported position
     // options
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
@@ -221,7 +222,8 @@ int finish_open(dpq_index* ix, const uint32_t* pos2id) {
     }
     if (pos2id) {
         ix->has_pos2id = true;
-        ix->pos2id_host.assign(pos2id + P.base_pos, pos2id + P.base_pos + P.n_local);
+        const int64_t b = P.base_pos - ix->pos_shift;  // pos2id is indexed by the tree's own positions
+        ix->pos2id_host.assign(pos2id + b, pos2id + b + P.n_local);
     }
     CU(cudaStreamSynchronize(ix->stream));
     // the device copy is authoritative from here on
@@ -275,10 +277,12 @@ int dpq_set_device(int device) {
     return DPQ_OK;
 }
 
-int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
-                   const uint32_t* pos2id, int rank, int n_ranks, dpq_index** out) {
+static int open_common(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                       const uint32_t* pos2id, int rank, int n_ranks, int64_t first_pos, dpq_index** out) {
     if (!payload || !out) return fail(DPQ_ERR_ARG, "dpq_index_open: null argument");
     *out = nullptr;
+    if (first_pos < 0 || first_pos + n_codes > 0xFFFFFFFFLL)
+        return fail(DPQ_ERR_ARG, "dpq_index_open_part: positions must stay below 2^32 - 1");
     int rc = check_device();
     if (rc) return rc;
     dpq_index* ix = new dpq_index();
@@ -287,9 +291,15 @@ int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int
     const char* eng = getenv("DPQ_ENGINE");
     std::string err = dpq::compile_program(payload, n_bytes, n_codes, M, K, rank, n_ranks,
                                            ix->chunk_nodes, &ix->prog, eng && eng[0] == '1' ? 1 : 0);
+    if (err.empty() && first_pos && !ix->prog.v2) err = "a forest part needs the fixed-record program (M <= 16, M*K <= 4096)";
     if (!err.empty()) {
         delete ix;
         return fail(DPQ_ERR_FORMAT, "dpq_index_open: " + err);
+    }
+    if (first_pos) {  // one tree of a forest: every position this index reports is shifted
+        ix->pos_shift = first_pos;
+        ix->prog.base_pos += first_pos;
+        for (auto& c : ix->prog.chunks2) c.first_pos += (uint32_t)first_pos;
     }
     rc = finish_open(ix, pos2id);
     if (rc) {
@@ -298,6 +308,16 @@ int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int
     }
     *out = ix;
     return DPQ_OK;
+}
+
+int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                   const uint32_t* pos2id, int rank, int n_ranks, dpq_index** out) {
+    return open_common(payload, n_bytes, n_codes, M, K, pos2id, rank, n_ranks, 0, out);
+}
+
+int dpq_index_open_part(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                        const uint32_t* pos2id, int64_t first_pos, dpq_index** out) {
+    return open_common(payload, n_bytes, n_codes, M, K, pos2id, 0, 1, first_pos, out);
 }
 
 int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,

@@ -288,9 +288,9 @@ int dpq_encode(const float* cw, int M, int K, int Ds, const float* x, int64_t n,
     CU(cudaMemcpy(d_cw.p, cw, (size_t)M * K * Ds * 4, cudaMemcpyHostToDevice));
     for (int64_t s = 0; s < n; s += chunk) {
         int64_t c = std::min(chunk, n - s);
-        CU(cudaMemcpy(d_x.p, x + (size_t)s * D, (size_t)c * D * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_x.p, x + (size_t)s * D, (size_t)c * D * 4, cudaMemcpyDefault));
         CU(launch_encode((const float*)d_cw.p, M, K, Ds, (const float*)d_x.p, c, D, (uint8_t*)d_c.p, 0));
-        CU(cudaMemcpy(codes + (size_t)s * M, d_c.p, (size_t)c * M, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(codes + (size_t)s * M, d_c.p, (size_t)c * M, cudaMemcpyDefault));
     }
     return DPQ_OK;
 }

@@ -4,36 +4,24 @@
 //   edges_to_tree_index_approx_dfs_layout (DCAT.h:1334-1487; CSR :1067-1104; DFS :1156-1183)
 //   qnodes_to_compressed_codes_opt        (DCAT.h:1730-1845)
 // with the K x K centroid tables of dmain:101-118 and the table distance of CT.h:827-835.
-// This stage is pointer chasing with bit-sensitive float compares (the child order depends
-// on float maxima), so it stays on the host and keeps the reference's expression shapes
-// (SURVEY App. E); the data-parallel stage (edge search) is edges.cu.
+// This file is the sequential host form (dpq_tree_from_edges: no GPU needed; keeps the
+// reference's expression shapes).  dpq_tree_build runs the edge search
+// (edges.cu) and the data-parallel form of this stage (layout.cu) on the device; the GPU
+// tests compare the two bit for bit.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
 #include <vector>
 
 #include "../../include/dpq.h"
+#include "tree_internal.h"
 
 namespace dpq {
 int api_fail(int code, const std::string& msg);
-}
-
-struct dpq_tree {
-    int M = 0, K = 0;
-    int64_t n = 0;
-    uint32_t root = 0;
-    int64_t n_diffs = 0;
-    std::vector<uint32_t> edges;  // [n-1][2]
-    std::vector<uint32_t> vec_id, parent_pos, child_num;
-    std::vector<uint8_t> depth;
-    std::vector<float> max_dist, max_dist2p;
-    std::vector<uint8_t> payload;
-    std::vector<uint8_t> codes_by_pos;  // [n][M]
-};
-
-namespace {
 
 // dmain:107-116: float accumulator, each term the double square of the float difference
 void centroid_tables(const float* cw, int M, int K, int Ds, std::vector<float>& T) {
@@ -52,6 +40,9 @@ void centroid_tables(const float* cw, int M, int K, int Ds, std::vector<float>& 
             }
         }
 }
+}  // namespace dpq
+
+namespace {
 
 struct Layout {
     const uint8_t* codes;
@@ -92,7 +83,7 @@ std::string layout_tree(const uint8_t* codes, int64_t n, int M, int K, const flo
 
     // farthest descendant within 16 levels, per node and per (node, child branch) (DCAT.h:1396-1417)
     std::vector<float> T;
-    centroid_tables(cw, M, K, Ds, T);
+    dpq::centroid_tables(cw, M, K, Ds, T);
     Layout L{codes, M, K, n, T};
     std::vector<float> far((size_t)n, 0.0f), far_via((size_t)n, 0.0f);
     for (int64_t v = 0; v < n; ++v) {
@@ -274,13 +265,26 @@ int dpq_tree_build(const uint8_t* codes, int64_t n_codes, int M, int K, const fl
     t->K = K;
     t->n = n_codes;
     t->edges.assign((size_t)std::max<int64_t>(2 * (n_codes - 1), 2), 0);
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = dpq_find_edges(codes, n_codes, M, K, max_height_folds, method, t->edges.data(), &t->root);
+    const auto t1 = std::chrono::steady_clock::now();
+    t->edge_us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
     if (rc) {
         delete t;
         return rc;
     }
     t->edges.resize((size_t)(2 * (n_codes - 1)));
-    return finish_tree(codes, n_codes, M, K, codewords, Ds, t, out);
+    // layout + stream on the device (layout.cu); DPQ_HOST_LAYOUT=1 keeps the sequential host walk
+    const char* host_layout = getenv("DPQ_HOST_LAYOUT");
+    if (host_layout && host_layout[0] == '1') return finish_tree(codes, n_codes, M, K, codewords, Ds, t, out);
+    rc = dpq::layout_tree_device(codes, n_codes, M, K, codewords, Ds, t);
+    t->layout_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t1).count();
+    if (rc) {
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return DPQ_OK;
 }
 
 int64_t dpq_tree_size(dpq_tree* t, const char* what) {
@@ -296,6 +300,8 @@ int64_t dpq_tree_size(dpq_tree* t, const char* what) {
     if (w == "root_id") return t->root;
     if (w == "n_diffs") return t->n_diffs;
     if (w == "n_codes") return t->n;
+    if (w == "edge_us") return t->edge_us;
+    if (w == "layout_us") return t->layout_us;
     return -1;
 }
 

@@ -46,6 +46,16 @@ int dpq_set_device(int device);   /* device used by handles created afterwards *
 int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
                    const uint32_t* pos2id, int rank, int n_ranks, dpq_index** out);
 
+/* One tree of a FOREST (the 1B-code layout): the code set is cut
+ * into parts by vector id, every part gets its own DeltaTree (dpq_tree_build on the GPU that
+ * will scan it -- the reference builds one tree, but a single global sort of 10^9 codes does
+ * not shard), and the parts' local top-k lists merge with dpq_merge_topk_device exactly as
+ * subtree shards do.  The whole tree is kept; first_pos is added to every position the index
+ * reports, so positions are unique across the forest (part p of equal parts: p * n_codes);
+ * pos2id is this tree's own [n_codes] table (callers add the part's first vector id). */
+int dpq_index_open_part(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
+                        const uint32_t* pos2id, int64_t first_pos, dpq_index** out);
+
 /* Same, reading "<dataset>/M{M}K{K}_Approx_compressed_codes_opt_N{N}" style files
  * (header int64 n_codes, int64 n_bytes; DCAT.h:2822-2824).  qnode_path (the 60-byte/node
  * "..._Approx_TreeNodesDFS_N{N}" file, DCAT.h:1484) may be NULL. */
@@ -142,7 +152,8 @@ int dpq_adc_tables(const float* codewords, int M, int K, int Ds, const float* qu
                    float* lut);
 
 /* PQTree::EncodePlain (pq_tree.cpp:192-253) over n vectors x[n][D], D <= M*Ds (zero
- * padded): codes[n][M], bit-exact (sequential FP32, no FMA, strict <). */
+ * padded): codes[n][M], bit-exact (sequential FP32, no FMA, strict <).  x and codes may be
+ * host or device pointers (unified addressing); codewords is a host pointer. */
 int dpq_encode(const float* codewords, int M, int K, int Ds, const float* x, int64_t n, int D,
                uint8_t* codes);
 
@@ -152,9 +163,10 @@ int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_
                    int method, uint32_t* edges, uint32_t* root_id);
 
 /* create_approx_tree (DCAT.h:970-1065), the whole `deltapq -task approx_tree` computation:
- * edge search on the GPU (dpq_find_edges), then on the host the DFS layout
+ * edge search on the GPU (dpq_find_edges), then the DFS layout
  * edges_to_tree_index_approx_dfs_layout (DCAT.h:1334-1487) and the stream writer
- * qnodes_to_compressed_codes_opt (DCAT.h:1730-1845).  codewords [M][K][Ds] feed the K x K
+ * qnodes_to_compressed_codes_opt (DCAT.h:1730-1845), also on the GPU (layout.cu; the
+ * sequential host form of the same stage is dpq_tree_from_edges).  codewords [M][K][Ds] feed the K x K
  * centroid tables (dmain:101-118) that order the children.  dpq_tree_from_edges is the host
  * half alone (no GPU needed).  Arrays are fetched by name with dpq_tree_size / dpq_tree_copy:
  *   "edges" uint32[n-1][2] (the ..._Approx_Edges file body), "root_id",
@@ -162,7 +174,8 @@ int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_
  *   "max_dist" "max_dist2p" (float), "codes_by_pos" uint8[n][M];
  *   "qnodes": the (n+1) x 60-byte ..._Approx_TreeNodesDFS file body (M == 8 only);
  *   "payload": the ..._Approx_compressed_codes_opt stream without its 16-byte header
- *   (M > 8: extension format, ceil(M/8) bitmap bytes); scalars "n_diffs", "n_codes". */
+ *   (M > 8: extension format, ceil(M/8) bitmap bytes); scalars "n_diffs", "n_codes",
+ *   "edge_us" / "layout_us" (wall time of the two stages of dpq_tree_build). */
 typedef struct dpq_tree dpq_tree;
 int dpq_tree_build(const uint8_t* codes, int64_t n_codes, int M, int K, const float* codewords, int Ds,
                    int max_height_folds, int method, dpq_tree** out);

@@ -268,6 +268,48 @@ def test_sharded_search_merges_to_whole(golden4000):
     whole.close()
 
 
+def test_forest_parts_merge_to_plain_adc():
+    """Config C5 layout on one GPU: the code set cut into 3 parts by vector id, one DeltaTree per
+    part (dpq_tree_build), opened with dpq_index_open_part; the merged top-k must be the top-k
+    of plain ADC over ALL codes (oracle tables: float entries, double sum), ids global."""
+    base = dg.sift_like(9000, 128, seed=21)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(3000, 128, seed=22), 8, 256, iters=3))
+    queries = dg.sift_like(40, 128, seed=23)
+    codes = dpq.encode(cw, base)
+    k, Q = 10, len(queries)
+    cuts = [0, 2500, 6001, 9000]
+    dq = dpq.DeviceBuffer(queries.nbytes).upload(queries)
+    dk = dpq.DeviceBuffer(3 * Q * k * 8)
+    do = dpq.DeviceBuffer(Q * k * 8)
+    parts, id_of_pos = [], np.zeros(9000, np.int64)
+    for p in range(3):
+        a, b = cuts[p], cuts[p + 1]
+        t = dpq.tree_build(codes[a:b], cw, want=("payload", "vec_id"))
+        ix = dpq.DeltaTreeIndex(t["payload"], b - a, 8, 256, pos2id=t["vec_id"], first_pos=a)
+        ix.set_codebook(cw)
+        ix.search_device(dq.ptr, Q, k, dk.ptr.value + p * Q * k * 8)
+        ix.sync()
+        id_of_pos[a:b] = t["vec_id"].astype(np.int64) + a
+        # the host-buffer path reports the same shifted positions and the part-local ids
+        hpos, hid, hdist = ix.search(queries, k)
+        lp, ld = dpq.unpack_keys(dk.download(np.uint64, (3, Q, k))[p])
+        assert np.array_equal(hpos, lp) and np.array_equal(hdist, ld)
+        assert hpos.min() >= a and hpos.max() < b
+        assert np.array_equal(hid, t["vec_id"][hpos - a])
+        parts.append(ix)
+    parts[0].merge_device(dk.ptr, 3, Q, k, do.ptr)
+    parts[0].sync()
+    pos, dist = dpq.unpack_keys(do.download(np.uint64, (Q, k)))
+    ids = id_of_pos[pos]
+    for i, q in enumerate(queries):
+        tab = po.lut(cw, q).astype(np.float64)                      # [M][K]
+        d_all = tab[np.arange(8)[None, :], codes].sum(axis=1).astype(np.float32)
+        order = np.lexsort((np.arange(9000), d_all))[:k]
+        assert_topk_equal(ids[i], dist[i], order, d_all[order], node_dist=d_all)
+    for ix in parts:
+        ix.close()
+
+
 def test_m16_extension_search(golden_m16):
     """Configs 3/4 (M=16): no reference tree oracle exists; parity is
     against the generalised restatement, top-100."""

@@ -101,3 +101,35 @@ def test_gpu_find_edges_sift_20k_and_diffs():
     assert np.array_equal(t["payload"], po.stream(codes, lay))
     bm, nd = dpq.edge_diffs(codes, t["edges"])
     assert nd == t["n_diffs"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(5000, 8, 256, 6), (1200, 16, 256, 4), (900, 12, 100, 3), (3000, 8, 256, 200),
+                                   (1, 8, 256, 2), (2, 8, 256, 2), (3, 16, 256, 2)])
+def test_gpu_layout_and_stream_equal_host_layout(shape):
+    """dpq_tree_build lays the tree out and writes the stream on the device (layout.cu);
+    dpq_tree_from_edges is the sequential host walk of the same reference stage
+    (DCAT.h:1334-1487, 1765-1842).  Every array must be identical."""
+    n, M, K, distinct = shape
+    rng = np.random.default_rng(n * 7 + M)
+    codes = rng.integers(0, min(K, distinct), size=(n, M)).astype(np.uint8)
+    codes[rng.random(n) < 0.2] = codes[0]
+    cw = rng.normal(size=(M, K, 4)).astype(np.float32)
+    g = dpq.tree_build(codes, cw)
+    h = dpq.tree_from_edges(codes, cw, g["edges"], g["root_id"])
+    for k in ("vec_id", "parent_pos", "child_num", "depth", "max_dist", "max_dist2p", "codes_by_pos", "payload"):
+        assert np.array_equal(g[k], h[k]), k
+    assert g["n_diffs"] == h["n_diffs"]
+    if M == 8:
+        assert np.array_equal(g["qnodes"], h["qnodes"])
+
+
+@pytest.mark.gpu
+def test_gpu_layout_sift_200k_equals_host_layout():
+    base = dg.sift_like(200000, 128, seed=11)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(4000, 128, seed=6), 8, 256, iters=3))
+    codes = dpq.encode(cw, base)
+    g = dpq.tree_build(codes, cw)
+    h = dpq.tree_from_edges(codes, cw, g["edges"], g["root_id"])
+    for k in ("vec_id", "parent_pos", "child_num", "depth", "max_dist", "max_dist2p", "codes_by_pos", "payload"):
+        assert np.array_equal(g[k], h[k]), k
