@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "libdpq.so")
 # every symbol include/dpq.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "dpq_version", "dpq_last_error", "dpq_device_count", "dpq_set_device",
-    "dpq_index_open", "dpq_index_open_part", "dpq_index_open_file", "dpq_index_set_codebook", "dpq_index_set_option",
+    "dpq_index_open", "dpq_index_open_part", "dpq_index_open_file", "dpq_index_open_part_file",
+    "dpq_multi_open_parts", "dpq_index_set_codebook", "dpq_index_set_option",
     "dpq_index_set_stream",
     "dpq_index_search", "dpq_index_search_device", "dpq_index_sync", "dpq_merge_topk_device",
     "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",

@@ -320,8 +320,8 @@ int dpq_index_open_part(const uint8_t* payload, int64_t n_bytes, int64_t n_codes
     return open_common(payload, n_bytes, n_codes, M, K, pos2id, 0, 1, first_pos, out);
 }
 
-int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,
-                        int n_ranks, dpq_index** out) {
+static int open_file_common(const char* tree_path, const char* qnode_path, int M, int K, int rank,
+                            int n_ranks, int64_t first_pos, dpq_index** out) {
     if (!tree_path || !out) return fail(DPQ_ERR_ARG, "dpq_index_open_file: null argument");
     FILE* f = fopen(tree_path, "rb");
     if (!f) return fail(DPQ_ERR_IO, std::string("cannot open ") + tree_path);
@@ -356,8 +356,18 @@ int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, in
         }
         fclose(q);
     }
-    return dpq_index_open(payload.data(), hdr[1], hdr[0], M, K, qnode_path ? pos2id.data() : nullptr,
-                          rank, n_ranks, out);
+    return open_common(payload.data(), hdr[1], hdr[0], M, K, qnode_path ? pos2id.data() : nullptr, rank, n_ranks,
+                       first_pos, out);
+}
+
+int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,
+                        int n_ranks, dpq_index** out) {
+    return open_file_common(tree_path, qnode_path, M, K, rank, n_ranks, 0, out);
+}
+
+int dpq_index_open_part_file(const char* tree_path, const char* qnode_path, int M, int K, int64_t first_pos,
+                             dpq_index** out) {
+    return open_file_common(tree_path, qnode_path, M, K, 0, 1, first_pos, out);
 }
 
 int dpq_index_set_codebook(dpq_index* ix, const float* cw, int Ds) {

@@ -62,6 +62,11 @@ int dpq_index_open_part(const uint8_t* payload, int64_t n_bytes, int64_t n_codes
 int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,
                         int n_ranks, dpq_index** out);
 
+/* dpq_index_open_part reading the part's files (tree file with its 16-byte header; 60-byte
+ * QNode file or NULL). */
+int dpq_index_open_part_file(const char* tree_path, const char* qnode_path, int M, int K, int64_t first_pos,
+                             dpq_index** out);
+
 /* Codebook [M][K][Ds] as PQ::ReadCodewords returns it (pq.cpp:288-312). */
 int dpq_index_set_codebook(dpq_index* idx, const float* codewords, int Ds);
 
@@ -109,10 +114,17 @@ int dpq_merge_topk_device(dpq_index* idx, const uint64_t* d_keys, int n_lists, i
 typedef struct dpq_multi dpq_multi;
 int dpq_multi_open_file(const char* tree_path, const char* qnode_path, int M, int K, int n_gpus,
                         dpq_multi** out);
+/* Forest variant (`deltapq -task query -parts P`, the 1B-code layout): n_parts independently
+ * built trees (files of `deltapq -task approx_tree -parts P`), part p reporting positions
+ * first_pos[p] + its own DFS position and ids first_pos[p] + its own vec_id (parts are vector-id
+ * ranges); the parts are dealt round-robin to the GPUs, each GPU merges its parts' lists, then
+ * the same single all-gather + merge.  qnode_paths (or single entries) may be NULL. */
+int dpq_multi_open_parts(const char* const* tree_paths, const char* const* qnode_paths, const int64_t* first_pos,
+                         int n_parts, int M, int K, int n_gpus, dpq_multi** out);
 int dpq_multi_set_codebook(dpq_multi* m, const float* codewords, int Ds);
 int dpq_multi_search(dpq_multi* m, const float* queries, int Q, int topk, uint32_t* out_pos,
                      uint32_t* out_id, float* out_dist);
-int64_t dpq_multi_stat(dpq_multi* m, int rank, const char* name); /* dpq_index_stat of one shard */
+int64_t dpq_multi_stat(dpq_multi* m, int rank, const char* name); /* dpq_index_stat of one shard / part */
 void dpq_multi_close(dpq_multi* m);
 
 /* Raw device allocation helpers for hosts without a CUDA binding (ctypes, cgo, JNI). */

@@ -146,3 +146,47 @@ def test_cli_query_multi_gpu_matches_single_gpu(tmp_path):
         assert r.returncode == 0, r.stderr
         outs.append(open(out).read())
     assert outs[0] == outs[1]
+
+
+def _parse_results(path):
+    lines = open(path).read().strip().split("\n")
+    nq, k = (int(v) for v in lines[0].split(","))
+    ids = np.zeros((nq, k), np.int64)
+    dist = np.zeros((nq, k), np.float64)
+    for i, line in enumerate(lines[1:]):
+        vals = line.rstrip(",").split(",")
+        ids[i] = [int(v) for v in vals[0::2]]
+        dist[i] = [float(v) for v in vals[1::2]]
+    return ids, dist
+
+
+@pytest.mark.gpu
+def test_cli_forest_parts_match_single_tree(tmp_path):
+    """`deltapq -task approx_tree -parts 3` + `-task query -parts 3` (the 1B-code layout: one tree
+    per vector-id range, dpq_multi_open_parts): same distances as the single-tree query and the
+    same ids wherever the distance is not tied; with 2 GPUs also `-gpus 2`."""
+    import deltapq_b200 as dpq
+    n, nq, M, K, k = 30001, 200, 8, 256, 10
+    d = str(tmp_path)
+    dg.make_dataset(d, n, nq, M=M, K=K, d=128, seed=61)
+    common = ["-dataset", d, "-m", str(M), "-k", str(K), "-N", str(n), "-ext", "fvecs"]
+    for cmd in ([BIN + "/pqtree", "-task", "encode"],
+                [BIN + "/deltapq", "-task", "approx_tree", "-h", "1", "-diff", "8"],
+                [BIN + "/deltapq", "-task", "approx_tree", "-h", "1", "-diff", "8", "-parts", "3"]):
+        r = run(cmd + common)
+        assert r.returncode == 0, r.stderr
+    assert os.path.exists(f"{d}/M8K256_Approx_compressed_codes_opt_N{n}.part2of3")
+    q = [BIN + "/deltapq", "-task", "query", "-query_size", str(nq), "-topk", str(k)]
+    r = run(q + ["-results", f"{d}/whole.txt"] + common)
+    assert r.returncode == 0, r.stderr
+    wid, wdist = _parse_results(f"{d}/whole.txt")
+    for g in (1, 2):
+        if g > dpq.device_count():
+            continue
+        r = run(q + ["-parts", "3", "-gpus", str(g), "-results", f"{d}/parts{g}.txt"] + common)
+        assert r.returncode == 0, r.stderr
+        pid, pdist = _parse_results(f"{d}/parts{g}.txt")
+        assert np.array_equal(pdist, wdist)
+        for i in range(nq):
+            untied = np.array([np.sum(wdist[i] == v) == 1 and v < wdist[i, -1] for v in wdist[i]])
+            assert np.array_equal(pid[i][untied], wid[i][untied]), i

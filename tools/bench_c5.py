@@ -335,4 +335,14 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    _holder, _print = [], print
+    with B.StdoutToStderr():  # library banners (NCCL) go to stderr; stdout carries the JSON line only
+        import builtins
+        builtins.print = lambda *a, **k: _holder.append(" ".join(str(x) for x in a))
+        try:
+            _rc = main()
+        finally:
+            builtins.print = _print
+    for _l in _holder:
+        _print(_l, flush=True)
+    sys.exit(_rc)
