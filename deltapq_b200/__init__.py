@@ -22,7 +22,7 @@ SYMBOLS = [
     "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",
     "dpq_free_host", "dpq_index_stat", "dpq_index_close", "dpq_adc_tables", "dpq_encode",
     "dpq_find_edges", "dpq_edge_diffs", "dpq_groundtruth_begin", "dpq_groundtruth_chunk",
-    "dpq_groundtruth_finish", "dpq_program_compile", "dpq_program_size", "dpq_program_copy",
+    "dpq_groundtruth_finish", "dpq_groundtruth_stat", "dpq_program_compile", "dpq_program_size", "dpq_program_copy",
     "dpq_program_free", "dpq_tree_build", "dpq_tree_from_edges", "dpq_tree_size", "dpq_tree_copy",
     "dpq_tree_free", "dpq_multi_open_file", "dpq_multi_set_codebook", "dpq_multi_search", "dpq_multi_stat",
     "dpq_multi_close",
@@ -79,6 +79,8 @@ def lib():
     L.dpq_groundtruth_begin.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
     L.dpq_groundtruth_chunk.argtypes = [vp, vp, i64, i64]
     L.dpq_groundtruth_finish.argtypes = [vp, vp, vp]
+    L.dpq_groundtruth_stat.restype = i64
+    L.dpq_groundtruth_stat.argtypes = [vp, C.c_char_p]
     L.dpq_program_compile.argtypes = [vp, i64, i64, i32, i32, i32, i32, i32, C.POINTER(vp)]
     L.dpq_program_size.restype = i64
     L.dpq_program_size.argtypes = [vp, C.c_char_p]
@@ -339,7 +341,8 @@ def tree_from_edges(codes, cw, edges, root_id):
     return _tree_out(t, M)
 
 
-def groundtruth(base, queries, topk, chunk=100000):
+def groundtruth(base, queries, topk, chunk=100000, stats=None):
+    """stats: optional dict that receives dpq_groundtruth_stat's counters (tensor-core path)."""
     base = np.ascontiguousarray(base, np.float32)
     q = np.ascontiguousarray(queries, np.float32)
     st = C.c_void_p()
@@ -347,6 +350,9 @@ def groundtruth(base, queries, topk, chunk=100000):
     for s in range(0, base.shape[0], chunk):
         blk = base[s:s + chunk]
         _check(lib().dpq_groundtruth_chunk(st, _ptr(blk), blk.shape[0], s))
+    if stats is not None:
+        for name in ("tc", "tc_vectors", "tc_flagged"):
+            stats[name] = int(lib().dpq_groundtruth_stat(st, name.encode()))
     ids = np.empty((q.shape[0], topk), np.uint32)
     dist = np.empty((q.shape[0], topk), np.float32)
     _check(lib().dpq_groundtruth_finish(st, _ptr(ids), _ptr(dist)))

@@ -6,11 +6,14 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/dpq.h"
+#include "gt_tc.cuh"
 
 namespace dpq {
 int api_fail(int code, const std::string& msg);  // api_common.cu
@@ -155,14 +158,17 @@ __global__ void edge_diff_kernel(const uint8_t* __restrict__ codes, int M, const
 // double running sum over d ascending; narrowed to float when it enters the heap.
 // Tile: 128 base vectors x 8 queries per block, base tile staged through shared memory.
 constexpr int GT_TB = 128, GT_TQ = 8;
+// qlist (optional): the launch covers the Q queries qlist[0..Q) of the query array; dist rows follow
+// the list order.
 __global__ void __launch_bounds__(GT_TB) gt_dist_kernel(const float* __restrict__ base, int64_t n,
                                                         const float* __restrict__ queries, int Q, int D,
-                                                        float* __restrict__ dist /*[Q][n]*/) {
+                                                        float* __restrict__ dist /*[Q][n]*/,
+                                                        const uint32_t* __restrict__ qlist) {
     extern __shared__ float s_q[];  // [GT_TQ][D]
     const int q0 = blockIdx.y * GT_TQ;
     for (int i = threadIdx.x; i < GT_TQ * D; i += blockDim.x) {
         int qq = q0 + i / D;
-        s_q[i] = qq < Q ? queries[(size_t)qq * D + i % D] : 0.0f;
+        s_q[i] = qq < Q ? queries[(size_t)(qlist ? qlist[qq] : (uint32_t)qq) * D + i % D] : 0.0f;
     }
     __syncthreads();
     const int64_t v = (int64_t)blockIdx.x * GT_TB + threadIdx.x;
@@ -190,12 +196,13 @@ __global__ void __launch_bounds__(GT_TB) gt_dist_kernel(const float* __restrict_
 constexpr int GT_SEL_T = 256, GT_BUF = 2048;
 __global__ void __launch_bounds__(GT_SEL_T) gt_select_kernel(const float* __restrict__ dist, int64_t n,
                                                              int64_t id0, int topk,
-                                                             unsigned long long* __restrict__ state /*[Q][topk]*/) {
+                                                             unsigned long long* __restrict__ state /*[Q][topk]*/,
+                                                             const uint32_t* __restrict__ qlist) {
     __shared__ unsigned long long s_buf[GT_BUF];
     __shared__ int s_n;
     __shared__ unsigned long long s_bound;
-    const int q = blockIdx.x;
-    unsigned long long* st = state + (size_t)q * topk;
+    const int q = blockIdx.x;  // row of dist; the state row is the listed query
+    unsigned long long* st = state + (size_t)(qlist ? qlist[q] : (uint32_t)q) * topk;
     // buffer starts with the current state
     for (int i = threadIdx.x; i < topk; i += blockDim.x) s_buf[i] = st[i];
     if (threadIdx.x == 0) {
@@ -268,7 +275,79 @@ struct dpq_gt {
     float* d_base = nullptr;
     float* d_dist = nullptr;
     size_t base_cap = 0, dist_cap = 0;
+    // tensor-core filter path (gt_tc.cu): topk <= 64 unless DPQ_GT_TC=0
+    bool tc = false, seeded = false;
+    int n_sms = 148;
+    float *d_qn = nullptr, *d_xn = nullptr;  // [3][Q] / [3][x_cap]: ||v||^2 low, high, ||v|| high
+    size_t x_cap = 0;
+    float *d_thr = nullptr, *d_qerr = nullptr;
+    uint32_t *d_cand = nullptr, *d_cnt = nullptr, *d_flag = nullptr, *d_ctl = nullptr;  // ctl: [0] flagged, [1] error
+    int64_t tc_vectors = 0, tc_candidates = 0, tc_flagged = 0;  // statistics
 };
+
+namespace {
+constexpr int64_t GT_TC_STEP = 131072;  // base vectors per filter launch: the cap tightens between launches
+constexpr int GT_TC_SEED = 4096;        // vectors scored densely first, so that every query has a finite cap
+constexpr int GT_TC_CAND = 4096;        // candidate slots per query per launch
+
+// dense exact path over base[0..n) (device) for the queries qlist[0..nq) (nullptr: all)
+int gt_dense(dpq_gt* st, const float* d_base, int64_t n, int64_t id0, const uint32_t* qlist, int nq) {
+    const int64_t step = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)256 << 20) / ((int64_t)nq * 4)));
+    const size_t db = (size_t)step * nq * 4;
+    if (db > st->dist_cap) {
+        if (st->d_dist) cudaFree(st->d_dist);
+        st->d_dist = nullptr;
+        st->dist_cap = 0;
+        CU(cudaMalloc(&st->d_dist, db));
+        st->dist_cap = db;
+    }
+    const size_t sm = (size_t)GT_TQ * st->D * 4;
+    cudaFuncSetAttribute(gt_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    for (int64_t s = 0; s < n; s += step) {
+        const int64_t c = std::min(step, n - s);
+        dim3 grid((unsigned)((c + GT_TB - 1) / GT_TB), (unsigned)((nq + GT_TQ - 1) / GT_TQ));
+        gt_dist_kernel<<<grid, GT_TB, sm>>>(d_base + (size_t)s * st->D, c, st->d_q, nq, st->D, st->d_dist, qlist);
+        gt_select_kernel<<<nq, GT_SEL_T>>>(st->d_dist, c, id0 + s, st->topk, st->d_state, qlist);
+        CU(cudaGetLastError());
+    }
+    return DPQ_OK;
+}
+
+// tensor-core filter + exact re-score over base[0..n) (device, norms already in d_xn)
+int gt_tc_range(dpq_gt* st, const float* d_base, int64_t n, int64_t id0, int64_t xoff) {
+    const int Q = st->Q;
+    // err <= c_err ||x|| ||q||: 2 x (dropped split terms 4 x 2^-18 + fp32 accumulation of 3 D products)
+    const int dpad = (st->D + 63) / 64 * 64;
+    const float c_err = 2.02f * (4.0f / 262144.0f + (3.0f * dpad + 8.0f) / 8388608.0f);
+    CU(dpq::launch_gt_thr(st->d_state, st->topk, Q, st->d_qn, st->d_qn + Q, st->d_qn + 2 * (size_t)Q, c_err, st->d_thr,
+                          st->d_qerr, 0));
+    CU(cudaMemsetAsync(st->d_cnt, 0, (size_t)Q * 4));
+    CU(cudaMemsetAsync(st->d_ctl, 0, 4));
+    dpq::GtTcArgs a;
+    a.base = d_base;
+    a.queries = st->d_q;
+    a.n = n;
+    a.Q = Q;
+    a.D = st->D;
+    a.x_nlo = st->d_xn + xoff;
+    a.x_len = st->d_xn + 2 * st->x_cap + xoff;
+    a.thr = st->d_thr;
+    a.qerr = st->d_qerr;
+    a.cand = st->d_cand;
+    a.cand_cnt = st->d_cnt;
+    a.cand_cap = GT_TC_CAND;
+    a.error = st->d_ctl + 1;
+    CU(dpq::launch_gt_tc_filter(a, st->n_sms, 0));
+    CU(dpq::launch_gt_rescore(a, id0, st->topk, st->d_state, st->d_flag, st->d_ctl, 0));
+    uint32_t ctl[2] = {0, 0};
+    CU(cudaMemcpy(ctl, st->d_ctl, 8, cudaMemcpyDeviceToHost));
+    if (ctl[1]) return dpq::api_fail(DPQ_ERR_CUDA, "ground truth: a tensor-core completion barrier never fired");
+    st->tc_vectors += n;
+    st->tc_flagged += ctl[0];
+    if (ctl[0]) return gt_dense(st, d_base, n, id0, st->d_flag, (int)ctl[0]);  // overflowed candidate lists
+    return DPQ_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -340,6 +419,21 @@ int dpq_groundtruth_begin(const float* queries, int Q, int D, int topk, dpq_gt**
     // (FLT_MAX, 0xFFFFFFFF) sentinels: results[i][j].second = FLT_MAX (pmain:609-611)
     std::vector<unsigned long long> init((size_t)Q * topk, ((unsigned long long)0x7F7FFFFFu << 32) | 0xFFFFFFFFull);
     CU(cudaMemcpy(st->d_state, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    const char* env = getenv("DPQ_GT_TC");
+    st->tc = topk <= 64 && !(env && env[0] == '0');
+    if (st->tc) {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, dpq::api_device()));
+        st->n_sms = prop.multiProcessorCount;
+        CU(cudaMalloc(&st->d_qn, (size_t)Q * 3 * 4));
+        CU(cudaMalloc(&st->d_thr, (size_t)Q * 4));
+        CU(cudaMalloc(&st->d_qerr, (size_t)Q * 4));
+        CU(cudaMalloc(&st->d_cand, (size_t)Q * GT_TC_CAND * 4));
+        CU(cudaMalloc(&st->d_cnt, (size_t)Q * 4));
+        CU(cudaMalloc(&st->d_flag, (size_t)Q * 4));
+        CU(cudaMalloc(&st->d_ctl, 16));
+        CU(dpq::launch_gt_prep(st->d_q, Q, D, st->d_qn, st->d_qn + Q, st->d_qn + 2 * (size_t)Q, 0));
+    }
     *out = st;
     return DPQ_OK;
 }
@@ -347,30 +441,53 @@ int dpq_groundtruth_begin(const float* queries, int Q, int D, int topk, dpq_gt**
 int dpq_groundtruth_chunk(dpq_gt* st, const float* base, int64_t n, int64_t id0) {
     if (!st || !base || n < 0) return dpq::api_fail(DPQ_ERR_ARG, "dpq_groundtruth_chunk: bad argument");
     CU(cudaSetDevice(dpq::api_device()));
-    const int64_t step = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)256 << 20) / ((int64_t)st->Q * 4)));
+    // upload granularity: the dense path is bounded by its [Q][step] distance buffer, the tensor-core
+    // path by the candidate lists (the cap tightens between launches)
+    const int64_t step = st->tc ? GT_TC_STEP
+                                : std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)256 << 20) / ((int64_t)st->Q * 4)));
     for (int64_t s = 0; s < n; s += step) {
-        int64_t c = std::min(step, n - s);
-        size_t bb = (size_t)c * st->D * 4, db = (size_t)c * st->Q * 4;
+        const int64_t c = std::min(step, n - s);
+        const size_t bb = (size_t)c * st->D * 4;
         if (bb > st->base_cap) {
             if (st->d_base) cudaFree(st->d_base);
+            st->d_base = nullptr;
+            st->base_cap = 0;
             CU(cudaMalloc(&st->d_base, bb));
             st->base_cap = bb;
         }
-        if (db > st->dist_cap) {
-            if (st->d_dist) cudaFree(st->d_dist);
-            CU(cudaMalloc(&st->d_dist, db));
-            st->dist_cap = db;
+        CU(cudaMemcpy(st->d_base, base + (size_t)s * st->D, bb, cudaMemcpyDefault));
+        int rc;
+        if (!st->tc) {
+            if ((rc = gt_dense(st, st->d_base, c, id0 + s, nullptr, st->Q))) return rc;
+            continue;
         }
-        CU(cudaMemcpy(st->d_base, base + (size_t)s * st->D, bb, cudaMemcpyHostToDevice));
-        dim3 grid((unsigned)((c + GT_TB - 1) / GT_TB), (unsigned)((st->Q + GT_TQ - 1) / GT_TQ));
-        size_t sm = (size_t)GT_TQ * st->D * 4;
-        cudaFuncSetAttribute(gt_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        gt_dist_kernel<<<grid, GT_TB, sm>>>(st->d_base, c, st->d_q, st->Q, st->D, st->d_dist);
-        gt_select_kernel<<<st->Q, GT_SEL_T>>>(st->d_dist, c, id0 + s, st->topk, st->d_state);
-        CU(cudaGetLastError());
+        if ((size_t)c > st->x_cap) {
+            if (st->d_xn) cudaFree(st->d_xn);
+            st->d_xn = nullptr;
+            st->x_cap = 0;
+            CU(cudaMalloc(&st->d_xn, (size_t)c * 3 * 4));
+            st->x_cap = (size_t)c;
+        }
+        CU(dpq::launch_gt_prep(st->d_base, c, st->D, st->d_xn, st->d_xn + st->x_cap, st->d_xn + 2 * st->x_cap, 0));
+        int64_t s0 = 0;
+        if (!st->seeded) {  // the first vectors densely: afterwards every query has k exact distances
+            s0 = std::min<int64_t>(c, GT_TC_SEED);
+            if ((rc = gt_dense(st, st->d_base, s0, id0 + s, nullptr, st->Q))) return rc;
+            st->seeded = true;
+        }
+        if (c > s0 && (rc = gt_tc_range(st, st->d_base + (size_t)s0 * st->D, c - s0, id0 + s + s0, s0))) return rc;
     }
     CU(cudaDeviceSynchronize());
     return DPQ_OK;
+}
+
+int64_t dpq_groundtruth_stat(dpq_gt* st, const char* name) {
+    if (!st || !name) return -1;
+    const std::string w(name);
+    if (w == "tc") return st->tc ? 1 : 0;
+    if (w == "tc_vectors") return st->tc_vectors;
+    if (w == "tc_flagged") return st->tc_flagged;
+    return -1;
 }
 
 int dpq_groundtruth_finish(dpq_gt* st, uint32_t* out_id, float* out_dist) {
@@ -381,6 +498,12 @@ int dpq_groundtruth_finish(dpq_gt* st, uint32_t* out_id, float* out_dist) {
     cudaFree(st->d_state);
     if (st->d_base) cudaFree(st->d_base);
     if (st->d_dist) cudaFree(st->d_dist);
+    for (void* p : {(void*)st->d_qn, (void*)st->d_xn, (void*)st->d_thr, (void*)st->d_qerr, (void*)st->d_cand,
+                    (void*)st->d_cnt, (void*)st->d_flag, (void*)st->d_ctl})
+        if (p) cudaFree(p);
+    if (getenv("DPQ_GT_STATS"))
+        fprintf(stderr, "dpq_groundtruth: tensor-core path %s, %lld vectors filtered, %lld query re-runs on the dense path\n",
+                st->tc ? "on" : "off", (long long)st->tc_vectors, (long long)st->tc_flagged);
     delete st;
     if (e != cudaSuccess) return dpq::api_fail(DPQ_ERR_CUDA, cudaGetErrorString(e));
     for (size_t i = 0; i < keys.size(); ++i) {

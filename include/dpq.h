@@ -204,10 +204,18 @@ int dpq_edge_diffs(const uint8_t* codes, int64_t n_codes, int M, const uint32_t*
                    int64_t n_edges, uint32_t* bitmaps, int64_t* n_diffs);
 
 /* Exact brute-force ground truth (pmain:138-166, 569-669): base[n][D] (ids id0..),
- * queries[Q][D]; accumulates into a state created by dpq_groundtruth_begin. */
+ * queries[Q][D]; accumulates into a state created by dpq_groundtruth_begin.  For topk <= 64
+ * the Q x n x D inner products run on the tensor cores (tcgen05, bf16 hi + lo split, fp32
+ * accumulators in TMEM) as a filter with a rigorous error bound, and only the candidates that
+ * can reach a query's top-k are re-scored in the reference's arithmetic (float difference,
+ * float product, double sum): results are identical to the plain exact kernels, which
+ * DPQ_GT_TC=0 in the environment selects for everything.  base may be a host or device pointer.
+ * dpq_groundtruth_stat: "tc" (1 when the filter path is on), "tc_vectors" (base vectors that went
+ * through it), "tc_flagged" (query re-runs on the plain path after a candidate list overflowed). */
 typedef struct dpq_gt dpq_gt;
 int dpq_groundtruth_begin(const float* queries, int Q, int D, int topk, dpq_gt** out);
 int dpq_groundtruth_chunk(dpq_gt* st, const float* base, int64_t n, int64_t id0);
+int64_t dpq_groundtruth_stat(dpq_gt* st, const char* name);
 int dpq_groundtruth_finish(dpq_gt* st, uint32_t* out_id, float* out_dist); /* frees st */
 
 #ifdef __cplusplus

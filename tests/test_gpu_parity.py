@@ -413,3 +413,44 @@ def test_medium_tree_end_to_end():
             assert np.array_equal(dist[i], odist)
             assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
     ix.close()
+
+
+@pytest.mark.parametrize("shape", [
+    # n, D, Q, topk, generator
+    (30000, 128, 130, 10, "sift"),      # Q not a multiple of 128, n not a multiple of 256
+    (9000, 960, 40, 5, "gist"),         # non-integer values: the bf16 hi + lo split and its error bound
+    (12345, 100, 300, 64, "sift"),      # D not a multiple of 64
+    (7000, 30, 17, 3, "gauss"),         # D not a multiple of 4, signed values
+    (3000, 128, 9, 10, "sift"),         # fewer vectors than the dense seed
+    (40000, 128, 64, 10, "dupes"),      # heavy exact ties
+])
+def test_groundtruth_tensor_core_filter_equals_plain_kernels(shape, monkeypatch):
+    """dpq_groundtruth_*: the tcgen05 filter + exact re-score path must give exactly what the
+    plain exact kernels (DPQ_GT_TC=0) and the oracle (pmain:138-166 arithmetic) give."""
+    n, D, Q, k, gen = shape
+    rng = np.random.default_rng(n + D)
+    if gen == "sift":
+        base, qs = dg.sift_like(n, D, seed=31), dg.sift_like(Q, D, seed=32)
+    elif gen == "gist":
+        base, qs = dg.gist_like(n, D, seed=33), dg.gist_like(Q, D, seed=34)
+    elif gen == "gauss":
+        base, qs = rng.normal(size=(n, D)).astype(np.float32), rng.normal(size=(Q, D)).astype(np.float32)
+    else:
+        pool = dg.sift_like(500, D, seed=35)
+        base, qs = pool[rng.integers(0, 500, n)], dg.sift_like(Q, D, seed=36)
+    monkeypatch.delenv("DPQ_GT_TC", raising=False)
+    st = {}
+    ids, dist = dpq.groundtruth(base, qs, k, chunk=17000, stats=st)
+    assert st["tc"] == 1
+    if n > 4096:
+        assert st["tc_vectors"] == n - 4096          # everything after the dense seed went through the filter
+        if gen != "dupes":
+            assert st["tc_flagged"] < Q              # ... and the candidate lists held
+    monkeypatch.setenv("DPQ_GT_TC", "0")
+    st0 = {}
+    pid, pdist = dpq.groundtruth(base, qs, k, chunk=17000, stats=st0)
+    assert st0["tc"] == 0
+    assert np.array_equal(dist, pdist) and np.array_equal(ids, pid)
+    oid, odist = po.groundtruth(base[:, :], qs[: min(Q, 24)], k, chunk=17000)
+    assert np.array_equal(dist[: min(Q, 24)], odist)
+    assert_topk_equal(ids[: min(Q, 24)], dist[: min(Q, 24)], oid, odist)
