@@ -277,12 +277,17 @@ struct dpq_gt {
     size_t base_cap = 0, dist_cap = 0;
     // tensor-core filter path (gt_tc.cu): topk <= 64 unless DPQ_GT_TC=0
     bool tc = false, seeded = false;
+    int tc_form = 2;  // 2: pipelined (pre-split operands, TMA, warp-specialised roles); 1: synchronous form
+    unsigned char *d_qsplit = nullptr, *d_xsplit = nullptr;
+    size_t xsplit_cap = 0;
     int n_sms = 148;
     float *d_qn = nullptr, *d_xn = nullptr;  // [3][Q] / [3][x_cap]: ||v||^2 low, high, ||v|| high
     size_t x_cap = 0;
     float *d_thr = nullptr, *d_qerr = nullptr;
     uint32_t *d_cand = nullptr, *d_cnt = nullptr, *d_flag = nullptr, *d_ctl = nullptr;  // ctl: [0] flagged, [1] error
     int64_t tc_vectors = 0, tc_candidates = 0, tc_flagged = 0;  // statistics
+    double tc_filter_ms = 0.0, tc_rescore_ms = 0.0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -337,10 +342,35 @@ int gt_tc_range(dpq_gt* st, const float* d_base, int64_t n, int64_t id0, int64_t
     a.cand_cnt = st->d_cnt;
     a.cand_cap = GT_TC_CAND;
     a.error = st->d_ctl + 1;
-    CU(dpq::launch_gt_tc_filter(a, st->n_sms, 0));
+    a.q_split = nullptr;
+    a.x_split = nullptr;
+    for (auto& e : st->ev)
+        if (!e) CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(st->ev[0], 0));
+    if (st->tc_form == 2) {
+        const size_t need = dpq::gt_split_bytes(n, st->D, false);
+        if (need > st->xsplit_cap) {
+            if (st->d_xsplit) cudaFree(st->d_xsplit);
+            st->d_xsplit = nullptr;
+            st->xsplit_cap = 0;
+            CU(cudaMalloc(&st->d_xsplit, need));
+            st->xsplit_cap = need;
+        }
+        CU(dpq::launch_gt_split(d_base, n, st->D, false, st->d_xsplit, 0));
+        a.q_split = st->d_qsplit;
+        a.x_split = st->d_xsplit;
+        CU(dpq::launch_gt_tc_filter2(a, st->n_sms, 0));
+    } else {
+        CU(dpq::launch_gt_tc_filter(a, st->n_sms, 0));
+    }
+    CU(cudaEventRecord(st->ev[1], 0));
     CU(dpq::launch_gt_rescore(a, id0, st->topk, st->d_state, st->d_flag, st->d_ctl, 0));
+    CU(cudaEventRecord(st->ev[2], 0));
     uint32_t ctl[2] = {0, 0};
     CU(cudaMemcpy(ctl, st->d_ctl, 8, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, st->ev[0], st->ev[1]) == cudaSuccess) st->tc_filter_ms += ms;
+    if (cudaEventElapsedTime(&ms, st->ev[1], st->ev[2]) == cudaSuccess) st->tc_rescore_ms += ms;
     if (ctl[1]) return dpq::api_fail(DPQ_ERR_CUDA, "ground truth: a tensor-core completion barrier never fired");
     st->tc_vectors += n;
     st->tc_flagged += ctl[0];
@@ -433,6 +463,11 @@ int dpq_groundtruth_begin(const float* queries, int Q, int D, int topk, dpq_gt**
         CU(cudaMalloc(&st->d_flag, (size_t)Q * 4));
         CU(cudaMalloc(&st->d_ctl, 16));
         CU(dpq::launch_gt_prep(st->d_q, Q, D, st->d_qn, st->d_qn + Q, st->d_qn + 2 * (size_t)Q, 0));
+        st->tc_form = (env && env[0] == '1') ? 1 : 2;
+        if (st->tc_form == 2) {
+            CU(cudaMalloc(&st->d_qsplit, dpq::gt_split_bytes(Q, D, true)));
+            CU(dpq::launch_gt_split(st->d_q, Q, D, true, st->d_qsplit, 0));
+        }
     }
     *out = st;
     return DPQ_OK;
@@ -484,9 +519,11 @@ int dpq_groundtruth_chunk(dpq_gt* st, const float* base, int64_t n, int64_t id0)
 int64_t dpq_groundtruth_stat(dpq_gt* st, const char* name) {
     if (!st || !name) return -1;
     const std::string w(name);
-    if (w == "tc") return st->tc ? 1 : 0;
+    if (w == "tc") return st->tc ? st->tc_form : 0;
     if (w == "tc_vectors") return st->tc_vectors;
     if (w == "tc_flagged") return st->tc_flagged;
+    if (w == "tc_filter_us") return (int64_t)(st->tc_filter_ms * 1e3);
+    if (w == "tc_rescore_us") return (int64_t)(st->tc_rescore_ms * 1e3);
     return -1;
 }
 
@@ -499,8 +536,10 @@ int dpq_groundtruth_finish(dpq_gt* st, uint32_t* out_id, float* out_dist) {
     if (st->d_base) cudaFree(st->d_base);
     if (st->d_dist) cudaFree(st->d_dist);
     for (void* p : {(void*)st->d_qn, (void*)st->d_xn, (void*)st->d_thr, (void*)st->d_qerr, (void*)st->d_cand,
-                    (void*)st->d_cnt, (void*)st->d_flag, (void*)st->d_ctl})
+                    (void*)st->d_cnt, (void*)st->d_flag, (void*)st->d_ctl, (void*)st->d_qsplit, (void*)st->d_xsplit})
         if (p) cudaFree(p);
+    for (auto& e : st->ev)
+        if (e) cudaEventDestroy(e);
     if (getenv("DPQ_GT_STATS"))
         fprintf(stderr, "dpq_groundtruth: tensor-core path %s, %lld vectors filtered, %lld query re-runs on the dense path\n",
                 st->tc ? "on" : "off", (long long)st->tc_vectors, (long long)st->tc_flagged);

@@ -211,7 +211,8 @@ int dpq_edge_diffs(const uint8_t* codes, int64_t n_codes, int M, const uint32_t*
  * float product, double sum): results are identical to the plain exact kernels, which
  * DPQ_GT_TC=0 in the environment selects for everything.  base may be a host or device pointer.
  * dpq_groundtruth_stat: "tc" (1 when the filter path is on), "tc_vectors" (base vectors that went
- * through it), "tc_flagged" (query re-runs on the plain path after a candidate list overflowed). */
+ * through it), "tc_flagged" (query re-runs on the plain path after a candidate list overflowed),
+ * "tc_filter_us" / "tc_rescore_us" (summed CUDA-event time of the two kernels). */
 typedef struct dpq_gt dpq_gt;
 int dpq_groundtruth_begin(const float* queries, int Q, int D, int topk, dpq_gt** out);
 int dpq_groundtruth_chunk(dpq_gt* st, const float* base, int64_t n, int64_t id0);

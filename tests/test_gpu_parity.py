@@ -419,7 +419,7 @@ def test_medium_tree_end_to_end():
     # n, D, Q, topk, generator
     (30000, 128, 130, 10, "sift"),      # Q not a multiple of 128, n not a multiple of 256
     (9000, 960, 40, 5, "gist"),         # non-integer values: the bf16 hi + lo split and its error bound
-    (12345, 100, 300, 64, "sift"),      # D not a multiple of 64
+    (12345, 100, 300, 64, "ints"),      # D not a multiple of 64
     (7000, 30, 17, 3, "gauss"),         # D not a multiple of 4, signed values
     (3000, 128, 9, 10, "sift"),         # fewer vectors than the dense seed
     (40000, 128, 64, 10, "dupes"),      # heavy exact ties
@@ -433,6 +433,9 @@ def test_groundtruth_tensor_core_filter_equals_plain_kernels(shape, monkeypatch)
         base, qs = dg.sift_like(n, D, seed=31), dg.sift_like(Q, D, seed=32)
     elif gen == "gist":
         base, qs = dg.gist_like(n, D, seed=33), dg.gist_like(Q, D, seed=34)
+    elif gen == "ints":
+        base = rng.integers(0, 256, size=(n, D)).astype(np.float32)
+        qs = rng.integers(0, 256, size=(Q, D)).astype(np.float32)
     elif gen == "gauss":
         base, qs = rng.normal(size=(n, D)).astype(np.float32), rng.normal(size=(Q, D)).astype(np.float32)
     else:
@@ -441,7 +444,11 @@ def test_groundtruth_tensor_core_filter_equals_plain_kernels(shape, monkeypatch)
     monkeypatch.delenv("DPQ_GT_TC", raising=False)
     st = {}
     ids, dist = dpq.groundtruth(base, qs, k, chunk=17000, stats=st)
-    assert st["tc"] == 1
+    assert st["tc"] == 2                              # pipelined form (TMA + warp-specialised roles)
+    monkeypatch.setenv("DPQ_GT_TC", "1")              # synchronous form of the same filter
+    st1 = {}
+    sid, sdist = dpq.groundtruth(base, qs, k, chunk=17000, stats=st1)
+    assert st1["tc"] == 1 and np.array_equal(sid, ids) and np.array_equal(sdist, dist)
     if n > 4096:
         assert st["tc_vectors"] == n - 4096          # everything after the dense seed went through the filter
         if gen != "dupes":
