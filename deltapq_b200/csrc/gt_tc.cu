@@ -283,16 +283,21 @@ __global__ void __launch_bounds__(NT, 2) gt_tc_filter_kernel(const GtTcArgs a) {
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // lower bound of the exact distance minus ||q||^2: ||x||^2 - 2 dot - err.  All 32 tests
+            // first (no side effects: the shared loads batch), the rare appends afterwards.
+            uint32_t hits = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float2 xs = s_x[c0 + j];
-                // lower bound of the exact distance minus ||q||^2: ||x||^2 - 2 dot - err
                 float lb = fmaf(-2.0f, __uint_as_float(r[j]), xs.x);
                 lb = fmaf(-xs.y, qerr, lb);
-                if (lb <= thr) {
-                    const uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
-                    if (slot < (uint32_t)a.cand_cap) a.cand[(size_t)q * a.cand_cap + slot] = (uint32_t)(x0 + c0 + j);
-                }
+                hits |= (lb <= thr ? 1u : 0u) << j;
+            }
+            while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
+                if (slot < (uint32_t)a.cand_cap) a.cand[(size_t)q * a.cand_cap + slot] = (uint32_t)(x0 + c0 + j);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -534,15 +539,19 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gt_tc_filter2_kernel(const GtTc
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t hits = 0;  // all 32 tests first (the shared loads batch), the rare appends afterwards
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float2 xs = sx[c0 + j];
                     float lb = fmaf(-2.0f, __uint_as_float(r[j]), xs.x);
                     lb = fmaf(-xs.y, qerr, lb);
-                    if (lb <= thr) {
-                        const uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
-                        if (slot < (uint32_t)a.cand_cap) a.cand[(size_t)q * a.cand_cap + slot] = (uint32_t)(x0 + c0 + j);
-                    }
+                    hits |= (lb <= thr ? 1u : 0u) << j;
+                }
+                while (hits) {
+                    const int j = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
+                    if (slot < (uint32_t)a.cand_cap) a.cand[(size_t)q * a.cand_cap + slot] = (uint32_t)(x0 + c0 + j);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
