@@ -16,10 +16,8 @@
 //   gt_rescore_kernel one warp per query: exact distance of every candidate, k best by
 //                     (distance, id) merged into the running state.
 //
-// Shared-memory operand layout = the canonical K-major, no-swizzle UMMA layout: 8-row x 16-byte
-// core matrices (128 contiguous bytes); core matrix (row group g, 8-element k column c) of a
-// tile with R rows sits at (c * R/8 + g) * 128, i.e. stride-byte-offset 128, leading-byte-offset
-// R/8 * 128 (descriptor fields in cute/arch/mma_sm100_desc.hpp terms).
+// Shared-memory operand layout = the canonical K-major UMMA layout with the 128-byte swizzle: a
+// chunk is 64 dims, so a tile row is exactly one 128-byte swizzle row (see smem_desc below).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -43,9 +41,14 @@ constexpr int SMEM_TOTAL = SMEM_OPER + TB * 8 + 64;
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
 
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-           (1ull << 46);  // version 1 (Blackwell), base offset 0, layout type 0 = no swizzle
+// K-major operand tile with the 128-byte swizzle: row r of the tile is 128 contiguous bytes (the
+// chunk's 64 bf16) at r * 128, its 16-byte piece c stored at position c ^ (r & 7); 8-row groups are
+// 1024 bytes apart (stride byte offset), the leading byte offset is unused (1).  One MMA k-step
+// (16 elements) advances the start address by 32 bytes inside the swizzle atom; tiles are 1024-byte
+// aligned (descriptor fields as in cute/arch/mma_sm100_desc.hpp, layout type 2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
 }
 
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -148,7 +151,7 @@ struct OperandFill {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int piece = kq + 4 * h, k8 = kh * 4 + (piece >> 1);
-                const int off = (k8 * (ROWS / 8) + (row >> 3)) * 128 + (row & 7) * 16 + (piece & 1) * 8;
+                const int off = row * 128 + ((k8 ^ (row & 7)) << 4) + (piece & 1) * 8;
                 *reinterpret_cast<uint2*>(s_hi + off) = h ? make_uint2(hi.z, hi.w) : make_uint2(hi.x, hi.y);
                 *reinterpret_cast<uint2*>(s_lo + off) = h ? make_uint2(lo.z, lo.w) : make_uint2(lo.x, lo.y);
             }
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(NT, 2) gt_tc_filter_kernel(const GtTcArgs a) {
     const float qerr = q < a.Q ? a.qerr[q] : 0.0f;
     const int n_chunks = (a.D + KC - 1) / KC;
     uint32_t phase = 0;
-    bool ok = true;
+    bool ok = (smem_u32(smem) & 1023u) == 0;  // the swizzle is a function of the absolute address
 
     for (int64_t t = t_lo; t < t_hi && ok; ++t) {
         const int64_t x0 = t * TB;
@@ -249,14 +252,12 @@ __global__ void __launch_bounds__(NT, 2) gt_tc_filter_kernel(const GtTcArgs a) {
             if (threadIdx.x == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ah = smem_u32(sA_hi), al = smem_u32(sA_lo), bh = smem_u32(sB_hi), bl = smem_u32(sB_lo);
-                constexpr uint32_t A_LBO = TQ / 8 * 128, B_LBO = TB / 8 * 128;
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {  // hi.hi, hi.lo, lo.hi
                     const uint32_t pa = part == 2 ? al : ah, pb = part == 1 ? bl : bh;
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
-                        mma_bf16(tmem, smem_desc(pa + 2 * k * A_LBO, A_LBO, 128), smem_desc(pb + 2 * k * B_LBO, B_LBO, 128),
-                                 (ch | part | k) != 0);
+                        mma_bf16(tmem, smem_desc(pa + 32 * k), smem_desc(pb + 32 * k), (ch | part | k) != 0);
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                  smem_u32(s_bar))
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gt_tc_filter2_kernel(const GtTc
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
-    bool ok = true;
+    bool ok = (smem_u32(smem) & 1023u) == 0;  // the swizzle is a function of the absolute address
 
     if (warp == 0) {
         if (lane == 0) {  // ---- producer
@@ -476,7 +477,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gt_tc_filter2_kernel(const GtTc
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer
             uint32_t it = 0, tc = 0;
-            constexpr uint32_t A_LBO = TQ / 8 * 128, B_LBO = TB / 8 * 128;
             for (int64_t t = t_lo; t < t_hi && ok; ++t, ++tc) {
                 const uint32_t buf = tc & 1u, m = tc >> 1;
                 ok = mbar_wait_bounded(acc_empty + buf, (m & 1u) ^ 1u);  // the epilogue drained this buffer
@@ -495,8 +495,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gt_tc_filter2_kernel(const GtTc
                         const uint32_t pa = part == 2 ? al : ah, pb = part == 1 ? bl : bh;
 #pragma unroll
                         for (int k = 0; k < KC / 16; ++k)
-                            mma_bf16(acc, smem_desc(pa + 2 * k * A_LBO, A_LBO, 128), smem_desc(pb + 2 * k * B_LBO, B_LBO, 128),
-                                     (ch | part | k) != 0);
+                            mma_bf16(acc, smem_desc(pa + 32 * k), smem_desc(pb + 32 * k), (ch | part | k) != 0);
                     }
                     umma_commit(empty + stage);  // the stage is free once these MMAs have read it
                 }
