@@ -327,7 +327,7 @@ int gt_tc_range(dpq_gt* st, const float* d_base, int64_t n, int64_t id0, int64_t
     CU(dpq::launch_gt_thr(st->d_state, st->topk, Q, st->d_qn, st->d_qn + Q, st->d_qn + 2 * (size_t)Q, c_err, st->d_thr,
                           st->d_qerr, 0));
     CU(cudaMemsetAsync(st->d_cnt, 0, (size_t)Q * 4));
-    CU(cudaMemsetAsync(st->d_ctl, 0, 4));
+    CU(cudaMemsetAsync(st->d_ctl, 0, 16));  // [0] flagged queries, [1] error flag
     dpq::GtTcArgs a;
     a.base = d_base;
     a.queries = st->d_q;
