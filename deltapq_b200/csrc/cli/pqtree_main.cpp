@@ -109,13 +109,25 @@ static int encode(const Args& a, const std::string& dataset, const std::string& 
     std::vector<float> buf;
     long long done = 0;
     const long long chunk = 1 << 20;
+    std::vector<uint8_t> raw;
+    const bool bvecs = ext == "bvecs";  // raw records go to the device as they are (dpq_encode_u8)
     while (N < 0 || done < N) {
         buf.clear();
         long long want = N < 0 ? chunk : std::min(chunk, N - done);
-        long long got = vf.read(want, buf);
+        long long got;
+        if (bvecs) {
+            raw.resize((size_t)want * vf.rec_bytes);
+            got = (long long)fread(raw.data(), (size_t)vf.rec_bytes, (size_t)want, vf.f);
+        } else {
+            got = vf.read(want, buf);
+        }
         if (got == 0) break;
         codes.resize((size_t)(done + got) * M);
-        DPQ_TRY(dpq_encode(cb.cw.data(), M, K, cb.Ds, buf.data(), got, vf.D, codes.data() + (size_t)done * M));
+        if (bvecs)
+            DPQ_TRY(dpq_encode_u8(cb.cw.data(), M, K, cb.Ds, raw.data(), got, vf.D, vf.rec_bytes, 4,
+                                  codes.data() + (size_t)done * M));
+        else
+            DPQ_TRY(dpq_encode(cb.cw.data(), M, K, cb.Ds, buf.data(), got, vf.D, codes.data() + (size_t)done * M));
         done += got;
         printf("\r%lld encoded", done);
         fflush(stdout);

@@ -103,6 +103,15 @@ __global__ void __launch_bounds__(256) encode_kernel_any(const float* __restrict
     codes[(size_t)v * M + m] = (uint8_t)best_k;
 }
 
+// bvecs components (utils.cpp:43-71 reads them into floats): rows of D bytes `stride` bytes apart
+__global__ void u8_to_float_kernel(const uint8_t* __restrict__ src, int64_t n, int D, int64_t stride, int64_t skip,
+                                   float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * D) return;
+    const int64_t v = i / D;
+    dst[i] = (float)src[v * stride + skip + (i - v * D)];
+}
+
 cudaError_t launch_encode(const float* d_cw, int M, int K, int Ds, const float* d_x, int64_t n, int D,
                           uint8_t* d_codes, cudaStream_t st) {
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)M), block(256);
@@ -398,6 +407,35 @@ int dpq_encode(const float* cw, int M, int K, int Ds, const float* x, int64_t n,
     for (int64_t s = 0; s < n; s += chunk) {
         int64_t c = std::min(chunk, n - s);
         CU(cudaMemcpy(d_x.p, x + (size_t)s * D, (size_t)c * D * 4, cudaMemcpyDefault));
+        CU(launch_encode((const float*)d_cw.p, M, K, Ds, (const float*)d_x.p, c, D, (uint8_t*)d_c.p, 0));
+        CU(cudaMemcpy(codes + (size_t)s * M, d_c.p, (size_t)c * M, cudaMemcpyDefault));
+    }
+    return DPQ_OK;
+}
+
+int dpq_encode_u8(const float* cw, int M, int K, int Ds, const uint8_t* x, int64_t n, int D, int64_t row_stride,
+                  int64_t row_offset, uint8_t* codes) {
+    if (!cw || !x || !codes || M < 1 || M > 64 || K < 1 || K > 256 || Ds < 1 || n < 0 || D < 1 || D > M * Ds ||
+        row_offset < 0 || row_stride < row_offset + D)
+        return dpq::api_fail(DPQ_ERR_ARG, "dpq_encode_u8: bad argument");
+    int rc = dpq::api_check_device();
+    if (rc) return rc;
+    if (n == 0) return DPQ_OK;
+    CU(cudaSetDevice(dpq::api_device()));
+    Buf d_cw, d_raw, d_x, d_c;
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 20);
+    CU(cudaMalloc(&d_cw.p, (size_t)M * K * Ds * 4));
+    CU(cudaMalloc(&d_raw.p, (size_t)chunk * row_stride));
+    CU(cudaMalloc(&d_x.p, (size_t)chunk * D * 4));
+    CU(cudaMalloc(&d_c.p, (size_t)chunk * M));
+    CU(cudaMemcpy(d_cw.p, cw, (size_t)M * K * Ds * 4, cudaMemcpyHostToDevice));
+    for (int64_t s = 0; s < n; s += chunk) {
+        const int64_t c = std::min(chunk, n - s);
+        // the last record may end before a whole stride (no trailing padding in the caller's buffer)
+        const size_t raw_bytes = (size_t)(c - 1) * row_stride + (size_t)(row_offset + D);
+        CU(cudaMemcpy(d_raw.p, x + (size_t)s * row_stride, raw_bytes, cudaMemcpyDefault));
+        u8_to_float_kernel<<<(unsigned)((c * D + 255) / 256), 256>>>((const uint8_t*)d_raw.p, c, D, row_stride, row_offset,
+                                                                     (float*)d_x.p);
         CU(launch_encode((const float*)d_cw.p, M, K, Ds, (const float*)d_x.p, c, D, (uint8_t*)d_c.p, 0));
         CU(cudaMemcpy(codes + (size_t)s * M, d_c.p, (size_t)c * M, cudaMemcpyDefault));
     }

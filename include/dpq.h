@@ -169,6 +169,13 @@ int dpq_adc_tables(const float* codewords, int M, int K, int Ds, const float* qu
 int dpq_encode(const float* codewords, int M, int K, int Ds, const float* x, int64_t n, int D,
                uint8_t* codes);
 
+/* Same for uint8 components (bvecs, utils.cpp:43-71 converts them to float before EncodePlain):
+ * vector i = the D bytes at x + i * row_stride + row_offset, so a block of raw .bvecs records
+ * (4-byte dimension header + D bytes each) is passed as it was read: row_stride = D + 4,
+ * row_offset = 4.  The conversion runs on the device; a quarter of the bytes cross PCIe. */
+int dpq_encode_u8(const float* codewords, int M, int K, int Ds, const uint8_t* x, int64_t n, int D,
+                  int64_t row_stride, int64_t row_offset, uint8_t* codes);
+
 /* find_edges_by_diff_approx (DCAT.h:1207-1332) with the canonical stable-sort tie rule:
  * edges[n_codes-1][2] = (parent id, child id) in emission order, *root_id. */
 int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_height_folds,

@@ -190,3 +190,30 @@ def test_cli_forest_parts_match_single_tree(tmp_path):
         for i in range(nq):
             untied = np.array([np.sum(wdist[i] == v) == 1 and v < wdist[i, -1] for v in wdist[i]])
             assert np.array_equal(pid[i][untied], wid[i][untied]), i
+
+
+@pytest.mark.gpu
+def test_cli_encode_bvecs_equals_fvecs(tmp_path):
+    """`pqtree -task encode -ext bvecs` (SIFT1B's format; raw records go to the device through
+    dpq_encode_u8) writes the same codes file as the fvecs run on the same components, and the
+    reference binary agrees when it is available."""
+    n, M, K = 7000, 8, 256
+    d = str(tmp_path / "b")
+    f = str(tmp_path / "f")
+    base, _, _ = dg.make_dataset(f, n, 10, M=M, K=K, d=128, seed=71)
+    os.makedirs(d)
+    dg.write_vecs(d + "/base.bvecs", base, ext="bvecs")
+    shutil.copy(f + f"/M{M}K{K}codewords.txt", d)
+    for path, ext in ((f, "fvecs"), (d, "bvecs")):
+        r = run([BIN + "/pqtree", "-dataset", path, "-task", "encode", "-m", str(M), "-k", str(K), "-N", str(n), "-ext", ext])
+        assert r.returncode == 0, r.stderr
+    name = f"/codes.bin.plain.M{M}K{K}N{n}"
+    assert filecmp.cmp(d + name, f + name, shallow=False)
+    if os.path.exists(os.path.join(po.REF_DIR, "pqtree")):
+        rdir = str(tmp_path / "r")
+        os.makedirs(rdir)
+        shutil.copy(d + "/base.bvecs", rdir)
+        shutil.copy(f + f"/M{M}K{K}codewords.txt", rdir)
+        r = run([po.REF_DIR + "/pqtree", "-dataset", rdir, "-task", "encode", "-m", str(M), "-k", str(K), "-N", str(n), "-ext", "bvecs"])
+        if r.returncode == 0 and os.path.exists(rdir + name):
+            assert filecmp.cmp(rdir + name, d + name, shallow=False)

@@ -461,3 +461,17 @@ def test_groundtruth_tensor_core_filter_equals_plain_kernels(shape, monkeypatch)
     oid, odist = po.groundtruth(base[:, :], qs[: min(Q, 24)], k, chunk=17000)
     assert np.array_equal(dist[: min(Q, 24)], odist)
     assert_topk_equal(ids[: min(Q, 24)], dist[: min(Q, 24)], oid, odist)
+
+
+def test_encode_u8_bvecs_records_equal_float_encode(tmp_path):
+    """dpq_encode_u8: raw .bvecs records (4-byte header + D bytes) converted on the device ==
+    dpq_encode of the same components as floats == the oracle (pq_tree.cpp:192-253)."""
+    base = dg.sift_like(5000, 128, seed=41)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(3000, 128, seed=42), 8, 256, iters=3))
+    path = str(tmp_path / "base.bvecs")
+    dg.write_vecs(path, base, ext="bvecs")
+    raw = np.fromfile(path, np.uint8)
+    assert raw.size == 5000 * 132
+    codes = dpq.encode_u8(cw, raw, 5000, 128, 132, 4)
+    assert np.array_equal(codes, dpq.encode(cw, base))
+    assert np.array_equal(codes[:1500], po.encode(cw, base[:1500]))
