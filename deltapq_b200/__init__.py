@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libdpq.so")
 SYMBOLS = [
     "dpq_version", "dpq_last_error", "dpq_device_count", "dpq_set_device",
     "dpq_index_open", "dpq_index_open_part", "dpq_index_open_file", "dpq_index_open_part_file",
-    "dpq_multi_open_parts", "dpq_index_set_codebook", "dpq_index_set_option",
+    "dpq_multi_open_parts", "dpq_index_open_tree", "dpq_index_set_codebook", "dpq_index_set_option",
     "dpq_index_set_stream",
     "dpq_index_search", "dpq_index_search_device", "dpq_index_sync", "dpq_merge_topk_device",
     "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",
@@ -54,6 +54,7 @@ def lib():
     L.dpq_last_error.restype = C.c_char_p
     L.dpq_index_open.argtypes = [vp, i64, i64, i32, i32, vp, i32, i32, C.POINTER(vp)]
     L.dpq_index_open_part.argtypes = [vp, i64, i64, i32, i32, vp, i64, C.POINTER(vp)]
+    L.dpq_index_open_tree.argtypes = [vp, i64, C.POINTER(vp)]
     L.dpq_index_open_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(vp)]
     L.dpq_index_set_codebook.argtypes = [vp, vp, i32]
     L.dpq_index_set_option.argtypes = [vp, C.c_char_p, i64]
@@ -321,15 +322,28 @@ def _tree_out(h, M, want=None):
         lib().dpq_tree_free(h)
 
 
-def tree_build(codes, cw, h=1, method=1, want=None):
+def tree_build(codes, cw, h=1, method=1, want=None, open_index_at=None):
     """`deltapq -task approx_tree` (DCAT.h:970): GPU edge search + GPU layout + stream.
     want: names of the arrays to fetch (default all; at 10^8 nodes the QNode file body alone
-    is 6 GB)."""
+    is 6 GB).  open_index_at: also open the tree as an index (first_pos = that value) straight
+    from the layout arrays; returned under "index"."""
     codes = np.ascontiguousarray(codes, np.uint8)
     cw = np.ascontiguousarray(cw, np.float32)
     n, M = codes.shape
     t = C.c_void_p()
     _check(lib().dpq_tree_build(_ptr(codes), n, M, cw.shape[1], _ptr(cw), cw.shape[2], h, method, C.byref(t)))
+    if open_index_at is not None:  # dpq_index_open_tree: program compiled on the GPU from the layout arrays
+        ix = DeltaTreeIndex.__new__(DeltaTreeIndex)
+        ix.M, ix.K, ix.Ds = M, cw.shape[1], None
+        ix._h = C.c_void_p()
+        try:
+            _check(lib().dpq_index_open_tree(t, int(open_index_at), C.byref(ix._h)))
+        except Exception:
+            lib().dpq_tree_free(t)
+            raise
+        out = _tree_out(t, M, want)
+        out["index"] = ix
+        return out
     return _tree_out(t, M, want)
 
 

@@ -14,6 +14,7 @@
 
 #include "../../include/dpq.h"
 #include "kernels.cuh"
+#include "tree_internal.h"
 
 namespace {
 
@@ -358,6 +359,82 @@ static int open_file_common(const char* tree_path, const char* qnode_path, int M
     }
     return open_common(payload.data(), hdr[1], hdr[0], M, K, qnode_path ? pos2id.data() : nullptr, rank, n_ranks,
                        first_pos, out);
+}
+
+int dpq_index_open_tree(dpq_tree* t, int64_t first_pos, dpq_index** out) {
+    if (!t || !out) return fail(DPQ_ERR_ARG, "dpq_index_open_tree: null argument");
+    *out = nullptr;
+    const int M = t->M, K = t->K;
+    const int64_t n = t->n;
+    const char* eng = getenv("DPQ_ENGINE");
+    if ((eng && eng[0] == '1') || !dpq::v2_shape_ok(M, K))  // first-generation program: through the byte stream
+        return open_common(t->payload.data(), (int64_t)t->payload.size(), n, M, K, t->vec_id.data(), 0, 1, first_pos, out);
+    if (first_pos < 0 || first_pos + n > 0xFFFFFFFFLL)
+        return fail(DPQ_ERR_ARG, "dpq_index_open_tree: positions must stay below 2^32 - 1");
+    if ((int64_t)t->codes_by_pos.size() != n * M || (int64_t)t->parent_pos.size() != n || (int64_t)t->depth.size() != n)
+        return fail(DPQ_ERR_ARG, "dpq_index_open_tree: the tree has no layout arrays");
+    int rc = check_device();
+    if (rc) return rc;
+    dpq_index* ix = new dpq_index();
+    ix->device = g_device;
+    dpq::ScanProgram& P = ix->prog;
+    P.M = M;
+    P.K = K;
+    P.fmt.rb = (M * K <= 2048) ? 11 : 12;
+    P.v2 = true;
+    P.shape = dpq::v2_shape(M, K);
+    P.n_codes = n;
+    P.n_bytes = (int64_t)t->payload.size();
+    P.base_pos = first_pos;
+    P.n_local = n;
+    P.local_bytes = P.n_bytes;
+    P.n_diffs = t->n_diffs;
+    P.depth_hist.assign((size_t)P.fmt.levels() + 1, 0);
+    ix->pos_shift = first_pos;
+    auto bail = [&](int code) {
+        dpq_index_close(ix);
+        return code;
+    };
+    if (cudaSetDevice(ix->device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(DPQ_ERR_CUDA, "dpq_index_open_tree: stream setup failed"));
+    const int64_t n_chunks = (n + P.v2_chunk_nodes - 1) / P.v2_chunk_nodes;
+    DevBuf d_ppos, d_depth, d_cnt;
+    auto drop = [&]() {
+        d_ppos.release();
+        d_depth.release();
+        d_cnt.release();
+    };
+    if ((rc = upload(ix->d_codes, t->codes_by_pos.data(), (size_t)n * M, ix->stream)) ||
+        (rc = upload(d_ppos, t->parent_pos.data(), (size_t)n * 4, ix->stream)) ||
+        (rc = upload(d_depth, t->depth.data(), (size_t)n, ix->stream)) ||
+        (rc = ix->d_recs.ensure((size_t)n * P.shape.rec_words() * 4)) ||
+        (rc = ix->d_chunks2.ensure((size_t)n_chunks * sizeof(dpq::ChunkDesc2))) || (rc = d_cnt.ensure(16))) {
+        drop();
+        return bail(rc);
+    }
+    // the first-generation buffers stay empty (16-byte placeholders keep the launch arguments valid)
+    if ((rc = ix->d_ops.ensure(16)) || (rc = ix->d_chunks.ensure(16)) || (rc = ix->d_anc.ensure(16))) {
+        drop();
+        return bail(rc);
+    }
+    cudaError_t e = cudaMemsetAsync(d_cnt.p, 0, 16, ix->stream);
+    if (e == cudaSuccess)
+        e = dpq::launch_build_recs(ix->d_codes.as<uint8_t>(), d_ppos.as<uint32_t>(), d_depth.as<uint8_t>(), n, M, K, P.shape,
+                                   P.v2_chunk_nodes, (uint32_t)first_pos, ix->d_recs.as<uint32_t>(),
+                                   ix->d_chunks2.as<dpq::ChunkDesc2>(), d_cnt.as<unsigned long long>(), ix->stream);
+    unsigned long long deltas = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&deltas, d_cnt.p, 8, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    drop();
+    if (e != cudaSuccess) return bail(fail(DPQ_ERR_CUDA, std::string("dpq_index_open_tree: ") + cudaGetErrorString(e)));
+    P.v2_delta_nodes = (int64_t)deltas;
+    ix->n_chunks = (int)n_chunks;
+    ix->ops_bytes = (size_t)n * P.shape.rec_words() * 4;
+    ix->has_pos2id = true;
+    ix->pos2id_host = t->vec_id;
+    *out = ix;
+    return DPQ_OK;
 }
 
 int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,

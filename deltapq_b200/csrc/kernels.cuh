@@ -113,6 +113,10 @@ void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  const V2Shape& sh, uint32_t bound0, cudaStream_t st);
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
+// program_dev.cu: fixed-record program from the layout arrays of a freshly built tree
+cudaError_t launch_build_recs(const uint8_t* codes_p, const uint32_t* parent_pos, const uint8_t* depth, int64_t n, int M,
+                              int K, const V2Shape& sh, int chunk_nodes, uint32_t pos_shift, uint32_t* recs,
+                              ChunkDesc2* chunks, unsigned long long* n_delta, cudaStream_t st);
 
 // ---- coarse search (scan8.cu): 8-bit packed filter over the whole tree + exact re-score ----
 constexpr int C8_QB = 112;          // queries per CTA: 7 lanes x 16 queries, one byte each

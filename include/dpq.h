@@ -62,6 +62,14 @@ int dpq_index_open_part(const uint8_t* payload, int64_t n_bytes, int64_t n_codes
 int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, int K, int rank,
                         int n_ranks, dpq_index** out);
 
+/* Opens a tree that dpq_tree_build / dpq_tree_from_edges just produced, without going through its
+ * byte stream: the device scan program is compiled on the GPU from the layout arrays (one thread
+ * per 64-node chunk) instead of decoding the sequential stream on the host (8.9 s per 125M nodes).
+ * Same index as dpq_index_open_part(payload, ..., vec_id, first_pos); t stays owned by the caller
+ * and may be freed afterwards.  (dpq_tree is declared further down.) */
+struct dpq_tree;
+int dpq_index_open_tree(struct dpq_tree* t, int64_t first_pos, dpq_index** out);
+
 /* dpq_index_open_part reading the part's files (tree file with its 16-byte header; 60-byte
  * QNode file or NULL). */
 int dpq_index_open_part_file(const char* tree_path, const char* qnode_path, int M, int K, int64_t first_pos,

@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--check-queries", type=int, default=4)
     ap.add_argument("--cpu-baseline-queries", type=int, default=4)
     ap.add_argument("--opts", default="")
+    ap.add_argument("--open-from-stream", action="store_true")
     args = ap.parse_args()
 
     import torch
@@ -136,10 +137,15 @@ def main():
         del d_codes
         torch.cuda.empty_cache()
         t2 = time.perf_counter()
-        tree = dpq.tree_build(codes, cw, h=1, method=1, want=("payload", "vec_id"))
-        t3 = time.perf_counter()
+        if args.open_from_stream:  # the file path: host decode of the byte stream (program.cpp)
+            tree = dpq.tree_build(codes, cw, h=1, method=1, want=("payload", "vec_id"))
+            t3 = time.perf_counter()
+            ix = dpq.DeltaTreeIndex(tree["payload"], n_part, PQ_M, PQ_K, pos2id=tree["vec_id"], first_pos=gp * n_part)
+        else:  # dpq_index_open_tree: the scan program compiled on the GPU from the layout arrays
+            tree = dpq.tree_build(codes, cw, h=1, method=1, want=("payload", "vec_id"), open_index_at=gp * n_part)
+            t3 = time.perf_counter()
+            ix = tree["index"]
         del codes
-        ix = dpq.DeltaTreeIndex(tree["payload"], n_part, PQ_M, PQ_K, pos2id=tree["vec_id"], first_pos=gp * n_part)
         ix.set_codebook(cw)
         for kv in (args.opts.split(",") if args.opts else []):
             kk, v = kv.split("=")
@@ -308,6 +314,8 @@ def main():
                        "l2": "256 MiB buffer written before every timed step; each part's program (16 B/node) exceeds L2",
                        "tree": "built in the run by libdpq on the scanning GPU (encode + edge search + layout)",
                        "setup_s_max_over_ranks": {k_: round(v, 2) for k_, v in setup.items()},
+                       "open": "host decode of the byte stream (open_s)" if args.open_from_stream else
+                               "scan program compiled on the GPU from the layout arrays (inside fetch_s)",
                        "opts": args.opts or "default"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "scan8_kernel" if coarse else "scan2_kernel",
