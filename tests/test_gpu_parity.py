@@ -486,14 +486,11 @@ def test_index_from_tree_arrays_equals_index_from_stream(shape, engine):
     cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(3000, 128, seed=52), M, 256, iters=3))
     queries = dg.sift_like(150, 128, seed=53)
     codes = dpq.encode(cw, base)
-    t = dpq.tree_build(codes, cw, want=("payload", "vec_id"), open_index_at=7)
-    a = t["index"]
-    b = dpq.DeltaTreeIndex(t["payload"], n, M, 256, pos2id=t["vec_id"], first_pos=7 if engine == "v2" else None)
+    # the first-generation program (DPQ_ENGINE=1) cannot shift positions; open_tree then goes through the stream
     shift = 7 if engine == "v2" else 0
-    if engine == "gen1":  # the first-generation program cannot shift positions: open_tree goes through the stream
-        a.close()
-        t = dpq.tree_build(codes, cw, want=("payload", "vec_id"), open_index_at=0)
-        a = t["index"]
+    t = dpq.tree_build(codes, cw, want=("payload", "vec_id"), open_index_at=shift)
+    a = t["index"]
+    b = dpq.DeltaTreeIndex(t["payload"], n, M, 256, pos2id=t["vec_id"], first_pos=shift if shift else None)
     for ix in (a, b):
         ix.set_codebook(cw)
     apos, aid, adist = a.search(queries, min(k, 256))
