@@ -374,6 +374,7 @@ def run_gpu(args):
             "config": {"workload": "SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, 10K queries per GPU per step, top-10 (BASELINE configs[1])",
                        "n_codes": args.n_codes, "queries_per_step": world * Q, "topk": k, "n_bytes": n_bytes_total,
                        "mean_diffs_per_node": round((n_bytes_total - 8 - (3 * (args.n_codes - 1) + 1) // 2) / (args.n_codes - 1), 3),
+                       "depth_hist": [ix.stat(f"depth_hist_{d}") for d in range(9)],
                        "sharding": "whole tree on one GPU" if world == 1 else
                                    f"queries sharded: {world} replicas of the tree, {Q} queries per GPU per step, NCCL all-gather of the result keys",
                        "l2": "256 MiB buffer written before every timed step (L2 flush, outside the events)",

@@ -301,7 +301,9 @@ struct dpq_gt {
 
 namespace {
 constexpr int64_t GT_TC_STEP = 131072;  // base vectors per filter launch: the cap tightens between launches
-constexpr int GT_TC_SEED = 4096;        // vectors scored densely first, so that every query has a finite cap
+// vectors scored densely first, so that every query has a finite cap: 64 per wanted neighbour keeps the
+// first launch's survivors (k * step / seed) at half the candidate slots
+inline int64_t gt_tc_seed(int topk) { return std::min<int64_t>(8192, std::max<int64_t>(1024, 64LL * topk)); }
 constexpr int GT_TC_CAND = 4096;        // candidate slots per query per launch
 
 // dense exact path over base[0..n) (device) for the queries qlist[0..nq) (nullptr: all)
@@ -544,7 +546,7 @@ int dpq_groundtruth_chunk(dpq_gt* st, const float* base, int64_t n, int64_t id0)
         CU(dpq::launch_gt_prep(st->d_base, c, st->D, st->d_xn, st->d_xn + st->x_cap, st->d_xn + 2 * st->x_cap, 0));
         int64_t s0 = 0;
         if (!st->seeded) {  // the first vectors densely: afterwards every query has k exact distances
-            s0 = std::min<int64_t>(c, GT_TC_SEED);
+            s0 = std::min<int64_t>(c, gt_tc_seed(st->topk));
             if ((rc = gt_dense(st, st->d_base, s0, id0 + s, nullptr, st->Q))) return rc;
             st->seeded = true;
         }
