@@ -503,10 +503,13 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     const dpq::ScanProgram& P = ix->prog;
     // coarse search (scan8.cu): 15-bit scan over a 1/S sample -> cap per query -> 8-bit scan of
     // the whole tree -> exact re-score.  Narrow shape, moderate k, trees large enough to pay.
-    const bool coarse = P.v2 && P.shape.nf == 8 && topk <= 64 && ix->opt_coarse != 0 &&
+    const bool coarse = P.v2 && topk <= 128 && ix->opt_coarse != 0 &&
                         (ix->opt_coarse == 1 || P.n_local >= ix->opt_coarse_min);
+    const dpq::C8Shape c8 = dpq::c8_shape(P.shape.nf);  // narrow: 112 queries per CTA, wide: 48
+    const int spw = P.shape.spw();
+    const int levels8 = std::min(ix->opt_levels8, 127 - c8.slack);  // the test constant stays <= 128
     const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : (P.n_local >= 400000 ? 16 : 8));
-    const int n_chunks_sample = (((ix->n_chunks + 3) / 4 + S - 1) / S) * 4;  // chunks the sample pass walks
+    const int n_chunks_sample = (((ix->n_chunks + spw - 1) / spw + S - 1) / S) * spw;  // chunks the sample pass walks
     int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
     if (rc) return rc;
     ix->last_coarse = coarse ? 1 : 0;
@@ -514,10 +517,10 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     int g8_groups = 0, g8_slices = 1;
     const int warps8 = ix->opt_warps8, bcap8 = ix->opt_bcap8;
     if (coarse) {
-        g8_groups = (Q + dpq::C8_QB - 1) / dpq::C8_QB;
+        g8_groups = (Q + c8.qb - 1) / c8.qb;
         g8_slices = ix->opt_slices;
         if (g8_slices <= 0) {
-            const int cpr = warps8 * 4;
+            const int cpr = warps8 * spw;
             double best = -1.0;
             g8_slices = 1;
             for (int s = 1; s <= 96 && s <= std::max(1, ix->n_chunks / cpr); ++s) {  // <= R8_MAXSL
@@ -536,7 +539,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     // slices of the SAMPLED coarse pass (seed = 1): same rule on the reduced chunk count
     int g8_slices_s = 1;
     if (coarse && ix->opt_seed == 1) {
-        const int cpr = warps8 * 4;
+        const int cpr = warps8 * spw;
         double best = -1.0;
         for (int s = 1; s <= 96 && s <= std::max(1, n_chunks_sample / cpr); ++s) {
             const int64_t items = (int64_t)g8_groups * s;
@@ -579,10 +582,10 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         ix->last_items8 = (int64_t)g8_groups * g8_slices;
         if ((rc = ix->d_cap0.ensure((size_t)Q * 4))) return rc;
         if ((rc = ix->d_cap1.ensure((size_t)Q * 4))) return rc;
-        if ((rc = ix->d_qlut8.ensure((size_t)g8_groups * 2048 * dpq::C8_ROW_BYTES))) return rc;
-        if ((rc = ix->d_cand8.ensure(items8 * dpq::C8_QB * bcap8 * 4))) return rc;
-        if ((rc = ix->d_cnt8.ensure(items8 * dpq::C8_QB * 4))) return rc;
-        if ((rc = ix->d_ovf8.ensure((size_t)g8_groups * dpq::C8_QB * 4))) return rc;
+        if ((rc = ix->d_qlut8.ensure((size_t)g8_groups * c8.lut_bytes()))) return rc;
+        if ((rc = ix->d_cand8.ensure(items8 * c8.qb * bcap8 * 4))) return rc;
+        if ((rc = ix->d_cnt8.ensure(items8 * c8.qb * 4))) return rc;
+        if ((rc = ix->d_ovf8.ensure((size_t)g8_groups * c8.qb * 4))) return rc;
         if ((rc = ix->d_flagged2.ensure((size_t)max_flagged * 4))) return rc;
         if ((rc = ix->d_fcnt2.ensure((size_t)max_flagged * 4))) return rc;
     }
@@ -699,8 +702,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the
             // sample (every S-th batch) -> exact re-score -> cap1 = the sample's k-th distance
             dpq::launch_presample(se.lutf, se.codes, P.n_local, P.M, P.K, Q, topk, ix->opt_presample, cap0, st);
-            dpq::launch_pack8(se.lutf, cap0, (int)MK, Q, ix->opt_levels8, ix->d_qlut8.as<uint8_t>(),
-                              ix->d_ovf8.as<uint32_t>(), g8_groups, st);
+            dpq::launch_pack8(se.lutf, cap0, (int)MK, Q, levels8, ix->d_qlut8.as<uint8_t>(),
+                              ix->d_ovf8.as<uint32_t>(), g8_groups, c8.nf, st);
             s8.recs = ix->d_recs.as<uint4>();
             s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
             s8.n_chunks = ix->n_chunks;
@@ -715,7 +718,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             s8.n_slices = g8_slices_s;
             s8.n_warps = warps8;
             s8.bcap = bcap8;
-            s8.thresh = ix->opt_levels8 + 5;
+            s8.thresh = levels8 + c8.slack + 1;
+            s8.nf = c8.nf;
             CU(dpq::launch_scan8(s8, st));
             r8.cand = s8.cand;
             r8.cand_cnt = s8.cand_cnt;
@@ -723,6 +727,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             r8.n_groups = g8_groups;
             r8.n_slices = g8_slices_s;
             r8.bcap = bcap8;
+            r8.qb = c8.qb;
             r8.lutf = se.lutf;
             r8.codes = se.codes;
             r8.base_pos = P.base_pos;
@@ -739,8 +744,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             r8.bound = nullptr;
             dpq::launch_rescore8(r8, st);
         }
-        dpq::launch_pack8(se.lutf, cap1, (int)MK, Q, ix->opt_levels8, ix->d_qlut8.as<uint8_t>(),
-                          ix->d_ovf8.as<uint32_t>(), g8_groups, st);
+        dpq::launch_pack8(se.lutf, cap1, (int)MK, Q, levels8, ix->d_qlut8.as<uint8_t>(),
+                          ix->d_ovf8.as<uint32_t>(), g8_groups, c8.nf, st);
         s8.recs = ix->d_recs.as<uint4>();
         s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
         s8.n_chunks = ix->n_chunks;
@@ -755,7 +760,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s8.n_slices = g8_slices;
         s8.n_warps = warps8;
         s8.bcap = bcap8;
-        s8.thresh = ix->opt_levels8 + 5;
+        s8.thresh = levels8 + c8.slack + 1;
+        s8.nf = c8.nf;
         CU(cudaEventRecord(ix->ev[4], st));
         CU(dpq::launch_scan8(s8, st));
         CU(cudaEventRecord(ix->ev[5], st));
@@ -765,6 +771,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         r8.n_groups = g8_groups;
         r8.n_slices = g8_slices;
         r8.bcap = bcap8;
+        r8.qb = c8.qb;
         r8.lutf = se.lutf;
         r8.codes = se.codes;
         r8.base_pos = P.base_pos;
@@ -937,7 +944,7 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
         if (cudaStreamSynchronize(ix->stream) != cudaSuccess) return -1;
         if (cudaMemcpy(c.data(), ix->d_cnt8.p, c.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         int64_t t = 0;
-        for (size_t i = 0; i < (size_t)ix->last_items8 * dpq::C8_QB && i < c.size(); ++i) t += c[i];
+        for (size_t i = 0; i < (size_t)ix->last_items8 * dpq::c8_shape(P.shape.nf).qb && i < c.size(); ++i) t += c[i];
         return t;
     }
     if (n == "v2_delta_nodes") return P.v2_delta_nodes;

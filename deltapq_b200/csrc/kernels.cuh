@@ -119,29 +119,43 @@ cudaError_t launch_build_recs(const uint8_t* codes_p, const uint32_t* parent_pos
                               ChunkDesc2* chunks, unsigned long long* n_delta, cudaStream_t st);
 
 // ---- coarse search (scan8.cu): 8-bit packed filter over the whole tree + exact re-score ----
-constexpr int C8_QB = 112;          // queries per CTA: 7 lanes x 16 queries, one byte each
+constexpr int C8_QB = 112;          // narrow shape: queries per CTA = 7 lanes x 16 queries, one byte each
 constexpr int C8_ROW_BYTES = 112;
 constexpr int C8_SAT = 31;          // table entries saturate at 31 (8 x 31 <= 255: byte sums never carry)
 // The unit is cap / L with L > 31 ("levels", default 80): finer than the saturation point, so a
 // large entry saturates.  Saturation only lowers a coarse sum (more false positives, never a
 // false negative); a node within the cap has coarse sum <= L + 8 * 0.5, so the test is
 // "sum < L + 5".  On the 1M SIFT-shaped tree L = 80 leaves 4.5x fewer survivors than L = 31.
+//
+// Wide shape (M <= 16, 4096 table rows): 48-byte rows = 3 lanes x 16 queries = 48 queries per CTA
+// (twice the 15-bit wide scan's 24), entries saturate at 15 (16 x 15 <= 255), rounding adds at most
+// 16 x 0.5, so the test is "sum < L + 9".
+struct C8Shape {
+    int nf;         // fields per record: 8 (narrow) or 16 (wide)
+    int qb;         // queries per CTA = table row bytes
+    int rows;       // table rows
+    int sat;        // saturation value of an entry
+    int slack;      // rounding slack of a sum: nf / 2
+    int lut_bytes() const { return rows * qb; }
+};
+inline C8Shape c8_shape(int nf) { return nf == 8 ? C8Shape{8, 112, 2048, 31, 4} : C8Shape{16, 48, 4096, 15, 8}; }
 struct Scan8Args {
     const uint4* recs;
     const ChunkDesc2* chunks;
     int n_chunks, chunk_nodes;
     int bt_stride;                // 1: every batch; S: every S-th batch (sample pass)
-    const uint8_t* qlut8;         // [n_groups][2048][112] coarse tables
-    uint32_t* cand;               // [n_items][112][bcap] candidate positions
-    uint32_t* cand_cnt;           // [n_items][112]
-    uint32_t* ovf;                // [n_groups*112]
+    const uint8_t* qlut8;         // [n_groups][rows][qb] coarse tables
+    uint32_t* cand;               // [n_items][qb][bcap] candidate positions
+    uint32_t* cand_cnt;           // [n_items][qb]
+    uint32_t* ovf;                // [n_groups*qb]
     int Q, n_groups, n_slices, n_warps, bcap;
-    int thresh;                   // hit iff coarse sum < thresh (= levels + 5 <= 128)
+    int thresh;                   // hit iff coarse sum < thresh (= levels + slack + 1 <= 128)
+    int nf;                       // 8: narrow shape, 16: wide shape (C8Shape)
 };
 // coarse tables: entry = min(31, rint(lut / unit)), unit = cap / levels, cap = the query's exact k-th
 // distance over the sample (out_key[q][topk-1]); transposed to [group][row][112] u8
 void launch_pack8(const float* d_lutf, const float* d_cap, int MK, int Q, int levels, uint8_t* d_qlut8,
-                  uint32_t* d_ovf, int n_groups, cudaStream_t st);
+                  uint32_t* d_ovf, int n_groups, int nf, cudaStream_t st);
 // cap of every query from the key lists of a finished search: cap[q] = distance of out_key[q][topk-1]
 void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap, cudaStream_t st);
 // cap0[q] = exact k-th smallest distance over R evenly strided nodes (float tables, reference
@@ -154,6 +168,7 @@ struct Rescore8Args {
     const uint32_t* cand_cnt;
     const uint32_t* ovf;
     int n_groups, n_slices, bcap;
+    int qb;                       // queries per group (C8Shape::qb)
     const float* lutf;            // [Q][M*K]
     const uint8_t* codes;         // [n_local][M]
     int64_t base_pos;

@@ -346,12 +346,60 @@ def test_search_other_shapes(M, K, Ds, engine):
     ix.set_codebook(cw)
     assert ix.stat("engine") == (2 if engine == "v2" else 1)
     queries = (rng.random((70, M * Ds)) * 40).astype(np.float32)
-    pos, ids, dist = ix.search(queries, k)
-    for i in range(0, 70, 6):
-        opos, odist, nd = po.scan(payload, n, cw, queries[i], k, want_node_dist=True)
-        np.testing.assert_allclose(dist[i], odist, rtol=REL_TOL)
+    for coarse in ((0, 1) if engine == "v2" else (0,)):  # 1: forced three-phase coarse search (narrow and wide shapes)
+        ix.set_option("coarse", coarse)
+        pos, ids, dist = ix.search(queries, k)
+        if engine == "v2":
+            assert ix.stat("last_coarse") == coarse
+        for i in range(0, 70, 6):
+            opos, odist, nd = po.scan(payload, n, cw, queries[i], k, want_node_dist=True)
+            np.testing.assert_allclose(dist[i], odist, rtol=REL_TOL)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+            assert np.array_equal(ids[i], lay["vec_id"][pos[i]])
+    ix.close()
+
+
+@pytest.mark.parametrize("opts", [dict(coarse=1), dict(coarse=1, sample=2), dict(coarse=1, bcap8=32),
+                                  dict(coarse=1, levels8=123), dict(coarse=1, seed=1)])
+def test_coarse_search_wide_shape_is_exact(golden_m16, engine, opts):
+    """The wide coarse scan (M = 16: 48 queries per CTA, entries saturating at 15, sixteen reads per
+    node) + exact re-score == the oracle, for top-10 and top-100 (configs C3 / C4)."""
+    if engine != "v2":
+        pytest.skip("coarse search belongs to the v2 engine")
+    g = golden_m16
+    codes, cw = g["codes"], g["cw"]
+    n = len(codes)
+    _, _, lay, payload = po.build_tree(codes, cw)
+    ix = dpq.DeltaTreeIndex(payload, n, 16, 256, pos2id=lay["vec_id"])
+    ix.set_codebook(cw)
+    for name, v in opts.items():
+        ix.set_option(name, v)
+    rng = np.random.default_rng(5)
+    queries = np.concatenate([g["queries"], np.clip(g["queries"] + rng.integers(-9, 10, g["queries"].shape), 0, 255)]).astype(np.float32)
+    for k in (1, 10, 100, 128):
+        pos, ids, dist = ix.search(queries, k)
+        assert ix.stat("last_coarse") == 1
+        for i in range(0, len(queries), 3):
+            opos, odist, nd = po.scan(payload, n, cw, queries[i], k, want_node_dist=True)
+            np.testing.assert_allclose(dist[i], odist, rtol=REL_TOL)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+    if opts.get("bcap8") == 32:
+        assert ix.stat("last_fallback") > 0
+    ix.close()
+
+
+def test_coarse_search_narrow_top100(golden4000, engine):
+    """topk in (64, 128] now also takes the coarse path on the narrow shape."""
+    if engine != "v2":
+        pytest.skip("coarse search belongs to the v2 engine")
+    g = golden4000
+    ix = _open(g, coarse=1)
+    pos, ids, dist = ix.search(g["queries"], 100)
+    assert ix.stat("last_coarse") == 1
+    for i in range(0, len(g["queries"]), 5):
+        opos, odist, nd = po.scan(g["payload"], int(g["n"]), g["cw"], g["queries"][i], 100, want_node_dist=True)
+        assert np.array_equal(dist[i], odist)
         assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
-        assert np.array_equal(ids[i], lay["vec_id"][pos[i]])
     ix.close()
 
 
