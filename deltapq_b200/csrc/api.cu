@@ -94,7 +94,7 @@ struct dpq_index {
     int opt_seed = 0;          // 0: sampled 15-bit scan gives the cap (default, 0.90 ms at C2);
                                // 1: exact presample -> sampled coarse scan -> re-score (1.18 ms at C2)
     int opt_presample = 2048;  // nodes scored exactly per query to seed the sample pass
-    int opt_bcap8 = 512, opt_warps8 = 24, opt_levels8 = 80;
+    int opt_bcap8 = 0, opt_warps8 = 24, opt_levels8 = 80;  // bcap8 0 = auto (512 narrow, 2048 wide)
     int64_t opt_coarse_min = 100000;  // nodes in the shard from which the coarse search pays (gpurun_out/probe22.log)
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
@@ -482,7 +482,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "dbg_bound") ix->opt_dbg_bound = (int)v;
     else if (n == "coarse") ix->opt_coarse = (int)v;
     else if (n == "sample") ix->opt_sample = std::max(0, (int)v);
-    else if (n == "bcap8") ix->opt_bcap8 = std::max(32, (int)v);
+    else if (n == "bcap8") ix->opt_bcap8 = v <= 0 ? 0 : std::max(32, (int)v);
     else if (n == "warps8") ix->opt_warps8 = std::max(2, std::min(24, (int)v));
     else if (n == "coarse_min") ix->opt_coarse_min = v;
     else if (n == "seed") ix->opt_seed = (int)v;
@@ -503,8 +503,11 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     const dpq::ScanProgram& P = ix->prog;
     // coarse search (scan8.cu): 15-bit scan over a 1/S sample -> cap per query -> 8-bit scan of
     // the whole tree -> exact re-score.  Narrow shape, moderate k, trees large enough to pay.
-    const bool coarse = P.v2 && topk <= 128 && ix->opt_coarse != 0 &&
-                        (ix->opt_coarse == 1 || P.n_local >= ix->opt_coarse_min);
+    // Automatic choice (gpurun_out/probe_wide.log, profiles/r1_summary.md): the narrow coarse scan pays
+    // up to topk 64; the wide one (saturation at 15, 6-10 % rounding slack) only for short lists -- at
+    // top-100 its sample pass and the re-score of ~4K survivors per query eat the scan's gain.
+    const bool coarse_auto = P.n_local >= ix->opt_coarse_min && topk <= (P.shape.nf == 8 ? 64 : 32);
+    const bool coarse = P.v2 && topk <= 128 && ix->opt_coarse != 0 && (ix->opt_coarse == 1 || coarse_auto);
     const dpq::C8Shape c8 = dpq::c8_shape(P.shape.nf);  // narrow: 112 queries per CTA, wide: 48
     const int spw = P.shape.spw();
     const int levels8 = std::min(ix->opt_levels8, 127 - c8.slack);  // the test constant stays <= 128
@@ -515,7 +518,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     ix->last_coarse = coarse ? 1 : 0;
     // geometry of the coarse pass: 112-query groups, slices by the same wave/round rule
     int g8_groups = 0, g8_slices = 1;
-    const int warps8 = ix->opt_warps8, bcap8 = ix->opt_bcap8;
+    const int warps8 = ix->opt_warps8;
+    const int bcap8 = ix->opt_bcap8 > 0 ? ix->opt_bcap8 : (P.shape.nf == 8 ? 512 : 2048);  // survivors per (slice, query)
     if (coarse) {
         g8_groups = (Q + c8.qb - 1) / c8.qb;
         g8_slices = ix->opt_slices;

@@ -1,7 +1,10 @@
-// Coarse search for the narrow shape (M <= 8): the whole tree is scanned with a 5-bit table in
-// packed 8-bit arithmetic -- four queries per 32-bit word, sixteen per 128-bit table read, 112
-// queries per CTA, i.e. HALF the shared-memory wavefronts per (node, query) of the 15-bit scan
-// (scan2.cu), which is bound by exactly those wavefronts (profiles/r1_summary.md).
+// Coarse search: the whole tree is scanned with a small-integer table in packed 8-bit arithmetic
+// -- four queries per 32-bit word, sixteen per 128-bit table read.  Narrow shape (M <= 8): 5-bit
+// entries, 112 queries per CTA, i.e. HALF the shared-memory wavefronts per (node, query) of the
+// 15-bit scan (scan2.cu), which is bound by exactly those wavefronts (profiles/r1_summary.md).
+// Wide shape (M <= 16): 4-bit entries (sixteen of them fit a byte sum), 48 queries per CTA against
+// the 15-bit wide scan's 24; its filter is weaker (saturation at 15 units, 16 x 0.5 rounding slack),
+// so it is chosen automatically only for short result lists (api.cu).
 //
 // Why it is exact.  Before this pass the 15-bit scan runs over a 1/16 sample of the tree and
 // select_kernel / the exact fallback give cap_q = the exact k-th distance over the sample, an
