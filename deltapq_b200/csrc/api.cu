@@ -19,7 +19,7 @@
 namespace {
 
 thread_local std::string g_err;
-int g_device = 0;
+thread_local int g_device = 0;  // like CUDA's current device: one selection per host thread
 
 int fail(int code, const std::string& msg) {
     g_err = msg;

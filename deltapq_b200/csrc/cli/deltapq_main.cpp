@@ -4,6 +4,9 @@
 // files.  Compute runs on the GPU through libdpq.
 #include "cli_common.hpp"
 
+#include <algorithm>
+#include <thread>
+
 using namespace cli;
 
 static std::string base_name(const std::string& dataset, int M, int K) {
@@ -77,12 +80,27 @@ static int approx_tree(const Args& a, const std::string& dataset, int M, int K) 
     if (P == 1) {
         if (int rc = build_one(dataset, M, K, H, method, codes.data(), N, cb, sfx)) return rc;
     } else {
-        for (int p = 0; p < P; ++p) {
-            const long long b = part_begin(N, p, P), e = part_begin(N, p + 1, P);
-            std::cout << "part " << p << ": ids [" << b << ", " << e << ")" << std::endl;
-            if (int rc = build_one(dataset, M, K, H, method, codes.data() + (size_t)b * M, e - b, cb, sfx + part_suffix(p, P)))
-                return rc;
-        }
+        // -gpus G: the parts are independent trees, so GPU g builds parts g, g + G, ... on its own host thread
+        int G = (int)a.num("-gpus", 1);
+        G = std::max(1, std::min(std::min(G, P), dpq_device_count()));
+        std::vector<int> rcs((size_t)G, 0);
+        auto worker = [&](int g) {
+            if (dpq_set_device(g) != DPQ_OK) {
+                rcs[(size_t)g] = 1;
+                return;
+            }
+            for (int p = g; p < P && !rcs[(size_t)g]; p += G) {
+                const long long b = part_begin(N, p, P), e = part_begin(N, p + 1, P);
+                rcs[(size_t)g] = build_one(dataset, M, K, H, method, codes.data() + (size_t)b * M, e - b, cb, sfx + part_suffix(p, P));
+            }
+        };
+        std::vector<std::thread> th;
+        for (int g = 1; g < G; ++g) th.emplace_back(worker, g);
+        worker(0);
+        for (auto& t : th) t.join();
+        for (int g = 0; g < G; ++g)
+            if (rcs[(size_t)g]) return die("approx_tree -parts: building a part failed on GPU " + std::to_string(g));
+        std::cout << P << " parts on " << G << " GPU(s)" << std::endl;
     }
     std::cout << "approx tree built in " << now_s() - t0 << " sec" << std::endl;
     return 0;

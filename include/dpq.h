@@ -30,7 +30,7 @@ typedef struct dpq_index dpq_index;
 int dpq_version(void);
 const char* dpq_last_error(void); /* thread-local text of the last failure */
 int dpq_device_count(void);       /* number of visible CUDA devices (0 without a GPU) */
-int dpq_set_device(int device);   /* device used by handles created afterwards */
+int dpq_set_device(int device);   /* device used by this host thread's calls and by handles it creates afterwards */
 
 /* ---- DeltaTree index (the scan operand) --------------------------------------------- */
 /* Opens a compressed DeltaTree ("DTC"; writer DCAT.h:1765-1842) that is

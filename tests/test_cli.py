@@ -176,6 +176,17 @@ def test_cli_forest_parts_match_single_tree(tmp_path):
         r = run(cmd + common)
         assert r.returncode == 0, r.stderr
     assert os.path.exists(f"{d}/M8K256_Approx_compressed_codes_opt_N{n}.part2of3")
+    if dpq.device_count() >= 2:  # -gpus 2: one builder thread per GPU, byte-identical part files
+        d2 = str(tmp_path / "g2")
+        os.makedirs(d2)
+        for f in ("base.fvecs", "query.fvecs", "M8K256codewords.txt", f"codes.bin.plain.M8K256N{n}"):
+            shutil.copy(os.path.join(d, f), d2)
+        r = run([BIN + "/deltapq", "-task", "approx_tree", "-h", "1", "-diff", "8", "-parts", "3", "-gpus", "2",
+                 "-dataset", d2] + common[2:])
+        assert r.returncode == 0, r.stderr
+        for p in range(3):
+            for stem in ("M8K256_Approx_compressed_codes_opt", "M8K256_Approx_TreeNodesDFS", "M8K256H1_Approx_Edges"):
+                assert filecmp.cmp(f"{d}/{stem}_N{n}.part{p}of3", f"{d2}/{stem}_N{n}.part{p}of3", shallow=False), (stem, p)
     q = [BIN + "/deltapq", "-task", "query", "-query_size", str(nq), "-topk", str(k)]
     r = run(q + ["-results", f"{d}/whole.txt"] + common)
     assert r.returncode == 0, r.stderr
