@@ -27,7 +27,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
@@ -250,6 +253,103 @@ __global__ void gather_ids_kernel(const uint32_t* __restrict__ live, int64_t n, 
 
 inline unsigned blocks(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
+// ---------------------------------------------------------------------------------------------
+// Futile-pass prefilter (M >= 12: thousands of kept-subspace combinations).  A pass with kept set S
+// merges something only if two pool codes agree on all of S, i.e. their changed-subspace mask is a
+// subset of the dropped set D.  The pool only ever shrinks, so the masks of all pairs of ORIGINAL
+// codes bound every later pass from above.  Every pair that differs in at most M - 2 subspaces
+// shares at least one pair of subspaces: bucketing the codes by each of the M (M - 1) / 2
+// two-subspace keys enumerates all those pairs.  active[m] = some pair has changed-subspace mask m;
+// the host then skips a pass when no active mask is a subset of its dropped set (exactly the passes
+// that would have found all keys distinct and changed nothing).
+__global__ void pair_key_kernel(const uint8_t* __restrict__ codes, int64_t n, int M, int sa, int sb,
+                                uint32_t* __restrict__ key, uint32_t* __restrict__ id) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    key[i] = (uint32_t)codes[(size_t)i * M + sa] | ((uint32_t)codes[(size_t)i * M + sb] << 8);
+    id[i] = (uint32_t)i;
+}
+
+// bucket work = sum over elements of the number of later elements in the same bucket
+__global__ void pair_work_kernel(const uint32_t* __restrict__ key, int64_t n, unsigned long long* __restrict__ work) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long w = 0;
+    if (i < n && (i == 0 || key[i - 1] != key[i])) {  // bucket head: walk to its end
+        int64_t j = i + 1;
+        while (j < n && key[j] == key[i]) ++j;
+        const unsigned long long len = (unsigned long long)(j - i);
+        w = len * (len - 1) / 2;
+    }
+    for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(work, w);
+}
+
+__global__ void pair_mask_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ id, int64_t n,
+                                 const uint8_t* __restrict__ codes, int M, uint32_t* __restrict__ active) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key[i];
+    uint8_t x[16];
+    const uint8_t* cx = codes + (size_t)id[i] * M;
+    for (int m = 0; m < M; ++m) x[m] = cx[m];
+    for (int64_t j = i + 1; j < n && key[j] == k; ++j) {
+        const uint8_t* cy = codes + (size_t)id[j] * M;
+        uint32_t mask = 0;
+        for (int m = 0; m < M; ++m) mask |= (uint32_t)(x[m] != cy[m]) << m;
+        const uint32_t bit = 1u << (mask & 31u);
+        if (!(active[mask >> 5] & bit)) atomicOr(&active[mask >> 5], bit);
+    }
+}
+
+// hit[D] != 0 iff some active changed-subspace mask is a subset of the dropped set D.  Empty when the
+// prefilter does not apply (few combinations, K > 256 keys, or buckets too large to enumerate).
+int futile_pass_prefilter(const uint8_t* d_codes, int64_t n, int M, std::vector<uint8_t>* hit) {
+    hit->clear();
+    if (M < 12 || M > 16 || n < 2) return DPQ_OK;
+    Buf d_key, d_key2, d_id, d_id2, d_active, d_work, d_tmp;
+    CU(d_key.alloc((size_t)n * 4));
+    CU(d_key2.alloc((size_t)n * 4));
+    CU(d_id.alloc((size_t)n * 4));
+    CU(d_id2.alloc((size_t)n * 4));
+    CU(d_active.alloc(((size_t)1 << M) / 8));
+    CU(d_work.alloc(8));
+    size_t tmp_bytes = 0;
+    {
+        cub::DoubleBuffer<uint32_t> kb(d_key.as<uint32_t>(), d_key2.as<uint32_t>());
+        cub::DoubleBuffer<uint32_t> vb(d_id.as<uint32_t>(), d_id2.as<uint32_t>());
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, 16));
+    }
+    CU(d_tmp.alloc(tmp_bytes));
+    CU(cudaMemset(d_active.p, 0, ((size_t)1 << M) / 8));
+    // at most ~2 x 10^10 pair comparisons in total (about a second); denser data keeps every pass
+    const unsigned long long budget = 20000000000ull;
+    unsigned long long spent = 0;
+    for (int sa = 0; sa < M; ++sa)
+        for (int sb = sa + 1; sb < M; ++sb) {
+            pair_key_kernel<<<blocks(n), 256>>>(d_codes, n, M, sa, sb, d_key.as<uint32_t>(), d_id.as<uint32_t>());
+            cub::DoubleBuffer<uint32_t> kb(d_key.as<uint32_t>(), d_key2.as<uint32_t>());
+            cub::DoubleBuffer<uint32_t> vb(d_id.as<uint32_t>(), d_id2.as<uint32_t>());
+            size_t t = tmp_bytes;
+            CU(cub::DeviceRadixSort::SortPairs(d_tmp.p, t, kb, vb, (int)n, 0, 16));
+            CU(cudaMemsetAsync(d_work.p, 0, 8));
+            pair_work_kernel<<<blocks(n), 256>>>(kb.Current(), n, d_work.as<unsigned long long>());
+            unsigned long long w = 0;
+            CU(cudaMemcpy(&w, d_work.p, 8, cudaMemcpyDeviceToHost));
+            spent += w;
+            if (spent > budget) return DPQ_OK;  // too dense: no prefilter
+            pair_mask_kernel<<<blocks(n), 256>>>(kb.Current(), vb.Current(), n, d_codes, M, d_active.as<uint32_t>());
+            CU(cudaGetLastError());
+        }
+    std::vector<uint32_t> active(((size_t)1 << M) / 32);
+    CU(cudaMemcpy(active.data(), d_active.p, active.size() * 4, cudaMemcpyDeviceToHost));
+    hit->assign((size_t)1 << M, 0);
+    for (size_t m = 0; m < hit->size(); ++m) (*hit)[m] = (active[m >> 5] >> (m & 31)) & 1u;
+    for (int b = 0; b < M; ++b)  // subset-sum over dropped sets: hit[D] |= hit[D without b]
+        for (size_t d = 0; d < hit->size(); ++d)
+            if (d & ((size_t)1 << b)) (*hit)[d] |= (*hit)[d ^ ((size_t)1 << b)];
+    return DPQ_OK;
+}
+
 }  // namespace
 
 extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_height_folds,
@@ -317,6 +417,15 @@ extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int 
     iota_kernel<<<blocks(n), 256>>>(d_ids.as<uint32_t>(), n);
     CU(cudaGetLastError());
 
+    // passes that cannot merge anything are skipped (exact: see futile_pass_prefilter)
+    std::vector<uint8_t> hit;
+    if (!getenv("DPQ_NO_PREFILTER") && K <= 256) {
+        rc = futile_pass_prefilter(d_codes.as<uint8_t>(), n, M, &hit);
+        if (rc) return rc;
+    }
+    const uint32_t all_bits = M >= 32 ? 0xFFFFFFFFu : ((1u << M) - 1u);
+    int64_t skipped_passes = 0;
+
     uint32_t* ids = d_ids.as<uint32_t>();
     uint32_t* ids_alt = d_ids2.as<uint32_t>();
     uint32_t* live = d_live.as<uint32_t>();
@@ -328,7 +437,11 @@ extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int 
                 d_cnt.as<unsigned long long>()};
     int64_t n_ids = n, n_edges = 0, n_fin = 0;
 
+    const bool stats = getenv("DPQ_EDGE_STATS") != nullptr;  // per-round pool size / passes / seconds on stderr
     for (int diff = 0; diff <= M && n_ids > 1; ++diff) {  // dmain:126 forces diff_argument = M
+        const auto round_t0 = std::chrono::steady_clock::now();
+        const int64_t round_n0 = n_ids;
+        int64_t round_passes = 0, round_live_sum = 0;
         CU(cudaMemsetAsync(is_merged, 0, (size_t)n_ids));
         iota_kernel<<<blocks(n_ids), 256>>>(live, n_ids);
         int64_t n_live = n_ids;
@@ -338,6 +451,13 @@ extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int 
             if (n_live < 2) break;  // no run of two can form any more in this round
             uint32_t selbits = 0;
             for (int m = 0; m < M; ++m) selbits |= sel[(size_t)m] ? (1u << m) : 0u;
+            // pairs that differ in more than M - 2 subspaces were not enumerated: those rounds always run
+            if (!hit.empty() && diff <= M - 2 && !hit[(size_t)(~selbits & all_bits)]) {
+                ++skipped_passes;
+                continue;
+            }
+            ++round_passes;
+            round_live_sum += n_live;
             mask_key_kernel<<<blocks(n_live), 256>>>(live, n_live, ids, dc, M, log_k, selbits,
                                                      d_klo.as<uint64_t>(), d_slot.as<uint32_t>());
             cub::DoubleBuffer<uint64_t> kb(d_klo.as<uint64_t>(), d_klo2.as<uint64_t>());
@@ -387,6 +507,13 @@ extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int 
         std::swap(ids, ids_alt);
         n_ids = n_live;
         CU(cudaGetLastError());
+        if (stats) {
+            CU(cudaDeviceSynchronize());
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - round_t0).count();
+            fprintf(stderr, "dpq_find_edges: diff %d pool %lld -> %lld, %lld passes (%lld skipped so far), mean live %lld, %.3f s\n",
+                    diff, (long long)round_n0, (long long)n_ids, (long long)round_passes, (long long)skipped_passes,
+                    (long long)(round_passes ? round_live_sum / round_passes : 0), sec);
+        }
     }
     if (n_edges + n_fin + (n_ids > 0 ? 1 : 0) != n_codes)
         return dpq::api_fail(DPQ_ERR_CUDA, "dpq_find_edges: internal edge count mismatch");

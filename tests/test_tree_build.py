@@ -133,3 +133,44 @@ def test_gpu_layout_sift_200k_equals_host_layout():
     h = dpq.tree_from_edges(codes, cw, g["edges"], g["root_id"])
     for k in ("vec_id", "parent_pos", "child_num", "depth", "max_dist", "max_dist2p", "codes_by_pos", "payload"):
         assert np.array_equal(g[k], h[k]), k
+
+
+def _planted_codes(n, M, K, rng, n_seeds, max_changes):
+    """Sparse codes (uniform over K^M) with planted near-duplicates: every code is a seed code with
+    0..max_changes random subspaces redrawn, so merges happen at many different diff levels."""
+    seeds = rng.integers(0, K, size=(n_seeds, M))
+    codes = seeds[rng.integers(0, n_seeds, n)].copy()
+    for i in range(n):
+        ch = rng.integers(0, max_changes + 1)
+        idx = rng.choice(M, size=ch, replace=False)
+        codes[i, idx] = rng.integers(0, K, size=ch)
+    return codes.astype(np.uint8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2000, 12, 256, 300, 8, 1), (1500, 16, 256, 200, 10, 1), (1800, 13, 50, 250, 6, 2)])
+def test_gpu_find_edges_futile_pass_prefilter_is_exact(shape, monkeypatch):
+    """M >= 12: passes whose dropped set contains no pair's changed-subspace mask are skipped
+    (edges.cu futile_pass_prefilter).  Edges must equal the oracle's and the unfiltered run's."""
+    n, M, K, n_seeds, max_changes, method = shape
+    rng = np.random.default_rng(n + M)
+    codes = _planted_codes(n, M, K, rng, n_seeds, max_changes)
+    monkeypatch.delenv("DPQ_NO_PREFILTER", raising=False)
+    ge, groot = dpq.find_edges(codes, K, 1, method)
+    oe, oroot = po.find_edges(codes, K, 1, method)
+    assert groot == oroot and np.array_equal(ge, oe)
+    monkeypatch.setenv("DPQ_NO_PREFILTER", "1")
+    ue, uroot = dpq.find_edges(codes, K, 1, method)
+    assert uroot == groot and np.array_equal(ue, ge)
+
+
+@pytest.mark.gpu
+def test_gpu_find_edges_prefilter_sift_m12_equals_unfiltered(monkeypatch):
+    base = dg.sift_like(30000, 120, seed=15)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(4000, 120, seed=16), 12, 256, iters=3))
+    codes = dpq.encode(cw, base)
+    monkeypatch.delenv("DPQ_NO_PREFILTER", raising=False)
+    ge, groot = dpq.find_edges(codes, 256, 1, 1)
+    monkeypatch.setenv("DPQ_NO_PREFILTER", "1")
+    ue, uroot = dpq.find_edges(codes, 256, 1, 1)
+    assert uroot == groot and np.array_equal(ue, ge)
