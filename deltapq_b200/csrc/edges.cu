@@ -98,15 +98,30 @@ __global__ void iota_kernel(uint32_t* a, int64_t n) {
     if (i < n) a[i] = (uint32_t)i;
 }
 
+// compact != 0: the kept centroid ids packed next to each other (subspace order kept).  Two blanked
+// 128-bit keys compare exactly like their compacted forms -- the dropped positions are zero in both
+// -- so sorting by the compact key gives the reference's order with kept * log_k key bits instead of
+// 128 (one radix sort, fewer digit passes).
 __global__ void mask_key_kernel(const uint32_t* __restrict__ live, int64_t n_live,
                                 const uint32_t* __restrict__ ids, const uint8_t* __restrict__ codes, int M,
-                                int log_k, uint32_t sel, uint64_t* __restrict__ key_lo,
+                                int log_k, uint32_t sel, int compact, uint64_t* __restrict__ key_lo,
                                 uint32_t* __restrict__ slot) {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_live) return;
     const uint32_t s = live[l];
     uint64_t lo, hi;
-    masked_key(codes, ids[s], M, log_k, sel, lo, hi);
+    if (compact) {
+        const uint8_t* c = codes + (size_t)ids[s] * M;
+        lo = 0;
+        int sh = 0;
+        for (int m = 0; m < M; ++m)
+            if ((sel >> m) & 1u) {
+                lo |= (uint64_t)c[m] << sh;
+                sh += log_k;
+            }
+    } else {
+        masked_key(codes, ids[s], M, log_k, sel, lo, hi);
+    }
     key_lo[l] = lo;
     slot[l] = s;
 }
@@ -458,13 +473,18 @@ extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int 
             }
             ++round_passes;
             round_live_sum += n_live;
-            mask_key_kernel<<<blocks(n_live), 256>>>(live, n_live, ids, dc, M, log_k, selbits,
+            // a centroid id needs log_k bits unless K is not a power of two (ids up to K - 1 < 2^log_k may
+            // not hold then): the compact form is used only when every id fits its field
+            const int kept = M - diff;
+            const bool compact = kept * log_k <= 64 && (1 << log_k) >= K;
+            mask_key_kernel<<<blocks(n_live), 256>>>(live, n_live, ids, dc, M, log_k, selbits, compact ? 1 : 0,
                                                      d_klo.as<uint64_t>(), d_slot.as<uint32_t>());
             cub::DoubleBuffer<uint64_t> kb(d_klo.as<uint64_t>(), d_klo2.as<uint64_t>());
             cub::DoubleBuffer<uint32_t> vb(d_slot.as<uint32_t>(), d_slot2.as<uint32_t>());
             t = tmp_bytes;
-            CU(cub::DeviceRadixSort::SortPairs(d_tmp.p, t, kb, vb, (int)n_live, 0, std::min(64, key_bits)));
-            if (wide) {  // LSD over the two halves: stable sort by the high half second
+            CU(cub::DeviceRadixSort::SortPairs(d_tmp.p, t, kb, vb, (int)n_live, 0,
+                                               compact ? std::max(1, kept * log_k) : std::min(64, key_bits)));
+            if (wide && !compact) {  // LSD over the two halves: stable sort by the high half second
                 gather_hi_kernel<<<blocks(n_live), 256>>>(vb.Current(), n_live, ids, dc, M, log_k, selbits, d_khi.as<uint64_t>());
                 cub::DoubleBuffer<uint64_t> kh(d_khi.as<uint64_t>(), d_khi2.as<uint64_t>());
                 t = tmp_bytes;
