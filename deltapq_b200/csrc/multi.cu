@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dpq.h"
@@ -203,13 +204,32 @@ int dpq_multi_open_parts(const char* const* tree_paths, const char* const* qnode
     int rc = begin_multi_open(n_gpus, n_parts, M, K, &m);
     if (rc) return rc;
     int64_t span = 0;
-    for (int p = 0; p < n_parts && !rc; ++p) {
-        const int r = p % n_gpus;  // parts are dealt round-robin to the GPUs
-        rc = dpq_set_device(r);
-        if (!rc) rc = dpq_index_open_part_file(tree_paths[p], nullptr, M, K, first_pos[p], &m->ix[(size_t)p]);
-        m->dev[(size_t)p] = r;
-        m->on[(size_t)r].push_back(p);
-        if (!rc) span = std::max<int64_t>(span, first_pos[p] + dpq_index_stat(m->ix[(size_t)p], "n_codes"));
+    {
+        // parts are dealt round-robin to the GPUs and opened concurrently: the host decode of a stream is
+        // sequential (seconds per 10^8 nodes), the parts are independent, the device selection is per thread
+        for (int p = 0; p < n_parts; ++p) {
+            m->dev[(size_t)p] = p % n_gpus;
+            m->on[(size_t)(p % n_gpus)].push_back(p);
+        }
+        std::vector<int> rcs((size_t)n_parts, 0);
+        std::vector<std::string> errs((size_t)n_parts);
+        const int n_threads = std::max(1, std::min(n_parts, (int)std::thread::hardware_concurrency()));
+        auto worker = [&](int t) {
+            for (int p = t; p < n_parts; p += n_threads) {
+                int r_ = dpq_set_device(m->dev[(size_t)p]);
+                if (!r_) r_ = dpq_index_open_part_file(tree_paths[p], nullptr, M, K, first_pos[p], &m->ix[(size_t)p]);
+                rcs[(size_t)p] = r_;
+                if (r_) errs[(size_t)p] = dpq_last_error();  // thread-local text: carry it to the caller's thread
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& t : th) t.join();
+        for (int p = 0; p < n_parts && !rc; ++p)
+            if (rcs[(size_t)p]) rc = dpq::api_fail(rcs[(size_t)p], errs[(size_t)p]);
+        for (int p = 0; p < n_parts && !rc; ++p)
+            span = std::max<int64_t>(span, first_pos[p] + dpq_index_stat(m->ix[(size_t)p], "n_codes"));
     }
     if (!rc) rc = finish_multi_open(m);
     if (!rc && qnode_paths) {  // ids of part p = first_pos[p] + its own vec_id (parts are id ranges)
