@@ -301,9 +301,10 @@ struct dpq_gt {
 
 namespace {
 constexpr int64_t GT_TC_STEP = 131072;  // base vectors per filter launch: the cap tightens between launches
-// vectors scored densely first, so that every query has a finite cap: 64 per wanted neighbour keeps the
-// first launch's survivors (k * step / seed) at half the candidate slots
-inline int64_t gt_tc_seed(int topk) { return std::min<int64_t>(8192, std::max<int64_t>(1024, 64LL * topk)); }
+// vectors scored densely first, so that every query has a finite cap.  The first launch's survivors
+// are about k * step / seed per query: 4096 keeps them (and the exact re-score) small -- a 1024 seed
+// tripled the re-score time -- and 64 per wanted neighbour keeps long lists inside the candidate slots
+inline int64_t gt_tc_seed(int topk) { return std::min<int64_t>(8192, std::max<int64_t>(4096, 64LL * topk)); }
 constexpr int GT_TC_CAND = 4096;        // candidate slots per query per launch
 
 // dense exact path over base[0..n) (device) for the queries qlist[0..nq) (nullptr: all)

@@ -469,7 +469,7 @@ def test_medium_tree_end_to_end():
     (9000, 960, 40, 5, "gist"),         # non-integer values: the bf16 hi + lo split and its error bound
     (12345, 100, 300, 64, "ints"),      # D not a multiple of 64
     (7000, 30, 17, 3, "gauss"),         # D not a multiple of 4, signed values
-    (700, 128, 9, 10, "sift"),          # fewer vectors than the dense seed
+    (3000, 128, 9, 10, "sift"),         # fewer vectors than the dense seed
     (40000, 128, 64, 10, "dupes"),      # heavy exact ties
 ])
 def test_groundtruth_tensor_core_filter_equals_plain_kernels(shape, monkeypatch):
@@ -497,7 +497,7 @@ def test_groundtruth_tensor_core_filter_equals_plain_kernels(shape, monkeypatch)
     st1 = {}
     sid, sdist = dpq.groundtruth(base, qs, k, chunk=17000, stats=st1)
     assert st1["tc"] == 1 and np.array_equal(sid, ids) and np.array_equal(sdist, dist)
-    seed = min(8192, max(1024, 64 * k))
+    seed = min(8192, max(4096, 64 * k))
     if n > seed:
         assert st["tc_vectors"] == n - seed          # everything after the dense seed went through the filter
         if gen != "dupes":
