@@ -35,6 +35,25 @@ def test_fails_loudly_without_gpu(golden1501):
         dpq.encode(g["cw"], g["base_head"])
     with pytest.raises(dpq.DpqError, match="no CUDA device"):
         dpq.adc_tables(g["cw"], g["queries"])
+    with pytest.raises(dpq.DpqError, match="no CUDA device"):
+        dpq.DeltaTreeIndex(g["payload"], int(g["n"]), 8, 256, first_pos=1000)          # dpq_index_open_part
+    with pytest.raises(dpq.DpqError, match="no CUDA device"):
+        dpq.encode_u8(g["cw"], np.zeros(132 * 4, np.uint8), 4, 128, 132, 4)
+    with pytest.raises(dpq.DpqError, match="no CUDA device"):
+        dpq.groundtruth(g["base_head"], g["queries"], 3)
+    with pytest.raises(dpq.DpqError, match="no CUDA device"):
+        dpq.tree_build(g["codes"], g["cw"])
+    # the host half of the build needs no GPU; opening its tree as an index does
+    L = dpq.lib()
+    codes = np.ascontiguousarray(g["codes"], np.uint8)
+    cw = np.ascontiguousarray(g["cw"], np.float32)
+    edges = np.ascontiguousarray(g["edges"], np.uint32)
+    t = C.c_void_p()
+    assert L.dpq_tree_from_edges(codes.ctypes.data_as(C.c_void_p), len(codes), 8, 256, cw.ctypes.data_as(C.c_void_p),
+                                 cw.shape[2], edges.ctypes.data_as(C.c_void_p), int(g["root"]), C.byref(t)) == 0
+    ix = C.c_void_p()
+    assert L.dpq_index_open_tree(t, 0, C.byref(ix)) == -2 and b"no CUDA device" in L.dpq_last_error()
+    L.dpq_tree_free(t)
 
 
 def test_rejects_malformed_stream(golden1501):
