@@ -89,7 +89,7 @@ struct dpq_index {
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
     int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
-    int opt_sample = 0;        // the sample pass walks every opt_sample-th batch (0 = auto: 16, or 8 below 400K nodes)
+    int opt_sample = 0;        // the sample pass walks every opt_sample-th batch (0 = auto: 8 / 16 / 32 / 64 by tree size)
     int opt_slices_s = 0;      // slices of the sample pass (0 = auto)
     int opt_seed = 0;          // 0: sampled 15-bit scan gives the cap (default, 0.90 ms at C2);
                                // 1: exact presample -> sampled coarse scan -> re-score (1.18 ms at C2)
@@ -511,7 +511,11 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     const dpq::C8Shape c8 = dpq::c8_shape(P.shape.nf);  // narrow: 112 queries per CTA, wide: 48
     const int spw = P.shape.spw();
     const int levels8 = std::min(ix->opt_levels8, 127 - c8.slack);  // the test constant stays <= 128
-    const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : (P.n_local >= 400000 ? 16 : 8));
+    // sample stride: a sparser sample is cheaper to scan but gives a looser cap (more coarse survivors to
+    // re-score).  Measured optimum: 32 at 1M nodes (+2 % over 16; 64 is slower), 64 at 125M nodes (+9 %;
+    // 256 overflows candidate lists): the sample keeps at least ~30K nodes (gpurun_out/b_opt.json runs).
+    const int S_auto = P.n_local >= 2000000 ? 64 : (P.n_local >= 1000000 ? 32 : (P.n_local >= 400000 ? 16 : 8));
+    const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : S_auto);
     const int n_chunks_sample = (((ix->n_chunks + spw - 1) / spw + S - 1) / S) * spw;  // chunks the sample pass walks
     int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
     if (rc) return rc;
