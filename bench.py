@@ -6,7 +6,7 @@ top-k) on B200, through libdpq.so's C ABI (include/dpq.h).
 
 Workload (BASELINE.json configs[1]): SIFT1M-shaped synthetic, 1M x 128-d, M=8 K=256 h=1,
 10K queries, top-10.  One step = one pass of the hot path over one batch of 10K queries.
-The tree is produced by the product's own pipeline (GPU encode, GPU edge search, host DFS
+The tree is produced by the product's own pipeline (GPU encode, GPU edge search, GPU DFS
 layout + stream writer); only the cpu_baseline leg / --impl reference touch oracle/.
 
 N > 1 (torchrun, one rank per GPU).  Primary number: the 16 MB tree is replicated and the
@@ -378,7 +378,7 @@ def run_gpu(args):
                        "sharding": "whole tree on one GPU" if world == 1 else
                                    f"queries sharded: {world} replicas of the tree, {Q} queries per GPU per step, NCCL all-gather of the result keys",
                        "l2": "256 MiB buffer written before every timed step (L2 flush, outside the events)",
-                       "tree": "built by libdpq (GPU encode + GPU edge search + host DFS layout)",
+                       "tree": "built by libdpq (GPU encode + GPU edge search + GPU DFS layout and stream)",
                        "setup_s": round(t_setup, 1), "opts": args.opts or "default"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": dom_name,
