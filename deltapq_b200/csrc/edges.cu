@@ -316,7 +316,7 @@ __global__ void pair_mask_kernel(const uint32_t* __restrict__ key, const uint32_
     }
 }
 
-// hit[D] != 0 iff some active changed-subspace mask is a subset of the dropped set D.  Empty when the
+// hit[D] != 0 iff some pair of codes has exactly the changed-subspace mask D.  Empty when the
 // prefilter does not apply (few combinations, K > 256 keys, or buckets too large to enumerate).
 int futile_pass_prefilter(const uint8_t* d_codes, int64_t n, int M, std::vector<uint8_t>* hit) {
     hit->clear();
@@ -357,11 +357,13 @@ int futile_pass_prefilter(const uint8_t* d_codes, int64_t n, int M, std::vector<
         }
     std::vector<uint32_t> active(((size_t)1 << M) / 32);
     CU(cudaMemcpy(active.data(), d_active.p, active.size() * 4, cudaMemcpyDeviceToHost));
+    // A pair with changed-subspace mask m lands in one run in the pass whose dropped set IS m (round
+    // |m|), and every run keeps at most its parent in the pool: afterwards no two pool codes have mask
+    // m.  So when a pass with dropped set D runs, every surviving pair with mask inside D has mask
+    // exactly D, and the pass can merge something only if active[D] (exact duplicates, mask 0, only
+    // matter to the first pass).
     hit->assign((size_t)1 << M, 0);
     for (size_t m = 0; m < hit->size(); ++m) (*hit)[m] = (active[m >> 5] >> (m & 31)) & 1u;
-    for (int b = 0; b < M; ++b)  // subset-sum over dropped sets: hit[D] |= hit[D without b]
-        for (size_t d = 0; d < hit->size(); ++d)
-            if (d & ((size_t)1 << b)) (*hit)[d] |= (*hit)[d ^ ((size_t)1 << b)];
     return DPQ_OK;
 }
 

@@ -135,26 +135,28 @@ def test_gpu_layout_sift_200k_equals_host_layout():
         assert np.array_equal(g[k], h[k]), k
 
 
-def _planted_codes(n, M, K, rng, n_seeds, max_changes):
+def _planted_codes(n, M, K, rng, n_seeds, max_changes, min_changes=0):
     """Sparse codes (uniform over K^M) with planted near-duplicates: every code is a seed code with
-    0..max_changes random subspaces redrawn, so merges happen at many different diff levels."""
+    min_changes..max_changes random subspaces redrawn, so merges happen at many different diff
+    levels (min_changes = 0 also plants exact duplicates)."""
     seeds = rng.integers(0, K, size=(n_seeds, M))
     codes = seeds[rng.integers(0, n_seeds, n)].copy()
     for i in range(n):
-        ch = rng.integers(0, max_changes + 1)
+        ch = rng.integers(min_changes, max_changes + 1)
         idx = rng.choice(M, size=ch, replace=False)
         codes[i, idx] = rng.integers(0, K, size=ch)
     return codes.astype(np.uint8)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("min_changes", [0, 1])
 @pytest.mark.parametrize("shape", [(2000, 12, 256, 300, 8, 1), (1500, 16, 256, 200, 10, 1), (1800, 13, 50, 250, 6, 2)])
-def test_gpu_find_edges_futile_pass_prefilter_is_exact(shape, monkeypatch):
+def test_gpu_find_edges_futile_pass_prefilter_is_exact(shape, min_changes, monkeypatch):
     """M >= 12: passes whose dropped set contains no pair's changed-subspace mask are skipped
     (edges.cu futile_pass_prefilter).  Edges must equal the oracle's and the unfiltered run's."""
     n, M, K, n_seeds, max_changes, method = shape
     rng = np.random.default_rng(n + M)
-    codes = _planted_codes(n, M, K, rng, n_seeds, max_changes)
+    codes = _planted_codes(n, M, K, rng, n_seeds, max_changes, min_changes)
     monkeypatch.delenv("DPQ_NO_PREFILTER", raising=False)
     ge, groot = dpq.find_edges(codes, K, 1, method)
     oe, oroot = po.find_edges(codes, K, 1, method)
