@@ -34,5 +34,7 @@ def test_a_pass_merges_only_if_its_dropped_set_is_some_pairs_exact_mask(seed, M,
             if any(len(r) > 1 for r in runs.values()):
                 merging_passes += 1
                 assert dropped in masks
-            pool = sorted(r[0] for r in runs.values())  # one survivor per run (the parent)
+            # one survivor per run; WHICH member (the parent rule: largest height / first member)
+            # does not matter for the invariant, so any choice must pass
+            pool = sorted(r[int(rng.integers(0, len(r)))] for r in runs.values())
     assert len(pool) == 1 and merging_passes > 0
