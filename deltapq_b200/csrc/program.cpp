@@ -7,6 +7,7 @@
 // 4-bit depths) because the reference's own M = 16 output is invalid.
 #include "dpq_internal.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -137,8 +138,10 @@ struct Emitter2 {
             for (int i = 0; i < nf; ++i) f[i] = i < M ? (uint32_t)(i * K + cur[i]) * (uint32_t)sh.lpg : zero_row;
         }
         const size_t at = p->recs.size();
-        for (int w = 0; w < half; ++w) p->recs.push_back(f[2 * w] | (f[2 * w + 1] << 16));
-        if (abs) p->recs[at] |= V2_ABS;
+        p->recs.resize(at + (size_t)half);
+        uint32_t* r = p->recs.data() + at;
+        for (int w = 0; w < half; ++w) r[w] = f[2 * w] | (f[2 * w + 1] << 16);
+        if (abs) r[0] |= V2_ABS;
         prev_rec = (long)at;
         prev_depth = depth;
         ++in_chunk;
@@ -176,6 +179,16 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
     E2.sh = P.shape;
     E2.chunk_nodes = P.v2_chunk_nodes;
 
+    // capacity up front (a shard holds about 1 / n_ranks of the nodes): no regrowth copies of GB-sized arrays
+    {
+        const size_t share = (size_t)(n_codes / n_ranks + n_codes / (8 * n_ranks) + 1024);
+        const size_t cap = std::min<size_t>((size_t)n_codes, share);
+        P.codes.reserve(cap * (size_t)M);
+        if (P.v2) {
+            P.recs.reserve(cap * (size_t)P.shape.rec_words());
+            P.chunks2.reserve(cap / (size_t)P.v2_chunk_nodes + 16);
+        }
+    }
     std::vector<uint8_t> stack((size_t)(levels + 1) * M, 0);
     int64_t off = 0;
     memcpy(stack.data(), payload, (size_t)M);
