@@ -33,6 +33,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))  # datagen: synthetic data + fil
 
 METRIC = "queries/sec @top10 on 1M-code DeltaTree (SIFT1M-shaped synthetic, M=8 K=256)"
 UNIT = "queries/s"
+WORKLOAD = ("SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, 10K queries per GPU per step, top-10 "
+            "(BASELINE configs[1])")
 N_CODES, N_QUERIES, DIM, PQ_M, PQ_K, TOPK = 1_000_000, 10_000, 128, 8, 256, 10
 
 
@@ -106,9 +108,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------ reference arm --
-def _ref_worker(args):
+_REF_STATE = {}
+
+
+def _ref_init(payload, n_codes, cw):
+    """Runs once in every worker process: the tree and codebook stay resident in the worker."""
+    _REF_STATE["tree"] = (payload, n_codes, cw)
+
+
+def _ref_worker(job):
     """One process = one single-threaded reference scanner (its globals are not thread safe)."""
-    payload, n_codes, cw, queries, topk = args
+    queries, topk = job
+    payload, n_codes, cw = _REF_STATE["tree"]
     from oracle import pyoracle as po
     if po.have_ref():
         _, _, secs = po.ref_scan(payload, n_codes, cw, queries, topk)
@@ -131,49 +142,52 @@ def cpu_reference_tree(base, cw):
     return payload
 
 
-def time_reference(payload, n_codes, cw, queries, topk, procs, per_proc):
-    """procs single-threaded reference scanners side by side, per_proc queries each."""
-    import multiprocessing as mp
-    jobs = [(payload, n_codes, cw, queries[i * per_proc:(i + 1) * per_proc], topk) for i in range(procs)]
-    t = time.perf_counter()
-    if procs == 1:
-        _ref_worker(jobs[0])
-    else:
-        with mp.get_context("fork").Pool(procs) as pool:
-            pool.map(_ref_worker, jobs)
-    return time.perf_counter() - t
-
-
 def run_reference(args):
+    """The reference's own CPU implementation of the path on all host cores: one persistent
+    single-threaded scanner process per core (the reference's query function keeps its state in
+    globals, so threads cannot share a process), started and warmed OUTSIDE the timed region; a
+    step hands every scanner its slice of a bounded sample of the 10K-query batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import multiprocessing as mp
     from oracle import pyoracle as po
     base, cw, queries = synth(args.n_codes, args.queries)
     payload = cpu_reference_tree(base, cw)
+    del base
     cores = len(os.sched_getaffinity(0))
     per_proc = args.ref_queries_per_proc
     kind = "reference" if po.have_ref() else "port"
-    # fork the pool once per step (the harness process is short lived by design: the reference
-    # leaks per query, SURVEY App. C.3); pool start-up is inside the timed region and is small
-    # against per_proc * ~20 ms of scanning
-    for _ in range(args.warmup):
-        time_reference(payload, args.n_codes, cw, queries, TOPK, cores, per_proc)
+    n_step = cores * per_proc
+    pool = mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(payload, args.n_codes, cw))
+
+    def step(i):
+        # a different window of the query set every step (wraps around the 10K queries)
+        idx = (np.arange(n_step) + i * n_step) % len(queries)
+        qs = queries[idx]
+        jobs = [(np.ascontiguousarray(qs[p * per_proc:(p + 1) * per_proc]), TOPK) for p in range(cores)]
+        pool.map(_ref_worker, jobs, chunksize=1)
+
+    for i in range(args.warmup):
+        step(i)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        time_reference(payload, args.n_codes, cw, queries, TOPK, cores, per_proc)
+    for i in range(args.steps):
+        step(args.warmup + i)
     dt = time.perf_counter() - t0
-    nq = cores * per_proc * args.steps
+    pool.close()
+    pool.join()
+    nq = n_step * args.steps
     qps = nq / dt
-    sample = (f"{cores * per_proc} of the {args.queries} queries per step ({per_proc} per process, {cores} "
-              f"single-threaded reference scanners side by side: DCAT.h:3731 in-memory scan via oracle/_ref)")
+    sample = (f"{n_step} of the {args.queries} queries per step ({per_proc} per process, {cores} persistent "
+              f"single-threaded reference scanners side by side: DCAT.h:3731 in-memory scan via oracle/_ref; "
+              f"workers forked and warmed before the timed region)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, 10K queries per GPU per step, top-10 (BASELINE configs[1])",
-                   "n_codes": args.n_codes, "queries_per_step": cores * per_proc, "topk": TOPK, "n_bytes": int(len(payload)),
+        "config": {"workload": WORKLOAD,
+                   "n_codes": args.n_codes, "queries_per_step": n_step, "topk": TOPK, "n_bytes": int(len(payload)),
                    "note": "same tree and query set as the GPU arm; each step is a bounded sample of the 10K-query batch"},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -356,9 +370,9 @@ def run_gpu(args):
     e2e_qps = world * Q * args.steps / e2e_s
 
     if rank == 0:
-        cpu_base = None
+        cpu_base, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_base = cpu_baseline(payload, args.n_codes, cw, queries, args.cpu_baseline_queries)
+            cpu_base, parity = cpu_baseline(payload, args.n_codes, cw, queries, args.cpu_baseline_queries, out_pos, out_dist)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
         if os.path.exists(tpath):
@@ -366,27 +380,53 @@ def run_gpu(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # Roofline of the dominant kernel.  The coarse scan is bound by the shared-memory / LSU data
+        # pipe, not by HBM (the 8 MB code array is L2 resident and one pass serves 112 queries):
+        # every (node, 112-query group) costs 8 table-row reads = 8 shared-memory wavefronts of 128 B,
+        # one wavefront per clock per SM.  achieved = algorithmic wavefront bytes / kernel time; peak =
+        # 148 SMs x 128 B x SM clock (sampled under load).  The SURVEY 8d figure (stream bytes x
+        # queries: an EFFECTIVE bandwidth that grows with the batch) and the physical DRAM traffic are
+        # reported beside it under their own names.
+        n_local = ix.stat("n_local")
+        qpg = 112 if coarse else 56
+        groups = (Q + qpg - 1) // qpg
+        wf_per_node = 8
+        alg_wavefronts = n_local * groups * wf_per_node
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        lsu_peak = 148 * 128 * sm_mhz * 1e6 / 1e9  # GB/s of shared-memory wavefronts
+        lsu_achieved = alg_wavefronts * 128 / dom_s / 1e9
         line = {
             "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u16 fixed-point filter + f64 exact re-score",
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 coarse filter + u16 fixed-point sample + f64 exact re-score",
             "data": "synthetic",
-            "config": {"workload": "SIFT1M-shaped synthetic 1Mx128 M=8 K=256 h=1, 10K queries per GPU per step, top-10 (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "n_codes": args.n_codes, "queries_per_step": world * Q, "topk": k, "n_bytes": n_bytes_total,
                        "mean_diffs_per_node": round((n_bytes_total - 8 - (3 * (args.n_codes - 1) + 1) // 2) / (args.n_codes - 1), 3),
                        "depth_hist": [ix.stat(f"depth_hist_{d}") for d in range(9)],
+                       "device_bytes_per_node": ix.stat("device_bytes_per_node"),
+                       "disk_bytes_per_node": round(n_bytes_total / args.n_codes, 3),
                        "sharding": "whole tree on one GPU" if world == 1 else
                                    f"queries sharded: {world} replicas of the tree, {Q} queries per GPU per step, NCCL all-gather of the result keys",
                        "l2": "256 MiB buffer written before every timed step (L2 flush, outside the events)",
                        "tree": "built by libdpq (GPU encode + GPU edge search + GPU DFS layout and stream)",
                        "setup_s": round(t_setup, 1), "opts": args.opts or "default"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": dom_name,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": dom_s * 1e3,
-                         "peak_source": peak_src,
-                         "note": "per GPU; effective bandwidth: one pass over the L2-resident tree serves 56 queries (SURVEY 8d); "
-                                 "traffic = physical DRAM bytes per launch from the committed ncu capture"},
+            "roofline": {"bound": "smem_lsu", "achieved": lsu_achieved, "peak": lsu_peak, "unit": "GB/s",
+                         "frac": lsu_achieved / lsu_peak, "traffic": traffic, "kernel": dom_name,
+                         "kernel_ms_per_launch": dom_s * 1e3,
+                         "algorithmic_wavefronts_per_launch": alg_wavefronts,
+                         "wavefronts_per_node_per_group": wf_per_node, "queries_per_group": qpg,
+                         "peak_source": f"148 SMs x 128 B/clk x {sm_mhz:.0f} MHz (nvidia-smi under load); one shared-memory wavefront per clock per SM",
+                         "effective_hbm_gbs": achieved, "effective_hbm_x_peak": achieved / peak,
+                         "hbm_peak_gbs": peak, "hbm_peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "dram_gbs": (traffic / dom_s / 1e9) if traffic else None,
+                         "note": "per GPU. frac = shared-memory wavefronts the algorithm needs / kernel time / pipe peak. "
+                                 "effective_hbm_* = SURVEY 8d bytes (Q x (stream bytes + 4D + 8k)) / kernel time: above 1 because one "
+                                 "L2-resident pass serves 112 queries; traffic / dram_gbs = physical DRAM bytes per launch from the "
+                                 "committed ncu capture (profiles/scan_traffic.json)"},
             "cpu_baseline": cpu_base,
+            "parity": parity,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": world * Q * DIM * 4,
                     "d2h_bytes_per_step": world * Q * k * 8},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -397,6 +437,8 @@ def run_gpu(args):
             "tree_sharded": tree_sharded,
         }
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            raise SystemExit("parity check against the reference CPU scan FAILED: " + str(parity.get("why")))
     ix.close()
     if world > 1:
         dist.barrier()
@@ -404,23 +446,44 @@ def run_gpu(args):
     return 0
 
 
-def cpu_baseline(payload, n_codes, cw, queries, n_q):
+def cpu_baseline(payload, n_codes, cw, queries, n_q, gpu_pos, gpu_dist):
     """The reference's own CPU scan (oracle/_ref when it was built, else the oracle port) on a
     bounded sample of the same workload, one thread (the reference query path is single
-    threaded by design)."""
+    threaded by design).  Its results are the parity check of THIS run: the GPU's top-k for the
+    same queries on the same tree must match them (distances within 1e-5 relative -- bit-equal
+    on this integer-valued data -- ids modulo ties at 1e-5: tests/helpers.assert_topk_equal)."""
     from oracle import pyoracle as po
+    from helpers import assert_topk_equal, REL_TOL
     kind = "reference" if po.have_ref() else "port"
     qs = np.ascontiguousarray(queries[:n_q])
     t = time.perf_counter()
     if kind == "reference":
-        _, _, secs = po.ref_scan(payload, n_codes, cw, qs, TOPK)
+        rpos, rdist, secs = po.ref_scan(payload, n_codes, cw, qs, TOPK)
     else:
-        for q in qs:
-            po.scan(payload, n_codes, cw, q, TOPK)
+        rpos = np.empty((n_q, TOPK), np.int32)
+        rdist = np.empty((n_q, TOPK), np.float32)
+        for i, q in enumerate(qs):
+            rpos[i], rdist[i] = po.scan(payload, n_codes, cw, q, TOPK)
         secs = time.perf_counter() - t
-    return {"value": n_q / secs, "unit": UNIT, "cores": 1, "kind": kind,
+    # the reference reports the trailing node of an even-N tree at position N (SURVEY App. C.1)
+    rpos = np.where(rpos == n_codes, n_codes - 1, rpos)
+    g_d = gpu_dist[:n_q].astype(np.float64)
+    r_d = rdist.astype(np.float64)
+    max_rel = float(np.max(np.abs(g_d - r_d) / np.maximum(np.abs(r_d), 1e-30)))
+    ok, why = True, None
+    try:
+        assert_topk_equal(gpu_pos[:n_q], gpu_dist[:n_q], rpos, rdist)
+    except AssertionError as e:  # reported in the line, then the run fails
+        ok, why = False, str(e)[:300]
+    parity = {"queries": int(n_q), "ok": ok, "max_rel": max_rel, "tol": REL_TOL,
+              "dist_bit_equal": bool(np.array_equal(gpu_dist[:n_q], rdist)),
+              "ids_equal_modulo_ties": ok, "against": kind + " CPU scan of the same queries on the same tree"}
+    if why:
+        parity["why"] = why
+    base = {"value": n_q / secs, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": f"first {n_q} of the {len(queries)} queries on the same 1M-code tree, in-memory scan "
                       f"(DCAT.h:3731), 1 thread, {secs:.1f} s"}
+    return base, parity
 
 
 class StdoutToStderr:
@@ -450,7 +513,7 @@ def main():
     ap.add_argument("--opts", default="", help="libdpq tuning options, e.g. pack=2,warps=16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-queries", type=int, default=600)
-    ap.add_argument("--ref-queries-per-proc", type=int, default=20)
+    ap.add_argument("--ref-queries-per-proc", type=int, default=100)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -386,28 +386,27 @@ def groundtruth(base, queries, topk, chunk=100000, stats=None):
 
 def compile_program(payload, n_codes, M, K, rank=0, n_ranks=1, chunk_nodes=256, engine=0):
     """Host-only: the device scan program of one shard as numpy arrays (for tests).
-    engine 0: second-generation fixed records when the shape allows it (prog["v2"] == 1);
-    engine 1: the first-generation op program."""
+    engine 0: the code-array program (prog["v2"] == 1: "codes_padded" [n_local][cstride] is
+    what the scan kernels read, "codes" its first M columns); engine 1: the first-generation op
+    program (ops / chunks / anc)."""
     payload = np.ascontiguousarray(payload, np.uint8)
     h = C.c_void_p()
     _check(lib().dpq_program_compile(_ptr(payload), payload.nbytes, n_codes, M, K, rank, n_ranks,
                                      -chunk_nodes if engine == 1 else chunk_nodes, C.byref(h)))
     try:
         out = {}
-        for name, dt in (("ops", np.uint32), ("chunks", np.uint32), ("anc", np.uint8), ("codes", np.uint8),
-                         ("recs", np.uint32), ("chunks2", np.uint32)):
+        for name, dt in (("ops", np.uint32), ("chunks", np.uint32), ("anc", np.uint8), ("codes", np.uint8)):
             nb = lib().dpq_program_size(h, name.encode())
             arr = np.empty(nb // np.dtype(dt).itemsize, dt)
             if nb:
                 _check(lib().dpq_program_copy(h, name.encode(), _ptr(arr)))
             out[name] = arr
         for name in ("n_local", "base_pos", "rb", "levels", "n_bytes", "n_diffs", "n_chunks", "v2",
-                     "v2_delta_nodes", "v2_nf", "v2_lpg"):
+                     "v2_nf", "v2_lpg", "cstride"):
             out[name] = int(lib().dpq_program_size(h, name.encode()))
         out["chunks"] = out["chunks"].reshape(-1, 4)
-        out["chunks2"] = out["chunks2"].reshape(-1, 4)
-        out["recs"] = out["recs"].reshape(-1, max(out["v2_nf"], 8) // 2)
-        out["codes"] = out["codes"].reshape(-1, M)
+        out["codes_padded"] = out["codes"].reshape(-1, max(out["cstride"], 1))
+        out["codes"] = np.ascontiguousarray(out["codes_padded"][:, :M])
         out["anc"] = out["anc"].reshape(-1, out["levels"], M)
         out["M"], out["K"] = M, K
         return out

@@ -76,8 +76,8 @@ struct dpq_index {
     dpq::ScanProgram prog;  // host copy (ops/codes released after upload)
     int Ds = 0;
     // device-resident tree
-    DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_recs, d_chunks2, d_ovf;
-    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_fcnt2, d_cap0, d_cap1;
+    DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_ovf;
+    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_cap0, d_cap1;
     int last_coarse = 0;
     int64_t last_items8 = 0;
     int n_chunks = 0;
@@ -99,8 +99,7 @@ struct dpq_index {
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
     // scratch
-    DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_fbuf,
-        d_fcnt, d_key, d_gthr;
+    DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_key, d_gthr;
     void* h_stage = nullptr;  // pinned staging for the host-buffer path
     size_t h_stage_cap = 0;
     // stats
@@ -214,12 +213,9 @@ int finish_open(dpq_index* ix, const uint32_t* pos2id) {
     if ((rc = upload(ix->d_codes, P.codes.data(), P.codes.size(), ix->stream))) return rc;
     ix->n_chunks = (int)P.chunks.size();
     ix->ops_bytes = P.ops.size() * 4;
-    if (P.v2) {
-        if ((rc = upload(ix->d_recs, P.recs.data(), P.recs.size() * 4, ix->stream))) return rc;
-        if ((rc = upload(ix->d_chunks2, P.chunks2.data(), P.chunks2.size() * sizeof(dpq::ChunkDesc2), ix->stream)))
-            return rc;
-        ix->n_chunks = (int)P.chunks2.size();
-        ix->ops_bytes = P.recs.size() * 4;
+    if (P.v2) {  // the code array IS the program: chunk c = nodes [c * 64, c * 64 + 64)
+        ix->n_chunks = (int)((P.n_local + P.v2_chunk_nodes - 1) / P.v2_chunk_nodes);
+        ix->ops_bytes = P.codes.size();
     }
     if (pos2id) {
         ix->has_pos2id = true;
@@ -232,8 +228,6 @@ int finish_open(dpq_index* ix, const uint32_t* pos2id) {
     std::vector<uint8_t>().swap(P.codes);
     std::vector<uint8_t>().swap(P.anc);
     std::vector<dpq::ChunkDesc>().swap(P.chunks);
-    std::vector<uint32_t>().swap(P.recs);
-    std::vector<dpq::ChunkDesc2>().swap(P.chunks2);
     return DPQ_OK;
 }
 
@@ -300,7 +294,6 @@ static int open_common(const uint8_t* payload, int64_t n_bytes, int64_t n_codes,
     if (first_pos) {  // one tree of a forest: every position this index reports is shifted
         ix->pos_shift = first_pos;
         ix->prog.base_pos += first_pos;
-        for (auto& c : ix->prog.chunks2) c.first_pos += (uint32_t)first_pos;
     }
     rc = finish_open(ix, pos2id);
     if (rc) {
@@ -371,7 +364,7 @@ int dpq_index_open_tree(dpq_tree* t, int64_t first_pos, dpq_index** out) {
         return open_common(t->payload.data(), (int64_t)t->payload.size(), n, M, K, t->vec_id.data(), 0, 1, first_pos, out);
     if (first_pos < 0 || first_pos + n > 0xFFFFFFFFLL)
         return fail(DPQ_ERR_ARG, "dpq_index_open_tree: positions must stay below 2^32 - 1");
-    if ((int64_t)t->codes_by_pos.size() != n * M || (int64_t)t->parent_pos.size() != n || (int64_t)t->depth.size() != n)
+    if ((int64_t)t->codes_by_pos.size() != n * M || (int64_t)t->depth.size() != n)
         return fail(DPQ_ERR_ARG, "dpq_index_open_tree: the tree has no layout arrays");
     int rc = check_device();
     if (rc) return rc;
@@ -383,13 +376,15 @@ int dpq_index_open_tree(dpq_tree* t, int64_t first_pos, dpq_index** out) {
     P.fmt.rb = (M * K <= 2048) ? 11 : 12;
     P.v2 = true;
     P.shape = dpq::v2_shape(M, K);
+    P.cstride = P.shape.nf;
     P.n_codes = n;
     P.n_bytes = (int64_t)t->payload.size();
     P.base_pos = first_pos;
     P.n_local = n;
     P.local_bytes = P.n_bytes;
     P.n_diffs = t->n_diffs;
-    P.depth_hist.assign((size_t)P.fmt.levels() + 1, 0);
+    P.depth_hist.assign(17, 0);
+    for (int64_t i = 0; i < n; ++i) P.depth_hist[std::min<int>(t->depth[(size_t)i], 16)]++;
     ix->pos_shift = first_pos;
     auto bail = [&](int code) {
         dpq_index_close(ix);
@@ -398,39 +393,27 @@ int dpq_index_open_tree(dpq_tree* t, int64_t first_pos, dpq_index** out) {
     if (cudaSetDevice(ix->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(DPQ_ERR_CUDA, "dpq_index_open_tree: stream setup failed"));
-    const int64_t n_chunks = (n + P.v2_chunk_nodes - 1) / P.v2_chunk_nodes;
-    DevBuf d_ppos, d_depth, d_cnt;
-    auto drop = [&]() {
-        d_ppos.release();
-        d_depth.release();
-        d_cnt.release();
-    };
-    if ((rc = upload(ix->d_codes, t->codes_by_pos.data(), (size_t)n * M, ix->stream)) ||
-        (rc = upload(d_ppos, t->parent_pos.data(), (size_t)n * 4, ix->stream)) ||
-        (rc = upload(d_depth, t->depth.data(), (size_t)n, ix->stream)) ||
-        (rc = ix->d_recs.ensure((size_t)n * P.shape.rec_words() * 4)) ||
-        (rc = ix->d_chunks2.ensure((size_t)n_chunks * sizeof(dpq::ChunkDesc2))) || (rc = d_cnt.ensure(16))) {
-        drop();
-        return bail(rc);
+    // the code array by position IS the device program; pad to the scan's word stride when M < stride
+    cudaError_t e = cudaSuccess;
+    if (M == P.cstride) {
+        if ((rc = upload(ix->d_codes, t->codes_by_pos.data(), (size_t)n * M, ix->stream))) return bail(rc);
+    } else {
+        DevBuf d_raw;
+        if ((rc = upload(d_raw, t->codes_by_pos.data(), (size_t)n * M, ix->stream)) ||
+            (rc = ix->d_codes.ensure((size_t)n * P.cstride))) {
+            d_raw.release();
+            return bail(rc);
+        }
+        e = dpq::launch_pad_codes(d_raw.as<uint8_t>(), n, M, P.cstride, ix->d_codes.as<uint8_t>(), ix->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        d_raw.release();
     }
     // the first-generation buffers stay empty (16-byte placeholders keep the launch arguments valid)
-    if ((rc = ix->d_ops.ensure(16)) || (rc = ix->d_chunks.ensure(16)) || (rc = ix->d_anc.ensure(16))) {
-        drop();
-        return bail(rc);
-    }
-    cudaError_t e = cudaMemsetAsync(d_cnt.p, 0, 16, ix->stream);
-    if (e == cudaSuccess)
-        e = dpq::launch_build_recs(ix->d_codes.as<uint8_t>(), d_ppos.as<uint32_t>(), d_depth.as<uint8_t>(), n, M, K, P.shape,
-                                   P.v2_chunk_nodes, (uint32_t)first_pos, ix->d_recs.as<uint32_t>(),
-                                   ix->d_chunks2.as<dpq::ChunkDesc2>(), d_cnt.as<unsigned long long>(), ix->stream);
-    unsigned long long deltas = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&deltas, d_cnt.p, 8, cudaMemcpyDeviceToHost, ix->stream);
+    if ((rc = ix->d_ops.ensure(16)) || (rc = ix->d_chunks.ensure(16)) || (rc = ix->d_anc.ensure(16))) return bail(rc);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
-    drop();
     if (e != cudaSuccess) return bail(fail(DPQ_ERR_CUDA, std::string("dpq_index_open_tree: ") + cudaGetErrorString(e)));
-    P.v2_delta_nodes = (int64_t)deltas;
-    ix->n_chunks = (int)n_chunks;
-    ix->ops_bytes = (size_t)n * P.shape.rec_words() * 4;
+    ix->n_chunks = (int)((n + P.v2_chunk_nodes - 1) / P.v2_chunk_nodes);
+    ix->ops_bytes = (size_t)n * P.cstride;
     ix->has_pos2id = true;
     ix->pos2id_host = t->vec_id;
     *out = ix;
@@ -493,6 +476,24 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     return DPQ_OK;
 }
 
+// slices of a pass over n_chunks chunks for n_groups query groups: whole waves of 148 one-CTA SMs and
+// whole rounds (warps x strands chunks) per item, as nearly as possible
+static int pick_slices(int n_groups, int n_chunks, int chunks_per_round, int max_slices) {
+    double best = -1.0;
+    int pick = 1;
+    for (int s = 1; s <= max_slices && s <= std::max(1, n_chunks / chunks_per_round); ++s) {
+        const int64_t items = (int64_t)n_groups * s;
+        const int64_t waves = (items + 147) / 148;
+        const double cpi = (double)n_chunks / s;
+        const double eff = (double)items / (double)(waves * 148) * (cpi / chunks_per_round) / std::ceil(cpi / chunks_per_round);
+        if (eff > best + 1e-9) {
+            best = eff;
+            pick = s;
+        }
+    }
+    return pick;
+}
+
 int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int topk,
                             uint64_t* d_out_key) {
     if (!ix || !d_queries || !d_out_key) return fail(DPQ_ERR_ARG, "dpq_index_search: null argument");
@@ -502,13 +503,10 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     dpq::ScanGeom g;
     const dpq::ScanProgram& P = ix->prog;
     // coarse search (scan8.cu): 15-bit scan over a 1/S sample -> cap per query -> 8-bit scan of
-    // the whole tree -> exact re-score.  Narrow shape, moderate k, trees large enough to pay.
-    // Automatic choice (gpurun_out/probe_wide.log, profiles/r1_summary.md): the narrow coarse scan pays
-    // up to topk 64; the wide one (saturation at 15, 6-10 % rounding slack) only for short lists -- at
-    // top-100 its sample pass and the re-score of ~4K survivors per query eat the scan's gain.
-    const bool coarse_auto = P.n_local >= ix->opt_coarse_min && topk <= (P.shape.nf == 8 ? 64 : 32);
+    // the whole tree -> exact re-score.  Trees large enough to pay, result lists up to 128.
+    const bool coarse_auto = P.n_local >= ix->opt_coarse_min && topk <= (P.shape.nf == 8 ? 64 : 128);
     const bool coarse = P.v2 && topk <= 128 && ix->opt_coarse != 0 && (ix->opt_coarse == 1 || coarse_auto);
-    const dpq::C8Shape c8 = dpq::c8_shape(P.shape.nf);  // narrow: 112 queries per CTA, wide: 48
+    const dpq::C8Shape c8 = dpq::c8_shape(P.shape.nf);  // 112 queries per CTA in both shapes
     const int spw = P.shape.spw();
     const int levels8 = std::min(ix->opt_levels8, 127 - c8.slack);  // the test constant stays <= 128
     // sample stride: a sparser sample is cheaper to scan but gives a looser cap (more coarse survivors to
@@ -520,71 +518,40 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
     if (rc) return rc;
     ix->last_coarse = coarse ? 1 : 0;
-    // geometry of the coarse pass: 112-query groups, slices by the same wave/round rule
-    int g8_groups = 0, g8_slices = 1;
+    // geometry of the coarse passes: 112-query groups, 4 strands per warp
     const int warps8 = ix->opt_warps8;
     const int bcap8 = ix->opt_bcap8 > 0 ? ix->opt_bcap8 : (P.shape.nf == 8 ? 512 : 2048);  // survivors per (slice, query)
+    const bool seeded = coarse && ix->opt_seed == 1;
+    const int n_chunks_sample8 = (((ix->n_chunks + 3) / 4 + S - 1) / S) * 4;
+    int g8_groups = 0, g8_slices = 1, g8_slices_s = 1;
     if (coarse) {
         g8_groups = (Q + c8.qb - 1) / c8.qb;
-        g8_slices = ix->opt_slices;
-        if (g8_slices <= 0) {
-            const int cpr = warps8 * spw;
-            double best = -1.0;
-            g8_slices = 1;
-            for (int s = 1; s <= 96 && s <= std::max(1, ix->n_chunks / cpr); ++s) {  // <= R8_MAXSL
-                const int64_t items = (int64_t)g8_groups * s;
-                const int64_t waves = (items + 147) / 148;
-                const double cpi = (double)ix->n_chunks / s;
-                const double eff = (double)items / (double)(waves * 148) * (cpi / cpr) / std::ceil(cpi / cpr);
-                if (eff > best + 1e-9) {
-                    best = eff;
-                    g8_slices = s;
-                }
-            }
-        }
-        g8_slices = std::max(1, std::min(std::min(g8_slices, 128), std::max(1, ix->n_chunks)));
+        g8_slices = ix->opt_slices > 0 ? ix->opt_slices : pick_slices(g8_groups, ix->n_chunks, warps8 * 4, 96);
+        g8_slices = std::max(1, std::min(std::min(g8_slices, 128), std::max(1, ix->n_chunks)));  // <= R8_MAXSL
+        if (seeded) g8_slices_s = pick_slices(g8_groups, n_chunks_sample8, warps8 * 4, 96);
     }
-    // slices of the SAMPLED coarse pass (seed = 1): same rule on the reduced chunk count
-    int g8_slices_s = 1;
-    if (coarse && ix->opt_seed == 1) {
-        const int cpr = warps8 * spw;
-        double best = -1.0;
-        for (int s = 1; s <= 96 && s <= std::max(1, n_chunks_sample / cpr); ++s) {
-            const int64_t items = (int64_t)g8_groups * s;
-            const int64_t waves = (items + 147) / 148;
-            const double cpi = (double)n_chunks_sample / s;
-            const double eff = (double)items / (double)(waves * 148) * (cpi / cpr) / std::ceil(cpi / cpr);
-            if (eff > best + 1e-9) {
-                best = eff;
-                g8_slices_s = s;
-            }
-        }
-    }
-    const bool seeded = coarse && ix->opt_seed == 1;
     const size_t MK = (size_t)P.M * P.K;
     const size_t rows = (size_t)1 << g.rb;
     const size_t LW = 32 * (size_t)g.pack;
     const size_t n_items = (size_t)g.n_groups * g.n_slices;
-    const int max_flagged = std::min(Q, 4096);
-    const int fcap = 2048;
+    const int max_flagged = Q;
     if ((rc = ix->d_lutf.ensure((size_t)Q * MK * 4))) return rc;
     if ((rc = ix->d_scale.ensure((size_t)g.n_groups * g.qpg * 8))) return rc;
-    if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * g.qgl * rows * 4))) return rc;
     if (P.v2) {
         if ((rc = ix->d_cand.ensure(n_items * g.qpg * g.bcap * 8))) return rc;
         if ((rc = ix->d_cnt.ensure(n_items * g.qpg * 4))) return rc;
         if ((rc = ix->d_ovf.ensure((size_t)g.n_groups * g.qpg * 4))) return rc;
         if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * P.shape.lut_bytes()))) return rc;
     } else {
+        if ((rc = ix->d_qlut.ensure((size_t)g.n_groups * g.qgl * rows * 4))) return rc;
         if ((rc = ix->d_cand.ensure(n_items * g.n_warps * g.bcap * LW * 8))) return rc;
         if ((rc = ix->d_cnt.ensure(n_items * g.n_warps * LW * 4))) return rc;
+        if ((rc = ix->d_ovf.ensure(16))) return rc;
     }
     if ((rc = ix->d_gthr.ensure((size_t)g.n_groups * g.qpg * 4))) return rc;
     if ((rc = ix->d_flagged.ensure((size_t)max_flagged * 4))) return rc;
     if ((rc = ix->d_ctrl.ensure(64))) return rc;
     if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
-    if ((rc = ix->d_fbuf.ensure((size_t)max_flagged * fcap * 8))) return rc;
-    if ((rc = ix->d_fcnt.ensure((size_t)max_flagged * 4))) return rc;
     if (coarse) {
         const size_t items8 = (size_t)g8_groups * std::max(g8_slices, g8_slices_s);
         ix->last_items8 = (int64_t)g8_groups * g8_slices;
@@ -595,10 +562,11 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         if ((rc = ix->d_cnt8.ensure(items8 * c8.qb * 4))) return rc;
         if ((rc = ix->d_ovf8.ensure((size_t)g8_groups * c8.qb * 4))) return rc;
         if ((rc = ix->d_flagged2.ensure((size_t)max_flagged * 4))) return rc;
-        if ((rc = ix->d_fcnt2.ensure((size_t)max_flagged * 4))) return rc;
     }
     cudaStream_t st = ix->stream;
-    uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();  // [0] n_flagged, [1] overflow
+    // ctrl words: [0] queries flagged by select_kernel, [2] by the final rescore8_kernel,
+    // [3] scratch (flags of the sample phase of the coarse search, which needs no fallback)
+    uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();
     {
         const int slot = std::min(ix->timed_calls, 4095);
         while ((int)ix->evs.size() < 6 * (slot + 1)) {
@@ -609,18 +577,20 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         ix->ev = ix->evs.data() + 6 * slot;
         ix->timed_calls = slot + 1;
     }
+    int launches = 0;
     CU(cudaEventRecord(ix->ev[0], st));
     CU(cudaMemsetAsync(ctrl, 0, 64, st));
-    CU(cudaMemsetAsync(ix->d_fcnt.p, 0, (size_t)max_flagged * 4, st));
-    if (coarse) CU(cudaMemsetAsync(ix->d_fcnt2.p, 0, (size_t)max_flagged * 4, st));
-    if (P.v2)
+    if (P.v2) {
         dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                          ix->d_scale.as<double>(), seeded ? nullptr : ix->d_qlut.as<uint16_t>(),
                          ix->d_gthr.as<uint32_t>(), ix->d_ovf.as<uint32_t>(), g.n_groups, P.shape,
                          (uint32_t)ix->opt_dbg_bound, st);
-    else
+        launches += seeded ? 1 : 2;
+    } else {
         dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                         ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);
+        launches += 1;
+    }
     dpq::ScanArgs sa;
     sa.g = g;
     sa.ops = ix->d_ops.as<uint4>();
@@ -636,8 +606,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if (P.v2 && !seeded) {
         dpq::Scan2Args s2;
         s2.shape = P.shape;
-        s2.recs = ix->d_recs.as<uint4>();
-        s2.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
+        s2.codes = ix->d_codes.as<uint8_t>();
+        s2.n_local = P.n_local;
+        s2.base_pos = (uint32_t)P.base_pos;
         s2.n_chunks = ix->n_chunks;
         s2.chunk_nodes = P.v2_chunk_nodes;
         s2.bt_stride = S;
@@ -656,10 +627,14 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         s2.epoch = std::max(1, ix->opt_epoch);
         s2.ramp = ix->opt_ramp;
         CU(dpq::launch_scan2(s2, st));
+        ++launches;
     } else if (!seeded) {
         CU(dpq::launch_scan(sa, st));
+        ++launches;
     }
     if (!coarse) CU(cudaEventRecord(ix->ev[2], st));
+    float* cap0 = ix->d_cap0.as<float>();
+    float* cap1 = ix->d_cap1.as<float>();
     dpq::SelectArgs se;
     se.g = g;
     se.v2 = P.v2 ? 1 : 0;
@@ -669,80 +644,83 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     se.lutf = ix->d_lutf.as<float>();
     se.scale = ix->d_scale.as<double>();
     se.codes = ix->d_codes.as<uint8_t>();
+    se.cstride = P.cstride;
     se.base_pos = P.base_pos;
     se.n_local = P.n_local;
     se.Q = Q;
     se.topk = topk;
     se.out_key = d_out_key;
     se.flagged = ix->d_flagged.as<uint32_t>();
-    se.n_flagged = ctrl;
     se.max_flagged = max_flagged;
-    se.bound = ix->d_bound.as<float>();
     se.force_fallback = ix->opt_force_fallback;
-    if (!seeded) dpq::launch_select(se, st);
+    // Coarse search: the sample pass only has to deliver a valid cap >= the true k-th distance, and
+    // select_kernel's bound[q] -- the exact k-th distance among the re-scored sample nodes, which are
+    // real nodes of the tree -- already is one (FLT_MAX when the sample held fewer than k nodes).  Its
+    // proof-failure / overflow flags concern the exactness of the SAMPLE's top-k only and are ignored.
+    se.n_flagged = coarse ? ctrl + 3 : ctrl;
+    se.bound = coarse ? cap1 : ix->d_bound.as<float>();
+    if (!seeded) {
+        dpq::launch_select(se, st);
+        ++launches;
+    }
     dpq::FallbackArgs fa;
     fa.flagged = se.flagged;
     fa.n_flagged = ctrl;
     fa.max_flagged = max_flagged;
     fa.lutf = se.lutf;
-    fa.bound = se.bound;
+    fa.bound = ix->d_bound.as<float>();
     fa.codes = se.codes;
+    fa.cstride = P.cstride;
     fa.base_pos = P.base_pos;
     fa.n_local = P.n_local;
     fa.M = P.M;
     fa.K = P.K;
     fa.topk = topk;
-    fa.buf = ix->d_fbuf.as<uint64_t>();
-    fa.buf_cnt = ix->d_fcnt.as<uint32_t>();
-    fa.cap = fcap;
     fa.out_key = d_out_key;
-    fa.overflow = ctrl + 1;
-    if (!seeded) dpq::launch_fallback(fa, st);
-    if (coarse) {
-        float* cap0 = ix->d_cap0.as<float>();
-        float* cap1 = ix->d_cap1.as<float>();
+    if (!coarse) {
+        dpq::launch_fallback(fa, st);
+        ++launches;
+    } else {
         dpq::Scan8Args s8;
+        s8.codes = ix->d_codes.as<uint8_t>();
+        s8.n_local = P.n_local;
+        s8.base_pos = (uint32_t)P.base_pos;
+        s8.n_chunks = ix->n_chunks;
+        s8.chunk_nodes = P.v2_chunk_nodes;
+        s8.qlut8 = ix->d_qlut8.as<uint8_t>();
+        s8.cand = ix->d_cand8.as<uint32_t>();
+        s8.cand_cnt = ix->d_cnt8.as<uint32_t>();
+        s8.ovf = ix->d_ovf8.as<uint32_t>();
+        s8.Q = Q;
+        s8.n_groups = g8_groups;
+        s8.n_warps = warps8;
+        s8.bcap = bcap8;
+        s8.thresh = levels8 + c8.slack + 1;
+        s8.nf = c8.nf;
         dpq::Rescore8Args r8;
-        if (!seeded) {
-            // d_out_key holds the exact top-k of the 15-bit SAMPLE pass: its k-th distance is the cap
-            dpq::launch_cap_from_keys(d_out_key, topk, Q, cap1, st);
-        } else {
+        r8.cand = s8.cand;
+        r8.cand_cnt = s8.cand_cnt;
+        r8.ovf = s8.ovf;
+        r8.n_groups = g8_groups;
+        r8.bcap = bcap8;
+        r8.qb = c8.qb;
+        r8.lutf = se.lutf;
+        r8.codes = se.codes;
+        r8.cstride = P.cstride;
+        r8.base_pos = P.base_pos;
+        r8.M = P.M;
+        r8.K = P.K;
+        r8.Q = Q;
+        r8.topk = topk;
+        if (seeded) {
             // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the
             // sample (every S-th batch) -> exact re-score -> cap1 = the sample's k-th distance
-            dpq::launch_presample(se.lutf, se.codes, P.n_local, P.M, P.K, Q, topk, ix->opt_presample, cap0, st);
-            dpq::launch_pack8(se.lutf, cap0, (int)MK, Q, levels8, ix->d_qlut8.as<uint8_t>(),
-                              ix->d_ovf8.as<uint32_t>(), g8_groups, c8.nf, st);
-            s8.recs = ix->d_recs.as<uint4>();
-            s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
-            s8.n_chunks = ix->n_chunks;
-            s8.chunk_nodes = P.v2_chunk_nodes;
+            dpq::launch_presample(se.lutf, se.codes, P.cstride, P.n_local, P.M, P.K, Q, topk, ix->opt_presample, cap0, st);
+            dpq::launch_pack8(se.lutf, cap0, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
             s8.bt_stride = S;
-            s8.qlut8 = ix->d_qlut8.as<uint8_t>();
-            s8.cand = ix->d_cand8.as<uint32_t>();
-            s8.cand_cnt = ix->d_cnt8.as<uint32_t>();
-            s8.ovf = ix->d_ovf8.as<uint32_t>();
-            s8.Q = Q;
-            s8.n_groups = g8_groups;
             s8.n_slices = g8_slices_s;
-            s8.n_warps = warps8;
-            s8.bcap = bcap8;
-            s8.thresh = levels8 + c8.slack + 1;
-            s8.nf = c8.nf;
             CU(dpq::launch_scan8(s8, st));
-            r8.cand = s8.cand;
-            r8.cand_cnt = s8.cand_cnt;
-            r8.ovf = s8.ovf;
-            r8.n_groups = g8_groups;
             r8.n_slices = g8_slices_s;
-            r8.bcap = bcap8;
-            r8.qb = c8.qb;
-            r8.lutf = se.lutf;
-            r8.codes = se.codes;
-            r8.base_pos = P.base_pos;
-            r8.M = P.M;
-            r8.K = P.K;
-            r8.Q = Q;
-            r8.topk = topk;
             r8.out_key = nullptr;
             r8.cap_in = cap0;
             r8.cap_out = cap1;
@@ -751,61 +729,33 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             r8.max_flagged = 0;
             r8.bound = nullptr;
             dpq::launch_rescore8(r8, st);
+            launches += 4;
         }
-        dpq::launch_pack8(se.lutf, cap1, (int)MK, Q, levels8, ix->d_qlut8.as<uint8_t>(),
-                          ix->d_ovf8.as<uint32_t>(), g8_groups, c8.nf, st);
-        s8.recs = ix->d_recs.as<uint4>();
-        s8.chunks = ix->d_chunks2.as<dpq::ChunkDesc2>();
-        s8.n_chunks = ix->n_chunks;
-        s8.chunk_nodes = P.v2_chunk_nodes;
+        dpq::launch_pack8(se.lutf, cap1, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
         s8.bt_stride = 1;
-        s8.qlut8 = ix->d_qlut8.as<uint8_t>();
-        s8.cand = ix->d_cand8.as<uint32_t>();
-        s8.cand_cnt = ix->d_cnt8.as<uint32_t>();
-        s8.ovf = ix->d_ovf8.as<uint32_t>();
-        s8.Q = Q;
-        s8.n_groups = g8_groups;
         s8.n_slices = g8_slices;
-        s8.n_warps = warps8;
-        s8.bcap = bcap8;
-        s8.thresh = levels8 + c8.slack + 1;
-        s8.nf = c8.nf;
         CU(cudaEventRecord(ix->ev[4], st));
         CU(dpq::launch_scan8(s8, st));
         CU(cudaEventRecord(ix->ev[5], st));
-        r8.cand = s8.cand;
-        r8.cand_cnt = s8.cand_cnt;
-        r8.ovf = s8.ovf;
-        r8.n_groups = g8_groups;
         r8.n_slices = g8_slices;
-        r8.bcap = bcap8;
-        r8.qb = c8.qb;
-        r8.lutf = se.lutf;
-        r8.codes = se.codes;
-        r8.base_pos = P.base_pos;
-        r8.M = P.M;
-        r8.K = P.K;
-        r8.Q = Q;
-        r8.topk = topk;
         r8.out_key = d_out_key;
         r8.cap_in = cap1;
         r8.cap_out = nullptr;
         r8.flagged = ix->d_flagged2.as<uint32_t>();
         r8.n_flagged = ctrl + 2;
         r8.max_flagged = max_flagged;
-        r8.bound = se.bound;
+        r8.bound = ix->d_bound.as<float>();
         dpq::launch_rescore8(r8, st);
         CU(cudaEventRecord(ix->ev[2], st));
         dpq::FallbackArgs fb = fa;
         fb.flagged = r8.flagged;
         fb.n_flagged = ctrl + 2;
-        fb.buf_cnt = ix->d_fcnt2.as<uint32_t>();
         dpq::launch_fallback(fb, st);
+        launches += 4;
     }
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
-    // lut (+ pack), scan, select, fallback collect/finish (+ pack8, scan8, rescore8, fallback x2)
-    ix->last_launches = coarse ? (seeded ? 10 : 12) : (P.v2 ? 6 : 5);
+    ix->last_launches = launches;
     ix->timing_valid = true;
     return DPQ_OK;
 }
@@ -818,7 +768,6 @@ int dpq_index_sync(dpq_index* ix) {
         uint32_t ctrl[4] = {0, 0, 0, 0};
         CU(cudaMemcpy(ctrl, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost));
         ix->last_fallback = (int64_t)ctrl[0] + ctrl[2];
-        if (ctrl[1]) return fail(DPQ_ERR_NOMEM, "exact fallback overflowed its buffers (massive ties)");
     }
     return DPQ_OK;
 }
@@ -874,7 +823,6 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     CU(cudaMemcpyAsync(hc, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
     CU(cudaStreamSynchronize(ix->stream));  // the one host sync of the call
     ix->last_fallback = (int64_t)hc[0] + hc[2];
-    if (hc[1]) return fail(DPQ_ERR_NOMEM, "exact fallback overflowed its buffers (massive ties)");
     const int64_t base = ix->prog.base_pos;
     const bool map = ix->has_pos2id;
     const uint32_t* p2i = ix->pos2id_host.data();
@@ -955,7 +903,8 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
         for (size_t i = 0; i < (size_t)ix->last_items8 * dpq::c8_shape(P.shape.nf).qb && i < c.size(); ++i) t += c[i];
         return t;
     }
-    if (n == "v2_delta_nodes") return P.v2_delta_nodes;
+    if (n == "v2_delta_nodes") return 0;  // the code-array engine has no delta records (kept for older tools)
+    if (n == "device_bytes_per_node") return P.n_local > 0 ? (int64_t)((ix->ops_bytes + (P.v2 ? 0 : ix->d_codes.cap)) / (size_t)P.n_local) : 0;
     if (n == "last_fallback") return ix->last_fallback;
     if (n.rfind("depth_hist_", 0) == 0) {
         size_t d = (size_t)atoi(n.c_str() + 11);
@@ -989,9 +938,9 @@ void dpq_index_close(dpq_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_fcnt2, &ix->d_recs, &ix->d_chunks2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
-                      &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_fbuf, &ix->d_fcnt, &ix->d_key,
+                      &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_key,
                       &ix->d_gthr})
         b->release();
     if (ix->h_stage) cudaFreeHost(ix->h_stage);

@@ -53,65 +53,48 @@ struct ChunkDesc {
 constexpr uint32_t CHUNK_EMIT_ROOT = 1u << 8;
 
 // ---------------------------------------------------------------------------------------
-// Second-generation layout ("v2", used when M <= 8 and the table has <= 2048 rows): ONE
-// fixed 16-byte record per node, eight 16-bit table-row fields, executed by a quarter-warp
-// ("strand") that serves 56 queries with 128-bit table loads.
+// Second-generation layout ("v2", used whenever M <= 16): the device copy of a shard is just
+// the nodes' PQ CODES by DFS position, padded to a power-of-two stride (8 bytes for M <= 8,
+// 16 bytes for M <= 16, pad bytes 0): 8 B/node at M = 8 -- what plain PQ codes take, against
+// 6.7 B/node for the delta-coded stream on disk -- and the SAME array serves
+// the scan kernels, the exact re-score and the exact fallback.  Every node gets the full
+// M-term lookup: with n changed subspaces the reference's delta rule costs 2n table reads per
+// (node, query) (subtract old, add new), and the trees here have n = 4.3 .. 5.2 on average, so
+// the delta form would read MORE table rows than the M = 8 of a full lookup (measured in round 1:
+// only 1.7 % of the nodes of the 1M-code tree could use a <= 4-pair delta record).  The delta
+// rule itself lives on in the first-generation engine below (DPQ_ENGINE=1), which every parity
+// test also runs.
 //
-//   field  = row * 7            row = m*K + centroid; the table row is 7 x 16 bytes
-//   x = plus0 | plus1 << 16     y = plus2 | plus3 << 16
-//   z = minus0 | minus1 << 16   w = minus2 | minus3 << 16
-//   x bit 14 (ABS)   : 1: dist = sum of all eight rows (full M-term lookup, rows of m = 0..7;
-//                         unused fields point at the all-zero row M*K)
-//                      0: dist = parent + (plus rows) - (minus rows): one (new, old) pair per
-//                         changed subspace, at most four, unused pairs are (row 0, row 0)
-//   x bit 15 (CHILD) : the strand's parent register takes this node's distance
-//
-// A node is delta-encoded when its edge changes <= 4 subspaces AND its parent's distance is
-// in the parent register (the node is the first child of the previous node, or a later child
-// with only leaves in between); otherwise it gets the full M-term record, which costs the
-// same eight table reads and needs no depth stack.  Chunks are v2_chunk_nodes consecutive
-// positions, each starting with a full record, so chunks are independent.
-//
-// Two shapes share this design:
-//   narrow (M <= 8,  M*K <= 2048): 8 fields = 16-byte record, 7 x 16-byte table rows (56 queries
-//           per CTA), a strand is a quarter warp (8 lanes, 7 active): 4 nodes per warp step;
-//   wide   (M <= 16, M*K <= 4096): 16 fields = 32-byte record (plus fields first, minus fields
-//           second, <= 8 changed subspaces for a delta record), 3 x 16-byte rows (24 queries per
-//           CTA), a strand is 4 lanes (3 active): 8 nodes per warp step.
-// In both the table fills shared memory: 2048 x 112 B = 229,376 B, 4096 x 48 B = 196,608 B.
-constexpr uint32_t V2_ABS = 1u << 14;
-constexpr uint32_t V2_CHILD = 1u << 15;
+// Scan tables are laid out [row][queries] with row = m * 256 + centroid (rows of subspaces
+// m >= M and of centroids >= K are all zero, so a pad byte reads a zero row):
+//   narrow (M <= 8):  2048 rows; 15-bit scan: 7 x 16-byte lanes = 56 queries per CTA, 8-bit
+//                     coarse scan: 112 queries per CTA; a strand is a quarter warp (8 lanes,
+//                     7 active) walking one 64-node chunk: 4 nodes per warp step;
+//   wide   (M <= 16): 4096 rows; 15-bit scan: 3 x 16-byte lanes = 24 queries per CTA (a strand
+//                     is 4 lanes, 3 active: 8 nodes per warp step); coarse scan: 4-bit entries,
+//                     56-byte rows = 112 queries per CTA (scan8.cu).
 struct V2Shape {
-    int nf;         // fields per record (8 or 16); record = 2*nf bytes
-    int lpg;        // active 16-byte lanes per strand = table row bytes / 16
+    int nf;         // table fields per node (8 or 16) = code stride in bytes
+    int lpg;        // active 16-byte lanes per strand of the 15-bit scan = table row bytes / 16
     int sw;         // lanes per strand (8 or 4)
-    int rows;       // table rows allocated (2048 or 4096)
-    int qb() const { return lpg * 8; }            // queries per CTA
+    int rows;       // table rows (nf * 256)
+    int qb() const { return lpg * 8; }            // queries per CTA (15-bit scan)
     int row_bytes() const { return lpg * 16; }
     int lut_bytes() const { return rows * row_bytes(); }
     int spw() const { return 32 / sw; }           // strands (= chunks in flight) per warp
-    int rec_words() const { return nf / 2; }
 };
 inline V2Shape v2_shape(int M, int K) {
-    if (M <= 8 && M * K <= 2048) return V2Shape{8, 7, 8, 2048};
+    (void)K;
+    if (M <= 8) return V2Shape{8, 7, 8, 2048};
     return V2Shape{16, 3, 4, 4096};
 }
-
-struct ChunkDesc2 {
-    uint32_t rec_begin;  // first record of this chunk (records of a chunk are contiguous)
-    uint32_t n_nodes;    // records in the chunk (== v2_chunk_nodes except the last)
-    uint32_t first_pos;  // global DFS position of the first record
-    uint32_t pad;
-};
 
 struct ScanProgram {
     int M = 0, K = 0;
     bool v2 = false;
     int v2_chunk_nodes = 64;
     V2Shape shape{8, 7, 8, 2048};
-    std::vector<uint32_t> recs;        // v2 records, shape.rec_words() words each
-    std::vector<ChunkDesc2> chunks2;
-    int64_t v2_delta_nodes = 0;        // nodes that got a delta record
+    int cstride = 0;                   // bytes per node in `codes` (v2: 8 or 16, zero padded; else M)
     OpFormat fmt{11};
     int64_t n_codes = 0;       // nodes in the whole tree
     int64_t n_bytes = 0;       // stream bytes of the whole tree
@@ -122,7 +105,7 @@ struct ScanProgram {
     std::vector<uint32_t> ops;        // node records, each a multiple of 4 words
     std::vector<ChunkDesc> chunks;
     std::vector<uint8_t> anc;         // [n_chunks][levels][M]
-    std::vector<uint8_t> codes;       // [n_local][M] decoded codes, by position - base_pos
+    std::vector<uint8_t> codes;       // [n_local][cstride] decoded codes, by position - base_pos
     std::vector<int64_t> depth_hist;  // nodes per depth (this shard)
 };
 
@@ -131,11 +114,6 @@ struct ScanProgram {
 std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
                             int rank, int n_ranks, int chunk_nodes, ScanProgram* out, int engine = 0);
 // engine: 0 = v2 when the shape allows it, 1 = always the first-generation op program
-// a full record needs either all nf fields used (M == nf) or a spare all-zero table row M*K
-inline bool v2_shape_ok(int M, int K) {
-    if (M > 16 || M * K > 4096) return false;
-    const V2Shape sh = v2_shape(M, K);
-    return M == sh.nf || M * K < sh.rows;
-}
+inline bool v2_shape_ok(int M, int K) { return M >= 1 && M <= 16 && K >= 1 && K <= 256; }
 
 }  // namespace dpq

@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
     const float* lut = a.lutf + (size_t)q * g.M * g.K;
     for (int j = lane; j < n_sel; j += 32) {
         uint32_t pos = (uint32_t)s_sel[w][j];
-        const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * g.M;
+        const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
         double d = 0.0;
         for (int m = 0; m < g.M; ++m) d += (double)lut[m * g.K + code[m]];
         s_exact[w][j] = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
@@ -613,50 +613,28 @@ void launch_select(const SelectArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------ fallback -----
-// Exact plain ADC scan over the decoded codes for the (rare) flagged queries.
-__global__ void __launch_bounds__(256) fallback_collect_kernel(const FallbackArgs a) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int n_flagged = min((int)*a.n_flagged, a.max_flagged);
-    for (int f = 0; f < n_flagged; ++f) {
-        const uint32_t q = a.flagged[f];
-        const float* lut = a.lutf + (size_t)q * a.M * a.K;
-        const float bound = a.bound[q];
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_local; i += stride) {
-            const uint8_t* code = a.codes + (size_t)i * a.M;
-            double d = 0.0;
-            for (int m = 0; m < a.M; ++m) d += (double)lut[m * a.K + code[m]];
-            float df = (float)d;
-            if (df <= bound) {
-                uint32_t slot = atomicAdd(&a.buf_cnt[f], 1u);
-                if (slot < (uint32_t)a.cap)
-                    a.buf[(size_t)f * a.cap + slot] =
-                        ((uint64_t)__float_as_uint(df) << 32) | (uint32_t)(i + a.base_pos);
-                else
-                    *a.overflow = 1u;
-            }
-        }
-    }
-}
+// Exact plain ADC scan over the decoded codes for the (rare) flagged queries: one CTA per
+// flagged query walks every node of the shard, scores it in the reference's arithmetic (float
+// table entries, double sum) and keeps a running top-k in shared memory.  The acceptance test is
+// on the full 64-bit key (distance bits << 32 | position, strict), so any number of nodes tying
+// at the k-th distance is handled: the buffer is reduced to the k best keys (bitonic sort)
+// whenever it is more than half full, and the k-th key becomes the new exclusive bound.
+constexpr int FB_T = 1024;
+constexpr int FB_BUF = 2048;  // >= FB_T + 256 (topk <= 256)
 
-__global__ void __launch_bounds__(256) fallback_finish_kernel(const FallbackArgs a) {
-    extern __shared__ uint64_t s_keys[];  // cap
-    const int n_flagged = min((int)*a.n_flagged, a.max_flagged);
-    if (threadIdx.x == 0 && blockIdx.x == 0 && (int)*a.n_flagged > a.max_flagged) *a.overflow = 2u;
-    for (int f = blockIdx.x; f < n_flagged; f += gridDim.x) {
-    const uint32_t q = a.flagged[f];
-    int n = min((int)a.buf_cnt[f], a.cap);
+__device__ __forceinline__ void fb_compact(uint64_t* s_keys, uint32_t* s_n, unsigned long long* s_thr, int topk) {
+    const int n = (int)*s_n;  // uniform: read after a barrier
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
-    for (int i = threadIdx.x; i < np2; i += blockDim.x)
-        s_keys[i] = i < n ? a.buf[(size_t)f * a.cap + i] : ~0ull;
+    for (int i = n + threadIdx.x; i < np2; i += FB_T) s_keys[i] = ~0ull;
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-                int ixj = i ^ j;
+            for (int i = threadIdx.x; i < np2; i += FB_T) {
+                const int ixj = i ^ j;
                 if (ixj > i) {
-                    uint64_t x = s_keys[i], y = s_keys[ixj];
-                    bool up = (i & k) == 0;
+                    const uint64_t x = s_keys[i], y = s_keys[ixj];
+                    const bool up = (i & k) == 0;
                     if ((x > y) == up) {
                         s_keys[i] = y;
                         s_keys[ixj] = x;
@@ -665,19 +643,56 @@ __global__ void __launch_bounds__(256) fallback_finish_kernel(const FallbackArgs
             }
             __syncthreads();
         }
-    for (int i = threadIdx.x; i < a.topk; i += blockDim.x)
-        a.out_key[(size_t)q * a.topk + i] =
-            i < n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+    if (threadIdx.x == 0) {
+        *s_n = (uint32_t)(n < topk ? n : topk);
+        if (n >= topk) *s_thr = s_keys[topk - 1] - 1ull;  // keys are unique: only strictly better keys pass
+    }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(fb_smem);  // [FB_BUF]
+    float* s_lut = reinterpret_cast<float*>(s_keys + FB_BUF);  // [M*K]
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_thr;
+    const int n_flagged = min((int)*a.n_flagged, a.max_flagged);
+    const int MK = a.M * a.K;
+    for (int f = blockIdx.x; f < n_flagged; f += gridDim.x) {
+        const uint32_t q = a.flagged[f];
+        for (int i = threadIdx.x; i < MK; i += FB_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
+        if (threadIdx.x == 0) {
+            s_n = 0u;
+            // inclusive bound: every node with distance <= bound[q] (any position) is a candidate
+            s_thr = ((unsigned long long)__float_as_uint(a.bound[q]) << 32) | 0xFFFFFFFFull;
+        }
+        __syncthreads();
+        for (int64_t base = 0; base < a.n_local; base += FB_T) {
+            const int64_t i = base + threadIdx.x;
+            if (i < a.n_local) {
+                const uint8_t* code = a.codes + (size_t)i * a.cstride;
+                double d = 0.0;
+                for (int m = 0; m < a.M; ++m) d += (double)s_lut[m * a.K + code[m]];
+                const uint64_t key = ((uint64_t)__float_as_uint((float)d) << 32) | (uint32_t)(i + a.base_pos);
+                if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;  // < FB_BUF: compacted above FB_BUF - FB_T
+            }
+            __syncthreads();
+            if (s_n > (uint32_t)(FB_BUF - FB_T)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
+        }
+        fb_compact(s_keys, &s_n, &s_thr, a.topk);
+        for (int i = threadIdx.x; i < a.topk; i += FB_T)
+            a.out_key[(size_t)q * a.topk + i] =
+                i < (int)s_n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+        __syncthreads();
     }
 }
 
 void launch_fallback(const FallbackArgs& a, cudaStream_t st) {
-    // Always enqueued; both kernels read the flagged count on the device and exit at once
-    // when it is zero, so the common path needs no host round trip.
-    fallback_collect_kernel<<<148 * 4, 256, 0, st>>>(a);
-    int blocks = a.max_flagged < 296 ? a.max_flagged : 296;
-    fallback_finish_kernel<<<blocks, 256, (size_t)a.cap * sizeof(uint64_t), st>>>(a);
+    // Always enqueued: the kernel reads the flagged count on the device and exits at once when it
+    // is zero, so the common path needs no host round trip.
+    const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
+    const int blocks = a.max_flagged < 296 ? a.max_flagged : 296;
+    fallback_kernel<<<blocks, FB_T, sm, st>>>(a);
 }
 
 // ------------------------------------------------------------------------ merge --------

@@ -43,11 +43,40 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
     return v;
 }
-// table address of a record field: base + field * 16 (one IMAD)
+// table address of a record field: base + field * 16 (one IMAD) -- first-generation records
 __device__ __forceinline__ uint32_t fld(uint32_t base, uint32_t field) {
     uint32_t r;
     asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(r) : "r"(field), "r"(base));
     return r;
+}
+// Code-array engine (dpq_internal.h "v2"): a node is NF code bytes in one 8- or 16-byte word.
+template <int NF>
+struct CodeWord;
+template <>
+struct CodeWord<8> {
+    using type = uint2;
+    __device__ static __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
+};
+template <>
+struct CodeWord<16> {
+    using type = uint4;
+    __device__ static __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
+};
+// table address of centroid byte `byte` of `word`: base + centroid * ROWB (PRMT + IMAD); the
+// subspace offset is added as a constant that ptxas folds into the load's immediate
+template <int ROWB>
+__device__ __forceinline__ uint32_t rowaddr(uint32_t base, uint32_t word, int byte) {
+    return __byte_perm(word, 0u, 0x4440u + (uint32_t)byte) * (uint32_t)ROWB + base;
+}
+__device__ __forceinline__ uint4 lds128v(uint32_t saddr, int off) { return lds128(saddr + (uint32_t)off); }
+template <int OFF>
+__device__ __forceinline__ uint4 lds128o(uint32_t saddr) {
+    return lds128(saddr + (uint32_t)OFF);
+}
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
 }
 // hints: pull the line three lines ahead of the record cursor into L2 (hides HBM latency when the
 // tree does not fit L2; a 16M-code tree ran 3.4x off the shared-memory bound without it), and the
@@ -96,9 +125,10 @@ cudaError_t launch_scan(const ScanArgs& a, cudaStream_t st);
 // ---- second-generation scan (scan2.cu) --------------------------------------------------
 struct Scan2Args {
     V2Shape shape;
-    const uint4* recs;            // one 16- or 32-byte record per node
-    const ChunkDesc2* chunks;
-    int n_chunks, chunk_nodes;
+    const uint8_t* codes;         // [n_local][shape.nf] codes by position (8- or 16-byte aligned words)
+    int64_t n_local;
+    uint32_t base_pos;            // global position of node 0 of the shard
+    int n_chunks, chunk_nodes;    // chunk c = nodes [c * chunk_nodes, ...)
     int bt_stride;                // 1: every batch; S: every S-th batch (sample pass)
     const uint16_t* qlut;         // [n_groups][2048][56] fixed-point tables
     uint64_t* cand;               // [n_items][56][bcap] candidate keys (dist << 32 | pos)
@@ -113,35 +143,32 @@ void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  const V2Shape& sh, uint32_t bound0, cudaStream_t st);
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
-// program_dev.cu: fixed-record program from the layout arrays of a freshly built tree
-cudaError_t launch_build_recs(const uint8_t* codes_p, const uint32_t* parent_pos, const uint8_t* depth, int64_t n, int M,
-                              int K, const V2Shape& sh, int chunk_nodes, uint32_t pos_shift, uint32_t* recs,
-                              ChunkDesc2* chunks, unsigned long long* n_delta, cudaStream_t st);
+// program_dev.cu: codes [n][M] -> padded code words [n][stride] (stride 8 or 16, pad bytes 0)
+cudaError_t launch_pad_codes(const uint8_t* codes, int64_t n, int M, int stride, uint8_t* out, cudaStream_t st);
 
 // ---- coarse search (scan8.cu): 8-bit packed filter over the whole tree + exact re-score ----
-constexpr int C8_QB = 112;          // narrow shape: queries per CTA = 7 lanes x 16 queries, one byte each
-constexpr int C8_ROW_BYTES = 112;
-constexpr int C8_SAT = 31;          // table entries saturate at 31 (8 x 31 <= 255: byte sums never carry)
-// The unit is cap / L with L > 31 ("levels", default 80): finer than the saturation point, so a
-// large entry saturates.  Saturation only lowers a coarse sum (more false positives, never a
-// false negative); a node within the cap has coarse sum <= L + 8 * 0.5, so the test is
-// "sum < L + 5".  On the 1M SIFT-shaped tree L = 80 leaves 4.5x fewer survivors than L = 31.
-//
-// Wide shape (M <= 16, 4096 table rows): 48-byte rows = 3 lanes x 16 queries = 48 queries per CTA
-// (twice the 15-bit wide scan's 24), entries saturate at 15 (16 x 15 <= 255), rounding adds at most
-// 16 x 0.5, so the test is "sum < L + 9".
+// Coarse tables (scan8.cu).  The unit is cap / L with L > SAT ("levels", default 80): finer than the
+// saturation point, so a large entry saturates.  Saturation only lowers a coarse sum (more false
+// positives, never a false negative); a node within the cap has coarse sum <= L + M * 0.5, so the
+// test is "sum < L + slack + 1".  On the 1M SIFT-shaped tree L = 80 leaves 4.5x fewer survivors
+// than L = 31.
+//   narrow (M <= 8):  one byte per entry, saturation 31 (8 x 31 <= 255), 112-byte rows, slack 4
+//   wide   (M <= 16): two 4-bit entries per byte, saturation 15 (16 x 15 <= 255), 56-byte rows, slack 8
+// Both serve 112 queries per CTA and fill shared memory (2048 x 112 = 4096 x 56 = 229,376 bytes).
 struct C8Shape {
-    int nf;         // fields per record: 8 (narrow) or 16 (wide)
-    int qb;         // queries per CTA = table row bytes
+    int nf;         // table fields per node: 8 (narrow) or 16 (wide)
+    int qb;         // queries per CTA
     int rows;       // table rows
+    int row_bytes;
     int sat;        // saturation value of an entry
     int slack;      // rounding slack of a sum: nf / 2
-    int lut_bytes() const { return rows * qb; }
+    int lut_bytes() const { return rows * row_bytes; }
 };
-inline C8Shape c8_shape(int nf) { return nf == 8 ? C8Shape{8, 112, 2048, 31, 4} : C8Shape{16, 48, 4096, 15, 8}; }
+inline C8Shape c8_shape(int nf) { return nf == 8 ? C8Shape{8, 112, 2048, 112, 31, 4} : C8Shape{16, 112, 4096, 56, 15, 8}; }
 struct Scan8Args {
-    const uint4* recs;
-    const ChunkDesc2* chunks;
+    const uint8_t* codes;         // [n_local][nf] codes by position
+    int64_t n_local;
+    uint32_t base_pos;
     int n_chunks, chunk_nodes;
     int bt_stride;                // 1: every batch; S: every S-th batch (sample pass)
     const uint8_t* qlut8;         // [n_groups][rows][qb] coarse tables
@@ -152,16 +179,16 @@ struct Scan8Args {
     int thresh;                   // hit iff coarse sum < thresh (= levels + slack + 1 <= 128)
     int nf;                       // 8: narrow shape, 16: wide shape (C8Shape)
 };
-// coarse tables: entry = min(31, rint(lut / unit)), unit = cap / levels, cap = the query's exact k-th
-// distance over the sample (out_key[q][topk-1]); transposed to [group][row][112] u8
-void launch_pack8(const float* d_lutf, const float* d_cap, int MK, int Q, int levels, uint8_t* d_qlut8,
+// coarse tables: entry = min(SAT, rint(lut / unit)), unit = cap / levels, cap = the query's exact k-th
+// distance over the sample; transposed to [group][m * 256 + centroid][112 queries]
+void launch_pack8(const float* d_lutf, const float* d_cap, int M, int K, int Q, int levels, uint8_t* d_qlut8,
                   uint32_t* d_ovf, int n_groups, int nf, cudaStream_t st);
 // cap of every query from the key lists of a finished search: cap[q] = distance of out_key[q][topk-1]
 void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap, cudaStream_t st);
 // cap0[q] = exact k-th smallest distance over R evenly strided nodes (float tables, reference
 // arithmetic): a valid, loose upper bound of the true k-th distance that seeds the sample pass
-void launch_presample(const float* d_lutf, const uint8_t* d_codes, int64_t n_local, int M, int K, int Q, int topk,
-                      int R, float* d_cap, cudaStream_t st);
+void launch_presample(const float* d_lutf, const uint8_t* d_codes, int cstride, int64_t n_local, int M, int K, int Q,
+                      int topk, int R, float* d_cap, cudaStream_t st);
 cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st);
 struct Rescore8Args {
     const uint32_t* cand;
@@ -170,7 +197,8 @@ struct Rescore8Args {
     int n_groups, n_slices, bcap;
     int qb;                       // queries per group (C8Shape::qb)
     const float* lutf;            // [Q][M*K]
-    const uint8_t* codes;         // [n_local][M]
+    const uint8_t* codes;         // node i's code = codes + i * cstride
+    int cstride;
     int64_t base_pos;
     int M, K, Q, topk;
     uint64_t* out_key;            // [Q][topk] (may be null for the sample pass)
@@ -203,7 +231,8 @@ struct SelectArgs {
     const uint32_t* cand_cnt;
     const float* lutf;       // [Q][M*K]
     const double* scale;     // [Q]
-    const uint8_t* codes;    // [n_local][M]
+    const uint8_t* codes;    // node i's code = codes + i * cstride
+    int cstride;
     int64_t base_pos;
     int64_t n_local;
     int Q, topk;
@@ -216,21 +245,18 @@ struct SelectArgs {
 };
 void launch_select(const SelectArgs& a, cudaStream_t st);
 
-// Exact fallback for flagged queries: collect every node with exact distance <= bound.
+// Exact fallback for flagged queries: a running top-k over every node of the shard (kernels.cu).
 struct FallbackArgs {
     const uint32_t* flagged;    // [max_flagged] query ids
     const uint32_t* n_flagged;  // [1] device-side count
     int max_flagged;
     const float* lutf;
-    const float* bound;
-    const uint8_t* codes;
+    const float* bound;         // [Q] inclusive distance bound known to hold the k-th best (FLT_MAX: none)
+    const uint8_t* codes;       // node i's code = codes + i * cstride
+    int cstride;
     int64_t base_pos, n_local;
     int M, K, topk;
-    uint64_t* buf;            // [max_flagged][cap]
-    uint32_t* buf_cnt;        // [max_flagged]
-    int cap;
-    uint64_t* out_key;        // [Q][topk]
-    uint32_t* overflow;       // [1]
+    uint64_t* out_key;          // [Q][topk]
 };
 void launch_fallback(const FallbackArgs& a, cudaStream_t st);
 

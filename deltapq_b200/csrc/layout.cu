@@ -222,7 +222,7 @@ __global__ void reclen_kernel(int64_t n, int M, const uint8_t* __restrict__ code
                               unsigned long long* __restrict__ len, uint32_t* __restrict__ err) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (p >= n) return;
-    if (depth_p[p] > 15) atomicOr(err, ERR_NIBBLE);
+    if (depth_p[p] > (M > 8 ? 15 : 7)) atomicOr(err, ERR_NIBBLE);  // M <= 8: the reader masks nibbles with &7 (DCAT.h:3794)
     const uint32_t bm = diff_bitmap(codes_p, M, (uint32_t)p, parent_pos[p]);
     len[p - 1] = (unsigned long long)((M + 7) / 8 + __popc(bm) + (int)(p & 1));
 }
@@ -296,7 +296,7 @@ int layout_tree_device(const uint8_t* codes, int64_t n, int M, int K, const floa
         if (f & ERR_TWO_PARENTS) return api_fail(DPQ_ERR_FORMAT, "dpq_tree: edges do not form a tree (a node has two parents)");
         if (f & ERR_NOT_SPANNING) return api_fail(DPQ_ERR_FORMAT, "dpq_tree: edges do not span all codes from the root");
         if (f & ERR_TOO_DEEP) return api_fail(DPQ_ERR_FORMAT, "dpq_tree: tree deeper than 255 levels (or a cycle)");
-        if (f & ERR_NIBBLE) return api_fail(DPQ_ERR_FORMAT, "dpq_tree: depth > 15 does not fit the stream's depth nibble");
+        if (f & ERR_NIBBLE) return api_fail(DPQ_ERR_FORMAT, "dpq_tree: tree too deep for the stream's depth nibble (depth <= 7 when M <= 8: the reader masks with &7, DCAT.h:3794; <= 15 otherwise)");
         return DPQ_OK;
     };
     uint32_t flags = 0;

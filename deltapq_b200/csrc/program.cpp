@@ -81,73 +81,6 @@ struct Emitter {
     }
 };
 
-// v2 emitter: one fixed record per node (see dpq_internal.h)
-struct Emitter2 {
-    ScanProgram* p;
-    int M, K;
-    V2Shape sh;
-    int chunk_nodes;
-    bool open = false;
-    int in_chunk = 0;
-    long prev_rec = -1;     // word index of the previous record in this chunk, or -1
-    int prev_depth = 0;
-    long reg_owner_depth = -1;  // depth of the node whose distance the parent register holds, -1: none
-    // the register holds dist(node at depth reg_owner_depth on the current path) iff that
-    // node is still on the path, i.e. no shallower-or-equal node was emitted since
-    void begin(uint32_t first_pos) {
-        ChunkDesc2 c;
-        c.rec_begin = (uint32_t)(p->recs.size() / (size_t)sh.rec_words());
-        c.n_nodes = 0;
-        c.first_pos = first_pos;
-        c.pad = 0;
-        p->chunks2.push_back(c);
-        open = true;
-        in_chunk = 0;
-        prev_rec = -1;
-        reg_owner_depth = -1;
-    }
-    void end() {
-        if (!open) return;
-        p->chunks2.back().n_nodes = (uint32_t)in_chunk;
-        open = false;
-    }
-    void node(int depth, const uint8_t* par, const uint8_t* cur) {
-        if (prev_rec >= 0 && depth == prev_depth + 1) {  // previous node is this node's parent
-            p->recs[(size_t)prev_rec] |= V2_CHILD;
-            reg_owner_depth = prev_depth;
-        } else if (reg_owner_depth >= depth) {
-            reg_owner_depth = -1;  // the register's node left the path
-        }
-        const int nf = sh.nf, half = sh.nf / 2;
-        int nd = 0;
-        for (int m = 0; m < M; ++m) nd += par[m] != cur[m];
-        uint32_t f[16];
-        const bool abs = !(reg_owner_depth >= 0 && reg_owner_depth == depth - 1 && nd <= half);
-        if (!abs) {
-            for (int i = 0; i < nf; ++i) f[i] = 0;
-            int j = 0;
-            for (int m = 0; m < M; ++m)
-                if (par[m] != cur[m]) {
-                    f[j] = (uint32_t)(m * K + cur[m]) * (uint32_t)sh.lpg;         // plus: new centroid
-                    f[half + j] = (uint32_t)(m * K + par[m]) * (uint32_t)sh.lpg;  // minus: old centroid
-                    ++j;
-                }
-            p->v2_delta_nodes++;
-        } else {
-            const uint32_t zero_row = (uint32_t)(M * K) * (uint32_t)sh.lpg;
-            for (int i = 0; i < nf; ++i) f[i] = i < M ? (uint32_t)(i * K + cur[i]) * (uint32_t)sh.lpg : zero_row;
-        }
-        const size_t at = p->recs.size();
-        p->recs.resize(at + (size_t)half);
-        uint32_t* r = p->recs.data() + at;
-        for (int w = 0; w < half; ++w) r[w] = f[2 * w] | (f[2 * w + 1] << 16);
-        if (abs) r[0] |= V2_ABS;
-        prev_rec = (long)at;
-        prev_depth = depth;
-        ++in_chunk;
-    }
-};
-
 }  // namespace
 
 std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
@@ -165,29 +98,25 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
     if (M * K > 4096) return "M*K > 4096 not supported";
     P.n_codes = n_codes;
     P.n_bytes = n_bytes;
-    const int levels = P.fmt.levels();
-    const int bmb = (M + 7) / 8;
-    const int dmask = M > 8 ? 15 : 7;  // DCAT.h:3794 masks nibbles with &7
-    P.depth_hist.assign((size_t)levels + 1, 0);
-    if (chunk_nodes < 4) chunk_nodes = 4;
     P.v2 = engine == 0 && v2_shape_ok(M, K);
     if (P.v2) P.shape = v2_shape(M, K);
-    Emitter2 E2;
-    E2.p = &P;
-    E2.M = M;
-    E2.K = K;
-    E2.sh = P.shape;
-    E2.chunk_nodes = P.v2_chunk_nodes;
+    // Depth limit of the FORMAT: a nibble, masked with &7 by the reference reader when M <= 8
+    // (DCAT.h:3794), 4 bits in the M > 8 extension.  The first-generation engine additionally keeps a
+    // per-warp depth stack of fmt.levels() entries; the code-array engine (v2) has no stack.
+    const int bmb = (M + 7) / 8;
+    const int dmask = M > 8 ? 15 : 7;
+    const int levels = P.v2 ? (M > 8 ? 16 : 8) : P.fmt.levels();
+    P.depth_hist.assign((size_t)std::max(levels, P.fmt.levels()) + 1, 0);
+    if (chunk_nodes < 4) chunk_nodes = 4;
+    const int cs = P.v2 ? P.shape.nf : M;
+    P.cstride = cs;
+    uint8_t padded[16] = {0};
 
     // capacity up front (a shard holds about 1 / n_ranks of the nodes): no regrowth copies of GB-sized arrays
     {
         const size_t share = (size_t)(n_codes / n_ranks + n_codes / (8 * n_ranks) + 1024);
         const size_t cap = std::min<size_t>((size_t)n_codes, share);
-        P.codes.reserve(cap * (size_t)M);
-        if (P.v2) {
-            P.recs.reserve(cap * (size_t)P.shape.rec_words());
-            P.chunks2.reserve(cap / (size_t)P.v2_chunk_nodes + 16);
-        }
+        P.codes.reserve(cap * (size_t)cs);
     }
     std::vector<uint8_t> stack((size_t)(levels + 1) * M, 0);
     int64_t off = 0;
@@ -207,14 +136,11 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
     if (rank == 0) {
         P.base_pos = 0;
         have_base = true;
-        P.codes.insert(P.codes.end(), payload, payload + M);
+        memcpy(padded, payload, (size_t)M);
+        P.codes.insert(P.codes.end(), padded, padded + cs);  // the root is an ordinary node at position 0
         P.n_local = 1;
         P.local_bytes = M;
         P.depth_hist[0] = 1;
-        if (P.v2) {  // the root is an ordinary full record at position 0
-            E2.begin(0u);
-            E2.node(0, payload, payload);
-        }
     }
     int cur_rank = 0;
     int depths = 0;
@@ -254,7 +180,6 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
         }
         if (cur_rank != rank) {
             if (E.open) E.end();
-            if (E2.open) E2.end();
             continue;
         }
         if (!have_base) {
@@ -262,13 +187,11 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
             have_base = true;
         }
         if (P.v2) {
-            // positions of one shard are contiguous except that rank 0 also holds the root
-            const bool gap = E2.open && P.chunks2.back().first_pos + (uint32_t)E2.in_chunk != (uint32_t)i;
-            if (!E2.open || E2.in_chunk >= E2.chunk_nodes || gap) {
-                E2.end();
-                E2.begin((uint32_t)i);
-            }
-            E2.node(d, par, cur);
+            // a shard is one contiguous range of positions: whole depth-1 subtrees are dealt out in
+            // stream order, and rank 0 holds the root (position 0) in front of its subtrees
+            if (P.base_pos + P.n_local != i) return "internal: shard positions not contiguous";
+            memcpy(padded, cur, (size_t)M);
+            P.codes.insert(P.codes.end(), padded, padded + cs);
         } else {
             if (!E.open || E.nodes_in_chunk >= chunk_nodes) {
                 E.end();
@@ -276,8 +199,8 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
                 pending_root = false;
             }
             E.node(d, par, cur);
+            P.codes.insert(P.codes.end(), cur, cur + M);
         }
-        P.codes.insert(P.codes.end(), cur, cur + M);
         P.n_local++;
         P.n_diffs += nd;
         P.local_bytes += bmb + nd;
@@ -285,7 +208,6 @@ std::string compile_program(const uint8_t* payload, int64_t n_bytes, int64_t n_c
         P.depth_hist[(size_t)d]++;
     }
     E.end();
-    E2.end();
     if (off != n_bytes) return "stream has trailing or missing bytes (n_bytes mismatch)";
     P.local_bytes += (local_nodes_records + 1) / 2;  // depth nibbles
     if (pending_root && !P.v2) {  // root only (n_codes == 1, or rank 0 owns no subtree)

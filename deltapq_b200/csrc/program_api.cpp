@@ -40,12 +40,10 @@ int64_t dpq_program_size(dpq_program* h, const char* what) {
     if (w == "chunks") return (int64_t)p.chunks.size() * (int64_t)sizeof(dpq::ChunkDesc);
     if (w == "anc") return (int64_t)p.anc.size();
     if (w == "codes") return (int64_t)p.codes.size();
-    if (w == "recs") return (int64_t)p.recs.size() * 4;
-    if (w == "chunks2") return (int64_t)p.chunks2.size() * (int64_t)sizeof(dpq::ChunkDesc2);
     if (w == "v2") return p.v2 ? 1 : 0;
     if (w == "v2_nf") return p.shape.nf;
     if (w == "v2_lpg") return p.shape.lpg;
-    if (w == "v2_delta_nodes") return p.v2_delta_nodes;
+    if (w == "cstride") return p.cstride;
     if (w == "n_ops") return (int64_t)p.ops.size();
     if (w == "n_chunks") return (int64_t)p.chunks.size();
     if (w == "n_local") return p.n_local;
@@ -62,8 +60,6 @@ int dpq_program_copy(dpq_program* h, const char* what, void* dst) {
     std::string w(what);
     const dpq::ScanProgram& p = h->p;
     if (w == "ops") memcpy(dst, p.ops.data(), p.ops.size() * 4);
-    else if (w == "recs") memcpy(dst, p.recs.data(), p.recs.size() * 4);
-    else if (w == "chunks2") memcpy(dst, p.chunks2.data(), p.chunks2.size() * sizeof(dpq::ChunkDesc2));
     else if (w == "chunks") memcpy(dst, p.chunks.data(), p.chunks.size() * sizeof(dpq::ChunkDesc));
     else if (w == "anc") memcpy(dst, p.anc.data(), p.anc.size());
     else if (w == "codes") memcpy(dst, p.codes.data(), p.codes.size());

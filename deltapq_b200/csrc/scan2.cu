@@ -1,28 +1,31 @@
-// Second-generation DeltaTree scan for sm_100a (M <= 8, table <= 2048 rows).
+// Second-generation DeltaTree scan for sm_100a (M <= 16): the 15-bit fixed-point scan.
 //
-// What the first-generation kernel's ncu capture showed (profiles/scan_r1_gen1.md): the scan
-// is bound by instruction issue, not by shared-memory wavefronts or HBM: 136 warp
-// instructions per node for 48 queries, most of it per-node control (variable-length
-// records, depth stack, ring refills) and address arithmetic for one 32-bit table read per
-// (lane, lookup).  This kernel removes that overhead structurally:
+// What the first-generation kernel's ncu capture showed (profiles/r1_summary.md): that scan is
+// bound by instruction issue, not by shared-memory wavefronts or HBM: 136 warp instructions per
+// node for 48 queries, most of it per-node control (variable-length records, depth stack, ring
+// refills) and address arithmetic for one 32-bit table read per (lane, lookup).  This kernel
+// removes that overhead structurally:
 //
-//   * one fixed 16-byte record per node (dpq_internal.h "v2"): a delta record (parent +
-//     new rows - old rows, edges that change <= 4 subspaces) or a full M-term record; both
-//     are exactly eight table reads, no variable length, no depth stack;
-//   * the warp is four quarter-warp STRANDS, each walking its own chunk of the tree, so one
-//     instruction advances four nodes;
-//   * the fixed-point ADC table is laid out [row][56 queries] (112-byte rows) and read with
-//     128-bit loads: lane j of a strand gets queries 8j..8j+7 of the row in one LDS.128, the
-//     eight lanes of a strand cover one contiguous row = one conflict-free wavefront;
+//   * the shard is its nodes' PQ codes by DFS position, 8 (M <= 8) or 16 bytes per node
+//     (dpq_internal.h "v2"); every node gets the full M-term lookup -- the delta rule would read
+//     2 x 4.3..5.2 table rows per node instead of 8 -- so there is no record decoding, no depth
+//     stack and no dependence between nodes;
+//   * the warp is four quarter-warp STRANDS (eight 4-lane strands in the wide shape), each
+//     walking its own 64-node chunk, so one instruction advances four (eight) nodes;
+//   * the fixed-point ADC table is laid out [m * 256 + centroid][56 queries] (112-byte rows) and
+//     read with 128-bit loads: lane j of a strand gets queries 8j..8j+7 of the row in one
+//     LDS.128, the lanes of a strand cover one contiguous row = one conflict-free wavefront; the
+//     row address is centroid * row_bytes + base (one IMAD), the subspace offset m * 256 * row_bytes
+//     is the load's immediate;
 //   * all arithmetic is packed 2 x 15-bit in 32-bit integer adds (exact, see kernels.cu);
 //   * top-k: CTA-wide candidate buffers (one per query, in global scratch) appended with one
-//     shared-memory atomic + one store; at epoch boundaries (every 32 iterations = 2048
-//     nodes per CTA, ramping up from 1) a CTA barrier lets the owner warp of a query compact
-//     its buffer to the k' best and tighten the bound, which is shared through shared
-//     memory (CTA) and global memory (the other tree slices of the same query group).
+//     shared-memory atomic + one store; at epoch boundaries (every 128 iterations, ramping up
+//     from 1) a CTA barrier lets the owner warp of a query compact its buffer to the k' best and
+//     tighten the bound, which is shared through shared memory (CTA) and global memory (the
+//     other tree slices of the same query group).
 //
-// The table for 56 queries fills shared memory (229,376 of 232,448 bytes); the tree records
-// stream from L2/HBM through L1 with one 16-byte load per strand per node.
+// The table for 56 queries fills shared memory (229,376 of 232,448 bytes); the codes stream from
+// L2/HBM through L1 with one 8- or 16-byte load per strand per node.
 #include "kernels.cuh"
 
 #include <cfloat>
@@ -86,19 +89,21 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
     }
 }
 
-// Quantise + transpose into the scan layout [group][row][QB] u16; rows >= M*K and queries >= Q
-// are zero.  Block = 64 rows of one group; reads and writes are both coalesced.
+// Quantise + transpose into the scan layout [group][m * 256 + centroid][QB] u16; rows of subspaces
+// >= M or centroids >= K and queries >= Q are zero.  Block = 64 rows of one group; reads and writes are both coalesced.
 __global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lutf, const double* __restrict__ scale,
-                                                    int MK, int Q, int QB, int rows, uint16_t* __restrict__ qlut,
+                                                    int M, int K, int Q, int QB, int rows, uint16_t* __restrict__ qlut,
                                                     uint32_t* __restrict__ gthr, uint32_t* __restrict__ ovf,
                                                     uint32_t bound0) {
+    const int MK = M * K;
     __shared__ uint16_t tile[64 * MAXQB];
     const int grp = blockIdx.x, row0 = blockIdx.y * 64;
     for (int i = threadIdx.x; i < 64 * QB; i += blockDim.x) {
         const int ql = i >> 6, r = i & 63;
         const int q = grp * QB + ql, row = row0 + r;
         uint16_t v = 0;
-        if (q < Q && row < MK) v = (uint16_t)__double2ll_rn((double)lutf[(size_t)q * MK + row] * scale[q]);
+        const int m = row >> 8, c = row & 255;  // scan-table row = m * 256 + centroid
+        if (q < Q && m < M && c < K) v = (uint16_t)__double2ll_rn((double)lutf[(size_t)q * MK + m * K + c] * scale[q]);
         tile[r * QB + ql] = v;
     }
     __syncthreads();
@@ -118,7 +123,7 @@ void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries
     if (lsm > 48 * 1024) cudaFuncSetAttribute(lut2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
     lut2_kernel<<<(Q + LUT2_QPB - 1) / LUT2_QPB, 256, lsm, st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf, d_scale);
     if (!d_qlut) return;
-    pack2_kernel<<<dim3((unsigned)n_groups, (unsigned)(sh.rows / 64)), 256, 0, st>>>(d_lutf, d_scale, M * K, Q, sh.qb(), sh.rows,
+    pack2_kernel<<<dim3((unsigned)n_groups, (unsigned)(sh.rows / 64)), 256, 0, st>>>(d_lutf, d_scale, M, K, Q, sh.qb(), sh.rows,
                                                                                     d_qlut, d_gthr, d_ovf, bound0);
 }
 
@@ -210,14 +215,16 @@ __device__ __noinline__ void own_compact(const Own2* o, int ql, int trigger) {
     }
 }
 
-// NF fields per record, LPG active 16-byte lanes per strand, SW lanes per strand.
+// NF table fields per node (= code stride), LPG active 16-byte lanes per strand, SW lanes per strand.
 template <int NF, int LPG, int SW>
 __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     constexpr int QB = LPG * 8;                  // queries per CTA
-    constexpr int ROWS = NF == 8 ? 2048 : 4096;
-    constexpr int LUT_BYTES = ROWS * LPG * 16;
+    constexpr int ROWS = NF * 256;
+    constexpr int ROWB = LPG * 16;               // table row bytes
+    constexpr int LUT_BYTES = ROWS * ROWB;
     constexpr int SPW = 32 / SW;                 // strands per warp = chunks in flight per warp
-    constexpr int RW = NF / 8;                   // uint4 words per record
+    constexpr int SUB = 256 * ROWB;              // table bytes per subspace
+    using CodeT = typename CodeWord<NF>::type;   // uint2 (8 codes) or uint4 (16 codes)
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + LUT_BYTES);  // [64] exclusive bounds
     uint32_t* s_cnt = s_thr + MAXQB;                                  // [64] candidates per query
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
     // my 8 queries: ql = jj*8 + 2k + h (word k, half h).  A dead half (idle lane, or a query
     // beyond Q in the last group) gets the bound word 0x7FFF: thr - d never has bit 15.
     uint32_t lut_base = smem_u32(smem) + (uint32_t)jj * 16u;
-    asm volatile("" : "+r"(lut_base));  // keep it one register: address = lut_base + field * 16
+    asm volatile("" : "+r"(lut_base));  // keep it one register: address = lut_base + centroid * ROWB (+ immediate)
     uint64_t* my_cand = a.cand + (size_t)item * QB * a.bcap;
     Own2 own{my_cand, s_cnt, s_thr, gthr, a.kp, a.bcap, lane};
     const int trigger = a.trigger;
@@ -278,84 +285,67 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
 
     const int n_rounds = (b_hi - b_lo + a.n_warps - 1) / a.n_warps;
     const int C = a.chunk_nodes;
-    constexpr int rs = RW;  // records of a chunk are contiguous
+    const CodeT* codes = reinterpret_cast<const CodeT*>(a.codes);
     int since = 0, epoch_len = a.ramp ? 1 : a.epoch;
-    uint32_t parp[4] = {1u, 1u, 1u, 1u};
+    constexpr int PF = 128 / (int)sizeof(CodeT);  // nodes per 128-byte line
 
     for (int round = 0; round < n_rounds; ++round) {
         const int bt = b_lo + round * a.n_warps + warp;
         const int c = bt * a.bt_stride * SPW + strand;
         int n_nodes = 0;
         uint32_t pos = 0;
-        uint32_t rix = 0;  // record slot (32-bit index off the uniform base pointer), in uint4 units
+        uint32_t nix = 0;  // node index in the shard (32-bit index off the uniform base pointer)
         if (bt < b_hi && c < a.n_chunks) {
-            const ChunkDesc2 cd = a.chunks[c];
-            n_nodes = (int)cd.n_nodes;
-            pos = cd.first_pos;
-            rix = cd.rec_begin * RW;
+            nix = (uint32_t)c * (uint32_t)C;
+            n_nodes = (int)min((int64_t)C, a.n_local - (int64_t)nix);
+            pos = a.base_pos + nix;
         }
-        uint4 rec[RW], nxt[RW];
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            rec[w] = make_uint4(0, 0, 0, 0);
-            if (n_nodes > 0) rec[w] = __ldg(a.recs + rix + w);
-        }
+        CodeT rec = CodeWord<NF>::zero(), nxt;
+        if (n_nodes > 0) rec = __ldg(codes + nix);
 #pragma unroll 1
         for (int it = 0; it < C; ++it) {
-            rix += (uint32_t)rs;
-            if ((it & 7) == 0 && it + 25 < n_nodes) {
-                prefetch_l2(a.recs + rix + 24 * rs);
-                prefetch_l1(a.recs + rix + 8 * rs);
+            ++nix;
+            if ((it & (PF - 1)) == 0 && it + 3 * PF + 1 < n_nodes) {
+                prefetch_l2(codes + nix + 3 * PF);
+                prefetch_l1(codes + nix + PF);
             }
-#pragma unroll
-            for (int w = 0; w < RW; ++w) {
-                nxt[w] = make_uint4(0, 0, 0, 0);
-                if (it + 1 < n_nodes) nxt[w] = __ldg(a.recs + rix + w);
-            }
-            // ABS: d = sum of all NF rows; delta: d = parent + plus - minus  (parp = parent + 1,
-            // -x = ~x + 1: one 32-bit subtraction of the packed sums)
-            const uint32_t dm = (rec[0].x & V2_ABS) ? 0u : 0xFFFFFFFFu;
+            nxt = CodeWord<NF>::zero();
+            if (it + 1 < n_nodes) nxt = __ldg(codes + nix);
+            // d = sum of the node's NF table rows (pad bytes read all-zero rows)
             uint32_t d[4];
-            if (NF == 8) {
-                // eight 128-bit table reads in flight: rows of the record's fields, this lane's 8 queries
-                const uint4 P0 = lds128(fld(lut_base, rec[0].x & 0x3FFFu));
-                const uint4 P1 = lds128(fld(lut_base, rec[0].x >> 16));
-                const uint4 P2 = lds128(fld(lut_base, rec[0].y & 0xFFFFu));
-                const uint4 P3 = lds128(fld(lut_base, rec[0].y >> 16));
-                const uint4 M0 = lds128(fld(lut_base, rec[0].z & 0xFFFFu));
-                const uint4 M1 = lds128(fld(lut_base, rec[0].z >> 16));
-                const uint4 M2 = lds128(fld(lut_base, rec[0].w & 0xFFFFu));
-                const uint4 M3 = lds128(fld(lut_base, rec[0].w >> 16));
-                d[0] = (P0.x + P1.x + P2.x) + (P3.x + (parp[0] & dm)) + ((M0.x + M1.x + M2.x + M3.x) ^ dm);
-                d[1] = (P0.y + P1.y + P2.y) + (P3.y + (parp[1] & dm)) + ((M0.y + M1.y + M2.y + M3.y) ^ dm);
-                d[2] = (P0.z + P1.z + P2.z) + (P3.z + (parp[2] & dm)) + ((M0.z + M1.z + M2.z + M3.z) ^ dm);
-                d[3] = (P0.w + P1.w + P2.w) + (P3.w + (parp[3] & dm)) + ((M0.w + M1.w + M2.w + M3.w) ^ dm);
+            if constexpr (NF == 8) {
+                // eight 128-bit table reads in flight: this lane's 8 queries of each row
+                const uint4 A0 = lds128o<0 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 0));
+                const uint4 A1 = lds128o<1 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 1));
+                const uint4 A2 = lds128o<2 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 2));
+                const uint4 A3 = lds128o<3 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 3));
+                const uint4 A4 = lds128o<4 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 0));
+                const uint4 A5 = lds128o<5 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 1));
+                const uint4 A6 = lds128o<6 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 2));
+                const uint4 A7 = lds128o<7 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 3));
+                d[0] = (A0.x + A1.x + A2.x) + (A3.x + A4.x + A5.x) + (A6.x + A7.x);
+                d[1] = (A0.y + A1.y + A2.y) + (A3.y + A4.y + A5.y) + (A6.y + A7.y);
+                d[2] = (A0.z + A1.z + A2.z) + (A3.z + A4.z + A5.z) + (A6.z + A7.z);
+                d[3] = (A0.w + A1.w + A2.w) + (A3.w + A4.w + A5.w) + (A6.w + A7.w);
             } else {
-                // sixteen reads: plus fields = first record word, minus fields = second
-                const uint4 rp = rec[0], rm = rec[RW - 1];
-                uint32_t sp[4], sm[4];
-                {
-                    const uint4 A0 = lds128(fld(lut_base, rp.x & 0x3FFFu)), A1 = lds128(fld(lut_base, rp.x >> 16));
-                    const uint4 A2 = lds128(fld(lut_base, rp.y & 0xFFFFu)), A3 = lds128(fld(lut_base, rp.y >> 16));
-                    const uint4 A4 = lds128(fld(lut_base, rp.z & 0xFFFFu)), A5 = lds128(fld(lut_base, rp.z >> 16));
-                    const uint4 A6 = lds128(fld(lut_base, rp.w & 0xFFFFu)), A7 = lds128(fld(lut_base, rp.w >> 16));
-                    sp[0] = (A0.x + A1.x + A2.x) + (A3.x + A4.x + A5.x) + (A6.x + A7.x);
-                    sp[1] = (A0.y + A1.y + A2.y) + (A3.y + A4.y + A5.y) + (A6.y + A7.y);
-                    sp[2] = (A0.z + A1.z + A2.z) + (A3.z + A4.z + A5.z) + (A6.z + A7.z);
-                    sp[3] = (A0.w + A1.w + A2.w) + (A3.w + A4.w + A5.w) + (A6.w + A7.w);
-                }
-                {
-                    const uint4 B0 = lds128(fld(lut_base, rm.x & 0xFFFFu)), B1 = lds128(fld(lut_base, rm.x >> 16));
-                    const uint4 B2 = lds128(fld(lut_base, rm.y & 0xFFFFu)), B3 = lds128(fld(lut_base, rm.y >> 16));
-                    const uint4 B4 = lds128(fld(lut_base, rm.z & 0xFFFFu)), B5 = lds128(fld(lut_base, rm.z >> 16));
-                    const uint4 B6 = lds128(fld(lut_base, rm.w & 0xFFFFu)), B7 = lds128(fld(lut_base, rm.w >> 16));
-                    sm[0] = (B0.x + B1.x + B2.x) + (B3.x + B4.x + B5.x) + (B6.x + B7.x);
-                    sm[1] = (B0.y + B1.y + B2.y) + (B3.y + B4.y + B5.y) + (B6.y + B7.y);
-                    sm[2] = (B0.z + B1.z + B2.z) + (B3.z + B4.z + B5.z) + (B6.z + B7.z);
-                    sm[3] = (B0.w + B1.w + B2.w) + (B3.w + B4.w + B5.w) + (B6.w + B7.w);
-                }
+                const uint32_t w4[4] = {rec.x, rec.y, rec.z, rec.w};
+                d[0] = d[1] = d[2] = d[3] = 0u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) d[k] = sp[k] + (parp[k] & dm) + (sm[k] ^ dm);
+                for (int h = 0; h < 2; ++h) {  // two halves of eight reads keep the register footprint of the narrow shape
+                    const uint32_t wa = w4[2 * h], wb = w4[2 * h + 1];
+                    const uint4 A0 = lds128v(rowaddr<ROWB>(lut_base, wa, 0), (8 * h + 0) * SUB);
+                    const uint4 A1 = lds128v(rowaddr<ROWB>(lut_base, wa, 1), (8 * h + 1) * SUB);
+                    const uint4 A2 = lds128v(rowaddr<ROWB>(lut_base, wa, 2), (8 * h + 2) * SUB);
+                    const uint4 A3 = lds128v(rowaddr<ROWB>(lut_base, wa, 3), (8 * h + 3) * SUB);
+                    const uint4 A4 = lds128v(rowaddr<ROWB>(lut_base, wb, 0), (8 * h + 4) * SUB);
+                    const uint4 A5 = lds128v(rowaddr<ROWB>(lut_base, wb, 1), (8 * h + 5) * SUB);
+                    const uint4 A6 = lds128v(rowaddr<ROWB>(lut_base, wb, 2), (8 * h + 6) * SUB);
+                    const uint4 A7 = lds128v(rowaddr<ROWB>(lut_base, wb, 3), (8 * h + 7) * SUB);
+                    d[0] += (A0.x + A1.x + A2.x) + (A3.x + A4.x + A5.x) + (A6.x + A7.x);
+                    d[1] += (A0.y + A1.y + A2.y) + (A3.y + A4.y + A5.y) + (A6.y + A7.y);
+                    d[2] += (A0.z + A1.z + A2.z) + (A3.z + A4.z + A5.z) + (A6.z + A7.z);
+                    d[3] += (A0.w + A1.w + A2.w) + (A3.w + A4.w + A5.w) + (A6.w + A7.w);
+                }
             }
             // candidate test: bit 15 / 31 of (thr - d) survives iff d < bound, per packed half
             const uint32_t am = it < n_nodes ? 0x80008000u : 0u;
@@ -381,14 +371,7 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
                         a.ovf[(size_t)grp * QB + ql] = 1u;  // exact fallback will redo this query
                 }
             }
-            if (rec[0].x & V2_CHILD) {
-                parp[0] = d[0] + 1u;
-                parp[1] = d[1] + 1u;
-                parp[2] = d[2] + 1u;
-                parp[3] = d[3] + 1u;
-            }
-#pragma unroll
-            for (int w = 0; w < RW; ++w) rec[w] = nxt[w];
+            rec = nxt;
             ++pos;
             if (++since == epoch_len) {  // epoch boundary (uniform over the CTA)
                 since = 0;

@@ -1,25 +1,30 @@
-// Coarse search: the whole tree is scanned with a small-integer table in packed 8-bit arithmetic
-// -- four queries per 32-bit word, sixteen per 128-bit table read.  Narrow shape (M <= 8): 5-bit
-// entries, 112 queries per CTA, i.e. HALF the shared-memory wavefronts per (node, query) of the
-// 15-bit scan (scan2.cu), which is bound by exactly those wavefronts (profiles/r1_summary.md).
-// Wide shape (M <= 16): 4-bit entries (sixteen of them fit a byte sum), 48 queries per CTA against
-// the 15-bit wide scan's 24; its filter is weaker (saturation at 15 units, 16 x 0.5 rounding slack),
-// so it is chosen automatically only for short result lists (api.cu).
+// Coarse search: the whole tree is scanned with a small-integer table in packed 8-bit arithmetic.
+// Narrow shape (M <= 8): 5-bit entries stored one per byte, four queries per 32-bit word, sixteen
+// per 128-bit table read, 112 queries per CTA, i.e. HALF the shared-memory wavefronts per (node,
+// query) of the 15-bit scan (scan2.cu), which is bound by exactly those wavefronts
+// (profiles/r1_summary.md).  Wide shape (M <= 16): 4-bit entries (sixteen of them fit a byte sum)
+// stored TWO per byte: a table row is 56 bytes = 112 queries, the 4096-row table fills shared memory
+// exactly like the narrow one, a lane reads 16 queries per 64-bit load and splits even / odd nibbles
+// into byte sums (three logic ops per word).  Round 1 kept one entry per byte (48-byte rows, 48
+// queries per CTA): two 48-byte rows of one quarter-warp phase overlap in banks 75 % of the time;
+// the nibble table needs half the wavefronts per (node, query).
 //
-// Why it is exact.  Before this pass the 15-bit scan runs over a 1/16 sample of the tree and
-// select_kernel / the exact fallback give cap_q = the exact k-th distance over the sample, an
-// upper bound of the true k-th distance T_q.  Coarse entry = min(31, rint(lut / unit)) with
-// unit = cap_q / L (L = 80 levels; entries saturate at 31 so that eight of them never carry out
-// of a byte).  Saturation only lowers a sum, and rounding adds at most 0.5 per entry, so a node
-// with distance d <= T_q <= cap_q has coarse sum <= d / unit + 4 <= L + 4: EVERY true top-k node
-// passes the test "sum < L + 5".  The survivors (a few hundred per query) are re-scored exactly
-// (float tables, double sum, reference arithmetic) by rescore8_kernel, which keeps the k best
-// by (distance, position).  A candidate buffer that overflows flags its query for the exact
-// fallback.  No result ever depends on the coarse values.
+// Why it is exact.  Before this pass the 15-bit scan runs over a 1/S sample of the tree and
+// select_kernel gives cap_q = the exact k-th distance over the sample (real nodes), an upper bound
+// of the true k-th distance T_q.  Coarse entry = min(SAT, rint(lut / unit)) with unit = cap_q / L
+// (L = 80 levels; entries saturate at SAT = 31 / 15 so that the M of them never carry out of a
+// byte).  Saturation only lowers a sum, and rounding adds at most 0.5 per entry, so a node with
+// distance d <= T_q <= cap_q has coarse sum <= d / unit + M/2 <= L + M/2: EVERY true top-k node
+// passes the test "sum < L + M/2 + 1".  (rint() is taken of the double product lut * (L / cap);
+// both roundings are below 2^-52 relative, far inside the half-unit the integer test leaves: the sum
+// of M roundings is at most M/2 and the bound is the next integer.)  The survivors (a few hundred
+// per query) are re-scored exactly (float tables, double sum, reference arithmetic) by
+// rescore8_kernel, which keeps the k best by (distance, position).  A candidate buffer that
+// overflows flags its query for the exact fallback.  No result ever depends on the coarse values.
 //
-// The kernel is scan2's strand design (one 16-byte record per node, four nodes per warp step,
-// eight 128-bit reads per node) with the candidate machinery reduced to an append: the bound is
-// the constant 36 for every query, so there are no epochs, barriers or compactions.
+// The kernels are scan2's strand design (one code word per node, four nodes per warp step) with the
+// candidate machinery reduced to an append: the bound is the same constant for every query, so
+// there are no epochs, barriers or compactions.
 #include "kernels.cuh"
 
 #include <cfloat>
@@ -38,7 +43,7 @@ void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap,
 // shared memory), then the k-th smallest by bisection on the float bit patterns (distances are
 // non-negative, so the integer order of the bits is the float order).
 constexpr int PS_T = 128;
-__global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict__ lutf, const uint8_t* __restrict__ codes,
+__global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict__ lutf, const uint8_t* __restrict__ codes, int cstride,
                                                          int64_t n_local, int M, int K, int topk, int R,
                                                          float* __restrict__ cap) {
     extern __shared__ float s_lut[];  // M*K
@@ -55,7 +60,7 @@ __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict
         const int i = t * PS_T + threadIdx.x;
         v[t] = 0x7F800000u;  // +inf: never counted
         if (i < R && (int64_t)i * stride < n_local) {
-            const uint8_t* c = codes + (size_t)((int64_t)i * stride) * M;
+            const uint8_t* c = codes + (size_t)((int64_t)i * stride) * cstride;
             double d = 0.0;
             for (int m = 0; m < M; ++m) d += (double)s_lut[m * K + c[m]];
             v[t] = __float_as_uint((float)d);
@@ -80,20 +85,25 @@ __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict
     }
     if (threadIdx.x == 0) cap[q] = __uint_as_float(lo);  // FLT_MAX when the sample holds fewer than k nodes
 }
-void launch_presample(const float* d_lutf, const uint8_t* d_codes, int64_t n_local, int M, int K, int Q, int topk,
-                      int R, float* d_cap, cudaStream_t st) {
+void launch_presample(const float* d_lutf, const uint8_t* d_codes, int cstride, int64_t n_local, int M, int K, int Q,
+                      int topk, int R, float* d_cap, cudaStream_t st) {
     if (R > PS_T * 16) R = PS_T * 16;
     const size_t sm = (size_t)M * K * sizeof(float);
-    presample_kernel<<<Q, PS_T, sm, st>>>(d_lutf, d_codes, n_local, M, K, topk, R, d_cap);
+    presample_kernel<<<Q, PS_T, sm, st>>>(d_lutf, d_codes, cstride, n_local, M, K, topk, R, d_cap);
 }
 
-template <int QB, int ROWS, int SAT>
+// Coarse tables [group][m * 256 + centroid][112 queries]: NIB = false: one byte per entry (112-byte
+// rows); NIB = true: two 4-bit entries per byte (56-byte rows, query ql in byte ql / 2, nibble ql & 1).
+template <int ROWS, int SAT, bool NIB>
 __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lutf, const float* __restrict__ capv,
-                                                    int MK, int Q, int levels, uint8_t* __restrict__ qlut8,
+                                                    int M, int K, int Q, int levels, uint8_t* __restrict__ qlut8,
                                                     uint32_t* __restrict__ ovf) {
-    __shared__ uint8_t tile[64 * QB];
+    constexpr int QB = 112;
+    constexpr int ROWB = NIB ? 56 : 112;
+    __shared__ __align__(16) uint8_t tile[64 * 112];
     __shared__ double s_inv[QB];
     const int grp = blockIdx.x, row0 = blockIdx.y * 64;
+    const int MK = M * K;
     if (threadIdx.x < QB) {
         const int q = grp * QB + threadIdx.x;
         double inv = 0.0;
@@ -111,35 +121,54 @@ __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lu
     for (int i = threadIdx.x; i < 64 * QB; i += blockDim.x) {
         const int ql = i >> 6, r = i & 63;
         const int q = grp * QB + ql, row = row0 + r;
+        const int m = row >> 8, c = row & 255;
         uint8_t v = 0;
-        if (q < Q && row < MK) {
-            const double x = (double)lutf[(size_t)q * MK + row] * s_inv[ql];
+        if (q < Q && m < M && c < K) {
+            const double x = (double)lutf[(size_t)q * MK + m * K + c] * s_inv[ql];
             v = x >= (double)SAT ? (uint8_t)SAT : (uint8_t)__double2int_rn(x);
         }
         tile[r * QB + ql] = v;
     }
     __syncthreads();
-    uint32_t* dst = reinterpret_cast<uint32_t*>(qlut8 + ((size_t)grp * ROWS + row0) * QB);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
-    for (int i = threadIdx.x; i < 64 * QB / 4; i += blockDim.x) dst[i] = src[i];
+    uint32_t* dst = reinterpret_cast<uint32_t*>(qlut8 + ((size_t)grp * ROWS + row0) * ROWB);
+    if (!NIB) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
+        for (int i = threadIdx.x; i < 64 * QB / 4; i += blockDim.x) dst[i] = src[i];
+    } else {
+        // eight consecutive queries (one 64-bit tile word) -> one 32-bit word of nibbles
+        const uint2* src = reinterpret_cast<const uint2*>(tile);
+        for (int i = threadIdx.x; i < 64 * QB / 8; i += blockDim.x) {
+            const uint2 w = src[i];
+            const uint32_t lo = (w.x & 0x0Fu) | ((w.x >> 4) & 0xF0u) | ((w.x >> 8) & 0xF00u) | ((w.x >> 12) & 0xF000u);
+            const uint32_t hi = (w.y & 0x0Fu) | ((w.y >> 4) & 0xF0u) | ((w.y >> 8) & 0xF00u) | ((w.y >> 12) & 0xF000u);
+            dst[i] = lo | (hi << 16);
+        }
+    }
 }
 
-void launch_pack8(const float* d_lutf, const float* d_cap, int MK, int Q, int levels, uint8_t* d_qlut8,
+void launch_pack8(const float* d_lutf, const float* d_cap, int M, int K, int Q, int levels, uint8_t* d_qlut8,
                   uint32_t* d_ovf, int n_groups, int nf, cudaStream_t st) {
     if (nf == 8)
-        pack8_kernel<112, 2048, 31><<<dim3((unsigned)n_groups, 2048 / 64), 256, 0, st>>>(d_lutf, d_cap, MK, Q, levels, d_qlut8, d_ovf);
+        pack8_kernel<2048, 31, false><<<dim3((unsigned)n_groups, 2048 / 64), 256, 0, st>>>(d_lutf, d_cap, M, K, Q, levels, d_qlut8, d_ovf);
     else
-        pack8_kernel<48, 4096, 15><<<dim3((unsigned)n_groups, 4096 / 64), 256, 0, st>>>(d_lutf, d_cap, MK, Q, levels, d_qlut8, d_ovf);
+        pack8_kernel<4096, 15, true><<<dim3((unsigned)n_groups, 4096 / 64), 256, 0, st>>>(d_lutf, d_cap, M, K, Q, levels, d_qlut8, d_ovf);
 }
 
-// NF fields per record, LPG active 16-byte lanes per strand, SW lanes per strand (as scan2_kernel).
-template <int NF, int LPG, int SW>
+// Both shapes: 112 queries per CTA, a strand is a quarter warp (8 lanes, 7 active), lane jj of a
+// strand owns queries jj*16 .. jj*16+15 in four 32-bit words of byte sums.
+//   NF = 8 : LDS.128 of the 112-byte row, word k byte b = query jj*16 + 4k + b
+//   NF = 16: LDS.64 of the 56-byte row (nibbles); sums E0, O0, E1, O1 = even / odd nibbles of the two
+//            loaded words: word w (k = w >> 1, parity p = w & 1) byte b = query jj*16 + 8k + 2b + p
+template <int NF>
 __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
-    constexpr int QB = LPG * 16;                 // queries per CTA
-    constexpr int ROWS = NF == 8 ? 2048 : 4096;
-    constexpr int LUT_BYTES = ROWS * QB;
-    constexpr int SPW = 32 / SW;                 // strands per warp = chunks in flight per warp
-    constexpr int RW = NF / 8;                   // uint4 words per record
+    constexpr int QB = 112;                      // queries per CTA
+    constexpr int ROWS = NF * 256;
+    constexpr int ROWB = NF == 8 ? 112 : 56;     // table row bytes
+    constexpr int LANEB = NF == 8 ? 16 : 8;      // bytes of a row one lane reads
+    constexpr int LUT_BYTES = ROWS * ROWB;
+    constexpr int SPW = 4;                       // strands per warp = chunks in flight per warp
+    constexpr int SUB = 256 * ROWB;              // table bytes per subspace
+    using CodeT = typename CodeWord<NF>::type;
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + LUT_BYTES);  // [128] candidates per query
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cnt + 128);
@@ -147,8 +176,8 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
     const int item = blockIdx.x;
     const int slice = item / a.n_groups, grp = item % a.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strand = lane / SW, j = lane % SW;
-    const int jj = j < LPG ? j : LPG - 1;
+    const int strand = lane >> 3, j = lane & 7;
+    const int jj = j < 7 ? j : 6;
     const int n_bt = ((a.n_chunks + SPW - 1) / SPW + a.bt_stride - 1) / a.bt_stride;  // batches this launch walks
     const int b_lo = (int)((int64_t)n_bt * slice / a.n_slices);
     const int b_hi = (int)((int64_t)n_bt * (slice + 1) / a.n_slices);
@@ -167,94 +196,78 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
     __syncthreads();
     mbar_wait(s_bar, 0);
 
-    // my 16 queries: ql = jj*16 + 4k + b (word k, byte b).  Per byte: hit iff sum < thresh (<= 128),
-    // tested as bit 7 of (0x80 + thresh - 1 - low7(sum)) with bit 7 of the sum clear; a dead
-    // byte (idle lane / query beyond Q) gets the constant 0x7F, which never sets bit 7.
-    uint32_t lut_base = smem_u32(smem) + (uint32_t)jj * 16u;
+    // Per byte: hit iff sum < thresh (<= 128), tested as bit 7 of (0x80 + thresh - 1 - low7(sum))
+    // with bit 7 of the sum clear; a dead byte (idle lane / query beyond Q) gets the constant 0x7F,
+    // which never sets bit 7.
+    uint32_t lut_base = smem_u32(smem) + (uint32_t)jj * (uint32_t)LANEB;
     asm volatile("" : "+r"(lut_base));
-    const int n_live = j < LPG ? min(16, max(0, a.Q - (grp * QB + jj * 16))) : 0;
+    const int n_live = j < 7 ? min(16, max(0, a.Q - (grp * QB + jj * 16))) : 0;
     uint32_t cmpc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         cmpc[k] = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) cmpc[k] |= (4 * k + b < n_live ? (0x80u + (uint32_t)a.thresh - 1u) : 0x7Fu) << (8 * b);
+        for (int b = 0; b < 4; ++b) {
+            const int r = NF == 8 ? 4 * k + b : 8 * (k >> 1) + 2 * b + (k & 1);  // query of (word k, byte b) within the lane
+            cmpc[k] |= (r < n_live ? (0x80u + (uint32_t)a.thresh - 1u) : 0x7Fu) << (8 * b);
+        }
     }
     uint32_t* my_cand = a.cand + (size_t)item * QB * a.bcap;
     const int n_rounds = (b_hi - b_lo + a.n_warps - 1) / a.n_warps;
     const int C = a.chunk_nodes;
-    uint32_t parp[4] = {1u, 1u, 1u, 1u};
+    const CodeT* codes = reinterpret_cast<const CodeT*>(a.codes);
+    constexpr int PF = 128 / (int)sizeof(CodeT);  // nodes per 128-byte line
 
     for (int round = 0; round < n_rounds; ++round) {
         const int bt = b_lo + round * a.n_warps + warp;
         const int c = bt * a.bt_stride * SPW + strand;
         int n_nodes = 0;
-        uint32_t pos = 0, rix = 0;
+        uint32_t pos = 0, nix = 0;
         if (bt < b_hi && c < a.n_chunks) {
-            const ChunkDesc2 cd = a.chunks[c];
-            n_nodes = (int)cd.n_nodes;
-            pos = cd.first_pos;
-            rix = cd.rec_begin * RW;
+            nix = (uint32_t)c * (uint32_t)C;
+            n_nodes = (int)min((int64_t)C, a.n_local - (int64_t)nix);
+            pos = a.base_pos + nix;
         }
-        uint4 rec[RW], nxt[RW];
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            rec[w] = make_uint4(0, 0, 0, 0);
-            if (n_nodes > 0) rec[w] = __ldg(a.recs + rix + w);
-        }
+        CodeT rec = CodeWord<NF>::zero(), nxt;
+        if (n_nodes > 0) rec = __ldg(codes + nix);
 #pragma unroll 1
         for (int it = 0; it < C; ++it) {
-            rix += (uint32_t)RW;
-            if ((it & 7) == 0 && it + 25 < n_nodes) {
-                prefetch_l2(a.recs + rix + 24 * RW);
-                prefetch_l1(a.recs + rix + 8 * RW);
+            ++nix;
+            if ((it & (PF - 1)) == 0 && it + 3 * PF + 1 < n_nodes) {
+                prefetch_l2(codes + nix + 3 * PF);
+                prefetch_l1(codes + nix + PF);
             }
-#pragma unroll
-            for (int w = 0; w < RW; ++w) {
-                nxt[w] = make_uint4(0, 0, 0, 0);
-                if (it + 1 < n_nodes) nxt[w] = __ldg(a.recs + rix + w);
-            }
-            const uint32_t dm = (rec[0].x & V2_ABS) ? 0u : 0xFFFFFFFFu;
+            nxt = CodeWord<NF>::zero();
+            if (it + 1 < n_nodes) nxt = __ldg(codes + nix);
             uint32_t d[4];
-            if (NF == 8) {
-                const uint4 P0 = lds128(fld(lut_base, rec[0].x & 0x3FFFu));
-                const uint4 P1 = lds128(fld(lut_base, rec[0].x >> 16));
-                const uint4 P2 = lds128(fld(lut_base, rec[0].y & 0xFFFFu));
-                const uint4 P3 = lds128(fld(lut_base, rec[0].y >> 16));
-                const uint4 M0 = lds128(fld(lut_base, rec[0].z & 0xFFFFu));
-                const uint4 M1 = lds128(fld(lut_base, rec[0].z >> 16));
-                const uint4 M2 = lds128(fld(lut_base, rec[0].w & 0xFFFFu));
-                const uint4 M3 = lds128(fld(lut_base, rec[0].w >> 16));
-                d[0] = (P0.x + P1.x + P2.x) + (P3.x + (parp[0] & dm)) + ((M0.x + M1.x + M2.x + M3.x) ^ dm);
-                d[1] = (P0.y + P1.y + P2.y) + (P3.y + (parp[1] & dm)) + ((M0.y + M1.y + M2.y + M3.y) ^ dm);
-                d[2] = (P0.z + P1.z + P2.z) + (P3.z + (parp[2] & dm)) + ((M0.z + M1.z + M2.z + M3.z) ^ dm);
-                d[3] = (P0.w + P1.w + P2.w) + (P3.w + (parp[3] & dm)) + ((M0.w + M1.w + M2.w + M3.w) ^ dm);
+            if constexpr (NF == 8) {
+                const uint4 A0 = lds128o<0 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 0));
+                const uint4 A1 = lds128o<1 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 1));
+                const uint4 A2 = lds128o<2 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 2));
+                const uint4 A3 = lds128o<3 * SUB>(rowaddr<ROWB>(lut_base, rec.x, 3));
+                const uint4 A4 = lds128o<4 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 0));
+                const uint4 A5 = lds128o<5 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 1));
+                const uint4 A6 = lds128o<6 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 2));
+                const uint4 A7 = lds128o<7 * SUB>(rowaddr<ROWB>(lut_base, rec.y, 3));
+                d[0] = (A0.x + A1.x + A2.x) + (A3.x + A4.x + A5.x) + (A6.x + A7.x);
+                d[1] = (A0.y + A1.y + A2.y) + (A3.y + A4.y + A5.y) + (A6.y + A7.y);
+                d[2] = (A0.z + A1.z + A2.z) + (A3.z + A4.z + A5.z) + (A6.z + A7.z);
+                d[3] = (A0.w + A1.w + A2.w) + (A3.w + A4.w + A5.w) + (A6.w + A7.w);
             } else {
-                // sixteen reads: plus fields = first record word, minus fields = second
-                const uint4 rp = rec[0], rm = rec[RW - 1];
-                uint32_t sp[4], sm[4];
-                {
-                    const uint4 A0 = lds128(fld(lut_base, rp.x & 0x3FFFu)), A1 = lds128(fld(lut_base, rp.x >> 16));
-                    const uint4 A2 = lds128(fld(lut_base, rp.y & 0xFFFFu)), A3 = lds128(fld(lut_base, rp.y >> 16));
-                    const uint4 A4 = lds128(fld(lut_base, rp.z & 0xFFFFu)), A5 = lds128(fld(lut_base, rp.z >> 16));
-                    const uint4 A6 = lds128(fld(lut_base, rp.w & 0xFFFFu)), A7 = lds128(fld(lut_base, rp.w >> 16));
-                    sp[0] = (A0.x + A1.x + A2.x) + (A3.x + A4.x + A5.x) + (A6.x + A7.x);
-                    sp[1] = (A0.y + A1.y + A2.y) + (A3.y + A4.y + A5.y) + (A6.y + A7.y);
-                    sp[2] = (A0.z + A1.z + A2.z) + (A3.z + A4.z + A5.z) + (A6.z + A7.z);
-                    sp[3] = (A0.w + A1.w + A2.w) + (A3.w + A4.w + A5.w) + (A6.w + A7.w);
-                }
-                {
-                    const uint4 B0 = lds128(fld(lut_base, rm.x & 0xFFFFu)), B1 = lds128(fld(lut_base, rm.x >> 16));
-                    const uint4 B2 = lds128(fld(lut_base, rm.y & 0xFFFFu)), B3 = lds128(fld(lut_base, rm.y >> 16));
-                    const uint4 B4 = lds128(fld(lut_base, rm.z & 0xFFFFu)), B5 = lds128(fld(lut_base, rm.z >> 16));
-                    const uint4 B6 = lds128(fld(lut_base, rm.w & 0xFFFFu)), B7 = lds128(fld(lut_base, rm.w >> 16));
-                    sm[0] = (B0.x + B1.x + B2.x) + (B3.x + B4.x + B5.x) + (B6.x + B7.x);
-                    sm[1] = (B0.y + B1.y + B2.y) + (B3.y + B4.y + B5.y) + (B6.y + B7.y);
-                    sm[2] = (B0.z + B1.z + B2.z) + (B3.z + B4.z + B5.z) + (B6.z + B7.z);
-                    sm[3] = (B0.w + B1.w + B2.w) + (B3.w + B4.w + B5.w) + (B6.w + B7.w);
-                }
+                const uint32_t w4[4] = {rec.x, rec.y, rec.z, rec.w};
+                d[0] = d[1] = d[2] = d[3] = 0u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) d[k] = sp[k] + (parp[k] & dm) + (sm[k] ^ dm);
+                for (int h = 0; h < 4; ++h) {  // four rows at a time: four 64-bit reads in flight per step
+                    const uint2 A0 = lds64(rowaddr<ROWB>(lut_base, w4[h], 0) + (uint32_t)((4 * h + 0) * SUB));
+                    const uint2 A1 = lds64(rowaddr<ROWB>(lut_base, w4[h], 1) + (uint32_t)((4 * h + 1) * SUB));
+                    const uint2 A2 = lds64(rowaddr<ROWB>(lut_base, w4[h], 2) + (uint32_t)((4 * h + 2) * SUB));
+                    const uint2 A3 = lds64(rowaddr<ROWB>(lut_base, w4[h], 3) + (uint32_t)((4 * h + 3) * SUB));
+                    constexpr uint32_t LO = 0x0F0F0F0Fu;
+                    d[0] += ((A0.x & LO) + (A1.x & LO)) + ((A2.x & LO) + (A3.x & LO));
+                    d[1] += (((A0.x >> 4) & LO) + ((A1.x >> 4) & LO)) + (((A2.x >> 4) & LO) + ((A3.x >> 4) & LO));
+                    d[2] += ((A0.y & LO) + (A1.y & LO)) + ((A2.y & LO) + (A3.y & LO));
+                    d[3] += (((A0.y >> 4) & LO) + ((A1.y >> 4) & LO)) + (((A2.y >> 4) & LO) + ((A3.y >> 4) & LO));
+                }
             }
             const uint32_t am = it < n_nodes ? 0x80808080u : 0u;
             const uint32_t h0 = (cmpc[0] - (d[0] & 0x7F7F7F7Fu)) & ~d[0];
@@ -271,21 +284,15 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
                     while (m) {
                         const int b = (__ffs(m) - 1) >> 3;
                         m &= m - 1;
-                        const int ql = jj * 16 + 4 * k + b;
+                        const int r = NF == 8 ? 4 * k + b : 8 * (k >> 1) + 2 * b + (k & 1);
+                        const int ql = jj * 16 + r;
                         const uint32_t slot = atomicAdd(&s_cnt[ql], 1u);
                         if (slot < (uint32_t)a.bcap) __stcg(my_cand + (size_t)ql * a.bcap + slot, pos);
                         else a.ovf[(size_t)grp * QB + ql] = 1u;
                     }
                 }
             }
-            if (rec[0].x & V2_CHILD) {
-                parp[0] = d[0] + 1u;
-                parp[1] = d[1] + 1u;
-                parp[2] = d[2] + 1u;
-                parp[3] = d[3] + 1u;
-            }
-#pragma unroll
-            for (int w = 0; w < RW; ++w) rec[w] = nxt[w];
+            rec = nxt;
             ++pos;
         }
     }
@@ -297,15 +304,10 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
 cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st) {
     const C8Shape sh = c8_shape(a.nf);
     const size_t smem = (size_t)sh.lut_bytes() + 128 * 4 + 16;
-    if (a.nf == 8) {
-        cudaError_t e = cudaFuncSetAttribute(scan8_kernel<8, 7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        scan8_kernel<8, 7, 8><<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(scan8_kernel<16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        scan8_kernel<16, 3, 4><<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);
-    }
+    void (*k)(const Scan8Args) = a.nf == 8 ? scan8_kernel<8> : scan8_kernel<16>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)(a.n_groups * a.n_slices), (unsigned)(a.n_warps * 32), smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(R8_WARPS * 32) rescore8_kernel(const Rescore8A
             }
             const size_t item = (size_t)lo * a.n_groups + grp;
             const uint32_t pos = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - off[lo]));
-            const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.M;
+            const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
             double d = 0.0;
             for (int m = 0; m < a.M; ++m) d += (double)lut[m * a.K + code[m]];
             key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;

@@ -157,7 +157,11 @@ std::string write_stream(dpq_tree* t) {
         const uint8_t* c = cp + (size_t)p * M;
         const uint8_t* q = cp + (size_t)t->parent_pos[(size_t)p] * M;
         for (int m = 0; m < M; ++m) nd += c[m] != q[m];
-        if (t->depth[(size_t)p] > 15) return "depth > 15 does not fit the stream's depth nibble";
+        // M <= 8: the reference reader masks every depth nibble with &7 (DCAT.h:3794), so a deeper
+        // tree (max_height_folds >= 2) cannot be represented; the M > 8 extension keeps 4 bits
+        if (t->depth[(size_t)p] > (M > 8 ? 15 : 7))
+            return M > 8 ? "depth > 15 does not fit the stream's depth nibble"
+                         : "depth > 7 is not representable when M <= 8 (the reader masks depth nibbles with &7, DCAT.h:3794)";
     }
     t->n_diffs = nd;
     const int64_t total = (int64_t)M + nd + (int64_t)bmb * (n - 1) + n / 2;  // M = 8: 8 + n_diffs + (3(n-1)+1)/2

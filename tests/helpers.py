@@ -25,40 +25,25 @@ def assert_topk_equal(pos_a, dist_a, pos_b, dist_b, node_dist=None, rel=REL_TOL)
 
 
 def interpret_program2(prog, table_q):
-    """Second-generation fixed records (dpq_internal.h "v2", scan2.cu) for ONE query on the
-    CPU: nf 16-bit fields per record (8: narrow, 16: wide), field = row * lpg, plus fields
-    first, minus fields second.  Returns (positions, distances, n_delta_records)."""
+    """Code-array program (dpq_internal.h "v2", scan2.cu / scan8.cu) for ONE query on the CPU, the
+    way the kernels read it: every node is `cstride` code bytes (pad bytes 0), the scan table has
+    cstride * 256 rows, row = m * 256 + centroid, rows of subspaces >= M / centroids >= K all zero.
+    Returns (positions, distances)."""
     M, K = prog["M"], prog["K"]
-    nf, lpg = prog["v2_nf"], prog["v2_lpg"]
-    tab = np.concatenate([np.asarray(table_q), np.zeros(1, np.asarray(table_q).dtype)])  # + the all-zero row M*K
-    out_pos, out_d, n_delta = [], [], 0
-    for rec_begin, n_nodes, first_pos, _ in prog["chunks2"]:
-        par = None
-        for i in range(int(n_nodes)):
-            words = [int(v) for v in prog["recs"][int(rec_begin) + i]]
-            f = []
-            for w in words:
-                f += [w & 0xFFFF, w >> 16]
-            flags, f[0] = f[0] >> 14, f[0] & 0x3FFF
-            assert len(f) == nf and all(v % lpg == 0 and v // lpg <= M * K for v in f)
-            rows = [v // lpg for v in f]
-            if flags & 1:
-                d = sum(tab[r] for r in rows)
-            else:
-                assert par is not None, "delta record without a parent in the register"
-                d = par + sum(tab[r] for r in rows[:nf // 2]) - sum(tab[r] for r in rows[nf // 2:])
-                n_delta += 1
-            if flags & 2:
-                par = d
-            out_pos.append(int(first_pos) + i)
-            out_d.append(d)
-    return np.array(out_pos, np.int64), np.array(out_d), n_delta
+    nf = prog["v2_nf"]
+    cp = prog["codes_padded"]
+    assert prog["cstride"] == nf == cp.shape[1] and np.all(cp[:, M:] == 0)
+    t = np.asarray(table_q)
+    scan_table = np.zeros((nf, 256), t.dtype)
+    scan_table[:M, :K] = t.reshape(M, K)
+    d = scan_table[np.arange(nf)[None, :], cp].sum(1)
+    pos = prog["base_pos"] + np.arange(prog["n_local"], dtype=np.int64)
+    return pos, d
 
 
 def interpret_any(prog, table_q):
     if prog.get("v2"):
-        pos, d, _ = interpret_program2(prog, table_q)
-        return pos, d
+        return interpret_program2(prog, table_q)
     return interpret_program(prog, table_q)
 
 

@@ -89,29 +89,45 @@ def test_program_reproduces_every_node_distance(golden4000, chunk_nodes, engine)
     assert np.array_equal(d[np.argsort(pos)], want)
 
 
-def test_v2_program_keeps_the_delta_recurrence(golden4000):
-    """Edges that change <= 4 subspaces and whose parent distance is in the strand's register
-    are delta records (parent + new rows - old rows); everything else is a full M-term record."""
+def test_v2_program_is_the_code_array(golden4000):
+    """The code-array program is the decoded codes by DFS position (what the oracle's decoder
+    gives), padded to the scan's word stride: 8 bytes per node at M = 8."""
     g = golden4000
     n = int(g["n"])
     prog = dpq.compile_program(g["payload"], n, 8, 256)
-    table = np.random.default_rng(9).integers(0, 1 << 20, 8 * 256).astype(np.int64)
-    pos, d, n_delta = interpret_program2(prog, table)
-    assert n_delta == prog["v2_delta_nodes"] > 0
     codes, depth, parent = po.decode(g["payload"], n, 8)
-    nd = (codes[1:] != codes[parent[1:]]).sum(1)
-    assert n_delta <= int((nd <= 4).sum())
-    # a first child with <= 4 changed subspaces is always delta encoded (within a chunk)
-    first_child = np.flatnonzero((parent[1:] == np.arange(n - 1)) & (nd <= 4)) + 1
-    recs = prog["recs"]
-    C = 64
-    starts = {int(c[2]): ci for ci, c in enumerate(prog["chunks2"])}
-    for p_ in first_child[:200]:
-        if int(p_) in starts:
-            continue
-        ci = max(c for s_, c in starts.items() if s_ <= int(p_))
-        slot = int(prog["chunks2"][ci][0]) + (int(p_) - int(prog["chunks2"][ci][2]))
-        assert not (int(recs[slot][0]) & (1 << 14)), p_
+    assert prog["cstride"] == 8 and prog["codes_padded"].shape == (n, 8)
+    assert np.array_equal(prog["codes"], codes)
+    assert prog["n_diffs"] == int((codes[1:] != codes[parent[1:]]).sum())
+
+
+def test_deep_streams(golden4000):
+    """the reader's depth limit follows the FORMAT (nibble & 7 when M <= 8, 4 bits in the
+    M > 8 extension), not the table size: an M = 16, K = 128 tree of depth 9 opens; an M <= 8 tree
+    deeper than 7 cannot be written (the reference reader would alias its depths)."""
+    rng = np.random.default_rng(11)
+    # a chain: node i differs from node i-1 in one subspace -> depth grows by one per node
+    for M, K, depth_ok in ((16, 128, 12), (8, 256, 7)):
+        n = depth_ok + 1
+        codes = np.zeros((n, M), np.uint8)
+        for i in range(1, n):
+            codes[i] = codes[i - 1]
+            codes[i, i % M] = 1 + i % (K - 1)
+        edges = np.array([[i - 1, i] for i in range(1, n)], np.uint32)
+        cw = rng.random((M, K, 2)).astype(np.float32)
+        t = dpq.tree_from_edges(codes, cw, edges, 0)
+        assert int(t["depth"].max()) == depth_ok
+        prog = dpq.compile_program(t["payload"], n, M, K)
+        assert prog["v2"] and np.array_equal(prog["codes"], codes[t["vec_id"]])
+    # one level deeper than the M <= 8 format can hold: refused by the writer
+    n = 9
+    codes = np.zeros((n, 8), np.uint8)
+    for i in range(1, n):
+        codes[i] = codes[i - 1]
+        codes[i, i % 8] = i
+    edges = np.array([[i - 1, i] for i in range(1, n)], np.uint32)
+    with pytest.raises(dpq.DpqError, match="depth"):
+        dpq.tree_from_edges(codes, rng.random((8, 256, 2)).astype(np.float32), edges, 0)
 
 
 @pytest.mark.parametrize("engine", [0, 1])
@@ -151,16 +167,16 @@ def test_m16_program(golden_m16):
     assert prog["rb"] == 12 and prog["levels"] == 16 and not prog["v2"]
     pos, d = interpret_program(prog, table)
     assert np.array_equal(d[np.argsort(pos)], want)
-    # wide second-generation records: 16 fields, 3 x 16-byte table rows
+    # wide code-array program: 16 code bytes per node, 3 x 16-byte table rows in the 15-bit scan
     prog = dpq.compile_program(payload, len(codes), 16, 256)
-    assert prog["v2"] and prog["v2_nf"] == 16 and prog["v2_lpg"] == 3 and prog["recs"].shape[1] == 8
-    pos, d, n_delta = interpret_program2(prog, table)
-    assert np.array_equal(d[np.argsort(pos)], want) and n_delta == prog["v2_delta_nodes"]
+    assert prog["v2"] and prog["v2_nf"] == 16 and prog["v2_lpg"] == 3 and prog["codes_padded"].shape[1] == 16
+    pos, d = interpret_program2(prog, table)
+    assert np.array_equal(d[np.argsort(pos)], want)
 
 
 @pytest.mark.parametrize("M,K", [(4, 256), (8, 100), (3, 16), (12, 256), (16, 200), (9, 64)])
 def test_v2_program_other_shapes(M, K):
-    """M < 8 / M < 16 full records pad with the all-zero table row M*K."""
+    """M < 8 / M < 16: pad code bytes are 0 and read the all-zero rows of the unused subspaces."""
     rng = np.random.default_rng(M * 1000 + K)
     n = 700
     codes = rng.integers(0, min(K, 5), (n, M)).astype(np.uint8)
@@ -169,7 +185,7 @@ def test_v2_program_other_shapes(M, K):
     prog = dpq.compile_program(payload, n, M, K)
     assert prog["v2"] and prog["v2_nf"] == (8 if M <= 8 else 16)
     table = rng.integers(0, 1 << 16, M * K).astype(np.int64)
-    pos, d, _ = interpret_program2(prog, table)
+    pos, d = interpret_program2(prog, table)
     want = table.reshape(M, K)[np.arange(M)[None, :], codes[lay["vec_id"]]].sum(1)
     assert np.array_equal(np.sort(pos), np.arange(n)) and np.array_equal(d[np.argsort(pos)], want)
 

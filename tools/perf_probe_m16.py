@@ -24,7 +24,24 @@ print("engine", ix.stat("engine"), "prog_bytes", ix.stat("ops_bytes"), flush=Tru
 for it in range(3):
     pos, ids, dist = ix.search(queries, topk)
     print(json.dumps(dict(scan_ms=ix.stat("last_scan_us") / 1e3, lut_ms=ix.stat("last_lut_us") / 1e3, total_ms=ix.stat("last_total_us") / 1e3,
-                          qps=round(Q / (ix.stat("last_total_us") * 1e-6)), fallback=ix.stat("last_fallback"))), flush=True)
+                          qps=round(Q / (ix.stat("last_total_us") * 1e-6)), fallback=ix.stat("last_fallback"),
+                          coarse=ix.stat("last_coarse"), scan8_ms=ix.stat("last_scan8_us") / 1e3,
+                          cand8_per_query=round(ix.stat("cand8_total") / Q, 1))), flush=True)
+for cfg in sys.argv[4:] if gist else sys.argv[3:]:
+    for kv in cfg.split(","):
+        kk, v = kv.split("="); ix.set_option(kk, int(v))
+    for kk in (100, 10):
+        best = None
+        for it in range(3):
+            p2, i2, d2 = ix.search(queries, kk)
+            tot = ix.stat("last_total_us")
+            if best is None or tot < best[0]:
+                best = (tot, ix.stat("last_scan_us"), ix.stat("last_lut_us"), ix.stat("last_scan8_us"))
+        print(json.dumps(dict(cfg=cfg, topk=kk, total_ms=best[0] / 1e3, scan_ms=best[1] / 1e3, lut_ms=best[2] / 1e3,
+                              scan8_ms=best[3] / 1e3, qps=round(Q / (best[0] * 1e-6)), coarse=ix.stat("last_coarse"),
+                              fallback=ix.stat("last_fallback"),
+                              cand8_per_query=round(ix.stat("cand8_total") / Q, 1) if ix.stat("last_coarse") else None,
+                              same_as_default=bool(kk != 100 or (np.array_equal(p2, pos) and np.array_equal(d2, dist))))), flush=True)
 for i in (0, Q // 2):
     opos, odist = po.scan(payload, N, cw, queries[i], topk)
     print("q", i, "dist allclose", bool(np.allclose(odist, dist[i], rtol=1e-5)), "exact", bool(np.array_equal(odist, dist[i])))
