@@ -355,6 +355,20 @@ def run_gpu(args):
         assert same, "sharded + merged top-k differs from the unsharded result"
         sh.close()
 
+    # ---- C5: one tree over 10^9 codes, subtree shards over the ranks (own block, never fails the line)
+    c5 = None
+    if args.c5_codes > 0:
+        t_c5 = time.perf_counter()
+        try:
+            del flush
+            torch.cuda.empty_cache()
+            c5 = c5_block(torch, dpq, dist, dev, rank, world, args, stream, barrier, max_over_ranks)
+        except Exception as e:  # recorded, the primary line stands
+            import traceback
+            c5 = {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
+        c5["block_s"] = round(time.perf_counter() - t_c5, 1)
+        torch.cuda.empty_cache()
+
     n_bytes_total = ix.stat("n_bytes_total")
     peak, peak_src = measured_peak()
     # algorithmic bytes of one scan launch: Q queries x (stream bytes + 4 D query
@@ -435,6 +449,7 @@ def run_gpu(args):
                                       "coarse_scan_kernel": dom_s * 1e3 if coarse else None,
                                       "scan_max_over_ranks": scan_ms_max / max(calls, 1), "exact_fallback_queries": fallback},
             "tree_sharded": tree_sharded,
+            "c5": c5,
         }
         print(json.dumps(line))
         if parity is not None and not parity["ok"]:
@@ -444,6 +459,222 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+# ------------------------------------------------------------------------ C5: 10^9 codes --
+def gen_codes_device(torch, dpq, dev, cw, n, seed, out, chunk=1 << 21):
+    """SIFT-like bvecs-shaped vectors (tests/datagen.sift_like's mixture, drawn with torch on the
+    device: integer components 0..255) -> codes [n][8] written into `out` (a device uint8 tensor),
+    never storing the vectors."""
+    n_clusters, sigma, nb, w = 256, 14.0, DIM // 16, 16
+    crng = np.random.default_rng(1234567)  # the centres of datagen.sift_like
+    centres = torch.from_numpy(np.clip(crng.gamma(2.0, 22.0, size=(nb, n_clusters, w)), 0, 255)).to(dev, torch.float32)
+    pop = 1.0 / np.arange(1, n_clusters + 1) ** 0.7
+    pop = torch.from_numpy(pop / pop.sum()).to(dev, torch.float32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    for s_ in range(0, n, chunk):
+        c = min(chunk, n - s_)
+        x = torch.empty((c, DIM), dtype=torch.float32, device=dev)
+        for b in range(nb):
+            cid = torch.multinomial(pop, c, replacement=True, generator=g)
+            blk = centres[b][cid] + sigma * torch.randn((c, w), device=dev, generator=g)
+            x[:, b * w:(b + 1) * w] = blk.round_().clamp_(0, 255)
+        dpq.encode_device(cw, x.data_ptr(), c, DIM, out[s_:].data_ptr())
+        del x
+    torch.cuda.synchronize()
+
+
+def plain_adc_topk_device(torch, dpq, cw, codes_dev, queries, k, slab=1 << 27):
+    """Exact top-k of plain ADC over ALL codes for a few queries (float table entries, double sum =
+    the reference's arithmetic), on the device in slabs: [(dist float32 [k], vector id int64 [k])]."""
+    tabs = dpq.adc_tables(cw, queries)  # [q][M][K] float32
+    out = []
+    n = codes_dev.shape[0]
+    for t in tabs:
+        tt = torch.from_numpy(t).to(codes_dev.device, torch.float64)
+        best_d, best_i = None, None
+        for s_ in range(0, n, slab):
+            blk = codes_dev[s_:s_ + slab]
+            d = torch.zeros(blk.shape[0], dtype=torch.float64, device=codes_dev.device)
+            for m in range(PQ_M):
+                d += tt[m][blk[:, m].long()]
+            d32 = d.to(torch.float32)
+            v, i = torch.topk(d32, min(4 * k, d32.shape[0]), largest=False, sorted=True)
+            i = i + s_
+            best_d = v if best_d is None else torch.cat([best_d, v])
+            best_i = i if best_i is None else torch.cat([best_i, i])
+            del d, d32, blk
+        bd, bi = best_d.cpu().numpy(), best_i.cpu().numpy().astype(np.int64)
+        order = np.lexsort((bi, bd))[:4 * k]
+        out.append((bd[order], bi[order]))
+    return out
+
+
+def c5_block(torch, dpq, dist, dev, rank, world, args, stream, barrier, max_over_ranks):
+    """BASELINE configs[4] / north_star: ONE DeltaTree over 10^9 SIFT1B-shaped codes, sharded by
+    whole depth-1 subtrees over the GPUs, local top-k per GPU with global positions, one
+    NCCL all-gather of Q x k keys per rank, device merge.  Every rank builds the same tree on its own
+    GPU (the build is a global sort: replicas) and keeps only its shard."""
+    import datagen as dg
+    n_total, Q, k = args.c5_codes, args.queries, TOPK
+    out = {"n_codes": n_total, "queries_per_step": Q, "topk": k}
+    t0 = time.perf_counter()
+    learn = dg.sift_like(20000, DIM, seed=3)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(learn, PQ_M, PQ_K, iters=6))
+    queries = dg.sift_like(Q, DIM, seed=2)
+    torch.cuda.empty_cache()
+    setup_err = None
+    try:
+        codes = torch.empty((n_total, PQ_M), dtype=torch.uint8, device=dev)
+    except Exception as e:  # out of memory: every rank must agree to skip before any collective
+        setup_err = repr(e)[:200]
+    if world > 1:
+        flag = torch.tensor([1.0 if setup_err else 0.0], device=dev)
+        dist.all_reduce(flag)
+        if float(flag[0]) > 0:
+            return {"error": "setup failed on some rank: " + str(setup_err)}
+    elif setup_err:
+        return {"error": "setup failed: " + setup_err}
+    n_gen = 8  # generated in 8 seeded pieces (the same data for every world size)
+    for p in range(n_gen):
+        lo, hi = n_total * p // n_gen, n_total * (p + 1) // n_gen
+        gen_codes_device(torch, dpq, dev, cw, hi - lo, 1000 + p, codes[lo:hi])
+    t1 = time.perf_counter()
+    nq_chk = min(args.c5_check_queries, Q)
+    truth = plain_adc_topk_device(torch, dpq, cw, codes, queries[:nq_chk], k) if nq_chk else []
+    torch.cuda.empty_cache()
+    t2 = time.perf_counter()
+    tree = dpq.DeviceTree(codes.data_ptr(), n_total, PQ_M, cw)
+    t3 = time.perf_counter()
+    del codes
+    torch.cuda.empty_cache()
+    ix = tree.shard(rank, world)
+    ix.set_codebook(cw)
+    ix.set_stream(stream.cuda_stream)
+    n_bytes = tree.stat("payload")
+    n_diffs = tree.stat("n_diffs")
+    out["setup_s"] = {"gen_encode": round(t1 - t0, 1), "plain_adc_truth": round(t2 - t1, 1),
+                      "edge_search": round(tree.stat("edge_us") / 1e6, 1), "layout_stream": round(tree.stat("layout_us") / 1e6, 1),
+                      "open_shard": round(time.perf_counter() - t3, 1)}
+    out["tree"] = {"n_bytes": n_bytes, "disk_bytes_per_node": round(n_bytes / n_total, 3),
+                   "mean_diffs_per_node": round(n_diffs / max(n_total - 1, 1), 3),
+                   "depth_hist": [tree.stat(f"depth_hist_{d}") for d in range(9)],
+                   "device_bytes_per_node": ix.stat("device_bytes_per_node"),
+                   "built": "one tree over all codes by dpq_tree_build_device on every rank's GPU (edge search + layout + stream, "
+                            "nothing leaves HBM); shard = whole depth-1 subtrees balanced by stream bytes"}
+    # rank 0 at N = 1 keeps the stream for the reference CPU sample and the ids of the check queries
+    payload = tree.fetch("payload", np.uint8) if (rank == 0 and world == 1 and args.c5_ref_queries > 0) else None
+    vec_id = tree.fetch("vec_id", np.uint32) if nq_chk else None
+    tree.free()
+    torch.cuda.empty_cache()
+
+    d_q = torch.from_numpy(queries).to(dev)
+    d_loc = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    d_all = torch.empty((world, Q, k), dtype=torch.int64, device=dev)
+    d_mrg = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        ix.search_device(d_q.data_ptr(), Q, k, d_loc.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all.view(-1), d_loc.view(-1))
+            ix.merge_device(d_all.data_ptr(), world, Q, k, d_mrg.data_ptr())
+        else:
+            d_mrg.copy_(d_loc)
+
+    steps = max(1, min(args.steps, args.c5_steps))
+    for _ in range(3):
+        flush.zero_()
+        step()
+    barrier()
+    ix.set_option("timing_reset", 1)
+    total_ms = timed_steps(torch, stream, flush, steps, step, barrier)
+    calls = max(ix.stat("timed_calls"), 1)
+    scan8_ms = ix.stat("sum_scan8_ns") / 1e6 / calls
+    scan_ms = ix.stat("sum_scan_ns") / 1e6 / calls
+    lut_ms = ix.stat("sum_lut_ns") / 1e6 / calls
+    ix.sync()
+    fallback = ix.stat("last_fallback")
+    n_local = ix.stat("n_local")
+    (total_ms, scan8_max) = max_over_ranks(total_ms, scan8_ms)
+    # e2e: host buffers through dpq_index_search on the shard, keys gathered and merged
+    h_q = dpq.pinned_array(queries.shape, np.float32)
+    h_q[...] = queries
+    barrier()
+    te = time.perf_counter()
+    pos, ids, dst = ix.search(h_q, k)
+    if world > 1:
+        keys = (dst.view(np.uint32).astype(np.uint64) << np.uint64(32)) | pos
+        d_keys = torch.from_numpy(keys.view(np.int64)).to(dev)
+        dist.all_gather_into_tensor(d_all.view(-1), d_keys.view(-1))
+        ix.merge_device(d_all.data_ptr(), world, Q, k, d_mrg.data_ptr())
+        _ = d_mrg.cpu()
+    barrier()
+    (e2e_s,) = max_over_ranks(time.perf_counter() - te)
+
+    step()
+    torch.cuda.synchronize()
+    mpos, mdist = dpq.unpack_keys(d_mrg.cpu().numpy().view(np.uint64))
+    ok = bool(np.all(np.diff(mdist.astype(np.float64), axis=1) >= 0))
+    check = None
+    if nq_chk:
+        same = True
+        for q in range(nq_chk):
+            td, ti = truth[q]
+            same &= bool(np.array_equal(td[:k], mdist[q]))
+            kth = td[k - 1]
+            got = {int(vec_id[p_]) for p_, d_ in zip(mpos[q], mdist[q]) if d_ < kth}
+            want = {int(i_) for i_, d_ in zip(ti, td) if d_ < kth}
+            same &= got == want
+        check = {"queries": nq_chk, "equals_plain_adc_over_all_codes": bool(same)}
+        ok &= bool(same)
+    qps = Q * steps / (total_ms / 1e3)
+    out.update({"value": qps, "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps, "warmup": 3,
+                "scaling": "strong", "n_local_nodes_rank0": n_local,
+                "sharding": f"one tree, {world} shard(s) of whole depth-1 subtrees; same {Q} queries on every shard; "
+                            f"NCCL all-gather of {Q * k * 8} B/rank + device merge",
+                "e2e": {"value": Q / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * Q * DIM * 4,
+                        "d2h_bytes_per_step": world * Q * k * 8},
+                "breakdown_ms_per_step": {"lut": lut_ms, "all_scan_phases": scan_ms, "coarse_scan_kernel_max_over_ranks": scan8_max,
+                                          "exact_fallback_queries": fallback},
+                "check": check, "ok": ok})
+    groups = (Q + 111) // 112
+    sm_mhz = 1965.0
+    out["roofline"] = {"bound": "smem_lsu", "kernel": "scan8_kernel", "kernel_ms_per_launch": scan8_ms,
+                       "achieved": n_local * groups * 8 * 128 / (scan8_ms / 1e3) / 1e9, "peak": 148 * 128 * sm_mhz * 1e6 / 1e9,
+                       "unit": "GB/s", "frac": (n_local * groups * 8 * 128 / (scan8_ms / 1e3) / 1e9) / (148 * 128 * sm_mhz * 1e6 / 1e9),
+                       "hbm_floor_ms": n_local * 8 / 6553e9 * 1e3 * groups,
+                       "note": "rank 0's shard; one pass of the 8 B/node code array per 112-query group"}
+    if payload is not None:
+        from oracle import pyoracle as po
+        from helpers import assert_topk_equal
+        nq = args.c5_ref_queries
+        kind = "reference" if po.have_ref() else "port"
+        tq = time.perf_counter()
+        if kind == "reference":
+            rpos, rdist, secs = po.ref_scan(payload, n_total, cw, np.ascontiguousarray(queries[:nq]), k)
+        else:
+            rpos = np.empty((nq, k), np.int32)
+            rdist = np.empty((nq, k), np.float32)
+            for i in range(nq):
+                rpos[i], rdist[i] = po.scan(payload, n_total, cw, queries[i], k)
+            secs = time.perf_counter() - tq
+        rpos = np.where(rpos == n_total, n_total - 1, rpos)
+        pok, why = True, None
+        try:
+            assert_topk_equal(mpos[:nq], mdist[:nq], rpos, rdist)
+        except AssertionError as e:
+            pok, why = False, str(e)[:300]
+        out["cpu_baseline"] = {"value": nq / secs, "unit": UNIT, "cores": 1, "kind": kind,
+                               "sample": f"{nq} queries over the same {n_total}-code tree, in-memory scan (DCAT.h:3731), 1 thread, {secs:.1f} s"}
+        out["parity"] = {"queries": nq, "ok": pok, "dist_bit_equal": bool(np.array_equal(mdist[:nq], rdist)),
+                         "against": kind + " CPU scan of the same queries on the same tree"}
+        if why:
+            out["parity"]["why"] = why
+        out["ok"] = bool(out["ok"] and pok)
+    ix.close()
+    return out
 
 
 def cpu_baseline(payload, n_codes, cw, queries, n_q, gpu_pos, gpu_dist):
@@ -514,6 +745,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-queries", type=int, default=600)
     ap.add_argument("--ref-queries-per-proc", type=int, default=100)
+    ap.add_argument("--c5-codes", type=int, default=1_000_000_000,
+                    help="codes of the single-tree C5 block (0 = skip the block)")
+    ap.add_argument("--c5-steps", type=int, default=3)
+    ap.add_argument("--c5-check-queries", type=int, default=4)
+    ap.add_argument("--c5-ref-queries", type=int, default=2)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(HERE, "libdpq.so")
 SYMBOLS = [
     "dpq_version", "dpq_last_error", "dpq_device_count", "dpq_set_device",
     "dpq_index_open", "dpq_index_open_part", "dpq_index_open_file", "dpq_index_open_part_file",
-    "dpq_multi_open_parts", "dpq_index_open_tree", "dpq_index_set_codebook", "dpq_index_set_option",
+    "dpq_multi_open_parts", "dpq_index_open_tree", "dpq_index_open_tree_shard", "dpq_tree_build_device",
+    "dpq_index_set_codebook", "dpq_index_set_option",
     "dpq_index_set_stream",
     "dpq_index_search", "dpq_index_search_device", "dpq_index_sync", "dpq_merge_topk_device",
     "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",
@@ -55,6 +56,8 @@ def lib():
     L.dpq_index_open.argtypes = [vp, i64, i64, i32, i32, vp, i32, i32, C.POINTER(vp)]
     L.dpq_index_open_part.argtypes = [vp, i64, i64, i32, i32, vp, i64, C.POINTER(vp)]
     L.dpq_index_open_tree.argtypes = [vp, i64, C.POINTER(vp)]
+    L.dpq_index_open_tree_shard.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.dpq_tree_build_device.argtypes = [vp, i64, i32, i32, vp, i32, i32, i32, C.POINTER(vp)]
     L.dpq_index_open_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, C.POINTER(vp)]
     L.dpq_index_set_codebook.argtypes = [vp, vp, i32]
     L.dpq_index_set_option.argtypes = [vp, C.c_char_p, i64]
@@ -345,6 +348,51 @@ def tree_build(codes, cw, h=1, method=1, want=None, open_index_at=None):
         out["index"] = ix
         return out
     return _tree_out(t, M, want)
+
+
+class DeviceTree:
+    """dpq_tree_build_device: one DeltaTree built and kept in HBM (the 10^9-code layout).  codes_ptr
+    is a DEVICE pointer to [n][M] codes (or a numpy array).  shard(rank, n_ranks) opens whole depth-1
+    subtrees as an index (dpq_index_open_tree_shard)."""
+
+    def __init__(self, codes, n, M, cw, h=1, method=1):
+        cw = np.ascontiguousarray(cw, np.float32)
+        self.M, self.K, self.n = M, cw.shape[1], n
+        self._t = C.c_void_p()
+        if isinstance(codes, np.ndarray):
+            self._keep = np.ascontiguousarray(codes, np.uint8)
+            ptr = _ptr(self._keep)
+        else:
+            ptr = C.c_void_p(int(codes))
+        _check(lib().dpq_tree_build_device(ptr, n, M, self.K, _ptr(cw), cw.shape[2], h, method, C.byref(self._t)))
+
+    def stat(self, name):
+        return int(lib().dpq_tree_size(self._t, name.encode()))
+
+    def fetch(self, name, dtype):
+        nb = self.stat(name)
+        arr = np.empty(nb // np.dtype(dtype).itemsize, dtype)
+        if nb:
+            _check(lib().dpq_tree_copy(self._t, name.encode(), _ptr(arr)))
+        return arr
+
+    def shard(self, rank=0, n_ranks=1):
+        ix = DeltaTreeIndex.__new__(DeltaTreeIndex)
+        ix.M, ix.K, ix.Ds = self.M, self.K, None
+        ix._h = C.c_void_p()
+        _check(lib().dpq_index_open_tree_shard(self._t, rank, n_ranks, C.byref(ix._h)))
+        return ix
+
+    def free(self):
+        if self._t:
+            lib().dpq_tree_free(self._t)
+            self._t = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def encode_device(cw, d_x_ptr, n, D, d_codes_ptr):

@@ -72,6 +72,8 @@ struct dpq_index {
     // "timing_reset" keep their own events so a bench loop can time K steps without syncing.
     std::vector<cudaEvent_t> evs;
     int timed_calls = 0;
+    int last_first_call = 0;        // first event slot of the last API call (a host-buffer search is several sub-batches)
+    bool host_call_active = false;
     cudaEvent_t* ev = nullptr;  // the last call's four events
     dpq::ScanProgram prog;  // host copy (ops/codes released after upload)
     int Ds = 0;
@@ -79,6 +81,7 @@ struct dpq_index {
     DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_ovf;
     DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_cap0, d_cap1;
     int last_coarse = 0;
+    int last_device_queries = 0;  // queries of the last dpq_index_search_device call (a host-buffer search runs sub-batches)
     int64_t last_items8 = 0;
     int n_chunks = 0;
     size_t ops_bytes = 0;
@@ -102,6 +105,8 @@ struct dpq_index {
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_key, d_gthr;
     void* h_stage = nullptr;  // pinned staging for the host-buffer path
     size_t h_stage_cap = 0;
+    cudaStream_t copy_stream = nullptr;  // host-buffer path: uploads / downloads overlap the searches
+    cudaEvent_t copy_ev[12] = {};
     // stats
     int last_launches = 0;
     int64_t last_fallback = 0;
@@ -359,6 +364,10 @@ int dpq_index_open_tree(dpq_tree* t, int64_t first_pos, dpq_index** out) {
     *out = nullptr;
     const int M = t->M, K = t->K;
     const int64_t n = t->n;
+    if (t->on_device) {
+        if (first_pos) return fail(DPQ_ERR_ARG, "dpq_index_open_tree: a device-resident tree opens at first_pos 0 (use dpq_index_open_tree_shard)");
+        return dpq_index_open_tree_shard(t, 0, 1, out);
+    }
     const char* eng = getenv("DPQ_ENGINE");
     if ((eng && eng[0] == '1') || !dpq::v2_shape_ok(M, K))  // first-generation program: through the byte stream
         return open_common(t->payload.data(), (int64_t)t->payload.size(), n, M, K, t->vec_id.data(), 0, 1, first_pos, out);
@@ -416,6 +425,82 @@ int dpq_index_open_tree(dpq_tree* t, int64_t first_pos, dpq_index** out) {
     ix->ops_bytes = (size_t)n * P.cstride;
     ix->has_pos2id = true;
     ix->pos2id_host = t->vec_id;
+    *out = ix;
+    return DPQ_OK;
+}
+
+// Shard `rank` of `n_ranks` of a tree that dpq_tree_build[_device] just produced: whole depth-1
+// subtrees balanced by stream bytes, the same deal as dpq_index_open(payload, ..., rank, n_ranks).
+// A device-resident tree never leaves HBM: the shard's slice of the code array is copied device to
+// device (and padded to the word stride when M is not 8 / 16).
+int dpq_index_open_tree_shard(dpq_tree* t, int rank, int n_ranks, dpq_index** out) {
+    if (!t || !out) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: null argument");
+    *out = nullptr;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: bad rank / n_ranks");
+    const int M = t->M, K = t->K;
+    const int64_t n = t->n;
+    const char* eng = getenv("DPQ_ENGINE");
+    const bool gen1 = (eng && eng[0] == '1') || !dpq::v2_shape_ok(M, K);
+    if (!t->on_device) {
+        if (n_ranks == 1 && !gen1) return dpq_index_open_tree(t, 0, out);
+        return open_common(t->payload.data(), (int64_t)t->payload.size(), n, M, K, t->vec_id.data(), rank, n_ranks, 0, out);
+    }
+    if (gen1) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: a device-resident tree needs the code-array engine");
+    if (n > 0xFFFFFFFELL) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: positions must stay below 2^32 - 1");
+    int rc = check_device();
+    if (rc) return rc;
+    if (g_device != t->device) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: the tree lives on another device");
+    std::vector<int64_t> bounds, bytes;
+    if ((rc = dpq::tree_shard_bounds(t, n_ranks, &bounds, &bytes))) return rc;
+    const int64_t lo = bounds[(size_t)rank], hi = bounds[(size_t)rank + 1];
+    dpq_index* ix = new dpq_index();
+    ix->device = g_device;
+    dpq::ScanProgram& P = ix->prog;
+    P.M = M;
+    P.K = K;
+    P.fmt.rb = (M * K <= 2048) ? 11 : 12;
+    P.v2 = true;
+    P.shape = dpq::v2_shape(M, K);
+    P.cstride = P.shape.nf;
+    P.n_codes = n;
+    P.n_bytes = t->payload_bytes;
+    P.base_pos = lo;
+    P.n_local = hi - lo;
+    P.local_bytes = bytes[(size_t)rank];
+    {   // changed subspaces = record bytes - bitmap bytes - depth bytes (one per odd position)
+        const int64_t rlo = std::max<int64_t>(lo, 1), recs = std::max<int64_t>(hi - rlo, 0);
+        const int64_t odd = recs > 0 ? ((hi - 1 + 1) / 2 - (rlo - 1 + 1) / 2) : 0;  // odd p in [rlo, hi)
+        P.n_diffs = bytes[(size_t)rank] - (rank == 0 ? M : 0) - (int64_t)((M + 7) / 8) * recs - odd;
+    }
+    int64_t hist[17] = {0};
+    auto bail = [&](int code) {
+        dpq_index_close(ix);
+        return code;
+    };
+    if (cudaSetDevice(ix->device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(DPQ_ERR_CUDA, "dpq_index_open_tree_shard: stream setup failed"));
+    if ((rc = dpq::depth_hist_device(ix->device, (const uint8_t*)t->d_depth + lo, P.n_local, hist))) return bail(rc);
+    P.depth_hist.assign(hist, hist + 17);
+    if ((rc = ix->d_codes.ensure((size_t)std::max<int64_t>(P.n_local, 1) * P.cstride))) return bail(rc);
+    cudaError_t e = cudaSuccess;
+    const uint8_t* src = (const uint8_t*)t->d_codes_by_pos + (size_t)lo * M;
+    if (P.n_local > 0) {
+        if (M == P.cstride)
+            e = cudaMemcpyAsync(ix->d_codes.p, src, (size_t)P.n_local * M, cudaMemcpyDeviceToDevice, ix->stream);
+        else
+            e = dpq::launch_pad_codes(src, P.n_local, M, P.cstride, ix->d_codes.as<uint8_t>(), ix->stream);
+    }
+    if ((rc = ix->d_ops.ensure(16)) || (rc = ix->d_chunks.ensure(16)) || (rc = ix->d_anc.ensure(16))) return bail(rc);
+    ix->pos2id_host.resize((size_t)P.n_local);
+    if (e == cudaSuccess && P.n_local > 0)
+        e = cudaMemcpyAsync(ix->pos2id_host.data(), (const uint32_t*)t->d_vec_id + lo, (size_t)P.n_local * 4,
+                            cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    if (e != cudaSuccess) return bail(fail(DPQ_ERR_CUDA, std::string("dpq_index_open_tree_shard: ") + cudaGetErrorString(e)));
+    ix->has_pos2id = true;
+    ix->n_chunks = (int)((P.n_local + P.v2_chunk_nodes - 1) / P.v2_chunk_nodes);
+    ix->ops_bytes = (size_t)P.n_local * P.cstride;
     *out = ix;
     return DPQ_OK;
 }
@@ -518,6 +603,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
     if (rc) return rc;
     ix->last_coarse = coarse ? 1 : 0;
+    ix->last_device_queries = Q;
     // geometry of the coarse passes: 112-query groups, 4 strands per warp
     const int warps8 = ix->opt_warps8;
     const int bcap8 = ix->opt_bcap8 > 0 ? ix->opt_bcap8 : (P.shape.nf == 8 ? 512 : 2048);  // survivors per (slice, query)
@@ -576,6 +662,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         }
         ix->ev = ix->evs.data() + 6 * slot;
         ix->timed_calls = slot + 1;
+        if (!ix->host_call_active) ix->last_first_call = slot;
     }
     int launches = 0;
     CU(cudaEventRecord(ix->ev[0], st));
@@ -755,7 +842,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     }
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
-    ix->last_launches = launches;
+    ix->last_launches = ix->host_call_active && ix->timed_calls - 1 > ix->last_first_call ? ix->last_launches + launches : launches;
     ix->timing_valid = true;
     return DPQ_OK;
 }
@@ -795,12 +882,12 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     const size_t qbytes = (size_t)Q * D * 4, kbytes = (size_t)Q * topk * 8;
     // pinned staging: [queries][keys][ctrl words]; a caller buffer that is already page-locked
     // (dpq_malloc_host, cudaHostRegister) is copied from directly
-    if (ix->h_stage_cap < qbytes + kbytes + 64) {
+    if (ix->h_stage_cap < qbytes + kbytes + 256) {
         if (ix->h_stage) cudaFreeHost(ix->h_stage);
         ix->h_stage = nullptr;
         ix->h_stage_cap = 0;
-        CU(cudaMallocHost(&ix->h_stage, qbytes + kbytes + 64));
-        ix->h_stage_cap = qbytes + kbytes + 64;
+        CU(cudaMallocHost(&ix->h_stage, qbytes + kbytes + 256));
+        ix->h_stage_cap = qbytes + kbytes + 256;
     }
     int rc;
     if ((rc = ix->d_queries.ensure(qbytes))) return rc;
@@ -811,28 +898,79 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     cudaPointerAttributes pa;
     const bool pinned = cudaPointerGetAttributes(&pa, queries) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     (void)cudaGetLastError();
-    const float* src = queries;
-    if (!pinned) {
-        memcpy(hq, queries, qbytes);
-        src = hq;
+    // Copies overlap the search: the batch is cut into sub-batches; a second stream uploads
+    // sub-batch i+1 and downloads the keys of sub-batch i-1 while the index stream searches
+    // sub-batch i (the searches themselves stay in order on one stream and share the scratch), and
+    // the host unpacks a sub-batch's keys while the GPU is busy with the next ones.
+    constexpr int kMaxSub = 4;
+    const int n_sub = Q >= 4096 ? 4 : (Q >= 1024 ? 2 : 1);
+    if (!ix->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 3 * kMaxSub; ++i) CU(cudaEventCreateWithFlags(&ix->copy_ev[i], cudaEventDisableTiming));
     }
-    CU(cudaMemcpyAsync(ix->d_queries.p, src, qbytes, cudaMemcpyHostToDevice, ix->stream));
-    if ((rc = dpq_index_search_device(ix, ix->d_queries.as<float>(), Q, topk, ix->d_key.as<uint64_t>())))
-        return rc;
-    CU(cudaMemcpyAsync(hk, ix->d_key.p, kbytes, cudaMemcpyDeviceToHost, ix->stream));
-    CU(cudaMemcpyAsync(hc, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
-    CU(cudaStreamSynchronize(ix->stream));  // the one host sync of the call
-    ix->last_fallback = (int64_t)hc[0] + hc[2];
+    cudaEvent_t* ev_up = ix->copy_ev;
+    cudaEvent_t* ev_done = ix->copy_ev + kMaxSub;
+    cudaEvent_t* ev_down = ix->copy_ev + 2 * kMaxSub;
+    int q_lo[kMaxSub + 1];
+    for (int i = 0; i <= n_sub; ++i) q_lo[i] = (int)((int64_t)Q * i / n_sub);
+    cudaStream_t cs = n_sub > 1 ? ix->copy_stream : ix->stream;
+    ix->last_first_call = std::min(ix->timed_calls, 4095);
+    ix->host_call_active = true;
+    struct Guard {
+        dpq_index* ix;
+        ~Guard() { ix->host_call_active = false; }
+    } guard{ix};
+    for (int i = 0; i < n_sub; ++i) {
+        const size_t o = (size_t)q_lo[i] * D, cnt = (size_t)(q_lo[i + 1] - q_lo[i]) * D;
+        const float* src = queries + o;
+        if (!pinned) {
+            memcpy(hq + o, queries + o, cnt * 4);
+            src = hq + o;
+        }
+        CU(cudaMemcpyAsync(ix->d_queries.as<float>() + o, src, cnt * 4, cudaMemcpyHostToDevice, cs));
+        if (n_sub > 1) CU(cudaEventRecord(ev_up[i], cs));
+    }
+    for (int i = 0; i < n_sub; ++i) {
+        const int n = q_lo[i + 1] - q_lo[i];
+        const size_t ko = (size_t)q_lo[i] * topk;
+        if (n_sub > 1) CU(cudaStreamWaitEvent(ix->stream, ev_up[i], 0));
+        if ((rc = dpq_index_search_device(ix, ix->d_queries.as<float>() + (size_t)q_lo[i] * D, n, topk,
+                                          ix->d_key.as<uint64_t>() + ko)))
+            return rc;
+        CU(cudaMemcpyAsync(hc + 4 * i, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
+        if (n_sub > 1) {
+            CU(cudaEventRecord(ev_done[i], ix->stream));
+            CU(cudaStreamWaitEvent(cs, ev_done[i], 0));
+        }
+        CU(cudaMemcpyAsync(hk + ko, ix->d_key.as<uint64_t>() + ko, (size_t)n * topk * 8, cudaMemcpyDeviceToHost, cs));
+        if (n_sub > 1) CU(cudaEventRecord(ev_down[i], cs));
+    }
     const int64_t base = ix->prog.base_pos;
     const bool map = ix->has_pos2id;
     const uint32_t* p2i = ix->pos2id_host.data();
-    for (size_t i = 0; i < (size_t)Q * topk; ++i) {
-        const uint32_t pos = (uint32_t)hk[i];
-        const uint32_t bits = (uint32_t)(hk[i] >> 32);
-        if (out_pos) out_pos[i] = pos;
-        if (out_dist) memcpy(&out_dist[i], &bits, 4);
-        if (out_id) out_id[i] = (map && pos != 0xFFFFFFFFu) ? p2i[(size_t)(pos - base)] : pos;
+    for (int i = 0; i < n_sub; ++i) {
+        if (n_sub > 1) CU(cudaEventSynchronize(ev_down[i]));
+        else CU(cudaStreamSynchronize(ix->stream));  // the one host sync of a small call
+        const size_t lo = (size_t)q_lo[i] * topk, hi = (size_t)q_lo[i + 1] * topk;
+        if (out_pos)
+            for (size_t j = lo; j < hi; ++j) out_pos[j] = (uint32_t)hk[j];
+        if (out_dist) {
+            uint32_t* od = reinterpret_cast<uint32_t*>(out_dist);
+            for (size_t j = lo; j < hi; ++j) od[j] = (uint32_t)(hk[j] >> 32);
+        }
+        if (out_id) {
+            if (map)
+                for (size_t j = lo; j < hi; ++j) {
+                    const uint32_t pos = (uint32_t)hk[j];
+                    out_id[j] = pos != 0xFFFFFFFFu ? p2i[(size_t)(pos - base)] : pos;
+                }
+            else
+                for (size_t j = lo; j < hi; ++j) out_id[j] = (uint32_t)hk[j];
+        }
     }
+    if (n_sub > 1) CU(cudaStreamSynchronize(ix->stream));  // the ctrl words of the last sub-batch
+    ix->last_fallback = 0;
+    for (int i = 0; i < n_sub; ++i) ix->last_fallback += (int64_t)hc[4 * i] + hc[4 * i + 2];
     return DPQ_OK;
 }
 
@@ -893,6 +1031,7 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
     if (n == "last_launches") return ix->last_launches;
     if (n == "engine") return P.v2 ? 2 : 1;
     if (n == "last_coarse") return ix->last_coarse;
+    if (n == "last_device_queries") return ix->last_device_queries;
     if (n == "cand8_total") {  // developer statistic: coarse survivors of the last search
         if (!ix->last_coarse || !ix->d_cnt8.p) return -1;
         cudaSetDevice(ix->device);
@@ -920,7 +1059,7 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
         const int which = n.find("scan8") != std::string::npos ? 3 : (n.find("scan") != std::string::npos ? 0 : (n.find("lut") != std::string::npos ? 1 : 2));
         if (which == 3 && !ix->last_coarse) return -1;
         double total_ms = 0;
-        const int first = last ? ix->timed_calls - 1 : 0;
+        const int first = last ? std::min(ix->last_first_call, ix->timed_calls - 1) : 0;
         for (int c = first; c < ix->timed_calls; ++c) {
             cudaEvent_t* e = ix->evs.data() + 6 * c;
             float ms = 0;
@@ -944,6 +1083,12 @@ void dpq_index_close(dpq_index* ix) {
                       &ix->d_gthr})
         b->release();
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
+    if (ix->copy_stream) {
+        cudaStreamSynchronize(ix->copy_stream);
+        for (auto& e : ix->copy_ev)
+            if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(ix->copy_stream);
+    }
     for (auto& e : ix->evs)
         if (e) cudaEventDestroy(e);
     if (ix->stream && ix->own_stream) cudaStreamDestroy(ix->stream);

@@ -42,6 +42,7 @@ namespace dpq {
 int api_fail(int code, const std::string& msg);
 int api_check_device();
 int api_device();
+int check_code_range(const uint8_t* codes, int64_t n, int M, int K);  // layout.cu
 }  // namespace dpq
 
 #define CU(call)                                                                                   \
@@ -369,15 +370,17 @@ int futile_pass_prefilter(const uint8_t* d_codes, int64_t n, int M, std::vector<
 
 }  // namespace
 
-extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_height_folds,
-                              int method, uint32_t* edges, uint32_t* root_id) {
-    if (!codes || !root_id || (n_codes > 1 && !edges) || n_codes < 1 || M < 1 || M > 16 || K < 1 || K > 256 ||
+// edges: host output (nullable when d_edges_out is given); d_edges_out: the device array is handed to the caller
+static int find_edges_core(const uint8_t* codes, int64_t n_codes, int M, int K, int max_height_folds, int method,
+                           uint32_t* edges, uint32_t** d_edges_out, uint32_t* root_id) {
+    if (!codes || !root_id || (n_codes > 1 && !edges && !d_edges_out) || n_codes < 1 || M < 1 || M > 16 || K < 1 || K > 256 ||
         max_height_folds < 1 || (method != 1 && method != 2))
         return dpq::api_fail(DPQ_ERR_ARG, "dpq_find_edges: bad argument (1<=M<=16, K<=256, method 1|2)");
     if (n_codes >= 0x7FFFFFFFLL) return dpq::api_fail(DPQ_ERR_ARG, "dpq_find_edges: n_codes must be < 2^31-1 (DCAT.h:982)");
     int rc = dpq::api_check_device();
     if (rc) return rc;
     CU(cudaSetDevice(dpq::api_device()));
+    if ((rc = dpq::check_code_range(codes, n_codes, M, K))) return rc;
     const int log_k = (int)std::lround(std::log2((double)K));  // DCAT.h:454
     const int max_height = M * max_height_folds;               // DCAT.h:1262
     const int key_bits = std::min(128, log_k * (M - 1) + 8);
@@ -429,7 +432,7 @@ extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int 
     }
     CU(d_tmp.alloc(tmp_bytes));
 
-    CU(cudaMemcpy(d_codes.p, codes, (size_t)n * M, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_codes.p, codes, (size_t)n * M, cudaMemcpyDefault));  // host or device source
     CU(cudaMemset(d_heights.p, 0, (size_t)n));
     iota_kernel<<<blocks(n), 256>>>(d_ids.as<uint32_t>(), n);
     CU(cudaGetLastError());
@@ -545,12 +548,33 @@ extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int 
         CU(cudaMemcpy(&fin[(size_t)n_fin], ids, 4, cudaMemcpyDeviceToHost));
         ++n_fin;
     }
-    if (n_edges) CU(cudaMemcpy(edges, d_edges.p, (size_t)n_edges * 8, cudaMemcpyDeviceToHost));
     *root_id = fin[0];  // DCAT.h:1297-1313: a star under the first finalist
+    std::vector<uint32_t> star((size_t)std::max<int64_t>(2 * (n_fin - 1), 0));
     for (int64_t i = 1; i < n_fin; ++i) {
-        edges[2 * n_edges] = fin[0];
-        edges[2 * n_edges + 1] = fin[(size_t)i];
-        ++n_edges;
+        star[(size_t)(2 * (i - 1))] = fin[0];
+        star[(size_t)(2 * (i - 1) + 1)] = fin[(size_t)i];
+    }
+    if (edges) {
+        if (n_edges) CU(cudaMemcpy(edges, d_edges.p, (size_t)n_edges * 8, cudaMemcpyDeviceToHost));
+        if (!star.empty()) memcpy(edges + 2 * n_edges, star.data(), star.size() * 4);
+    }
+    if (d_edges_out) {  // the star goes behind the device copy, which the caller takes over
+        if (!star.empty())
+            CU(cudaMemcpy(d_edges.as<uint32_t>() + 2 * n_edges, star.data(), star.size() * 4, cudaMemcpyHostToDevice));
+        *d_edges_out = d_edges.as<uint32_t>();
+        d_edges.p = nullptr;
     }
     return DPQ_OK;
 }
+
+extern "C" int dpq_find_edges(const uint8_t* codes, int64_t n_codes, int M, int K, int max_height_folds,
+                              int method, uint32_t* edges, uint32_t* root_id) {
+    return find_edges_core(codes, n_codes, M, K, max_height_folds, method, edges, nullptr, root_id);
+}
+
+namespace dpq {
+int find_edges_device(const uint8_t* codes, int64_t n, int M, int K, int max_height_folds, int method,
+                      uint32_t** d_edges_out, uint32_t* root_id) {
+    return find_edges_core(codes, n, M, K, max_height_folds, method, nullptr, d_edges_out, root_id);
+}
+}  // namespace dpq

@@ -246,9 +246,138 @@ __global__ void stream_kernel(int64_t n, int M, const uint8_t* __restrict__ code
 
 }  // namespace
 
+dpq_tree::~dpq_tree() { dpq::tree_release_device(this); }
+
 namespace dpq {
 
-int layout_tree_device(const uint8_t* codes, int64_t n, int M, int K, const float* cw, int Ds, dpq_tree* t) {
+void tree_release_device(dpq_tree* t) {
+    if (!t->on_device) return;
+    cudaSetDevice(t->device);
+    for (void** p : {&t->d_codes_by_pos, &t->d_depth, &t->d_vec_id, &t->d_payload, &t->d_roff}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    (void)cudaGetLastError();
+}
+
+// Depth-1 subtree shards of a device-resident tree, exactly as the stream reader deals them
+// (program.cpp: a depth-1 node whose record starts at stream byte `off` goes to rank
+// floor(off * n_ranks / n_bytes), and takes its subtree along): first[c] = the first depth-1 position
+// dealt to rank c.
+__global__ void shard_first_kernel(const uint8_t* __restrict__ depth, const unsigned long long* __restrict__ roff,
+                                   int64_t n, int M, unsigned long long n_bytes, int n_ranks,
+                                   unsigned int* __restrict__ first) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (p >= n || depth[p] != 1) return;
+    const unsigned long long off = (unsigned long long)M + roff[p - 1];
+    int c = (int)(off * (unsigned long long)n_ranks / n_bytes);
+    if (c >= n_ranks) c = n_ranks - 1;
+    atomicMin(&first[c], (unsigned int)p);
+}
+
+// bounds[r] .. bounds[r + 1] = the positions of shard r (rank 0 also holds the root at position 0);
+// bytes[r] = stream bytes of the shard's records (+ M root bytes for rank 0)
+int tree_shard_bounds(const dpq_tree* t, int n_ranks, std::vector<int64_t>* bounds, std::vector<int64_t>* bytes) {
+    CU(cudaSetDevice(t->device));
+    const int64_t n = t->n;
+    Buf d_first;
+    CU(d_first.alloc((size_t)n_ranks * 4));
+    CU(cudaMemset(d_first.p, 0xFF, (size_t)n_ranks * 4));
+    if (n > 1)
+        shard_first_kernel<<<blocks(n - 1), 256>>>((const uint8_t*)t->d_depth, (const unsigned long long*)t->d_roff, n, t->M,
+                                                   (unsigned long long)t->payload_bytes, n_ranks, d_first.as<unsigned int>());
+    std::vector<unsigned int> first((size_t)n_ranks);
+    CU(cudaMemcpy(first.data(), d_first.p, (size_t)n_ranks * 4, cudaMemcpyDeviceToHost));
+    bounds->assign((size_t)n_ranks + 1, n);
+    for (int r = n_ranks - 1; r >= 1; --r)
+        (*bounds)[(size_t)r] = std::min<int64_t>((*bounds)[(size_t)r + 1], first[(size_t)r] == 0xFFFFFFFFu ? n : (int64_t)first[(size_t)r]);
+    (*bounds)[0] = 0;
+    bytes->assign((size_t)n_ranks, 0);
+    auto off_of = [&](int64_t p, unsigned long long* o) -> int {  // stream offset of node p's record (p >= 1), or the end
+        if (p >= n) {
+            *o = (unsigned long long)t->payload_bytes;
+            return DPQ_OK;
+        }
+        unsigned long long v = 0;
+        CU(cudaMemcpy(&v, (const unsigned long long*)t->d_roff + (p - 1), 8, cudaMemcpyDeviceToHost));
+        *o = v + (unsigned long long)t->M;
+        return DPQ_OK;
+    };
+    for (int r = 0; r < n_ranks; ++r) {
+        const int64_t lo = std::max<int64_t>((*bounds)[(size_t)r], 1), hi = (*bounds)[(size_t)r + 1];
+        unsigned long long a = 0, b = 0;
+        int rc;
+        if (hi > lo) {
+            if ((rc = off_of(lo, &a)) || (rc = off_of(hi, &b))) return rc;
+        }
+        (*bytes)[(size_t)r] = (int64_t)(b - a) + (r == 0 ? t->M : 0);
+    }
+    return DPQ_OK;
+}
+
+int depth_hist_device(int device, const uint8_t* d_depth, int64_t n, int64_t* hist17);
+
+__global__ void code_range_kernel(const uint8_t* __restrict__ codes, int64_t bytes, int K, uint32_t* __restrict__ bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += stride)
+        if (codes[i] >= K) *bad = 1u;
+}
+
+// every code byte must be a centroid id < K: a larger byte (foreign or corrupt codes file, -k mismatch)
+// would index the K x K centroid tables and the ADC table rows out of bounds.  codes: host or device.
+int check_code_range(const uint8_t* codes, int64_t n, int M, int K) {
+    if (K >= 256) return DPQ_OK;
+    const int64_t bytes = n * M;
+    cudaPointerAttributes pa;
+    const bool on_dev = cudaPointerGetAttributes(&pa, codes) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+    (void)cudaGetLastError();
+    bool bad = false;
+    if (on_dev) {
+        Buf d_bad;
+        CU(d_bad.alloc(16));
+        CU(cudaMemset(d_bad.p, 0, 16));
+        code_range_kernel<<<1184, 256>>>(codes, bytes, K, d_bad.as<uint32_t>());
+        uint32_t f = 0;
+        CU(cudaMemcpy(&f, d_bad.p, 4, cudaMemcpyDeviceToHost));
+        bad = f != 0;
+    } else {
+        for (int64_t i = 0; i < bytes && !bad; ++i) bad = codes[i] >= K;
+    }
+    if (bad) return api_fail(DPQ_ERR_ARG, "codes hold a centroid id >= K");
+    return DPQ_OK;
+}
+
+// dpq_tree_copy of a device-resident tree: D2H of one of its arrays
+int tree_copy_device(const dpq_tree* t, const void* src, void* dst, size_t bytes) {
+    CU(cudaSetDevice(t->device));
+    if (bytes) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return DPQ_OK;
+}
+
+__global__ void depth_hist_kernel(const uint8_t* __restrict__ depth, int64_t n, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int s[17];
+    if (threadIdx.x < 17) s[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&s[min((int)depth[i], 16)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 17 && s[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+}
+
+int depth_hist_device(int device, const uint8_t* d_depth, int64_t n, int64_t* hist17) {
+    CU(cudaSetDevice(device));
+    Buf d_hist;
+    CU(d_hist.alloc(17 * 8));
+    CU(cudaMemset(d_hist.p, 0, 17 * 8));
+    if (n > 0) depth_hist_kernel<<<592, 256>>>(d_depth, n, d_hist.as<unsigned long long>());
+    unsigned long long hist[17];
+    CU(cudaMemcpy(hist, d_hist.p, sizeof(hist), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 17; ++i) hist17[i] = (int64_t)hist[i];
+    return DPQ_OK;
+}
+
+int layout_tree_device(const uint8_t* codes, int64_t n, int M, int K, const float* cw, int Ds, dpq_tree* t,
+                       const uint32_t* d_edges_in, bool keep_on_device) {
     int rc = api_check_device();
     if (rc) return rc;
     CU(cudaSetDevice(api_device()));
@@ -276,7 +405,8 @@ int layout_tree_device(const uint8_t* codes, int64_t n, int M, int K, const floa
     CU(d_err.alloc(16));
     CU(cudaMemcpy(d_codes.p, codes, (size_t)n * M, cudaMemcpyDefault));
     CU(cudaMemcpy(d_T.p, T.data(), T.size() * 4, cudaMemcpyHostToDevice));
-    if (E) CU(cudaMemcpy(d_edges.p, t->edges.data(), (size_t)E * 8, cudaMemcpyHostToDevice));
+    if (E) CU(cudaMemcpy(d_edges.p, d_edges_in ? (const void*)d_edges_in : (const void*)t->edges.data(), (size_t)E * 8,
+                         cudaMemcpyDefault));
     CU(cudaMemset(d_nkids.p, 0, (size_t)(n + 1) * 4));
     CU(cudaMemset(d_far.p, 0, (size_t)n * 4));
     CU(cudaMemset(d_farvia.p, 0, (size_t)n * 4));
@@ -393,6 +523,22 @@ int layout_tree_device(const uint8_t* codes, int64_t n, int M, int K, const floa
     stream_kernel<<<blocks(n), 256>>>(n, M, d_codesp.as<uint8_t>(), d_ppos.as<uint32_t>(), d_depthp.as<uint8_t>(), roff,
                                       d_out.as<uint8_t>());
     CU(cudaGetLastError());
+    if (keep_on_device) {  // hand the buffers the index needs to the tree object; nothing crosses PCIe
+        int64_t hist[17];
+        if ((rc = depth_hist_device(api_device(), d_depthp.as<uint8_t>(), n, hist))) return rc;
+        t->depth_hist.assign(hist, hist + 17);
+        CU(cudaDeviceSynchronize());
+        t->on_device = true;
+        t->device = api_device();
+        t->payload_bytes = (int64_t)total;
+        t->d_codes_by_pos = d_codesp.p;
+        t->d_depth = d_depthp.p;
+        t->d_vec_id = d_vec.p;
+        t->d_payload = d_out.p;
+        t->d_roff = d_key2.p;
+        d_codesp.p = d_depthp.p = d_vec.p = d_out.p = d_key2.p = nullptr;
+        return DPQ_OK;
+    }
 
     t->vec_id.resize((size_t)n);
     t->parent_pos.resize((size_t)n);

@@ -172,11 +172,28 @@ int dpq_multi_open_file(const char* tree_path, const char* qnode_path, int M, in
     dpq_multi* m = nullptr;
     int rc = begin_multi_open(n_gpus, n_gpus, M, K, &m);
     if (rc) return rc;
-    for (int r = 0; r < n_gpus && !rc; ++r) {
-        rc = dpq_set_device(r);
-        if (!rc) rc = dpq_index_open_file(tree_path, nullptr, M, K, r, n_gpus, &m->ix[(size_t)r]);
-        m->dev[(size_t)r] = r;
-        m->on[(size_t)r].push_back(r);
+    {
+        // one host thread per shard: the stream decode is sequential (seconds per 10^8 nodes), the
+        // shards are independent and the device selection is per thread, so the open takes one decode
+        // time instead of n_gpus of them
+        for (int r = 0; r < n_gpus; ++r) {
+            m->dev[(size_t)r] = r;
+            m->on[(size_t)r].push_back(r);
+        }
+        std::vector<int> rcs((size_t)n_gpus, 0);
+        std::vector<std::string> errs((size_t)n_gpus);
+        auto worker = [&](int r) {
+            int r_ = dpq_set_device(r);
+            if (!r_) r_ = dpq_index_open_file(tree_path, nullptr, M, K, r, n_gpus, &m->ix[(size_t)r]);
+            rcs[(size_t)r] = r_;
+            if (r_) errs[(size_t)r] = dpq_last_error();  // thread-local text: carry it to the caller's thread
+        };
+        std::vector<std::thread> th;
+        for (int r = 1; r < n_gpus; ++r) th.emplace_back(worker, r);
+        worker(0);
+        for (auto& t : th) t.join();
+        for (int r = 0; r < n_gpus && !rc; ++r)
+            if (rcs[(size_t)r]) rc = dpq::api_fail(rcs[(size_t)r], errs[(size_t)r]);
     }
     if (!rc) rc = finish_multi_open(m);
     if (!rc && qnode_path) {
@@ -268,6 +285,18 @@ int dpq_multi_search(dpq_multi* m, const float* queries, int Q, int topk, uint32
                      float* out_dist) {
     if (!m || !queries || Q < 1 || topk < 1) return dpq::api_fail(DPQ_ERR_ARG, "dpq_multi_search: bad argument");
     if (m->Ds < 1) return dpq::api_fail(DPQ_ERR_ARG, "dpq_multi_search: codebook not set");
+    constexpr int kMaxBatch = 32768;  // bounds the per-index scratch (float tables: 8 KB per query at M = 8), as dpq_index_search
+    if (Q > kMaxBatch) {
+        const size_t D = (size_t)m->M * m->Ds;
+        for (int q0 = 0; q0 < Q; q0 += kMaxBatch) {
+            const int nq = std::min(kMaxBatch, Q - q0);
+            const size_t o = (size_t)q0 * topk;
+            int rc = dpq_multi_search(m, queries + (size_t)q0 * D, nq, topk, out_pos ? out_pos + o : nullptr,
+                                      out_id ? out_id + o : nullptr, out_dist ? out_dist + o : nullptr);
+            if (rc) return rc;
+        }
+        return DPQ_OK;
+    }
     const size_t qbytes = (size_t)Q * m->M * m->Ds * 4, kbytes = (size_t)Q * topk * 8;
     if (m->h_cap < qbytes + kbytes) {
         if (m->h_stage) cudaFreeHost(m->h_stage);

@@ -250,6 +250,9 @@ int dpq_tree_from_edges(const uint8_t* codes, int64_t n_codes, int M, int K, con
     if (bad_args(codes, n_codes, M, K, codewords, Ds, out) || (n_codes > 1 && !edges))
         return dpq::api_fail(DPQ_ERR_ARG, "dpq_tree_from_edges: bad argument");
     *out = nullptr;
+    if (K < 256)
+        for (int64_t i = 0; i < n_codes * M; ++i)
+            if (codes[i] >= K) return dpq::api_fail(DPQ_ERR_ARG, "dpq_tree_from_edges: codes hold a centroid id >= K");
     dpq_tree* t = new dpq_tree();
     t->M = M;
     t->K = K;
@@ -264,6 +267,7 @@ int dpq_tree_build(const uint8_t* codes, int64_t n_codes, int M, int K, const fl
     if (bad_args(codes, n_codes, M, K, codewords, Ds, out))
         return dpq::api_fail(DPQ_ERR_ARG, "dpq_tree_build: bad argument");
     *out = nullptr;
+    if (int rc0 = dpq::check_code_range(codes, n_codes, M, K)) return rc0;
     dpq_tree* t = new dpq_tree();
     t->M = M;
     t->K = K;
@@ -291,9 +295,48 @@ int dpq_tree_build(const uint8_t* codes, int64_t n_codes, int M, int K, const fl
     return DPQ_OK;
 }
 
+int dpq_tree_build_device(const uint8_t* codes, int64_t n_codes, int M, int K, const float* codewords, int Ds,
+                          int max_height_folds, int method, dpq_tree** out) {
+    if (bad_args(codes, n_codes, M, K, codewords, Ds, out))
+        return dpq::api_fail(DPQ_ERR_ARG, "dpq_tree_build_device: bad argument");
+    *out = nullptr;
+    if (int rc0 = dpq::check_code_range(codes, n_codes, M, K)) return rc0;
+    dpq_tree* t = new dpq_tree();
+    t->M = M;
+    t->K = K;
+    t->n = n_codes;
+    uint32_t* d_edges = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = dpq::find_edges_device(codes, n_codes, M, K, max_height_folds, method, &d_edges, &t->root);
+    const auto t1 = std::chrono::steady_clock::now();
+    t->edge_us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    if (!rc) rc = dpq::layout_tree_device(codes, n_codes, M, K, codewords, Ds, t, d_edges, true);
+    if (d_edges) dpq_free(d_edges);
+    t->layout_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t1).count();
+    if (rc) {
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return DPQ_OK;
+}
+
 int64_t dpq_tree_size(dpq_tree* t, const char* what) {
     if (!t || !what) return -1;
     const std::string w(what);
+    if (t->on_device) {  // what a device-resident tree can still hand out (copied D2H on request)
+        if (w == "vec_id") return t->n * 4;
+        if (w == "depth") return t->n;
+        if (w == "codes_by_pos") return t->n * t->M;
+        if (w == "payload") return t->payload_bytes;
+        if (w == "on_device") return 1;
+        if (w.rfind("depth_hist_", 0) == 0) {
+            const size_t d = (size_t)atoi(w.c_str() + 11);
+            return d < t->depth_hist.size() ? t->depth_hist[d] : 0;
+        }
+        if (w == "edges" || w == "parent_pos" || w == "child_num" || w == "max_dist" || w == "max_dist2p" || w == "qnodes")
+            return -1;
+    }
     if (w == "edges") return (int64_t)t->edges.size() * 4;
     if (w == "vec_id" || w == "parent_pos" || w == "child_num" || w == "max_dist" || w == "max_dist2p")
         return t->n * 4;
@@ -312,6 +355,13 @@ int64_t dpq_tree_size(dpq_tree* t, const char* what) {
 int dpq_tree_copy(dpq_tree* t, const char* what, void* dst) {
     if (!t || !what || !dst) return dpq::api_fail(DPQ_ERR_ARG, "dpq_tree_copy: null argument");
     const std::string w(what);
+    if (t->on_device) {
+        if (w == "vec_id") return dpq::tree_copy_device(t, t->d_vec_id, dst, (size_t)t->n * 4);
+        if (w == "depth") return dpq::tree_copy_device(t, t->d_depth, dst, (size_t)t->n);
+        if (w == "codes_by_pos") return dpq::tree_copy_device(t, t->d_codes_by_pos, dst, (size_t)t->n * t->M);
+        if (w == "payload") return dpq::tree_copy_device(t, t->d_payload, dst, (size_t)t->payload_bytes);
+        return dpq::api_fail(DPQ_ERR_ARG, "dpq_tree_copy: a device-resident tree keeps vec_id, depth, codes_by_pos and payload only");
+    }
     auto put = [&](const void* src, size_t bytes) {
         if (bytes) memcpy(dst, src, bytes);
         return DPQ_OK;

@@ -63,12 +63,19 @@ int dpq_index_open_file(const char* tree_path, const char* qnode_path, int M, in
                         int n_ranks, dpq_index** out);
 
 /* Opens a tree that dpq_tree_build / dpq_tree_from_edges just produced, without going through its
- * byte stream: the device scan program is compiled on the GPU from the layout arrays (one thread
- * per 64-node chunk) instead of decoding the sequential stream on the host (8.9 s per 125M nodes).
+ * byte stream: the device scan program is the tree's code array by DFS position (8 bytes per node at
+ * M = 8), uploaded as it is instead of decoding the sequential stream on the host.
  * Same index as dpq_index_open_part(payload, ..., vec_id, first_pos); t stays owned by the caller
  * and may be freed afterwards.  (dpq_tree is declared further down.) */
 struct dpq_tree;
 int dpq_index_open_tree(struct dpq_tree* t, int64_t first_pos, dpq_index** out);
+
+/* Shard `rank` of `n_ranks` of such a tree: whole depth-1 subtrees balanced by stream bytes (SURVEY
+ * 8e; subtree ranges as in DCAT.h:1156-1183), the same deal as dpq_index_open(payload, ..., rank,
+ * n_ranks); positions stay global.  With a device-resident tree (dpq_tree_build_device) nothing
+ * crosses PCIe: the shard's slice of the code array is copied device to device.  This is how the
+ * 10^9-code tree of config C5 is opened on 1 / 2 / 4 / 8 GPUs. */
+int dpq_index_open_tree_shard(struct dpq_tree* t, int rank, int n_ranks, dpq_index** out);
 
 /* dpq_index_open_part reading the part's files (tree file with its 16-byte header; 60-byte
  * QNode file or NULL). */
@@ -208,6 +215,16 @@ int dpq_tree_build(const uint8_t* codes, int64_t n_codes, int M, int K, const fl
                    int max_height_folds, int method, dpq_tree** out);
 int dpq_tree_from_edges(const uint8_t* codes, int64_t n_codes, int M, int K, const float* codewords,
                         int Ds, const uint32_t* edges, uint32_t root_id, dpq_tree** out);
+/* dpq_tree_build with the result left in HBM: codes may be a host or a DEVICE pointer, the edges
+ * go from the edge search to the layout without leaving the device, and of the layout only what an
+ * index needs is kept (codes by position, depth, vec_id, the byte stream and its record offsets).
+ * dpq_tree_size / dpq_tree_copy serve "vec_id", "depth", "codes_by_pos", "payload" (copied to the
+ * host on request) and the scalars ("on_device" = 1, "depth_hist_<d>"); open it with
+ * dpq_index_open_tree_shard.  One tree over 10^9 codes (DCAT.h:970-1065 builds ONE tree over all N,
+ * guard N < INT_MAX at :982) needs about 110 GB of HBM during the edge search and none of the
+ * 43 bytes per node of host memory the host-resident form takes. */
+int dpq_tree_build_device(const uint8_t* codes, int64_t n_codes, int M, int K, const float* codewords, int Ds,
+                          int max_height_folds, int method, dpq_tree** out);
 int64_t dpq_tree_size(dpq_tree* t, const char* what); /* bytes for arrays, value for scalars */
 int dpq_tree_copy(dpq_tree* t, const char* what, void* dst);
 void dpq_tree_free(dpq_tree* t);

@@ -550,3 +550,42 @@ def test_index_from_tree_arrays_equals_index_from_stream(shape, engine):
         assert a.stat(name) == b.stat(name), name
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("n,M", [(30000, 8), (7000, 16), (5000, 5)])
+def test_device_resident_tree_and_its_shards(n, M, engine):
+    """dpq_tree_build_device leaves the tree in HBM (the 10^9-code layout): same stream, vec_id and
+    codes as the host-resident build, and dpq_index_open_tree_shard deals the same depth-1-subtree
+    shards as the stream reader does (dpq_index_open(payload, rank, n_ranks))."""
+    if engine == "gen1":
+        pytest.skip("a device-resident tree needs the code-array engine")
+    base = dg.sift_like(n, 128, seed=61)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(3000, 128, seed=62), M, 256, iters=3))
+    queries = dg.sift_like(200, 128, seed=63)
+    codes = dpq.encode(cw, base)
+    host = dpq.tree_build(codes, cw, want=("payload", "vec_id", "codes_by_pos", "depth"))
+    dcodes = dpq.DeviceBuffer(codes.nbytes).upload(codes)
+    dt = dpq.DeviceTree(dcodes.ptr.value, n, M, cw)          # codes passed as a DEVICE pointer
+    assert dt.stat("on_device") == 1 and dt.stat("n_diffs") == host["n_diffs"] and dt.stat("root_id") == host["root_id"]
+    assert np.array_equal(dt.fetch("payload", np.uint8), host["payload"])
+    assert np.array_equal(dt.fetch("vec_id", np.uint32), host["vec_id"])
+    assert np.array_equal(dt.fetch("depth", np.uint8), host["depth"])
+    assert np.array_equal(dt.fetch("codes_by_pos", np.uint8).reshape(-1, M), host["codes_by_pos"])
+    assert sum(dt.stat(f"depth_hist_{d}") for d in range(17)) == n
+    k = 10
+    for R in (1, 3):
+        for r in range(R):
+            a = dt.shard(r, R)
+            b = dpq.DeltaTreeIndex(host["payload"], n, M, 256, pos2id=host["vec_id"], rank=r, n_ranks=R)
+            for name in ("n_codes", "n_local", "base_pos", "n_diffs", "n_chunks", "engine"):
+                assert a.stat(name) == b.stat(name), (name, r, R)
+            assert abs(a.stat("n_bytes") - b.stat("n_bytes")) <= 1  # the shard's depth nibbles round differently
+            for ix in (a, b):
+                ix.set_codebook(cw)
+            apos, aid, adist = a.search(queries, k)
+            bpos, bid, bdist = b.search(queries, k)
+            assert np.array_equal(apos, bpos) and np.array_equal(aid, bid) and np.array_equal(adist, bdist)
+            a.close()
+            b.close()
+    dt.free()
+    dcodes.free()

@@ -36,7 +36,7 @@ for cfg in configs:
     eff = Q * n_bytes / (scan_us * 1e-6) / 1e9
     print(json.dumps(dict(cfg=cfg, scan_ms=scan_us / 1e3, lut_ms=lut / 1e3, total_ms=tot / 1e3,
                           qps_total=round(Q / (tot * 1e-6)), eff_GBs=round(eff, 1),
-                          fallback=ix.stat("last_fallback"), cand8_per_query=round(ix.stat("cand8_total") / Q, 1))), flush=True)
+                          fallback=ix.stat("last_fallback"), cand8_per_query=round(ix.stat("cand8_total") / max(ix.stat("last_device_queries"), 1), 1))), flush=True)
     if ref is None:
         ref = (pos, dist)
     else:

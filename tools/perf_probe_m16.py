@@ -26,7 +26,7 @@ for it in range(3):
     print(json.dumps(dict(scan_ms=ix.stat("last_scan_us") / 1e3, lut_ms=ix.stat("last_lut_us") / 1e3, total_ms=ix.stat("last_total_us") / 1e3,
                           qps=round(Q / (ix.stat("last_total_us") * 1e-6)), fallback=ix.stat("last_fallback"),
                           coarse=ix.stat("last_coarse"), scan8_ms=ix.stat("last_scan8_us") / 1e3,
-                          cand8_per_query=round(ix.stat("cand8_total") / Q, 1))), flush=True)
+                          cand8_per_query=round(ix.stat("cand8_total") / max(ix.stat("last_device_queries"), 1), 1))), flush=True)
 for cfg in sys.argv[4:] if gist else sys.argv[3:]:
     for kv in cfg.split(","):
         kk, v = kv.split("="); ix.set_option(kk, int(v))
@@ -40,7 +40,7 @@ for cfg in sys.argv[4:] if gist else sys.argv[3:]:
         print(json.dumps(dict(cfg=cfg, topk=kk, total_ms=best[0] / 1e3, scan_ms=best[1] / 1e3, lut_ms=best[2] / 1e3,
                               scan8_ms=best[3] / 1e3, qps=round(Q / (best[0] * 1e-6)), coarse=ix.stat("last_coarse"),
                               fallback=ix.stat("last_fallback"),
-                              cand8_per_query=round(ix.stat("cand8_total") / Q, 1) if ix.stat("last_coarse") else None,
+                              cand8_per_query=round(ix.stat("cand8_total") / max(ix.stat("last_device_queries"), 1), 1) if ix.stat("last_coarse") else None,
                               same_as_default=bool(kk != 100 or (np.array_equal(p2, pos) and np.array_equal(d2, dist))))), flush=True)
 for i in (0, Q // 2):
     opos, odist = po.scan(payload, N, cw, queries[i], topk)
