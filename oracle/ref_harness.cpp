@@ -8,7 +8,9 @@
 //   * query_processing_scan_compressed_codes_opt_in_memory   (deltapq_create_approx_tree.h:3731)
 //   * the ADC table it leaves in the global m_sub_distances    (deltapq_create_approx_tree.h:3750-3758)
 //   * PQTree::EncodePlain                                      (pq_tree.cpp:192-253)
-//   * the ground-truth brute force loop                        (main.cpp:138-166)
+// (The ground-truth brute force of main.cpp:138-166 lives in the TU that owns main(); it is pinned
+// through the reference BINARY instead: tests/golden/make_golden_gt.py runs `pqtree -task groundtruth`
+// and commits what it wrote.)
 // Nothing here is product code; only tests/, smoke() and bench.py's CPU-baseline leg use it.
 #include "pq_tree.h"
 #include "utils.h"

@@ -91,3 +91,26 @@ def interpret_program(prog, table_q):
             p += 4 * rq
         assert p == end
     return np.array(out_pos, np.int64), np.array(out_d)
+
+
+def gt_fixture(name):
+    import hashlib
+    import os
+    import datagen as dg
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    gen = dg.gist_like if str(z["kind"]) == "gist" else dg.sift_like
+    base = gen(int(z["n"]), int(z["d"]), seed=int(z["seed"]))
+    assert hashlib.sha1(base.tobytes()).hexdigest() == str(z["base_sha1"]), "datagen drifted: regenerate the fixture"
+    return base, z["queries"], int(z["topk"]), z["ref_ids"], z["ref_dist_text"]
+
+
+def assert_gt_equals_reference_text(ids, dist, ref_ids, ref_text):
+    """ids equal the reference's (modulo ties within the text precision); distances equal what the
+    reference PRINTED: default ostream float formatting, 6 significant digits (pqbase.cpp:294-312)."""
+    printed = np.array([[float("%g" % v) for v in row] for row in dist])
+    np.testing.assert_allclose(printed, ref_text, rtol=2e-6)
+    for q in range(len(ids)):
+        if not np.array_equal(ids[q], ref_ids[q]):  # only neighbours whose printed distances tie may swap
+            diff = ids[q] != ref_ids[q]
+            assert set(ids[q][diff]) == set(ref_ids[q][diff]), q        # the same neighbours ...
+            assert len(set(ref_text[q][diff])) < int(diff.sum()), q         # ... swapped inside a printed-distance tie

@@ -6,7 +6,7 @@ import pytest
 
 import datagen as dg
 import deltapq_b200 as dpq
-from helpers import assert_topk_equal, REL_TOL
+from helpers import assert_topk_equal, REL_TOL, gt_fixture, assert_gt_equals_reference_text
 from oracle import pyoracle as po
 
 pytestmark = pytest.mark.gpu
@@ -589,3 +589,17 @@ def test_device_resident_tree_and_its_shards(n, M, engine):
             b.close()
     dt.free()
     dcodes.free()
+
+
+@pytest.mark.parametrize("name", ["gist_gt_n3000_d960", "gist_gt_n5000_d96"])
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_groundtruth_vs_reference_binary(name, tc, monkeypatch):
+    """dpq_groundtruth_* (tensor-core filter + exact re-score, and the plain exact kernels) against
+    what the unmodified reference's `pqtree -task groundtruth` wrote for GIST-shaped non-integer
+    floats (tests/golden/make_golden_gt.py): same ids, same printed distances."""
+    monkeypatch.setenv("DPQ_GT_TC", tc)
+    base, queries, k, ref_ids, ref_text = gt_fixture(name)
+    ids, dist = dpq.groundtruth(base, queries, k, chunk=1700)
+    assert_gt_equals_reference_text(ids, dist, ref_ids, ref_text)
+    oid, odist = po.groundtruth(base, queries, k)
+    assert np.array_equal(dist, odist)

@@ -1,9 +1,13 @@
 """CPU: the oracle restatement against fixtures produced by the UNMODIFIED reference
 (tests/golden/make_golden.py).  Bit-exact for codes, edges, QNode records, stream bytes,
 ADC tables and distances; positions modulo exact ties."""
-import numpy as np
+import os
 
-from helpers import assert_topk_equal
+import numpy as np
+import pytest
+
+import datagen as dg
+from helpers import assert_topk_equal, gt_fixture, assert_gt_equals_reference_text
 from oracle import pyoracle as po
 
 
@@ -99,3 +103,13 @@ def test_groundtruth_small():
     for i in range(5):
         order = np.argsort(d[i], kind="stable")[:7]
         assert np.array_equal(dist[i], d[i][order].astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["gist_gt_n3000_d960", "gist_gt_n5000_d96"])
+def test_groundtruth_oracle_vs_reference_binary(name):
+    """The ground-truth port (oracle/dpq_oracle.c, float product / double sum, main.cpp:150-156)
+    against what `pqtree -task groundtruth` of the unmodified reference wrote for GIST-shaped
+    non-integer floats (tests/golden/make_golden_gt.py)."""
+    base, queries, k, ref_ids, ref_text = gt_fixture(name)
+    ids, dist = po.groundtruth(base, queries, k, chunk=1000)
+    assert_gt_equals_reference_text(ids, dist, ref_ids, ref_text)
