@@ -72,8 +72,6 @@ struct dpq_index {
     // "timing_reset" keep their own events so a bench loop can time K steps without syncing.
     std::vector<cudaEvent_t> evs;
     int timed_calls = 0;
-    int last_first_call = 0;        // first event slot of the last API call (a host-buffer search is several sub-batches)
-    bool host_call_active = false;
     cudaEvent_t* ev = nullptr;  // the last call's four events
     dpq::ScanProgram prog;  // host copy (ops/codes released after upload)
     int Ds = 0;
@@ -91,11 +89,16 @@ struct dpq_index {
     // options
     int opt_slices = 0, opt_pack = 2, opt_warps = 16, opt_slack = -1, opt_force_fallback = 0;
     int opt_epoch = 128, opt_trigger = 0, opt_ramp = 1;
+    int opt_latency = -1;      // -1 auto (Q <= 16, topk <= 32, M <= 8), 0 off, 1 on: lanes = nodes scan (scan1.cu)
+    int last_latency = 0;
+    DevBuf d_cand1, d_cnt1;    // latency mode: candidate positions [Q][ccap], counts + overflow flags
     int opt_coarse = -1;       // -1 auto, 0 off, 1 on: 8-bit coarse pass + exact re-score (scan8.cu)
     int opt_sample = 0;        // the sample pass walks every opt_sample-th batch (0 = auto: 8 / 16 / 32 / 64 by tree size)
     int opt_slices_s = 0;      // slices of the sample pass (0 = auto)
-    int opt_seed = 0;          // 0: sampled 15-bit scan gives the cap (default, 0.90 ms at C2);
-                               // 1: exact presample -> sampled coarse scan -> re-score (1.18 ms at C2)
+    int opt_seed = -1;         // 0: sampled 15-bit scan gives the cap (narrow shape default);
+                               // 1: exact presample -> sampled coarse scan -> re-score (wide shape default); -1: auto
+    int opt_refine = -1;       // stride of a second, denser sampled coarse pass that tightens the cap before the
+                               // full pass (0: none; -1 auto: 4 for the wide shape with topk > 32)
     int opt_presample = 2048;  // nodes scored exactly per query to seed the sample pass
     int opt_bcap8 = 0, opt_warps8 = 24, opt_levels8 = 80;  // bcap8 0 = auto (512 narrow, 2048 wide)
     int64_t opt_coarse_min = 100000;  // nodes in the shard from which the coarse search pays (gpurun_out/probe22.log)
@@ -105,8 +108,7 @@ struct dpq_index {
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_key, d_gthr;
     void* h_stage = nullptr;  // pinned staging for the host-buffer path
     size_t h_stage_cap = 0;
-    cudaStream_t copy_stream = nullptr;  // host-buffer path: uploads / downloads overlap the searches
-    cudaEvent_t copy_ev[12] = {};
+    bool host_keys = false;  // the caller's out_key is mapped HOST memory: keep intermediate key lists on the device
     // stats
     int last_launches = 0;
     int64_t last_fallback = 0;
@@ -277,6 +279,8 @@ int dpq_set_device(int device) {
     return DPQ_OK;
 }
 
+static int open_tree_shard_impl(dpq_tree* t, int rank, int n_ranks, int64_t first_pos, dpq_index** out);
+
 static int open_common(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
                        const uint32_t* pos2id, int rank, int n_ranks, int64_t first_pos, dpq_index** out) {
     if (!payload || !out) return fail(DPQ_ERR_ARG, "dpq_index_open: null argument");
@@ -285,10 +289,20 @@ static int open_common(const uint8_t* payload, int64_t n_bytes, int64_t n_codes,
         return fail(DPQ_ERR_ARG, "dpq_index_open_part: positions must stay below 2^32 - 1");
     int rc = check_device();
     if (rc) return rc;
-    dpq_index* ix = new dpq_index();
-    ix->device = g_device;
     // DPQ_ENGINE=1 in the environment keeps the first-generation op program / kernel
     const char* eng = getenv("DPQ_ENGINE");
+    const char* host_dec = getenv("DPQ_HOST_DECODE");  // 1: decode the stream on one host core (program.cpp) instead of the GPU
+    if (!(eng && eng[0] == '1') && !(host_dec && host_dec[0] == '1') && dpq::v2_shape_ok(M, K)) {
+        if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(DPQ_ERR_FORMAT, "dpq_index_open: bad rank / n_ranks");
+        dpq_tree* t = nullptr;
+        rc = dpq::decode_stream_device(payload, n_bytes, n_codes, M, K, pos2id, &t);  // program_dev.cu
+        if (rc) return fail(rc, std::string("dpq_index_open: ") + g_err);
+        rc = open_tree_shard_impl(t, rank, n_ranks, first_pos, out);
+        delete t;
+        return rc;
+    }
+    dpq_index* ix = new dpq_index();
+    ix->device = g_device;
     std::string err = dpq::compile_program(payload, n_bytes, n_codes, M, K, rank, n_ranks,
                                            ix->chunk_nodes, &ix->prog, eng && eng[0] == '1' ? 1 : 0);
     if (err.empty() && first_pos && !ix->prog.v2) err = "a forest part needs the fixed-record program (M <= 16, M*K <= 4096)";
@@ -433,6 +447,8 @@ int dpq_index_open_tree(dpq_tree* t, int64_t first_pos, dpq_index** out) {
 // subtrees balanced by stream bytes, the same deal as dpq_index_open(payload, ..., rank, n_ranks).
 // A device-resident tree never leaves HBM: the shard's slice of the code array is copied device to
 // device (and padded to the word stride when M is not 8 / 16).
+static int open_tree_shard_impl(dpq_tree* t, int rank, int n_ranks, int64_t first_pos, dpq_index** out);
+
 int dpq_index_open_tree_shard(dpq_tree* t, int rank, int n_ranks, dpq_index** out) {
     if (!t || !out) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: null argument");
     *out = nullptr;
@@ -446,7 +462,14 @@ int dpq_index_open_tree_shard(dpq_tree* t, int rank, int n_ranks, dpq_index** ou
         return open_common(t->payload.data(), (int64_t)t->payload.size(), n, M, K, t->vec_id.data(), rank, n_ranks, 0, out);
     }
     if (gen1) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: a device-resident tree needs the code-array engine");
-    if (n > 0xFFFFFFFELL) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: positions must stay below 2^32 - 1");
+    return open_tree_shard_impl(t, rank, n_ranks, 0, out);
+}
+
+// device-resident tree -> index of one shard; first_pos shifts every reported position (forest parts)
+static int open_tree_shard_impl(dpq_tree* t, int rank, int n_ranks, int64_t first_pos, dpq_index** out) {
+    const int M = t->M, K = t->K;
+    const int64_t n = t->n;
+    if (first_pos < 0 || first_pos + n > 0xFFFFFFFFLL) return fail(DPQ_ERR_ARG, "dpq_index_open: positions must stay below 2^32 - 1");
     int rc = check_device();
     if (rc) return rc;
     if (g_device != t->device) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: the tree lives on another device");
@@ -464,7 +487,8 @@ int dpq_index_open_tree_shard(dpq_tree* t, int rank, int n_ranks, dpq_index** ou
     P.cstride = P.shape.nf;
     P.n_codes = n;
     P.n_bytes = t->payload_bytes;
-    P.base_pos = lo;
+    P.base_pos = lo + first_pos;
+    ix->pos_shift = first_pos;
     P.n_local = hi - lo;
     P.local_bytes = bytes[(size_t)rank];
     {   // changed subspaces = record bytes - bitmap bytes - depth bytes (one per odd position)
@@ -492,13 +516,15 @@ int dpq_index_open_tree_shard(dpq_tree* t, int rank, int n_ranks, dpq_index** ou
             e = dpq::launch_pad_codes(src, P.n_local, M, P.cstride, ix->d_codes.as<uint8_t>(), ix->stream);
     }
     if ((rc = ix->d_ops.ensure(16)) || (rc = ix->d_chunks.ensure(16)) || (rc = ix->d_anc.ensure(16))) return bail(rc);
-    ix->pos2id_host.resize((size_t)P.n_local);
-    if (e == cudaSuccess && P.n_local > 0)
-        e = cudaMemcpyAsync(ix->pos2id_host.data(), (const uint32_t*)t->d_vec_id + lo, (size_t)P.n_local * 4,
-                            cudaMemcpyDeviceToHost, ix->stream);
+    if (t->d_vec_id) {
+        ix->pos2id_host.resize((size_t)P.n_local);
+        if (e == cudaSuccess && P.n_local > 0)
+            e = cudaMemcpyAsync(ix->pos2id_host.data(), (const uint32_t*)t->d_vec_id + lo, (size_t)P.n_local * 4,
+                                cudaMemcpyDeviceToHost, ix->stream);
+        ix->has_pos2id = true;
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) return bail(fail(DPQ_ERR_CUDA, std::string("dpq_index_open_tree_shard: ") + cudaGetErrorString(e)));
-    ix->has_pos2id = true;
     ix->n_chunks = (int)((P.n_local + P.v2_chunk_nodes - 1) / P.v2_chunk_nodes);
     ix->ops_bytes = (size_t)P.n_local * P.cstride;
     *out = ix;
@@ -549,11 +575,13 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "ramp") ix->opt_ramp = (int)v;
     else if (n == "dbg_bound") ix->opt_dbg_bound = (int)v;
     else if (n == "coarse") ix->opt_coarse = (int)v;
+    else if (n == "latency") ix->opt_latency = (int)v;
     else if (n == "sample") ix->opt_sample = std::max(0, (int)v);
     else if (n == "bcap8") ix->opt_bcap8 = v <= 0 ? 0 : std::max(32, (int)v);
     else if (n == "warps8") ix->opt_warps8 = std::max(2, std::min(24, (int)v));
     else if (n == "coarse_min") ix->opt_coarse_min = v;
     else if (n == "seed") ix->opt_seed = (int)v;
+    else if (n == "refine") ix->opt_refine = (int)v;
     else if (n == "slices_s") ix->opt_slices_s = (int)v;
     else if (n == "presample") ix->opt_presample = std::max(64, std::min(2048, (int)v));
     else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
@@ -579,6 +607,140 @@ static int pick_slices(int n_groups, int n_chunks, int chunks_per_round, int max
     return pick;
 }
 
+// Latency mode: exact tables -> exact presample (cap0) -> [scan1 over every S-th chunk -> exact re-score ->
+// cap1] -> scan1 over the whole shard -> exact re-score -> exact fallback for overflowed lists.
+static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk, uint64_t* d_out_key) {
+    const dpq::ScanProgram& P = ix->prog;
+    const size_t MK = (size_t)P.M * P.K;
+    const int ccap = 32768;
+    int rc;
+    if ((rc = ix->d_lutf.ensure((size_t)Q * MK * 4))) return rc;
+    if ((rc = ix->d_scale.ensure((size_t)((Q + 7) / 8) * 8 * 8 + 64))) return rc;
+    if ((rc = ix->d_cand1.ensure((size_t)Q * ccap * 4))) return rc;
+    if ((rc = ix->d_cnt1.ensure((size_t)Q * 8 * 2))) return rc;
+    if ((rc = ix->d_cap0.ensure((size_t)Q * 4))) return rc;
+    if ((rc = ix->d_cap1.ensure((size_t)Q * 4))) return rc;
+    if ((rc = ix->d_flagged.ensure((size_t)Q * 4))) return rc;
+    if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
+    if ((rc = ix->d_ctrl.ensure(64))) return rc;
+    cudaStream_t st = ix->stream;
+    uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();
+    {
+        const int slot = std::min(ix->timed_calls, 4095);
+        while ((int)ix->evs.size() < 6 * (slot + 1)) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            ix->evs.push_back(e);
+        }
+        ix->ev = ix->evs.data() + 6 * slot;
+        ix->timed_calls = slot + 1;
+    }
+    int launches = 0;
+    CU(cudaEventRecord(ix->ev[0], st));
+    CU(cudaMemsetAsync(ctrl, 0, 64, st));
+    dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(), ix->d_scale.as<double>(),
+                     nullptr, nullptr, nullptr, 0, P.shape, 0u, st);
+    CU(cudaEventRecord(ix->ev[1], st));
+    float* cap0 = ix->d_cap0.as<float>();
+    float* cap1 = ix->d_cap1.as<float>();
+    dpq::launch_presample(ix->d_lutf.as<float>(), ix->d_codes.as<uint8_t>(), P.cstride, P.n_local, P.M, P.K, Q, topk, 2048, cap0, st);
+    launches += 2;
+    uint32_t* cnt = ix->d_cnt1.as<uint32_t>();  // [0..Q) counts, [Q..2Q) overflow flags; a second pair behind for the final pass
+    dpq::Scan1Args s1;
+    s1.codes = ix->d_codes.as<uint8_t>();
+    s1.n_local = P.n_local;
+    s1.base_pos = (uint32_t)P.base_pos;
+    s1.lutf = ix->d_lutf.as<float>();
+    s1.scale = ix->d_scale.as<double>();
+    s1.M = P.M;
+    s1.K = P.K;
+    s1.Q = Q;
+    s1.n_pairs = (Q + 1) / 2;
+    s1.cand = ix->d_cand1.as<uint32_t>();
+    s1.ccap = ccap;
+    dpq::Rescore1Args r1;
+    r1.cand = s1.cand;
+    r1.ccap = ccap;
+    r1.lutf = s1.lutf;
+    r1.codes = s1.codes;
+    r1.cstride = P.cstride;
+    r1.base_pos = P.base_pos;
+    r1.M = P.M;
+    r1.K = P.K;
+    r1.Q = Q;
+    r1.topk = topk;
+    const int64_t n_chunks = (P.n_local + 2047) / 2048;
+    auto ranges_for = [&](int64_t chunks) { return (int)std::max<int64_t>(1, std::min<int64_t>(chunks, 148 / s1.n_pairs)); };
+    CU(cudaMemsetAsync(cnt, 0, (size_t)Q * 16, st));
+    const float* cap = cap0;
+    // presample: k-th of 2048 nodes -> about topk * n / 2048 nodes under cap0; a first pass over every S-th
+    // chunk (about a million nodes) tightens the cap when the whole shard would overflow the candidate lists
+    if ((double)P.n_local / 2048.0 * topk > ccap / 4) {
+        const int S = (int)std::max<int64_t>(2, P.n_local >> 20);
+        s1.chunk_stride = S;
+        s1.cap = cap0;
+        s1.cand_cnt = cnt;
+        s1.ovf = cnt + Q;
+        s1.n_ranges = ranges_for((n_chunks + S - 1) / S);
+        CU(dpq::launch_scan1(s1, st));
+        r1.cand_cnt = s1.cand_cnt;
+        r1.ovf = s1.ovf;
+        r1.out_key = nullptr;
+        r1.cap_in = cap0;
+        r1.cap_out = cap1;
+        r1.flagged = nullptr;
+        r1.n_flagged = nullptr;
+        r1.max_flagged = 0;
+        r1.bound = nullptr;
+        dpq::launch_rescore1(r1, st);
+        launches += 2;
+        cap = cap1;
+    }
+    s1.chunk_stride = 1;
+    s1.cap = cap;
+    s1.cand_cnt = cnt + 2 * Q;
+    s1.ovf = cnt + 3 * Q;
+    s1.n_ranges = ranges_for(n_chunks);
+    CU(cudaEventRecord(ix->ev[4], st));
+    CU(dpq::launch_scan1(s1, st));
+    CU(cudaEventRecord(ix->ev[5], st));
+    r1.cand_cnt = s1.cand_cnt;
+    r1.ovf = s1.ovf;
+    r1.out_key = d_out_key;
+    r1.cap_in = cap;
+    r1.cap_out = nullptr;
+    r1.flagged = ix->d_flagged.as<uint32_t>();
+    r1.n_flagged = ctrl + 2;
+    r1.max_flagged = Q;
+    r1.bound = ix->d_bound.as<float>();
+    dpq::launch_rescore1(r1, st);
+    CU(cudaEventRecord(ix->ev[2], st));
+    dpq::FallbackArgs fb;
+    fb.flagged = r1.flagged;
+    fb.n_flagged = ctrl + 2;
+    fb.max_flagged = Q;
+    fb.lutf = s1.lutf;
+    fb.bound = r1.bound;
+    fb.codes = s1.codes;
+    fb.cstride = P.cstride;
+    fb.base_pos = P.base_pos;
+    fb.n_local = P.n_local;
+    fb.M = P.M;
+    fb.K = P.K;
+    fb.topk = topk;
+    fb.out_key = d_out_key;
+    dpq::launch_fallback(fb, st);
+    launches += 3;
+    CU(cudaEventRecord(ix->ev[3], st));
+    CU(cudaGetLastError());
+    ix->last_launches = launches;
+    ix->last_coarse = 0;
+    ix->last_latency = 1;
+    ix->last_device_queries = Q;
+    ix->timing_valid = true;
+    return DPQ_OK;
+}
+
 int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int topk,
                             uint64_t* d_out_key) {
     if (!ix || !d_queries || !d_out_key) return fail(DPQ_ERR_ARG, "dpq_index_search: null argument");
@@ -587,6 +749,13 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaSetDevice(ix->device));
     dpq::ScanGeom g;
     const dpq::ScanProgram& P = ix->prog;
+    {   // latency mode (scan1.cu): a handful of queries, lanes = nodes, the code array streams once per query pair
+        const bool can = P.v2 && P.shape.nf == 8 && Q <= 16 && topk <= 32;
+        const bool auto_on = P.n_local >= 4096 && (double)P.n_local * topk <= 6e9;
+        ix->last_latency = 0;
+        if (can && ix->opt_latency != 0 && !ix->opt_force_fallback && (ix->opt_latency == 1 || auto_on))
+            return search_latency(ix, d_queries, Q, topk, d_out_key);
+    }
     // coarse search (scan8.cu): 15-bit scan over a 1/S sample -> cap per query -> 8-bit scan of
     // the whole tree -> exact re-score.  Trees large enough to pay, result lists up to 128.
     const bool coarse_auto = P.n_local >= ix->opt_coarse_min && topk <= (P.shape.nf == 8 ? 64 : 128);
@@ -607,14 +776,21 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     // geometry of the coarse passes: 112-query groups, 4 strands per warp
     const int warps8 = ix->opt_warps8;
     const int bcap8 = ix->opt_bcap8 > 0 ? ix->opt_bcap8 : (P.shape.nf == 8 ? 512 : 2048);  // survivors per (slice, query)
-    const bool seeded = coarse && ix->opt_seed == 1;
+    const bool seeded = coarse && (ix->opt_seed == 1 || (ix->opt_seed < 0 && P.shape.nf == 16));
     const int n_chunks_sample8 = (((ix->n_chunks + 3) / 4 + S - 1) / S) * 4;
-    int g8_groups = 0, g8_slices = 1, g8_slices_s = 1;
+    // second refinement level: a denser sampled coarse pass (stride S2 < S) under the first cap.  Long result
+    // lists need it: the cap of a 1/S sample is about the (k S)-th distance of the tree, and the coarse filter
+    // passes a multiple of that many nodes (26K survivors per query at top-100, S = 32, M = 16).
+    int S2 = ix->opt_refine >= 0 ? ix->opt_refine : (P.shape.nf == 16 && topk > 32 ? 4 : 0);
+    if (!coarse || S2 < 2 || S2 >= S) S2 = 0;
+    const int n_chunks_refine8 = S2 ? (((ix->n_chunks + 3) / 4 + S2 - 1) / S2) * 4 : 0;
+    int g8_groups = 0, g8_slices = 1, g8_slices_s = 1, g8_slices_r = 1;
     if (coarse) {
         g8_groups = (Q + c8.qb - 1) / c8.qb;
         g8_slices = ix->opt_slices > 0 ? ix->opt_slices : pick_slices(g8_groups, ix->n_chunks, warps8 * 4, 96);
         g8_slices = std::max(1, std::min(std::min(g8_slices, 128), std::max(1, ix->n_chunks)));  // <= R8_MAXSL
         if (seeded) g8_slices_s = pick_slices(g8_groups, n_chunks_sample8, warps8 * 4, 96);
+        if (S2) g8_slices_r = pick_slices(g8_groups, n_chunks_refine8, warps8 * 4, 96);
     }
     const size_t MK = (size_t)P.M * P.K;
     const size_t rows = (size_t)1 << g.rb;
@@ -639,7 +815,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_ctrl.ensure(64))) return rc;
     if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
     if (coarse) {
-        const size_t items8 = (size_t)g8_groups * std::max(g8_slices, g8_slices_s);
+        const size_t items8 = (size_t)g8_groups * std::max(std::max(g8_slices, g8_slices_s), g8_slices_r);
         ix->last_items8 = (int64_t)g8_groups * g8_slices;
         if ((rc = ix->d_cap0.ensure((size_t)Q * 4))) return rc;
         if ((rc = ix->d_cap1.ensure((size_t)Q * 4))) return rc;
@@ -662,7 +838,6 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         }
         ix->ev = ix->evs.data() + 6 * slot;
         ix->timed_calls = slot + 1;
-        if (!ix->host_call_active) ix->last_first_call = slot;
     }
     int launches = 0;
     CU(cudaEventRecord(ix->ev[0], st));
@@ -737,6 +912,10 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     se.Q = Q;
     se.topk = topk;
     se.out_key = d_out_key;
+    if (coarse && ix->host_keys) {  // the sample's own top-k is scratch: keep it off PCIe
+        if ((rc = ix->d_key.ensure((size_t)Q * topk * 8))) return rc;
+        se.out_key = ix->d_key.as<uint64_t>();
+    }
     se.flagged = ix->d_flagged.as<uint32_t>();
     se.max_flagged = max_flagged;
     se.force_fallback = ix->opt_force_fallback;
@@ -818,7 +997,25 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             dpq::launch_rescore8(r8, st);
             launches += 4;
         }
-        dpq::launch_pack8(se.lutf, cap1, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
+        const float* cap = cap1;
+        if (S2) {  // cap1 -> coarse scan of every S2-th batch -> exact re-score -> cap2 (kept in the cap0 buffer)
+            dpq::launch_pack8(se.lutf, cap1, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
+            s8.bt_stride = S2;
+            s8.n_slices = g8_slices_r;
+            CU(dpq::launch_scan8(s8, st));
+            r8.n_slices = g8_slices_r;
+            r8.out_key = nullptr;
+            r8.cap_in = cap1;
+            r8.cap_out = cap0;
+            r8.flagged = nullptr;
+            r8.n_flagged = nullptr;
+            r8.max_flagged = 0;
+            r8.bound = nullptr;
+            dpq::launch_rescore8(r8, st);
+            launches += 3;
+            cap = cap0;
+        }
+        dpq::launch_pack8(se.lutf, cap, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
         s8.bt_stride = 1;
         s8.n_slices = g8_slices;
         CU(cudaEventRecord(ix->ev[4], st));
@@ -826,7 +1023,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         CU(cudaEventRecord(ix->ev[5], st));
         r8.n_slices = g8_slices;
         r8.out_key = d_out_key;
-        r8.cap_in = cap1;
+        r8.cap_in = cap;
         r8.cap_out = nullptr;
         r8.flagged = ix->d_flagged2.as<uint32_t>();
         r8.n_flagged = ctrl + 2;
@@ -842,7 +1039,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     }
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
-    ix->last_launches = ix->host_call_active && ix->timed_calls - 1 > ix->last_first_call ? ix->last_launches + launches : launches;
+    ix->last_launches = launches;
     ix->timing_valid = true;
     return DPQ_OK;
 }
@@ -881,96 +1078,66 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     }
     const size_t qbytes = (size_t)Q * D * 4, kbytes = (size_t)Q * topk * 8;
     // pinned staging: [queries][keys][ctrl words]; a caller buffer that is already page-locked
-    // (dpq_malloc_host, cudaHostRegister) is copied from directly
+    // (dpq_malloc_host, cudaHostRegister) is used directly
     if (ix->h_stage_cap < qbytes + kbytes + 256) {
         if (ix->h_stage) cudaFreeHost(ix->h_stage);
         ix->h_stage = nullptr;
         ix->h_stage_cap = 0;
-        CU(cudaMallocHost(&ix->h_stage, qbytes + kbytes + 256));
+        CU(cudaHostAlloc(&ix->h_stage, qbytes + kbytes + 256, cudaHostAllocMapped));
         ix->h_stage_cap = qbytes + kbytes + 256;
     }
     int rc;
-    if ((rc = ix->d_queries.ensure(qbytes))) return rc;
-    if ((rc = ix->d_key.ensure(kbytes))) return rc;
     float* hq = reinterpret_cast<float*>(ix->h_stage);
     uint64_t* hk = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes);
     uint32_t* hc = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes + kbytes);
+    // No copy engine in the way: the kernels read the queries from, and write the result keys to,
+    // page-locked HOST memory through its device mapping (unified addressing).  The ADC-table kernel
+    // pulls each query's D floats over PCIe exactly once while it computes (5 MB at C2, hidden behind
+    // its arithmetic), the final re-score writes Q x k keys straight into the staging buffer, and the
+    // call ends with ONE stream synchronisation -- the sub-batch pipeline this replaces (H2D || search
+    // || D2H on two streams) lost more to four small searches than the overlap won.
+    const float* src = queries;
+    void* dq = nullptr;
     cudaPointerAttributes pa;
-    const bool pinned = cudaPointerGetAttributes(&pa, queries) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    const bool pinned = cudaPointerGetAttributes(&pa, queries) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                        cudaHostGetDevicePointer(&dq, const_cast<float*>(queries), 0) == cudaSuccess && dq;
     (void)cudaGetLastError();
-    // Copies overlap the search: the batch is cut into sub-batches; a second stream uploads
-    // sub-batch i+1 and downloads the keys of sub-batch i-1 while the index stream searches
-    // sub-batch i (the searches themselves stay in order on one stream and share the scratch), and
-    // the host unpacks a sub-batch's keys while the GPU is busy with the next ones.
-    constexpr int kMaxSub = 4;
-    const int n_sub = Q >= 4096 ? 4 : (Q >= 1024 ? 2 : 1);
-    if (!ix->copy_stream) {
-        CU(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 3 * kMaxSub; ++i) CU(cudaEventCreateWithFlags(&ix->copy_ev[i], cudaEventDisableTiming));
+    if (!pinned) {
+        memcpy(hq, queries, qbytes);
+        src = hq;
+        CU(cudaHostGetDevicePointer(&dq, hq, 0));
     }
-    cudaEvent_t* ev_up = ix->copy_ev;
-    cudaEvent_t* ev_done = ix->copy_ev + kMaxSub;
-    cudaEvent_t* ev_down = ix->copy_ev + 2 * kMaxSub;
-    int q_lo[kMaxSub + 1];
-    for (int i = 0; i <= n_sub; ++i) q_lo[i] = (int)((int64_t)Q * i / n_sub);
-    cudaStream_t cs = n_sub > 1 ? ix->copy_stream : ix->stream;
-    ix->last_first_call = std::min(ix->timed_calls, 4095);
-    ix->host_call_active = true;
-    struct Guard {
-        dpq_index* ix;
-        ~Guard() { ix->host_call_active = false; }
-    } guard{ix};
-    for (int i = 0; i < n_sub; ++i) {
-        const size_t o = (size_t)q_lo[i] * D, cnt = (size_t)(q_lo[i + 1] - q_lo[i]) * D;
-        const float* src = queries + o;
-        if (!pinned) {
-            memcpy(hq + o, queries + o, cnt * 4);
-            src = hq + o;
-        }
-        CU(cudaMemcpyAsync(ix->d_queries.as<float>() + o, src, cnt * 4, cudaMemcpyHostToDevice, cs));
-        if (n_sub > 1) CU(cudaEventRecord(ev_up[i], cs));
-    }
-    for (int i = 0; i < n_sub; ++i) {
-        const int n = q_lo[i + 1] - q_lo[i];
-        const size_t ko = (size_t)q_lo[i] * topk;
-        if (n_sub > 1) CU(cudaStreamWaitEvent(ix->stream, ev_up[i], 0));
-        if ((rc = dpq_index_search_device(ix, ix->d_queries.as<float>() + (size_t)q_lo[i] * D, n, topk,
-                                          ix->d_key.as<uint64_t>() + ko)))
-            return rc;
-        CU(cudaMemcpyAsync(hc + 4 * i, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
-        if (n_sub > 1) {
-            CU(cudaEventRecord(ev_done[i], ix->stream));
-            CU(cudaStreamWaitEvent(cs, ev_done[i], 0));
-        }
-        CU(cudaMemcpyAsync(hk + ko, ix->d_key.as<uint64_t>() + ko, (size_t)n * topk * 8, cudaMemcpyDeviceToHost, cs));
-        if (n_sub > 1) CU(cudaEventRecord(ev_down[i], cs));
-    }
+    (void)src;
+    void* dk = nullptr;
+    CU(cudaHostGetDevicePointer(&dk, hk, 0));
+    void* dc = nullptr;
+    CU(cudaHostGetDevicePointer(&dc, hc, 0));
+    ix->host_keys = true;  // the sample phase of the coarse search keeps its scratch keys on the device
+    rc = dpq_index_search_device(ix, reinterpret_cast<const float*>(dq), Q, topk, reinterpret_cast<uint64_t*>(dk));
+    ix->host_keys = false;
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hc, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));  // the one host sync of the call
+    ix->last_fallback = (int64_t)hc[0] + hc[2];
     const int64_t base = ix->prog.base_pos;
     const bool map = ix->has_pos2id;
     const uint32_t* p2i = ix->pos2id_host.data();
-    for (int i = 0; i < n_sub; ++i) {
-        if (n_sub > 1) CU(cudaEventSynchronize(ev_down[i]));
-        else CU(cudaStreamSynchronize(ix->stream));  // the one host sync of a small call
-        const size_t lo = (size_t)q_lo[i] * topk, hi = (size_t)q_lo[i + 1] * topk;
-        if (out_pos)
-            for (size_t j = lo; j < hi; ++j) out_pos[j] = (uint32_t)hk[j];
-        if (out_dist) {
-            uint32_t* od = reinterpret_cast<uint32_t*>(out_dist);
-            for (size_t j = lo; j < hi; ++j) od[j] = (uint32_t)(hk[j] >> 32);
-        }
-        if (out_id) {
-            if (map)
-                for (size_t j = lo; j < hi; ++j) {
-                    const uint32_t pos = (uint32_t)hk[j];
-                    out_id[j] = pos != 0xFFFFFFFFu ? p2i[(size_t)(pos - base)] : pos;
-                }
-            else
-                for (size_t j = lo; j < hi; ++j) out_id[j] = (uint32_t)hk[j];
-        }
+    const size_t nk = (size_t)Q * topk;
+    if (out_pos)
+        for (size_t j = 0; j < nk; ++j) out_pos[j] = (uint32_t)hk[j];
+    if (out_dist) {
+        uint32_t* od = reinterpret_cast<uint32_t*>(out_dist);
+        for (size_t j = 0; j < nk; ++j) od[j] = (uint32_t)(hk[j] >> 32);
     }
-    if (n_sub > 1) CU(cudaStreamSynchronize(ix->stream));  // the ctrl words of the last sub-batch
-    ix->last_fallback = 0;
-    for (int i = 0; i < n_sub; ++i) ix->last_fallback += (int64_t)hc[4 * i] + hc[4 * i + 2];
+    if (out_id) {
+        if (map)
+            for (size_t j = 0; j < nk; ++j) {
+                const uint32_t pos = (uint32_t)hk[j];
+                out_id[j] = pos != 0xFFFFFFFFu ? p2i[(size_t)(pos - base)] : pos;
+            }
+        else
+            for (size_t j = 0; j < nk; ++j) out_id[j] = (uint32_t)hk[j];
+    }
     return DPQ_OK;
 }
 
@@ -1031,6 +1198,7 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
     if (n == "last_launches") return ix->last_launches;
     if (n == "engine") return P.v2 ? 2 : 1;
     if (n == "last_coarse") return ix->last_coarse;
+    if (n == "last_latency") return ix->last_latency;
     if (n == "last_device_queries") return ix->last_device_queries;
     if (n == "cand8_total") {  // developer statistic: coarse survivors of the last search
         if (!ix->last_coarse || !ix->d_cnt8.p) return -1;
@@ -1057,9 +1225,9 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
         cudaSetDevice(ix->device);
         if (cudaEventSynchronize(ix->ev[3]) != cudaSuccess) return -1;
         const int which = n.find("scan8") != std::string::npos ? 3 : (n.find("scan") != std::string::npos ? 0 : (n.find("lut") != std::string::npos ? 1 : 2));
-        if (which == 3 && !ix->last_coarse) return -1;
+        if (which == 3 && !ix->last_coarse && !ix->last_latency) return -1;  // scan8 or, in latency mode, the full scan1 pass
         double total_ms = 0;
-        const int first = last ? std::min(ix->last_first_call, ix->timed_calls - 1) : 0;
+        const int first = last ? ix->timed_calls - 1 : 0;
         for (int c = first; c < ix->timed_calls; ++c) {
             cudaEvent_t* e = ix->evs.data() + 6 * c;
             float ms = 0;
@@ -1077,18 +1245,12 @@ void dpq_index_close(dpq_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_cand1, &ix->d_cnt1, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
                       &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_key,
                       &ix->d_gthr})
         b->release();
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
-    if (ix->copy_stream) {
-        cudaStreamSynchronize(ix->copy_stream);
-        for (auto& e : ix->copy_ev)
-            if (e) cudaEventDestroy(e);
-        cudaStreamDestroy(ix->copy_stream);
-    }
     for (auto& e : ix->evs)
         if (e) cudaEventDestroy(e);
     if (ix->stream && ix->own_stream) cudaStreamDestroy(ix->stream);

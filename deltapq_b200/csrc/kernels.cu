@@ -619,36 +619,7 @@ void launch_select(const SelectArgs& a, cudaStream_t st) {
 // on the full 64-bit key (distance bits << 32 | position, strict), so any number of nodes tying
 // at the k-th distance is handled: the buffer is reduced to the k best keys (bitonic sort)
 // whenever it is more than half full, and the k-th key becomes the new exclusive bound.
-constexpr int FB_T = 1024;
-constexpr int FB_BUF = 2048;  // >= FB_T + 256 (topk <= 256)
-
-__device__ __forceinline__ void fb_compact(uint64_t* s_keys, uint32_t* s_n, unsigned long long* s_thr, int topk) {
-    const int n = (int)*s_n;  // uniform: read after a barrier
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int i = n + threadIdx.x; i < np2; i += FB_T) s_keys[i] = ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np2; i += FB_T) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t x = s_keys[i], y = s_keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) {
-                        s_keys[i] = y;
-                        s_keys[ixj] = x;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    if (threadIdx.x == 0) {
-        *s_n = (uint32_t)(n < topk ? n : topk);
-        if (n >= topk) *s_thr = s_keys[topk - 1] - 1ull;  // keys are unique: only strictly better keys pass
-    }
-    __syncthreads();
-}
+constexpr int FB_T = 1024;  // FB_BUF (kernels.cuh) >= FB_T + 256 (topk <= 256)
 
 __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
     extern __shared__ __align__(16) unsigned char fb_smem[];
@@ -685,6 +656,62 @@ __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
                 i < (int)s_n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
         __syncthreads();
     }
+}
+
+// Latency mode: exact re-score of scan1's candidate lists, one CTA per query (same running top-k).
+__global__ void __launch_bounds__(FB_T) rescore1_kernel(const Rescore1Args a) {
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(fb_smem);   // [FB_BUF]
+    float* s_lut = reinterpret_cast<float*>(s_keys + FB_BUF);  // [M*K]
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_thr;
+    const int q = blockIdx.x;
+    const int MK = a.M * a.K;
+    for (int i = threadIdx.x; i < MK; i += FB_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
+    if (threadIdx.x == 0) {
+        s_n = 0u;
+        s_thr = ~0ull;
+    }
+    __syncthreads();
+    const int total = (int)min(a.cand_cnt[q], (uint32_t)a.ccap);
+    const uint32_t* cand = a.cand + (size_t)q * a.ccap;
+    for (int base = 0; base < total; base += FB_T) {
+        const int i = base + threadIdx.x;
+        if (i < total) {
+            const uint32_t pos = cand[i];
+            const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
+            double d = 0.0;
+            for (int m = 0; m < a.M; ++m) d += (double)s_lut[m * a.K + code[m]];
+            const uint64_t key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
+            if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;
+        }
+        __syncthreads();
+        if (s_n > (uint32_t)(FB_BUF - FB_T)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
+    }
+    fb_compact(s_keys, &s_n, &s_thr, a.topk);
+    const int n = (int)s_n;
+    if (a.out_key)
+        for (int i = threadIdx.x; i < a.topk; i += FB_T)
+            a.out_key[(size_t)q * a.topk + i] = i < n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+    if (threadIdx.x == 0) {
+        // the k best found are real nodes: their k-th distance bounds the true k-th from above
+        const float found = n >= a.topk ? __uint_as_float((uint32_t)(s_keys[a.topk - 1] >> 32)) : FLT_MAX;
+        const float known = a.cap_in ? a.cap_in[q] : FLT_MAX;
+        const float cap = fminf(found, known);
+        if (a.cap_out) a.cap_out[q] = cap;
+        if (a.flagged) {
+            a.bound[q] = cap;
+            if (a.ovf[q]) {  // dropped candidates may hide a true top-k node: exact fallback
+                const uint32_t slot = atomicAdd(a.n_flagged, 1u);
+                if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;
+            }
+        }
+    }
+}
+
+void launch_rescore1(const Rescore1Args& a, cudaStream_t st) {
+    const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
+    rescore1_kernel<<<a.Q, FB_T, sm, st>>>(a);
 }
 
 void launch_fallback(const FallbackArgs& a, cudaStream_t st) {

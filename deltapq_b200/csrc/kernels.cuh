@@ -73,6 +73,11 @@ template <int OFF>
 __device__ __forceinline__ uint4 lds128o(uint32_t saddr) {
     return lds128(saddr + (uint32_t)OFF);
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t saddr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
@@ -245,6 +250,40 @@ struct SelectArgs {
 };
 void launch_select(const SelectArgs& a, cudaStream_t st);
 
+// Block-wide running top-k used by the exact kernels (fallback, re-score): s_keys[0 .. *s_n) holds
+// candidate keys (distance bits << 32 | position, unique); the call sorts them (bitonic, whole CTA),
+// keeps the topk smallest and makes the k-th key the new exclusive bound *s_thr.  Every thread of
+// the CTA must call it; *s_n is read after a barrier.
+constexpr int FB_BUF = 2048;
+__device__ __forceinline__ void fb_compact(uint64_t* s_keys, uint32_t* s_n, unsigned long long* s_thr, int topk) {
+    const int T = (int)blockDim.x;
+    const int n = (int)*s_n;  // uniform: read after a barrier
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + threadIdx.x; i < np2; i += T) s_keys[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += T) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t x = s_keys[i], y = s_keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        s_keys[i] = y;
+                        s_keys[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        *s_n = (uint32_t)(n < topk ? n : topk);
+        if (n >= topk) *s_thr = s_keys[topk - 1] - 1ull;  // keys are unique: only strictly better keys pass
+    }
+    __syncthreads();
+}
+
 // Exact fallback for flagged queries: a running top-k over every node of the shard (kernels.cu).
 struct FallbackArgs {
     const uint32_t* flagged;    // [max_flagged] query ids
@@ -262,5 +301,44 @@ void launch_fallback(const FallbackArgs& a, cudaStream_t st);
 
 void launch_merge(const uint64_t* d_keys, int n_lists, int Q, int topk, uint64_t* d_out,
                   cudaStream_t st);
+
+// ---- latency mode (scan1.cu): lanes = nodes, two queries per pass over the code array ----
+struct Scan1Args {
+    const uint8_t* codes;         // [n_local][8] codes by position (16-byte aligned)
+    int64_t n_local;
+    uint32_t base_pos;
+    const float* lutf;            // [Q][M*K] exact tables
+    const double* scale;          // [Q] 32751 / sum of the per-subspace maxima (lut2_kernel)
+    const float* cap;             // [Q] inclusive distance bound (FLT_MAX: none)
+    int M, K, Q;
+    int n_pairs;                  // ceil(Q / 2): query pairs, each pair has its own CTAs
+    int n_ranges;                 // tree ranges per pair (n_pairs * n_ranges CTAs, one per SM)
+    int chunk_stride;             // 1: every 2048-node chunk; S: every S-th chunk (sample pass)
+    uint32_t* cand;               // [Q][ccap] candidate positions
+    uint32_t* cand_cnt;           // [Q]
+    uint32_t* ovf;                // [Q]
+    int ccap;
+};
+cudaError_t launch_scan1(const Scan1Args& a, cudaStream_t st);
+// exact re-score of scan1's candidate lists: one CTA per query, running top-k on (distance, position)
+struct Rescore1Args {
+    const uint32_t* cand;         // [Q][ccap]
+    const uint32_t* cand_cnt;     // [Q]
+    const uint32_t* ovf;          // [Q]
+    int ccap;
+    const float* lutf;
+    const uint8_t* codes;
+    int cstride;
+    int64_t base_pos;
+    int M, K, Q, topk;
+    uint64_t* out_key;            // [Q][topk] or null (sample pass)
+    const float* cap_in;          // [Q]
+    float* cap_out;               // [Q] min(cap_in, exact k-th distance found), or null
+    uint32_t* flagged;            // queries whose list overflowed -> exact fallback (or null)
+    uint32_t* n_flagged;
+    int max_flagged;
+    float* bound;                 // [Q] bound for the fallback
+};
+void launch_rescore1(const Rescore1Args& a, cudaStream_t st);
 
 }  // namespace dpq

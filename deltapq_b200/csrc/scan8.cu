@@ -312,126 +312,98 @@ cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------ exact re-score --
-// One warp per query: every coarse survivor is scored exactly (float tables, double sum of the
-// node's M entries = what the reference's double accumulation rounds to) and the k best keys
-// (distance bits << 32 | position) are kept in a small shared-memory buffer that is reduced by
-// rank counting whenever it fills.
-constexpr int R8_WARPS = 4;
-constexpr int R8_BUF = 192;  // >= topk + 32 (coarse search serves topk <= 128); rank counting is O(n^2 / 32)
-
-__device__ __forceinline__ int r8_compact(uint64_t* buf, int n, int k, int lane) {
-    // keep the min(n, k) smallest of buf[0..n) sorted ascending (keys unique); n <= R8_BUF
-    uint64_t mine[R8_BUF / 32];
-    int rank[R8_BUF / 32];
-    const int per = (n + 31) >> 5;
-#pragma unroll
-    for (int t = 0; t < R8_BUF / 32; ++t) {
-        mine[t] = ~0ull;
-        rank[t] = 0;
-        if (t < per && t * 32 + lane < n) mine[t] = buf[t * 32 + lane];
-    }
-    __syncwarp();
-    for (int i = 0; i < n; ++i) {
-        const uint64_t o = buf[i];  // broadcast read
-#pragma unroll
-        for (int t = 0; t < R8_BUF / 32; ++t) rank[t] += o < mine[t];
-    }
-    __syncwarp();
-    const int keep = n < k ? n : k;
-#pragma unroll
-    for (int t = 0; t < R8_BUF / 32; ++t)
-        if (t < per && t * 32 + lane < n && rank[t] < keep) buf[rank[t]] = mine[t];
-    __syncwarp();
-    return keep;
-}
-
+// One CTA per query: the query's exact float table is staged in shared memory, every coarse
+// survivor is scored exactly (float entries, double sum of the node's M entries = what the
+// reference's double accumulation rounds to) and the k best keys (distance bits << 32 | position)
+// are kept by the block-wide running top-k (fb_compact): the buffer is sorted and cut to k whenever
+// it fills, and the k-th key becomes the acceptance bound.  The per-(slice, query) candidate lists
+// are addressed as one flat index space so that every step scores blockDim.x candidates no matter
+// how they are spread over the slices.
+constexpr int R8_T = 256;
 constexpr int R8_MAXSL = 128;  // slices per group the flattened candidate index can address
 
-__global__ void __launch_bounds__(R8_WARPS * 32) rescore8_kernel(const Rescore8Args a) {
-    __shared__ uint64_t s_buf[R8_WARPS][R8_BUF];
-    __shared__ uint32_t s_off[R8_WARPS][R8_MAXSL + 1];  // exclusive prefix of the per-slice counts
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q = blockIdx.x * R8_WARPS + w;
-    if (q >= a.Q) return;
+__global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
+    extern __shared__ __align__(16) unsigned char r8_smem[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(r8_smem);   // [FB_BUF]
+    float* s_lut = reinterpret_cast<float*>(s_keys + FB_BUF);  // [M*K]
+    __shared__ uint32_t s_off[R8_MAXSL + 1];  // exclusive prefix of the per-slice counts
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_thr;
+    const int q = blockIdx.x;
     const int grp = q / a.qb, ql = q % a.qb;
-    const float* lut = a.lutf + (size_t)q * a.M * a.K;
-    uint64_t* buf = s_buf[w];
-    uint32_t* off = s_off[w];
-    // all slices' counts at once (one load per lane), then one flat candidate index space so
-    // that every step scores 32 candidates no matter how they are spread over the slices
-    uint32_t run = 0;
-    for (int s0 = 0; s0 < a.n_slices; s0 += 32) {
-        const int s = s0 + lane;
-        uint32_t c = 0;
-        if (s < a.n_slices) c = a.cand_cnt[((size_t)s * a.n_groups + grp) * a.qb + ql];
-        uint32_t incl = c;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+    const int MK = a.M * a.K;
+    for (int i = threadIdx.x; i < MK; i += R8_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
+    if (threadIdx.x < 32) {  // warp 0: counts of all slices, exclusive prefix
+        const int lane = threadIdx.x;
+        uint32_t run = 0;
+        for (int s0 = 0; s0 < a.n_slices; s0 += 32) {
+            const int s = s0 + lane;
+            uint32_t c = 0;
+            if (s < a.n_slices) c = a.cand_cnt[((size_t)s * a.n_groups + grp) * a.qb + ql];
+            uint32_t incl = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (s < a.n_slices) s_off[s] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (s < a.n_slices) off[s] = run + incl - c;
-        run += __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {
+            s_off[a.n_slices] = run;
+            s_n = 0u;
+            // a valid cap known beforehand bounds the candidates worth keeping (inclusive, any position)
+            const float cap = a.cap_in ? a.cap_in[q] : FLT_MAX;
+            s_thr = ((unsigned long long)__float_as_uint(cap) << 32) | 0xFFFFFFFFull;
+        }
     }
-    if (lane == 0) off[a.n_slices] = run;
-    __syncwarp();
-    const int total = (int)run;
-    int n = 0;
-    uint64_t bound = ~0ull;  // k-th best key so far (exclusive)
-    const int k = a.topk;
-    for (int i0 = 0; i0 < total; i0 += 32) {
-        uint64_t key = ~0ull;
-        const int i = i0 + lane;
+    __syncthreads();
+    const int total = (int)s_off[a.n_slices];
+    for (int base = 0; base < total; base += R8_T) {
+        const int i = base + threadIdx.x;
         if (i < total) {
             int lo = 0, hi = a.n_slices;  // slice s with off[s] <= i < off[s+1]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (off[mid] <= (uint32_t)i) lo = mid;
+                if (s_off[mid] <= (uint32_t)i) lo = mid;
                 else hi = mid;
             }
             const size_t item = (size_t)lo * a.n_groups + grp;
-            const uint32_t pos = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - off[lo]));
+            const uint32_t pos = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - s_off[lo]));
             const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
             double d = 0.0;
-            for (int m = 0; m < a.M; ++m) d += (double)lut[m * a.K + code[m]];
-            key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
+            for (int m = 0; m < a.M; ++m) d += (double)s_lut[m * a.K + code[m]];
+            const uint64_t key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
+            if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;  // < FB_BUF: compacted above FB_BUF - R8_T
         }
-        const bool take = key < bound;
-        const uint32_t mk = __ballot_sync(0xffffffffu, take);
-        if (mk) {
-            if (n + 32 > R8_BUF) {  // make room: reduce to the k best, tighten the bound
-                n = r8_compact(buf, n, k, lane);
-                if (n == k) bound = buf[k - 1];
-                __syncwarp();
-            }
-            const bool still = take && key < bound;
-            const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
-            if (still) buf[n + __popc(mk2 & ((1u << lane) - 1u))] = key;
-            n += __popc(mk2);
-            __syncwarp();
-        }
+        __syncthreads();
+        if (s_n > (uint32_t)(FB_BUF - R8_T)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
     }
-    n = r8_compact(buf, n, k, lane);
+    fb_compact(s_keys, &s_n, &s_thr, a.topk);
+    const int n = (int)s_n, k = a.topk;
     if (a.out_key)
-        for (int i = lane; i < k; i += 32)
-            a.out_key[(size_t)q * k + i] = i < n ? buf[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
-    // the k best found are real nodes: their k-th distance bounds the true k-th from above even
-    // when candidates were dropped
-    const float found = n >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
-    const float known = a.cap_in ? a.cap_in[q] : FLT_MAX;
-    if (lane == 0 && a.cap_out) a.cap_out[q] = fminf(found, known);
-    if (lane == 0 && a.flagged) {
-        // a dropped candidate (buffer overflow) may hide a true top-k node: exact fallback, bounded
-        // by the best k found so far
-        a.bound[q] = fminf(found, known);
-        if (a.ovf[(size_t)grp * a.qb + ql]) {
-            const uint32_t slot = atomicAdd(a.n_flagged, 1u);
-            if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;
+        for (int i = threadIdx.x; i < k; i += R8_T)
+            a.out_key[(size_t)q * k + i] = i < n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+    if (threadIdx.x == 0) {
+        // the k best found are real nodes: their k-th distance bounds the true k-th from above even
+        // when candidates were dropped
+        const float found = n >= k ? __uint_as_float((uint32_t)(s_keys[k - 1] >> 32)) : FLT_MAX;
+        const float known = a.cap_in ? a.cap_in[q] : FLT_MAX;
+        if (a.cap_out) a.cap_out[q] = fminf(found, known);
+        if (a.flagged) {
+            // a dropped candidate (buffer overflow) may hide a true top-k node: exact fallback, bounded
+            // by the best k found so far
+            a.bound[q] = fminf(found, known);
+            if (a.ovf[(size_t)grp * a.qb + ql]) {
+                const uint32_t slot = atomicAdd(a.n_flagged, 1u);
+                if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;
+            }
         }
     }
 }
 
 void launch_rescore8(const Rescore8Args& a, cudaStream_t st) {
-    rescore8_kernel<<<(a.Q + R8_WARPS - 1) / R8_WARPS, R8_WARPS * 32, 0, st>>>(a);
+    const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
+    rescore8_kernel<<<a.Q, R8_T, sm, st>>>(a);
 }
 
 }  // namespace dpq

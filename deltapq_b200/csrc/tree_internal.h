@@ -49,6 +49,9 @@ int tree_copy_device(const dpq_tree* t, const void* src, void* dst, size_t bytes
 // depth-1 subtree shards of a device-resident tree (same deal as the stream reader, program.cpp)
 int tree_shard_bounds(const dpq_tree* t, int n_ranks, std::vector<int64_t>* bounds, std::vector<int64_t>* bytes);
 int depth_hist_device(int device, const uint8_t* d_depth, int64_t n, int64_t* hist17);
+// the on-disk stream decoded on the GPU into a device-resident tree (program_dev.cu); payload / pos2id: host
+int decode_stream_device(const uint8_t* payload, int64_t n_bytes, int64_t n, int M, int K, const uint32_t* pos2id,
+                         dpq_tree** out);
 // DPQ_ERR_ARG when a code byte is >= K (host or device pointer; no-op for K == 256)
 int check_code_range(const uint8_t* codes, int64_t n, int M, int K);
 }  // namespace dpq

@@ -200,3 +200,66 @@ def test_massive_ties_take_the_exact_fallback():
     assert ix.stat("last_fallback") == len(many)
     assert np.array_equal(pos[:64], pos[64:128]) and np.array_equal(pos[:64], pos[-64:])
     ix.close()
+
+
+@pytest.mark.parametrize("n", [120_000, 1_000_000])
+def test_latency_mode_vs_oracle(sift1m, n):
+    """Latency mode (scan1.cu: lanes = nodes, two queries per pass of the code array) is what a call
+    with a handful of queries takes automatically; same answers as the oracle and as the batched
+    path, for odd / even query counts and the presample-only and sampled-pass variants."""
+    codes, cw, queries = sift1m
+    t = dpq.tree_build(codes[:n], cw, want=("payload", "vec_id"), open_index_at=0)
+    ix = t["index"]
+    ix.set_codebook(cw)
+    for Q, k in ((1, 10), (2, 10), (5, 32), (16, 1), (7, 10)):
+        q = np.ascontiguousarray(queries[100:100 + Q])
+        ix.set_option("latency", -1)
+        pos, ids, dist = ix.search(q, k)
+        assert ix.stat("last_latency") == 1 and ix.stat("last_coarse") == 0
+        assert np.array_equal(ids, t["vec_id"][pos])
+        for i in range(Q):
+            opos, odist, nd = po.scan(t["payload"], n, cw, q[i], k, want_node_dist=True)
+            assert np.array_equal(dist[i], odist), (Q, k, i)
+            assert_topk_equal(pos[i], dist[i], opos, odist, node_dist=nd)
+        ix.set_option("latency", 0)
+        bpos, _, bdist = ix.search(q, k)
+        assert ix.stat("last_latency") == 0
+        assert np.array_equal(bpos, pos) and np.array_equal(bdist, dist)
+    ix.close()
+
+
+def test_latency_mode_small_and_odd_trees(sift1m):
+    """Forced latency mode on trees smaller than one chunk, odd node counts, shards and duplicates."""
+    codes, cw, queries = sift1m
+    for n in (1, 2, 65, 2049, 5001):
+        t = dpq.tree_build(codes[:n], cw, want=("payload", "vec_id"), open_index_at=0)
+        ix = t["index"]
+        ix.set_codebook(cw)
+        ix.set_option("latency", 1)
+        k = min(10, 32)
+        q = np.ascontiguousarray(queries[:3])
+        pos, ids, dist = ix.search(q, k)
+        assert ix.stat("last_latency") == 1
+        for i in range(3):
+            opos, odist, nd = po.scan(t["payload"], n, cw, q[i], k, want_node_dist=True)
+            m = min(n, k)
+            assert np.array_equal(dist[i][:m], odist[:m])
+            assert_topk_equal(pos[i][:m], dist[i][:m], opos[:m], odist[:m], node_dist=nd)
+            assert np.all(pos[i][m:] == 0xFFFFFFFF)
+        ix.close()
+    # a shard that does not start at position 0, and heavy duplicates (cap = many ties)
+    n = 50_000
+    dup = codes[:n].copy()
+    dup[1000:30000] = dup[7]
+    t = dpq.tree_build(dup, cw, want=("payload", "vec_id"))
+    for r in range(3):
+        ix = dpq.DeltaTreeIndex(t["payload"], n, 8, 256, pos2id=t["vec_id"], rank=r, n_ranks=3)
+        ix.set_codebook(cw)
+        q = np.ascontiguousarray(queries[:4])
+        ix.set_option("latency", 1)
+        a = ix.search(q, 10)
+        assert ix.stat("last_latency") == 1
+        ix.set_option("latency", 0)
+        b = ix.search(q, 10)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        ix.close()

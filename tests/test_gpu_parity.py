@@ -552,7 +552,7 @@ def test_index_from_tree_arrays_equals_index_from_stream(shape, engine):
     b.close()
 
 
-@pytest.mark.parametrize("n,M", [(30000, 8), (7000, 16), (5000, 5)])
+@pytest.mark.parametrize("n,M", [(30000, 8), (7000, 16), (5000, 4)])
 def test_device_resident_tree_and_its_shards(n, M, engine):
     """dpq_tree_build_device leaves the tree in HBM (the 10^9-code layout): same stream, vec_id and
     codes as the host-resident build, and dpq_index_open_tree_shard deals the same depth-1-subtree
@@ -603,3 +603,56 @@ def test_groundtruth_vs_reference_binary(name, tc, monkeypatch):
     assert_gt_equals_reference_text(ids, dist, ref_ids, ref_text)
     oid, odist = po.groundtruth(base, queries, k)
     assert np.array_equal(dist, odist)
+
+
+def test_gpu_stream_decoder_equals_host_decoder(golden4000, golden1501, golden_m16, monkeypatch, engine):
+    """dpq_index_open decodes the on-disk stream on the GPU (program_dev.cu: speculative record
+    boundaries, per-level parent scans, level-order codes); DPQ_HOST_DECODE=1 keeps the sequential
+    host decoder (program.cpp).  Same shards, same statistics, same answers; malformed streams are
+    refused by both."""
+    if engine == "gen1":
+        pytest.skip("the first-generation program is compiled on the host")
+    cases = [(golden4000["payload"], 4000, 8, golden4000["cw"], golden4000["queries"], golden4000["vec_id"]),
+             (golden1501["payload"], 1501, 8, golden1501["cw"], golden1501["queries"], golden1501["vec_id"])]
+    g = golden_m16
+    _, _, lay, payload16 = po.build_tree(g["codes"], g["cw"])
+    cases.append((payload16, len(g["codes"]), 16, g["cw"], g["queries"], lay["vec_id"]))
+    # a bigger tree: many 4 KB stream blocks, every depth
+    base = dg.sift_like(60000, 128, seed=71)
+    cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(3000, 128, seed=72), 8, 256, iters=3))
+    t = dpq.tree_build(dpq.encode(cw, base), cw, want=("payload", "vec_id"))
+    cases.append((t["payload"], 60000, 8, cw, dg.sift_like(100, 128, seed=73), t["vec_id"]))
+    for payload, n, M, cw_, queries, vec_id in cases:
+        for R in (1, 3):
+            for r in range(R):
+                monkeypatch.delenv("DPQ_HOST_DECODE", raising=False)
+                a = dpq.DeltaTreeIndex(payload, n, M, 256, pos2id=vec_id, rank=r, n_ranks=R)
+                monkeypatch.setenv("DPQ_HOST_DECODE", "1")
+                b = dpq.DeltaTreeIndex(payload, n, M, 256, pos2id=vec_id, rank=r, n_ranks=R)
+                for name in ("n_codes", "n_local", "base_pos", "n_diffs", "n_chunks", "engine"):
+                    assert a.stat(name) == b.stat(name), (name, n, r, R)
+                assert abs(a.stat("n_bytes") - b.stat("n_bytes")) <= 1
+                assert [a.stat(f"depth_hist_{d}") for d in range(16)] == [b.stat(f"depth_hist_{d}") for d in range(16)]
+                for ix in (a, b):
+                    ix.set_codebook(cw_)
+                apos, aid, adist = a.search(queries, 10)
+                bpos, bid, bdist = b.search(queries, 10)
+                assert np.array_equal(apos, bpos) and np.array_equal(aid, bid) and np.array_equal(adist, bdist)
+                a.close()
+                b.close()
+    monkeypatch.delenv("DPQ_HOST_DECODE", raising=False)
+    payload, n = golden1501["payload"], 1501
+    with pytest.raises(dpq.DpqError, match="trunc|mismatch|missing"):
+        dpq.DeltaTreeIndex(payload[:-3], n, 8, 256)
+    with pytest.raises(dpq.DpqError, match="trunc|mismatch|missing"):
+        dpq.DeltaTreeIndex(np.concatenate([payload, np.zeros(5, np.uint8)]), n, 8, 256)
+    bad = payload.copy()
+    bad[8] = 0x77  # depth jump 0 -> 7
+    with pytest.raises(dpq.DpqError, match="depth"):
+        dpq.DeltaTreeIndex(bad, n, 8, 256)
+    with pytest.raises(dpq.DpqError, match="centroid"):
+        dpq.DeltaTreeIndex(payload, n, 8, 3)   # K = 3: the stream's centroid ids do not fit
+    # a one-node tree and a two-node tree
+    one = dpq.DeltaTreeIndex(np.arange(8, dtype=np.uint8), 1, 8, 256)
+    assert one.stat("n_local") == 1
+    one.close()
