@@ -230,10 +230,16 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    gloo = dist.new_group(backend="gloo") if world > 1 else None
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():  # waits on the CPU: the GPUs stay free for whoever works meanwhile
+        torch.cuda.synchronize()
+        dist.barrier(group=gloo)
 
     def max_over_ranks(*vals):
         if world == 1:
@@ -313,6 +319,8 @@ def run_gpu(args):
         pos, ids, dst = ix.search(h_queries, k)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_host = {"enqueue_us": ix.stat("last_host_enqueue_us"), "gpu_wait_us": ix.stat("last_host_wait_us"),
+                "unpack_us": ix.stat("last_host_unpack_us")}
     clocks = sampler.stop() if rank == 0 else None
     total_ms, e2e_s, scan_ms_max = max_over_ranks(total_ms, e2e_s, scan_ns / 1e6)
 
@@ -354,6 +362,33 @@ def run_gpu(args):
                                 f"NCCL all-gather of {Q * k * 8} B/rank + device merge"}
         assert same, "sharded + merged top-k differs from the unsharded result"
         sh.close()
+
+    # ---- the C++ multi-GPU path (dpq_multi_*, NCCL bound at run time, no torch): rank 0 saves the tree and
+    # runs tools/multi_probe.py in a SUBPROCESS with a timeout; the other ranks wait on the host
+    multi_cpp = None
+    if not args.no_multi_cpp:
+        if rank == 0:
+            import shutil
+            tmpd = tempfile.mkdtemp(prefix="dpq_multi_")
+            try:
+                with open(os.path.join(tmpd, "tree.bin"), "wb") as f:
+                    f.write(np.array([args.n_codes, len(payload)], np.int64).tobytes())
+                    f.write(payload.tobytes())
+                qn = np.zeros((args.n_codes + 1, 60), np.uint8)
+                qn[:args.n_codes, 0:4] = tree["vec_id"].astype(np.uint32).view(np.uint8).reshape(-1, 4)
+                qn.tofile(os.path.join(tmpd, "qnodes.bin"))
+                del qn
+                np.savez(os.path.join(tmpd, "multi_probe.npz"), cw=cw, queries=queries0, topk=k, n_codes=args.n_codes)
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "multi_probe.py"), tmpd, str(world), "5"],
+                                   capture_output=True, text=True, timeout=240)
+                last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                multi_cpp = json.loads(last[-1]) if last else {"error": (r.stderr or r.stdout)[-300:], "rc": r.returncode}
+            except Exception as e:  # recorded, never fatal
+                multi_cpp = {"error": repr(e)[:300]}
+            finally:
+                shutil.rmtree(tmpd, ignore_errors=True)
+        if world > 1:
+            host_barrier()
 
     # ---- C5: one tree over 10^9 codes, subtree shards over the ranks (own block, never fails the line)
     c5 = None
@@ -442,13 +477,16 @@ def run_gpu(args):
             "cpu_baseline": cpu_base,
             "parity": parity,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": world * Q * DIM * 4,
-                    "d2h_bytes_per_step": world * Q * k * 8},
+                    "d2h_bytes_per_step": world * Q * k * 8, "host_breakdown_last_call": e2e_host,
+                    "how": "dpq_index_search with the queries in page-locked host memory: the kernels read them and write the "
+                           "result keys through the device mapping of that memory (PCIe traffic inside the timed region), one stream sync"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "breakdown_ms_per_step": {"lut": lut_ns / 1e6 / max(calls, 1), "all_scan_phases": scan_s * 1e3,
                                       "coarse_scan_kernel": dom_s * 1e3 if coarse else None,
                                       "scan_max_over_ranks": scan_ms_max / max(calls, 1), "exact_fallback_queries": fallback},
             "tree_sharded": tree_sharded,
+            "multi_cpp": multi_cpp,
             "c5": c5,
         }
         print(json.dumps(line))
@@ -745,6 +783,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-queries", type=int, default=600)
     ap.add_argument("--ref-queries-per-proc", type=int, default=100)
+    ap.add_argument("--no-multi-cpp", action="store_true", help="skip the C++ multi-GPU probe (tools/multi_probe.py)")
     ap.add_argument("--c5-codes", type=int, default=1_000_000_000,
                     help="codes of the single-tree C5 block (0 = skip the block)")
     ap.add_argument("--c5-steps", type=int, default=3)

@@ -99,6 +99,13 @@ def lib():
     L.dpq_tree_copy.argtypes = [vp, C.c_char_p, vp]
     L.dpq_tree_free.argtypes = [vp]
     L.dpq_tree_free.restype = None
+    L.dpq_multi_open_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, C.POINTER(vp)]
+    L.dpq_multi_set_codebook.argtypes = [vp, vp, i32]
+    L.dpq_multi_search.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.dpq_multi_stat.restype = i64
+    L.dpq_multi_stat.argtypes = [vp, i32, C.c_char_p]
+    L.dpq_multi_close.argtypes = [vp]
+    L.dpq_multi_close.restype = None
     _lib = L
     return L
 
@@ -247,6 +254,39 @@ class DeltaTreeIndex:
             self.close()
         except Exception:
             pass
+
+
+class MultiIndex:
+    """dpq_multi_*: one process drives one subtree shard per GPU (devices 0..n_gpus-1), NCCL
+    all-gather of the key lists (libnccl bound at run time) + device merge: `deltapq -task query
+    -gpus N` without torch."""
+
+    def __init__(self, tree_path, M, K, n_gpus, qnode_path=None):
+        self.M, self.K, self.n_gpus = M, K, n_gpus
+        self._h = C.c_void_p()
+        _check(lib().dpq_multi_open_file(tree_path.encode(), qnode_path.encode() if qnode_path else None, M, K, n_gpus,
+                                         C.byref(self._h)))
+
+    def set_codebook(self, cw):
+        cw = np.ascontiguousarray(cw, np.float32)
+        _check(lib().dpq_multi_set_codebook(self._h, _ptr(cw), cw.shape[2]))
+
+    def search(self, queries, topk):
+        q = np.ascontiguousarray(queries, np.float32)
+        Q = q.shape[0]
+        pos = np.empty((Q, topk), np.uint32)
+        ids = np.empty((Q, topk), np.uint32)
+        dist = np.empty((Q, topk), np.float32)
+        _check(lib().dpq_multi_search(self._h, _ptr(q), Q, topk, _ptr(pos), _ptr(ids), _ptr(dist)))
+        return pos, ids, dist
+
+    def stat(self, rank, name):
+        return int(lib().dpq_multi_stat(self._h, rank, name.encode()))
+
+    def close(self):
+        if self._h:
+            lib().dpq_multi_close(self._h)
+            self._h = C.c_void_p()
 
 
 def adc_tables(cw, queries):

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -105,10 +106,11 @@ struct dpq_index {
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
     // scratch
-    DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_key, d_gthr;
+    DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_key, d_gthr, d_fpart;
     void* h_stage = nullptr;  // pinned staging for the host-buffer path
     size_t h_stage_cap = 0;
     bool host_keys = false;  // the caller's out_key is mapped HOST memory: keep intermediate key lists on the device
+    int64_t host_us[3] = {0, 0, 0};  // last dpq_index_search: enqueue, wait for the GPU, unpack (host wall clock)
     // stats
     int last_launches = 0;
     int64_t last_fallback = 0;
@@ -475,7 +477,8 @@ static int open_tree_shard_impl(dpq_tree* t, int rank, int n_ranks, int64_t firs
     if (g_device != t->device) return fail(DPQ_ERR_ARG, "dpq_index_open_tree_shard: the tree lives on another device");
     std::vector<int64_t> bounds, bytes;
     if ((rc = dpq::tree_shard_bounds(t, n_ranks, &bounds, &bytes))) return rc;
-    const int64_t lo = bounds[(size_t)rank], hi = bounds[(size_t)rank + 1];
+    int64_t lo = bounds[(size_t)rank], hi = bounds[(size_t)rank + 1];
+    if (hi == lo) lo = hi = n;  // an empty shard reports base_pos = n_codes like the stream reader (program.cpp)
     dpq_index* ix = new dpq_index();
     ix->device = g_device;
     dpq::ScanProgram& P = ix->prog;
@@ -623,6 +626,7 @@ static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk
     if ((rc = ix->d_flagged.ensure((size_t)Q * 4))) return rc;
     if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
     if ((rc = ix->d_ctrl.ensure(64))) return rc;
+    if ((rc = ix->d_fpart.ensure((size_t)Q * dpq::fallback_slices(topk) * topk * 8))) return rc;
     cudaStream_t st = ix->stream;
     uint32_t* ctrl = ix->d_ctrl.as<uint32_t>();
     {
@@ -728,9 +732,10 @@ static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk
     fb.M = P.M;
     fb.K = P.K;
     fb.topk = topk;
+    fb.part = ix->d_fpart.as<uint64_t>();
     fb.out_key = d_out_key;
     dpq::launch_fallback(fb, st);
-    launches += 3;
+    launches += 4;
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
     ix->last_launches = launches;
@@ -775,7 +780,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     ix->last_device_queries = Q;
     // geometry of the coarse passes: 112-query groups, 4 strands per warp
     const int warps8 = ix->opt_warps8;
-    const int bcap8 = ix->opt_bcap8 > 0 ? ix->opt_bcap8 : (P.shape.nf == 8 ? 512 : 2048);  // survivors per (slice, query)
+    const int bcap8 = ix->opt_bcap8 > 0 ? ix->opt_bcap8 : (P.shape.nf == 8 ? 512 : 4096);  // survivors per (slice, query)
     const bool seeded = coarse && (ix->opt_seed == 1 || (ix->opt_seed < 0 && P.shape.nf == 16));
     const int n_chunks_sample8 = (((ix->n_chunks + 3) / 4 + S - 1) / S) * 4;
     // second refinement level: a denser sampled coarse pass (stride S2 < S) under the first cap.  Long result
@@ -814,6 +819,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     if ((rc = ix->d_flagged.ensure((size_t)max_flagged * 4))) return rc;
     if ((rc = ix->d_ctrl.ensure(64))) return rc;
     if ((rc = ix->d_bound.ensure((size_t)Q * 4))) return rc;
+    if ((rc = ix->d_fpart.ensure((size_t)max_flagged * dpq::fallback_slices(topk) * topk * 8))) return rc;
     if (coarse) {
         const size_t items8 = (size_t)g8_groups * std::max(std::max(g8_slices, g8_slices_s), g8_slices_r);
         ix->last_items8 = (int64_t)g8_groups * g8_slices;
@@ -942,10 +948,11 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     fa.M = P.M;
     fa.K = P.K;
     fa.topk = topk;
+    fa.part = ix->d_fpart.as<uint64_t>();
     fa.out_key = d_out_key;
     if (!coarse) {
         dpq::launch_fallback(fa, st);
-        ++launches;
+        launches += 2;
     } else {
         dpq::Scan8Args s8;
         s8.codes = ix->d_codes.as<uint8_t>();
@@ -1035,7 +1042,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         fb.flagged = r8.flagged;
         fb.n_flagged = ctrl + 2;
         dpq::launch_fallback(fb, st);
-        launches += 4;
+        launches += 5;
     }
     CU(cudaEventRecord(ix->ev[3], st));
     CU(cudaGetLastError());
@@ -1096,6 +1103,7 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     // its arithmetic), the final re-score writes Q x k keys straight into the staging buffer, and the
     // call ends with ONE stream synchronisation -- the sub-batch pipeline this replaces (H2D || search
     // || D2H on two streams) lost more to four small searches than the overlap won.
+    const auto t_begin = std::chrono::steady_clock::now();
     const float* src = queries;
     void* dq = nullptr;
     cudaPointerAttributes pa;
@@ -1117,7 +1125,9 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     ix->host_keys = false;
     if (rc) return rc;
     CU(cudaMemcpyAsync(hc, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
+    const auto t_enq = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(ix->stream));  // the one host sync of the call
+    const auto t_sync = std::chrono::steady_clock::now();
     ix->last_fallback = (int64_t)hc[0] + hc[2];
     const int64_t base = ix->prog.base_pos;
     const bool map = ix->has_pos2id;
@@ -1138,6 +1148,13 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
         else
             for (size_t j = 0; j < nk; ++j) out_id[j] = (uint32_t)hk[j];
     }
+    const auto t_end = std::chrono::steady_clock::now();
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
+    };
+    ix->host_us[0] = us(t_begin, t_enq);
+    ix->host_us[1] = us(t_enq, t_sync);
+    ix->host_us[2] = us(t_sync, t_end);
     return DPQ_OK;
 }
 
@@ -1199,6 +1216,9 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
     if (n == "engine") return P.v2 ? 2 : 1;
     if (n == "last_coarse") return ix->last_coarse;
     if (n == "last_latency") return ix->last_latency;
+    if (n == "last_host_enqueue_us") return ix->host_us[0];
+    if (n == "last_host_wait_us") return ix->host_us[1];
+    if (n == "last_host_unpack_us") return ix->host_us[2];
     if (n == "last_device_queries") return ix->last_device_queries;
     if (n == "cand8_total") {  // developer statistic: coarse survivors of the last search
         if (!ix->last_coarse || !ix->d_cnt8.p) return -1;
@@ -1247,7 +1267,7 @@ void dpq_index_close(dpq_index* ix) {
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_cand1, &ix->d_cnt1, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
-                      &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_key,
+                      &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_key, &ix->d_fpart,
                       &ix->d_gthr})
         b->release();
     if (ix->h_stage) cudaFreeHost(ix->h_stage);

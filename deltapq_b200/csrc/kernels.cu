@@ -621,6 +621,8 @@ void launch_select(const SelectArgs& a, cudaStream_t st) {
 // whenever it is more than half full, and the k-th key becomes the new exclusive bound.
 constexpr int FB_T = 1024;  // FB_BUF (kernels.cuh) >= FB_T + 256 (topk <= 256)
 
+// grid = (slices, query slots): block (s, y) scans slice s of the shard for the flagged queries y, y + gridDim.y, ...
+// and leaves its k best keys in part[f][s][topk]; fallback_merge_kernel sorts a query's slices together.
 __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
     extern __shared__ __align__(16) unsigned char fb_smem[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(fb_smem);  // [FB_BUF]
@@ -629,7 +631,9 @@ __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
     __shared__ unsigned long long s_thr;
     const int n_flagged = min((int)*a.n_flagged, a.max_flagged);
     const int MK = a.M * a.K;
-    for (int f = blockIdx.x; f < n_flagged; f += gridDim.x) {
+    const int slice = blockIdx.x, n_slices = gridDim.x;
+    const int64_t lo = a.n_local * slice / n_slices, hi = a.n_local * (slice + 1) / n_slices;
+    for (int f = blockIdx.y; f < n_flagged; f += gridDim.y) {
         const uint32_t q = a.flagged[f];
         for (int i = threadIdx.x; i < MK; i += FB_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
         if (threadIdx.x == 0) {
@@ -638,9 +642,9 @@ __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
             s_thr = ((unsigned long long)__float_as_uint(a.bound[q]) << 32) | 0xFFFFFFFFull;
         }
         __syncthreads();
-        for (int64_t base = 0; base < a.n_local; base += FB_T) {
+        for (int64_t base = lo; base < hi; base += FB_T) {
             const int64_t i = base + threadIdx.x;
-            if (i < a.n_local) {
+            if (i < hi) {
                 const uint8_t* code = a.codes + (size_t)i * a.cstride;
                 double d = 0.0;
                 for (int m = 0; m < a.M; ++m) d += (double)s_lut[m * a.K + code[m]];
@@ -651,9 +655,32 @@ __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
             if (s_n > (uint32_t)(FB_BUF - FB_T)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
         }
         fb_compact(s_keys, &s_n, &s_thr, a.topk);
-        for (int i = threadIdx.x; i < a.topk; i += FB_T)
+        uint64_t* part = a.part + ((size_t)f * n_slices + slice) * a.topk;
+        for (int i = threadIdx.x; i < a.topk; i += FB_T) part[i] = i < (int)s_n ? s_keys[i] : ~0ull;
+        __syncthreads();
+    }
+}
+
+// one CTA per flagged query: the slices' k best keys (<= FB_BUF of them) sorted together -> out_key
+__global__ void __launch_bounds__(256) fallback_merge_kernel(const FallbackArgs a, int n_slices) {
+    __shared__ uint64_t s_keys[FB_BUF];
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_thr;
+    const int n_flagged = min((int)*a.n_flagged, a.max_flagged);
+    for (int f = blockIdx.x; f < n_flagged; f += gridDim.x) {
+        const uint32_t q = a.flagged[f];
+        const int total = n_slices * a.topk;
+        const uint64_t* part = a.part + (size_t)f * total;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) s_keys[i] = part[i];
+        if (threadIdx.x == 0) {
+            s_n = (uint32_t)total;  // empty slots are ~0 keys: they sort to the end
+            s_thr = ~0ull;
+        }
+        __syncthreads();
+        fb_compact(s_keys, &s_n, &s_thr, a.topk);
+        for (int i = threadIdx.x; i < a.topk; i += blockDim.x)
             a.out_key[(size_t)q * a.topk + i] =
-                i < (int)s_n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+                s_keys[i] != ~0ull ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
         __syncthreads();
     }
 }
@@ -717,9 +744,12 @@ void launch_rescore1(const Rescore1Args& a, cudaStream_t st) {
 void launch_fallback(const FallbackArgs& a, cudaStream_t st) {
     // Always enqueued: the kernel reads the flagged count on the device and exits at once when it
     // is zero, so the common path needs no host round trip.
+    // The shard is cut into slices so that a handful of flagged queries still fill the machine.
     const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
-    const int blocks = a.max_flagged < 296 ? a.max_flagged : 296;
-    fallback_kernel<<<blocks, FB_T, sm, st>>>(a);
+    const int n_slices = fallback_slices(a.topk);
+    const int qslots = a.max_flagged < 64 ? a.max_flagged : 64;
+    fallback_kernel<<<dim3((unsigned)n_slices, (unsigned)qslots), FB_T, sm, st>>>(a);
+    fallback_merge_kernel<<<a.max_flagged < 296 ? a.max_flagged : 296, 256, 0, st>>>(a, n_slices);
 }
 
 // ------------------------------------------------------------------------ merge --------

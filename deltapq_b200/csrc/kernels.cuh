@@ -295,8 +295,11 @@ struct FallbackArgs {
     int cstride;
     int64_t base_pos, n_local;
     int M, K, topk;
+    uint64_t* part;             // [max_flagged][fallback_slices(topk)][topk] per-slice results
     uint64_t* out_key;          // [Q][topk]
 };
+// slices of the exact fallback: as many as fit the merge buffer (slices x topk <= FB_BUF), at most 16
+inline int fallback_slices(int topk) { return topk >= 1 ? (FB_BUF / topk < 16 ? (FB_BUF / topk < 1 ? 1 : FB_BUF / topk) : 16) : 1; }
 void launch_fallback(const FallbackArgs& a, cudaStream_t st);
 
 void launch_merge(const uint64_t* d_keys, int n_lists, int Q, int topk, uint64_t* d_out,

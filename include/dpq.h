@@ -37,7 +37,9 @@ int dpq_set_device(int device);   /* device used by this host thread's calls and
  * already in host memory.  payload = the stream WITHOUT its 16-byte header, exactly what
  * query_processing_scan_compressed_codes_opt_in_memory (DCAT.h:3731) takes.  pos2id maps a
  * DFS position to the vector id (QNode.vec_id, DCAT.h:79) and may be NULL.
- * The tree is decoded once, re-laid out for the device and uploaded.
+ * The stream is uploaded and decoded ON THE GPU (program_dev.cu) into the device program: the
+ * nodes' codes by DFS position, 8 bytes per node at M <= 8 (16 at M <= 16).  DPQ_HOST_DECODE=1
+ * keeps the sequential host decoder.
  *
  * rank / n_ranks shard the tree by whole depth-1 subtrees balanced by stream bytes
  * (SURVEY 8e): rank r keeps only its subtrees, prefixed by the global root code; reported
@@ -46,11 +48,11 @@ int dpq_set_device(int device);   /* device used by this host thread's calls and
 int dpq_index_open(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
                    const uint32_t* pos2id, int rank, int n_ranks, dpq_index** out);
 
-/* One tree of a FOREST (the 1B-code layout): the code set is cut
- * into parts by vector id, every part gets its own DeltaTree (dpq_tree_build on the GPU that
- * will scan it -- the reference builds one tree, but a single global sort of 10^9 codes does
- * not shard), and the parts' local top-k lists merge with dpq_merge_topk_device exactly as
- * subtree shards do.  The whole tree is kept; first_pos is added to every position the index
+/* One tree of a FOREST: the code set is cut into parts by vector id, every part gets its own
+ * DeltaTree (dpq_tree_build on the GPU that will scan it), and the parts' local top-k lists
+ * merge with dpq_merge_topk_device exactly as subtree shards do.  (The reference builds ONE
+ * tree over all codes; so does dpq_tree_build_device + dpq_index_open_tree_shard below, which
+ * is what config C5 runs.  The forest is for code sets that arrive in pieces.)  The whole tree is kept; first_pos is added to every position the index
  * reports, so positions are unique across the forest (part p of equal parts: p * n_codes);
  * pos2id is this tree's own [n_codes] table (callers add the part's first vector id). */
 int dpq_index_open_part(const uint8_t* payload, int64_t n_bytes, int64_t n_codes, int M, int K,
@@ -93,8 +95,10 @@ int dpq_index_set_stream(dpq_index* idx, void* cuda_stream);
 
 /* Tuning knobs (optional): "slices", "warps", "slack" (extra candidates re-scored exactly),
  * "epoch", "trigger", "ramp" (candidate collection of the 15-bit scan); "coarse" (-1 auto, 0 off,
- * 1 on), "sample", "levels8", "bcap8", "warps8", "coarse_min" (coarse search); first-generation
- * engine only: "pack" (1 = 31-bit, 2 = 2x15-bit filter). */
+ * 1 on), "sample", "seed" (1: the sample pass is a coarse scan seeded by an exact presample),
+ * "refine" (stride of a second, denser sample pass), "levels8", "bcap8", "warps8", "coarse_min"
+ * (coarse search); "latency" (-1 auto, 0 off, 1 on: lanes = nodes scan for a handful of queries);
+ * first-generation engine only: "pack" (1 = 31-bit, 2 = 2x15-bit filter). */
 int dpq_index_set_option(dpq_index* idx, const char* name, int64_t value);
 
 /* Replaces the per-query loop dmain:328-344 calling
@@ -157,7 +161,8 @@ int dpq_free_host(void* hptr);
  * last search, CUDA events), "last_total_us"; "sum_scan_ns" / "sum_lut_ns" / "sum_total_ns" /
  * "timed_calls": the same summed over every search since set_option("timing_reset");
  * "last_coarse" (1 when the last search used the sample -> 8-bit coarse scan -> exact re-score
- * path), "last_scan8_us" / "sum_scan8_ns" (the coarse scan kernel alone), "engine". */
+ * path), "last_latency" (1: latency mode), "last_scan8_us" / "sum_scan8_ns" (the coarse scan kernel
+ * alone; in latency mode the full scan1 pass), "device_bytes_per_node", "engine". */
 int64_t dpq_index_stat(dpq_index* idx, const char* name);
 
 void dpq_index_close(dpq_index* idx);

@@ -656,3 +656,38 @@ def test_gpu_stream_decoder_equals_host_decoder(golden4000, golden1501, golden_m
     one = dpq.DeltaTreeIndex(np.arange(8, dtype=np.uint8), 1, 8, 256)
     assert one.stat("n_local") == 1
     one.close()
+
+
+def test_multi_index_single_gpu_and_probe(golden4000, tmp_path, engine):
+    """dpq_multi_* through ctypes with one GPU (the path `deltapq -task query -gpus N` and
+    bench.py's multi_cpp block use; with N > 1 it all-gathers over NCCL): equals the plain index."""
+    import json
+    import subprocess
+    import sys
+    import os
+    g = golden4000
+    n = int(g["n"])
+    tree, qnode = str(tmp_path / "tree.bin"), str(tmp_path / "qnodes.bin")
+    with open(tree, "wb") as f:
+        f.write(np.array([n, len(g["payload"])], np.int64).tobytes())
+        f.write(g["payload"].tobytes())
+    qn = np.zeros((n + 1, 60), np.uint8)
+    qn[:n, 0:4] = g["vec_id"].astype(np.uint32).view(np.uint8).reshape(-1, 4)
+    qn.tofile(qnode)
+    mx = dpq.MultiIndex(tree, 8, 256, 1, qnode_path=qnode)
+    mx.set_codebook(g["cw"])
+    pos, ids, dist = mx.search(g["queries"], 10)
+    assert mx.stat(0, "n_local") == n
+    mx.close()
+    ix = _open(g)
+    opos, oids, odist = ix.search(g["queries"], 10)
+    ix.close()
+    assert np.array_equal(pos, opos) and np.array_equal(ids, oids) and np.array_equal(dist, odist)
+    if engine == "v2":
+        np.savez(str(tmp_path / "multi_probe.npz"), cw=g["cw"], queries=g["queries"], topk=10, n_codes=n)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "multi_probe.py"), str(tmp_path), "1", "2"],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        assert out["equals_single_gpu"] and out["shard_nodes"] == [n]
