@@ -225,13 +225,15 @@ class DeltaTreeIndex:
     def stat(self, name):
         return int(lib().dpq_index_stat(self._h, name.encode()))
 
-    def search(self, queries, topk):
-        """Host buffers in, host buffers out: (pos [Q][k], id [Q][k], dist [Q][k])."""
+    def search(self, queries, topk, out=None):
+        """Host buffers in, host buffers out: (pos [Q][k], id [Q][k], dist [Q][k]).  out: a tuple of
+        caller-owned result arrays to fill (the C ABI's caller-owned buffers) instead of new ones."""
         q = np.ascontiguousarray(queries, np.float32)
         Q = q.shape[0]
-        pos = np.empty((Q, topk), np.uint32)
-        ids = np.empty((Q, topk), np.uint32)
-        dist = np.empty((Q, topk), np.float32)
+        if out is None:
+            out = (np.empty((Q, topk), np.uint32), np.empty((Q, topk), np.uint32), np.empty((Q, topk), np.float32))
+        pos, ids, dist = out
+        assert pos.shape == ids.shape == dist.shape == (Q, topk) and pos.flags.c_contiguous
         _check(lib().dpq_index_search(self._h, _ptr(q), Q, topk, _ptr(pos), _ptr(ids), _ptr(dist)))
         return pos, ids, dist
 

@@ -100,7 +100,7 @@ struct dpq_index {
                                // 1: exact presample -> sampled coarse scan -> re-score (wide shape default); -1: auto
     int opt_refine = -1;       // stride of a second, denser sampled coarse pass that tightens the cap before the
                                // full pass (0: none; -1 auto: 4 for the wide shape with topk > 32)
-    int opt_presample = 2048;  // nodes scored exactly per query to seed the sample pass
+    int opt_presample = 0;     // nodes scored exactly per query to seed the sample pass (0 auto: 2048, or 8192 for topk > 32)
     int opt_bcap8 = 0, opt_warps8 = 24, opt_levels8 = 80;  // bcap8 0 = auto (512 narrow, 2048 wide)
     int64_t opt_coarse_min = 100000;  // nodes in the shard from which the coarse search pays (gpurun_out/probe22.log)
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
@@ -586,7 +586,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "seed") ix->opt_seed = (int)v;
     else if (n == "refine") ix->opt_refine = (int)v;
     else if (n == "slices_s") ix->opt_slices_s = (int)v;
-    else if (n == "presample") ix->opt_presample = std::max(64, std::min(2048, (int)v));
+    else if (n == "presample") ix->opt_presample = v <= 0 ? 0 : std::max(64, std::min(8192, (int)v));
     else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
@@ -618,7 +618,7 @@ static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk
     const int ccap = 32768;
     int rc;
     if ((rc = ix->d_lutf.ensure((size_t)Q * MK * 4))) return rc;
-    if ((rc = ix->d_scale.ensure((size_t)((Q + 7) / 8) * 8 * 8 + 64))) return rc;
+    if ((rc = ix->d_scale.ensure((size_t)Q * 16 * 4 + 64))) return rc;
     if ((rc = ix->d_cand1.ensure((size_t)Q * ccap * 4))) return rc;
     if ((rc = ix->d_cnt1.ensure((size_t)Q * 8 * 2))) return rc;
     if ((rc = ix->d_cap0.ensure((size_t)Q * 4))) return rc;
@@ -642,8 +642,7 @@ static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk
     int launches = 0;
     CU(cudaEventRecord(ix->ev[0], st));
     CU(cudaMemsetAsync(ctrl, 0, 64, st));
-    dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(), ix->d_scale.as<double>(),
-                     nullptr, nullptr, nullptr, 0, P.shape, 0u, st);
+    dpq::launch_lut_small(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(), ix->d_scale.as<float>(), st);
     CU(cudaEventRecord(ix->ev[1], st));
     float* cap0 = ix->d_cap0.as<float>();
     float* cap1 = ix->d_cap1.as<float>();
@@ -655,7 +654,7 @@ static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk
     s1.n_local = P.n_local;
     s1.base_pos = (uint32_t)P.base_pos;
     s1.lutf = ix->d_lutf.as<float>();
-    s1.scale = ix->d_scale.as<double>();
+    s1.mmax = ix->d_scale.as<float>();
     s1.M = P.M;
     s1.K = P.K;
     s1.Q = Q;
@@ -988,7 +987,8 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         if (seeded) {
             // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the
             // sample (every S-th batch) -> exact re-score -> cap1 = the sample's k-th distance
-            dpq::launch_presample(se.lutf, se.codes, P.cstride, P.n_local, P.M, P.K, Q, topk, ix->opt_presample, cap0, st);
+            dpq::launch_presample(se.lutf, se.codes, P.cstride, P.n_local, P.M, P.K, Q, topk,
+                                  ix->opt_presample > 0 ? ix->opt_presample : (topk > 32 ? 8192 : 2048), cap0, st);
             dpq::launch_pack8(se.lutf, cap0, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
             s8.bt_stride = S;
             s8.n_slices = g8_slices_s;

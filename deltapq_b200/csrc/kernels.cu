@@ -566,8 +566,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectArgs
     for (int j = lane; j < n_sel; j += 32) {
         uint32_t pos = (uint32_t)s_sel[w][j];
         const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
-        double d = 0.0;
-        for (int m = 0; m < g.M; ++m) d += (double)lut[m * g.K + code[m]];
+        const double d = exact_dist(lut, code, a.cstride, g.M, g.K);
         s_exact[w][j] = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
     }
     __syncwarp();
@@ -646,8 +645,7 @@ __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
             const int64_t i = base + threadIdx.x;
             if (i < hi) {
                 const uint8_t* code = a.codes + (size_t)i * a.cstride;
-                double d = 0.0;
-                for (int m = 0; m < a.M; ++m) d += (double)s_lut[m * a.K + code[m]];
+                const double d = exact_dist(s_lut, code, a.cstride, a.M, a.K);
                 const uint64_t key = ((uint64_t)__float_as_uint((float)d) << 32) | (uint32_t)(i + a.base_pos);
                 if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;  // < FB_BUF: compacted above FB_BUF - FB_T
             }
@@ -686,7 +684,8 @@ __global__ void __launch_bounds__(256) fallback_merge_kernel(const FallbackArgs 
 }
 
 // Latency mode: exact re-score of scan1's candidate lists, one CTA per query (same running top-k).
-__global__ void __launch_bounds__(FB_T) rescore1_kernel(const Rescore1Args a) {
+constexpr int R1_T = 256;
+__global__ void __launch_bounds__(R1_T) rescore1_kernel(const Rescore1Args a) {
     extern __shared__ __align__(16) unsigned char fb_smem[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(fb_smem);   // [FB_BUF]
     float* s_lut = reinterpret_cast<float*>(s_keys + FB_BUF);  // [M*K]
@@ -694,7 +693,7 @@ __global__ void __launch_bounds__(FB_T) rescore1_kernel(const Rescore1Args a) {
     __shared__ unsigned long long s_thr;
     const int q = blockIdx.x;
     const int MK = a.M * a.K;
-    for (int i = threadIdx.x; i < MK; i += FB_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
+    for (int i = threadIdx.x; i < MK; i += R1_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
     if (threadIdx.x == 0) {
         s_n = 0u;
         s_thr = ~0ull;
@@ -702,23 +701,22 @@ __global__ void __launch_bounds__(FB_T) rescore1_kernel(const Rescore1Args a) {
     __syncthreads();
     const int total = (int)min(a.cand_cnt[q], (uint32_t)a.ccap);
     const uint32_t* cand = a.cand + (size_t)q * a.ccap;
-    for (int base = 0; base < total; base += FB_T) {
+    for (int base = 0; base < total; base += R1_T) {
         const int i = base + threadIdx.x;
         if (i < total) {
             const uint32_t pos = cand[i];
             const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
-            double d = 0.0;
-            for (int m = 0; m < a.M; ++m) d += (double)s_lut[m * a.K + code[m]];
+            const double d = exact_dist(s_lut, code, a.cstride, a.M, a.K);
             const uint64_t key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
             if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;
         }
         __syncthreads();
-        if (s_n > (uint32_t)(FB_BUF - FB_T)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
+        if (s_n > (uint32_t)max(256, 2 * a.topk)) fb_compact(s_keys, &s_n, &s_thr, a.topk);  // early: small sorts, tight bound
     }
     fb_compact(s_keys, &s_n, &s_thr, a.topk);
     const int n = (int)s_n;
     if (a.out_key)
-        for (int i = threadIdx.x; i < a.topk; i += FB_T)
+        for (int i = threadIdx.x; i < a.topk; i += R1_T)
             a.out_key[(size_t)q * a.topk + i] = i < n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
     if (threadIdx.x == 0) {
         // the k best found are real nodes: their k-th distance bounds the true k-th from above
@@ -738,7 +736,7 @@ __global__ void __launch_bounds__(FB_T) rescore1_kernel(const Rescore1Args a) {
 
 void launch_rescore1(const Rescore1Args& a, cudaStream_t st) {
     const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
-    rescore1_kernel<<<a.Q, FB_T, sm, st>>>(a);
+    rescore1_kernel<<<a.Q, R1_T, sm, st>>>(a);
 }
 
 void launch_fallback(const FallbackArgs& a, cudaStream_t st) {

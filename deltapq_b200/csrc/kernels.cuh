@@ -148,6 +148,9 @@ void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries
                  double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  const V2Shape& sh, uint32_t bound0, cudaStream_t st);
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
+// small batches: exact tables + per-subspace maxima mmax[Q][16], one block per (query, subspace)
+void launch_lut_small(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf, float* d_mmax,
+                      cudaStream_t st);
 // program_dev.cu: codes [n][M] -> padded code words [n][stride] (stride 8 or 16, pad bytes 0)
 cudaError_t launch_pad_codes(const uint8_t* codes, int64_t n, int M, int stride, uint8_t* out, cudaStream_t st);
 
@@ -250,6 +253,31 @@ struct SelectArgs {
 };
 void launch_select(const SelectArgs& a, cudaStream_t st);
 
+// Exact distance of one node in the reference's arithmetic: float table entries summed in double.
+// The node's code is fetched with ONE vector load when the stride is 8 or 16 bytes (the code-array
+// engine): sixteen byte loads per candidate, each lane on another line, made the exact kernels
+// L1-transaction bound (ncu launch list, round 2).
+__device__ __forceinline__ double exact_dist(const float* __restrict__ lut, const uint8_t* __restrict__ code, int cstride,
+                                             int M, int K) {
+    double d = 0.0;
+    if (cstride == 8) {
+        const uint2 w = *reinterpret_cast<const uint2*>(code);
+        const uint32_t ww[2] = {w.x, w.y};
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+            if (m < M) d += (double)lut[m * K + ((ww[m >> 2] >> (8 * (m & 3))) & 0xFFu)];
+    } else if (cstride == 16) {
+        const uint4 w = *reinterpret_cast<const uint4*>(code);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            if (m < M) d += (double)lut[m * K + ((ww[m >> 2] >> (8 * (m & 3))) & 0xFFu)];
+    } else {
+        for (int m = 0; m < M; ++m) d += (double)lut[m * K + code[m]];
+    }
+    return d;
+}
+
 // Block-wide running top-k used by the exact kernels (fallback, re-score): s_keys[0 .. *s_n) holds
 // candidate keys (distance bits << 32 | position, unique); the call sorts them (bitonic, whole CTA),
 // keeps the topk smallest and makes the k-th key the new exclusive bound *s_thr.  Every thread of
@@ -311,7 +339,7 @@ struct Scan1Args {
     int64_t n_local;
     uint32_t base_pos;
     const float* lutf;            // [Q][M*K] exact tables
-    const double* scale;          // [Q] 32751 / sum of the per-subspace maxima (lut2_kernel)
+    const float* mmax;            // [Q][16] per-subspace maxima of the tables (lut_small_kernel)
     const float* cap;             // [Q] inclusive distance bound (FLT_MAX: none)
     int M, K, Q;
     int n_pairs;                  // ceil(Q / 2): query pairs, each pair has its own CTAs

@@ -55,9 +55,15 @@ __global__ void __launch_bounds__(S1_T, 1) scan1_kernel(const Scan1Args a) {
     const int q0 = 2 * pair, q1 = 2 * pair + 1;
     const bool live1 = q1 < a.Q;
     const int MK = a.M * a.K;
-    // fixed-point scale of each query: scale2[q] = 32751 / sum of the per-subspace maxima (lut2_kernel)
-    const double sc0 = a.scale[q0] * (65500.0 / 32751.0);
-    const double sc1 = live1 ? a.scale[q1] * (65500.0 / 32751.0) : 0.0;
+    // fixed-point scale of each query: 65500 / sum of the per-subspace maxima, so that a node's M entries
+    // sum below 2^16 (+ M/2 of rounding)
+    auto scale_of = [&](int q) -> double {
+        double sum = 0.0;
+        for (int m = 0; m < a.M; ++m) sum += (double)a.mmax[q * 16 + m];
+        return sum > 0.0 ? 65500.0 / sum : 1.0;
+    };
+    const double sc0 = scale_of(q0);
+    const double sc1 = live1 ? scale_of(q1) : 0.0;
     for (int e = threadIdx.x; e < 2048; e += S1_T) {
         const int m = e >> 8, c = e & 255;
         uint32_t w = 0;

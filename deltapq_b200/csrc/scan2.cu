@@ -89,6 +89,36 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
     }
 }
 
+// Small batches (latency mode): one block per (query, subspace), so that even a single query spreads
+// over M SMs and the dependent accumulation chain is Ds long instead of M * Ds.  Same arithmetic.
+// mmax[q][16]: the per-subspace maxima (the fixed-point scale is derived from their sum).
+__global__ void __launch_bounds__(256) lut_small_kernel(const float* __restrict__ cw, int M, int K, int Ds,
+                                                        const float* __restrict__ queries, float* __restrict__ lutf,
+                                                        float* __restrict__ mmax) {
+    extern __shared__ float s_q[];  // [Ds]
+    __shared__ int s_max;
+    const int q = blockIdx.x, m = blockIdx.y, k = threadIdx.x;
+    const int D = M * Ds;
+    for (int i = k; i < Ds; i += blockDim.x) s_q[i] = queries[(size_t)q * D + m * Ds + i];
+    if (k == 0) s_max = 0;
+    __syncthreads();
+    float acc = 0.0f;
+    if (k < K) {
+        acc = adc_entry(cw + ((size_t)m * K + k) * Ds, s_q, Ds);
+        lutf[(size_t)q * M * K + m * K + k] = acc;
+    }
+    int vi = __float_as_int(acc);  // >= 0: integer order == float order
+    for (int o = 16; o; o >>= 1) vi = max(vi, __shfl_xor_sync(0xffffffffu, vi, o));
+    if ((k & 31) == 0) atomicMax(&s_max, vi);
+    __syncthreads();
+    if (k == 0) mmax[q * 16 + m] = __int_as_float(s_max);
+}
+
+void launch_lut_small(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf, float* d_mmax,
+                      cudaStream_t st) {
+    lut_small_kernel<<<dim3((unsigned)Q, (unsigned)M), 256, (size_t)Ds * sizeof(float), st>>>(d_cw, M, K, Ds, d_queries, d_lutf, d_mmax);
+}
+
 // Quantise + transpose into the scan layout [group][m * 256 + centroid][QB] u16; rows of subspaces
 // >= M or centroids >= K and queries >= Q are zero.  Block = 64 rows of one group; reads and writes are both coalesced.
 __global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lutf, const double* __restrict__ scale,

@@ -42,7 +42,7 @@ void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap,
 // One block per query: exact distances of R evenly strided nodes (the query's float table in
 // shared memory), then the k-th smallest by bisection on the float bit patterns (distances are
 // non-negative, so the integer order of the bits is the float order).
-constexpr int PS_T = 128;
+template <int PS_T>
 __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict__ lutf, const uint8_t* __restrict__ codes, int cstride,
                                                          int64_t n_local, int M, int K, int topk, int R,
                                                          float* __restrict__ cap) {
@@ -61,8 +61,7 @@ __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict
         v[t] = 0x7F800000u;  // +inf: never counted
         if (i < R && (int64_t)i * stride < n_local) {
             const uint8_t* c = codes + (size_t)((int64_t)i * stride) * cstride;
-            double d = 0.0;
-            for (int m = 0; m < M; ++m) d += (double)s_lut[m * K + c[m]];
+            const double d = exact_dist(s_lut, c, cstride, M, K);
             v[t] = __float_as_uint((float)d);
         }
     }
@@ -87,9 +86,14 @@ __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict
 }
 void launch_presample(const float* d_lutf, const uint8_t* d_codes, int cstride, int64_t n_local, int M, int K, int Q,
                       int topk, int R, float* d_cap, cudaStream_t st) {
-    if (R > PS_T * 16) R = PS_T * 16;
+    // 16 values per thread: 128 threads for R <= 2048, 512 threads up to 8192
     const size_t sm = (size_t)M * K * sizeof(float);
-    presample_kernel<<<Q, PS_T, sm, st>>>(d_lutf, d_codes, cstride, n_local, M, K, topk, R, d_cap);
+    if (R <= 128 * 16) {
+        presample_kernel<128><<<Q, 128, sm, st>>>(d_lutf, d_codes, cstride, n_local, M, K, topk, R, d_cap);
+    } else {
+        if (R > 512 * 16) R = 512 * 16;
+        presample_kernel<512><<<Q, 512, sm, st>>>(d_lutf, d_codes, cstride, n_local, M, K, topk, R, d_cap);
+    }
 }
 
 // Coarse tables [group][m * 256 + centroid][112 queries]: NIB = false: one byte per entry (112-byte
@@ -370,13 +374,14 @@ __global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
             const size_t item = (size_t)lo * a.n_groups + grp;
             const uint32_t pos = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - s_off[lo]));
             const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
-            double d = 0.0;
-            for (int m = 0; m < a.M; ++m) d += (double)s_lut[m * a.K + code[m]];
+            const double d = exact_dist(s_lut, code, a.cstride, a.M, a.K);
             const uint64_t key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
             if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;  // < FB_BUF: compacted above FB_BUF - R8_T
         }
         __syncthreads();
-        if (s_n > (uint32_t)(FB_BUF - R8_T)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
+        // compact early (a small sort) so that the k-th key becomes the bound soon: later candidates are
+        // then rejected by one compare instead of being stored and sorted
+        if (s_n > (uint32_t)max(256, 2 * a.topk)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
     }
     fb_compact(s_keys, &s_n, &s_thr, a.topk);
     const int n = (int)s_n, k = a.topk;
