@@ -109,7 +109,6 @@ struct dpq_index {
     DevBuf d_queries, d_lutf, d_scale, d_qlut, d_cand, d_cnt, d_flagged, d_ctrl, d_bound, d_key, d_gthr, d_fpart;
     void* h_stage = nullptr;  // pinned staging for the host-buffer path
     size_t h_stage_cap = 0;
-    bool host_keys = false;  // the caller's out_key is mapped HOST memory: keep intermediate key lists on the device
     int64_t host_us[3] = {0, 0, 0};  // last dpq_index_search: enqueue, wait for the GPU, unpack (host wall clock)
     // stats
     int last_launches = 0;
@@ -770,7 +769,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     // sample stride: a sparser sample is cheaper to scan but gives a looser cap (more coarse survivors to
     // re-score).  Measured optimum: 32 at 1M nodes (+2 % over 16; 64 is slower), 64 at 125M nodes (+9 %;
     // 256 overflows candidate lists): the sample keeps at least ~30K nodes (gpurun_out/b_opt.json runs).
-    const int S_auto = P.n_local >= 2000000 ? 64 : (P.n_local >= 1000000 ? 32 : (P.n_local >= 400000 ? 16 : 8));
+    int S_auto = P.n_local >= 2000000 ? 64 : (P.n_local >= 1000000 ? 32 : (P.n_local >= 400000 ? 16 : 8));
+    // wide shape, short lists: a denser sample (1M codes, M = 16, top-10: 2.42 ms at 16 vs 2.8 ms at 32)
+    if (P.shape.nf == 16 && topk <= 32 && S_auto > 16 && P.n_local < 2000000) S_auto = 16;
     const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : S_auto);
     const int n_chunks_sample = (((ix->n_chunks + spw - 1) / spw + S - 1) / S) * spw;  // chunks the sample pass walks
     int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
@@ -785,7 +786,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     // second refinement level: a denser sampled coarse pass (stride S2 < S) under the first cap.  Long result
     // lists need it: the cap of a 1/S sample is about the (k S)-th distance of the tree, and the coarse filter
     // passes a multiple of that many nodes (26K survivors per query at top-100, S = 32, M = 16).
-    int S2 = ix->opt_refine >= 0 ? ix->opt_refine : (P.shape.nf == 16 && topk > 32 ? 4 : 0);
+    int S2 = ix->opt_refine >= 0 ? ix->opt_refine : (P.shape.nf == 16 && topk > 32 ? 8 : 0);
     if (!coarse || S2 < 2 || S2 >= S) S2 = 0;
     const int n_chunks_refine8 = S2 ? (((ix->n_chunks + 3) / 4 + S2 - 1) / S2) * 4 : 0;
     int g8_groups = 0, g8_slices = 1, g8_slices_s = 1, g8_slices_r = 1;
@@ -917,10 +918,6 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     se.Q = Q;
     se.topk = topk;
     se.out_key = d_out_key;
-    if (coarse && ix->host_keys) {  // the sample's own top-k is scratch: keep it off PCIe
-        if ((rc = ix->d_key.ensure((size_t)Q * topk * 8))) return rc;
-        se.out_key = ix->d_key.as<uint64_t>();
-    }
     se.flagged = ix->d_flagged.as<uint32_t>();
     se.max_flagged = max_flagged;
     se.force_fallback = ix->opt_force_fallback;
@@ -1083,28 +1080,31 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
         ix->last_fallback = fb;
         return DPQ_OK;
     }
-    const size_t qbytes = (size_t)Q * D * 4, kbytes = (size_t)Q * topk * 8;
-    // pinned staging: [queries][keys][ctrl words]; a caller buffer that is already page-locked
-    // (dpq_malloc_host, cudaHostRegister) is used directly
-    if (ix->h_stage_cap < qbytes + kbytes + 256) {
+    const size_t qbytes = (size_t)Q * D * 4, nk = (size_t)Q * topk, kbytes = nk * 8;
+    // pinned, device-mapped staging: [queries][pos][id][dist][ctrl words]; a caller buffer that is
+    // already page-locked (dpq_malloc_host, cudaHostRegister) is read directly
+    const size_t need = qbytes + 3 * nk * 4 + 256;
+    if (ix->h_stage_cap < need) {
         if (ix->h_stage) cudaFreeHost(ix->h_stage);
         ix->h_stage = nullptr;
         ix->h_stage_cap = 0;
-        CU(cudaHostAlloc(&ix->h_stage, qbytes + kbytes + 256, cudaHostAllocMapped));
-        ix->h_stage_cap = qbytes + kbytes + 256;
+        CU(cudaHostAlloc(&ix->h_stage, need, cudaHostAllocMapped));
+        ix->h_stage_cap = need;
     }
     int rc;
-    float* hq = reinterpret_cast<float*>(ix->h_stage);
-    uint64_t* hk = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes);
-    uint32_t* hc = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes + kbytes);
-    // No copy engine in the way: the kernels read the queries from, and write the result keys to,
-    // page-locked HOST memory through its device mapping (unified addressing).  The ADC-table kernel
-    // pulls each query's D floats over PCIe exactly once while it computes (5 MB at C2, hidden behind
-    // its arithmetic), the final re-score writes Q x k keys straight into the staging buffer, and the
-    // call ends with ONE stream synchronisation -- the sub-batch pipeline this replaces (H2D || search
-    // || D2H on two streams) lost more to four small searches than the overlap won.
     const auto t_begin = std::chrono::steady_clock::now();
-    const float* src = queries;
+    float* hq = reinterpret_cast<float*>(ix->h_stage);
+    uint32_t* h_pos = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ix->h_stage) + qbytes);
+    uint32_t* h_id = h_pos + nk;
+    uint32_t* h_dist = h_id + nk;
+    uint32_t* hc = h_dist + nk;
+    // No copy engine in the way: the kernels read the queries from page-locked HOST memory through its
+    // device mapping (unified addressing) -- the ADC-table kernel pulls each query's D floats over PCIe
+    // exactly once while it computes -- and unpack_kernel writes positions, ids (pos2id lives on the
+    // device) and distances straight into the mapped staging buffer.  ONE stream synchronisation, then
+    // three sequential copies into the caller's arrays.  (The sub-batch pipeline H2D || search || D2H on
+    // two streams lost more to four small searches than the overlap won; the id translation on the host
+    // was a 100K-element random gather: 0.2-0.45 ms per 10K x 10 results.)
     void* dq = nullptr;
     cudaPointerAttributes pa;
     const bool pinned = cudaPointerGetAttributes(&pa, queries) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
@@ -1112,42 +1112,28 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     (void)cudaGetLastError();
     if (!pinned) {
         memcpy(hq, queries, qbytes);
-        src = hq;
         CU(cudaHostGetDevicePointer(&dq, hq, 0));
     }
-    (void)src;
-    void* dk = nullptr;
-    CU(cudaHostGetDevicePointer(&dk, hk, 0));
-    void* dc = nullptr;
-    CU(cudaHostGetDevicePointer(&dc, hc, 0));
-    ix->host_keys = true;  // the sample phase of the coarse search keeps its scratch keys on the device
-    rc = dpq_index_search_device(ix, reinterpret_cast<const float*>(dq), Q, topk, reinterpret_cast<uint64_t*>(dk));
-    ix->host_keys = false;
+    void* d_stage_out = nullptr;
+    CU(cudaHostGetDevicePointer(&d_stage_out, h_pos, 0));
+    if ((rc = ix->d_key.ensure(kbytes))) return rc;
+    const bool want_id = out_id != nullptr;
+    if (want_id && ix->has_pos2id && !ix->d_pos2id.p) {  // first host-buffer call: the id table moves to the device
+        if ((rc = ix->d_pos2id.ensure(std::max<size_t>(ix->pos2id_host.size(), 1) * 4))) return rc;
+        CU(cudaMemcpyAsync(ix->d_pos2id.p, ix->pos2id_host.data(), ix->pos2id_host.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+    }
+    rc = dpq_index_search_device(ix, reinterpret_cast<const float*>(dq), Q, topk, ix->d_key.as<uint64_t>());
     if (rc) return rc;
+    dpq::launch_unpack(ix->d_key.as<uint64_t>(), nk, want_id && ix->has_pos2id ? ix->d_pos2id.as<uint32_t>() : nullptr,
+                       (uint32_t)ix->prog.base_pos, reinterpret_cast<uint32_t*>(d_stage_out), ix->stream);
     CU(cudaMemcpyAsync(hc, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
     const auto t_enq = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(ix->stream));  // the one host sync of the call
     const auto t_sync = std::chrono::steady_clock::now();
     ix->last_fallback = (int64_t)hc[0] + hc[2];
-    const int64_t base = ix->prog.base_pos;
-    const bool map = ix->has_pos2id;
-    const uint32_t* p2i = ix->pos2id_host.data();
-    const size_t nk = (size_t)Q * topk;
-    if (out_pos)
-        for (size_t j = 0; j < nk; ++j) out_pos[j] = (uint32_t)hk[j];
-    if (out_dist) {
-        uint32_t* od = reinterpret_cast<uint32_t*>(out_dist);
-        for (size_t j = 0; j < nk; ++j) od[j] = (uint32_t)(hk[j] >> 32);
-    }
-    if (out_id) {
-        if (map)
-            for (size_t j = 0; j < nk; ++j) {
-                const uint32_t pos = (uint32_t)hk[j];
-                out_id[j] = pos != 0xFFFFFFFFu ? p2i[(size_t)(pos - base)] : pos;
-            }
-        else
-            for (size_t j = 0; j < nk; ++j) out_id[j] = (uint32_t)hk[j];
-    }
+    if (out_pos) memcpy(out_pos, h_pos, nk * 4);
+    if (out_id) memcpy(out_id, h_id, nk * 4);
+    if (out_dist) memcpy(out_dist, h_dist, nk * 4);
     const auto t_end = std::chrono::steady_clock::now();
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();

@@ -18,10 +18,11 @@ import datagen as dg  # noqa: E402
 import deltapq_b200 as dpq  # noqa: E402
 
 n_big = int(sys.argv[1]) if len(sys.argv) > 1 else 125_000_000
+only_big = len(sys.argv) > 2 and sys.argv[2] == "only_big"  # profiling runs: the big shard, Q = 2, latency mode only
 dev = torch.device("cuda", 0)
 cw = dg.roundtrip_codebook(dg.kmeans_codebook(dg.sift_like(20000, 128, seed=3), 8, 256, iters=6))
 queries = dg.sift_like(64, 128, seed=2)
-for n in (1_000_000, n_big):
+for n in ((n_big,) if only_big else (1_000_000, n_big)):
     codes = torch.empty((n, 8), dtype=torch.uint8, device=dev)
     B.gen_codes_device(torch, dpq, dev, cw, n, 1000, codes)
     tree = dpq.DeviceTree(codes.data_ptr(), n, 8, cw)
@@ -32,9 +33,9 @@ for n in (1_000_000, n_big):
     ix.set_codebook(cw)
     d_key = torch.empty((64, 10), dtype=torch.int64, device=dev)
     ref = {}
-    for mode in (1, 0):
+    for mode in ((1,) if only_big else (1, 0)):
         ix.set_option("latency", mode)
-        for Q in (1, 2, 4, 8, 16, 32):
+        for Q in ((2,) if only_big else (1, 2, 4, 8, 16, 32)):
             if mode == 1 and Q > 16:
                 continue
             d_q = torch.from_numpy(np.ascontiguousarray(queries[:Q])).to(dev)
