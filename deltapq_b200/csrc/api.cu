@@ -78,7 +78,7 @@ struct dpq_index {
     int Ds = 0;
     // device-resident tree
     DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_ovf;
-    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_cap0, d_cap1;
+    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_cap0, d_cap1, d_part8, d_done8;
     int last_coarse = 0;
     int last_device_queries = 0;  // queries of the last dpq_index_search_device call (a host-buffer search runs sub-batches)
     int64_t last_items8 = 0;
@@ -98,6 +98,7 @@ struct dpq_index {
     int opt_slices_s = 0;      // slices of the sample pass (0 = auto)
     int opt_seed = -1;         // 0: sampled 15-bit scan gives the cap (narrow shape default);
                                // 1: exact presample -> sampled coarse scan -> re-score (wide shape default); -1: auto
+    int opt_parts8 = 0;        // CTAs per query of the exact re-score (0 auto)
     int opt_refine = -1;       // stride of a second, denser sampled coarse pass that tightens the cap before the
                                // full pass (0: none; -1 auto: 4 for the wide shape with topk > 32)
     int opt_presample = 0;     // nodes scored exactly per query to seed the sample pass (0 auto: 2048, or 8192 for topk > 32)
@@ -584,6 +585,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "coarse_min") ix->opt_coarse_min = v;
     else if (n == "seed") ix->opt_seed = (int)v;
     else if (n == "refine") ix->opt_refine = (int)v;
+    else if (n == "parts8") ix->opt_parts8 = std::max(0, std::min(16, (int)v));
     else if (n == "slices_s") ix->opt_slices_s = (int)v;
     else if (n == "presample") ix->opt_presample = v <= 0 ? 0 : std::max(64, std::min(8192, (int)v));
     else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
@@ -797,6 +799,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         if (seeded) g8_slices_s = pick_slices(g8_groups, n_chunks_sample8, warps8 * 4, 96);
         if (S2) g8_slices_r = pick_slices(g8_groups, n_chunks_refine8, warps8 * 4, 96);
     }
+    // exact re-score: CTAs per query.  Long lists / the wide shape have thousands of survivors per query with a
+    // heavy tail: several CTAs per query (ranges of slices) and a last-arrival merge
+    const int r8_parts = !coarse ? 1 : (ix->opt_parts8 > 0 ? ix->opt_parts8 : ((P.shape.nf == 16 || topk > 32) ? 8 : 1));
     const size_t MK = (size_t)P.M * P.K;
     const size_t rows = (size_t)1 << g.rb;
     const size_t LW = 32 * (size_t)g.pack;
@@ -830,6 +835,12 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         if ((rc = ix->d_cnt8.ensure(items8 * c8.qb * 4))) return rc;
         if ((rc = ix->d_ovf8.ensure((size_t)g8_groups * c8.qb * 4))) return rc;
         if ((rc = ix->d_flagged2.ensure((size_t)max_flagged * 4))) return rc;
+        if (r8_parts > 1) {
+            if ((rc = ix->d_part8.ensure((size_t)Q * r8_parts * topk * 8))) return rc;
+            const bool fresh = ix->d_done8.cap < (size_t)Q * 4;
+            if ((rc = ix->d_done8.ensure((size_t)Q * 4))) return rc;
+            if (fresh) CU(cudaMemsetAsync(ix->d_done8.p, 0, ix->d_done8.cap, ix->stream));  // counters reset themselves afterwards
+        }
     }
     cudaStream_t st = ix->stream;
     // ctrl words: [0] queries flagged by select_kernel, [2] by the final rescore8_kernel,
@@ -981,6 +992,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         r8.K = P.K;
         r8.Q = Q;
         r8.topk = topk;
+        r8.part = ix->d_part8.as<uint64_t>();
+        r8.part_done = ix->d_done8.as<uint32_t>();
+        auto parts_for = [&](int slices) { return std::max(1, std::min(std::min(r8_parts, slices), std::max(1, 2048 / topk))); };
         if (seeded) {
             // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the
             // sample (every S-th batch) -> exact re-score -> cap1 = the sample's k-th distance
@@ -991,6 +1005,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             s8.n_slices = g8_slices_s;
             CU(dpq::launch_scan8(s8, st));
             r8.n_slices = g8_slices_s;
+            r8.n_parts = parts_for(g8_slices_s);
             r8.out_key = nullptr;
             r8.cap_in = cap0;
             r8.cap_out = cap1;
@@ -1008,6 +1023,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             s8.n_slices = g8_slices_r;
             CU(dpq::launch_scan8(s8, st));
             r8.n_slices = g8_slices_r;
+            r8.n_parts = parts_for(g8_slices_r);
             r8.out_key = nullptr;
             r8.cap_in = cap1;
             r8.cap_out = cap0;
@@ -1026,6 +1042,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         CU(dpq::launch_scan8(s8, st));
         CU(cudaEventRecord(ix->ev[5], st));
         r8.n_slices = g8_slices;
+        r8.n_parts = parts_for(g8_slices);
         r8.out_key = d_out_key;
         r8.cap_in = cap;
         r8.cap_out = nullptr;
@@ -1251,7 +1268,7 @@ void dpq_index_close(dpq_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_cand1, &ix->d_cnt1, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_cand1, &ix->d_cnt1, &ix->d_part8, &ix->d_done8, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
                       &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_key, &ix->d_fpart,
                       &ix->d_gthr})

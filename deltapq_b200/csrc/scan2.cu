@@ -335,9 +335,8 @@ __global__ void __launch_bounds__(512, 1) scan2_kernel(const Scan2Args a) {
 #pragma unroll 1
         for (int it = 0; it < C; ++it) {
             ++nix;
-            if ((it & (PF - 1)) == 0 && it + 3 * PF + 1 < n_nodes) {
-                prefetch_l2(codes + nix + 3 * PF);
-                prefetch_l1(codes + nix + PF);
+            if ((it & (PF - 1)) == 0) {  // warp-uniform: one L2 prefetch per 128-byte line of codes, three lines ahead
+                if (it + 3 * PF + 1 < n_nodes) prefetch_l2(codes + nix + 3 * PF);
             }
             nxt = CodeWord<NF>::zero();
             if (it + 1 < n_nodes) nxt = __ldg(codes + nix);

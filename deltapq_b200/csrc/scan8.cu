@@ -27,6 +27,7 @@
 // there are no epochs, barriers or compactions.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace dpq {
@@ -237,9 +238,8 @@ __global__ void __launch_bounds__(768, 1) scan8_kernel(const Scan8Args a) {
 #pragma unroll 1
         for (int it = 0; it < C; ++it) {
             ++nix;
-            if ((it & (PF - 1)) == 0 && it + 3 * PF + 1 < n_nodes) {
-                prefetch_l2(codes + nix + 3 * PF);
-                prefetch_l1(codes + nix + PF);
+            if ((it & (PF - 1)) == 0) {  // warp-uniform: one L2 prefetch per 128-byte line of codes, three lines ahead
+                if (it + 3 * PF + 1 < n_nodes) prefetch_l2(codes + nix + 3 * PF);
             }
             nxt = CodeWord<NF>::zero();
             if (it + 1 < n_nodes) nxt = __ldg(codes + nix);
@@ -333,27 +333,34 @@ __global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
     __shared__ uint32_t s_off[R8_MAXSL + 1];  // exclusive prefix of the per-slice counts
     __shared__ uint32_t s_n;
     __shared__ unsigned long long s_thr;
+    __shared__ int s_last;
     const int q = blockIdx.x;
+    // a query's candidate lists are cut into n_parts ranges of slices, one CTA each: candidate counts
+    // are heavy tailed (a query in a dense region passes 20x the average), and one CTA per query
+    // made the kernel wait for its slowest block
+    const int part = blockIdx.y, n_parts = gridDim.y;
+    const int sl_lo = a.n_slices * part / n_parts, sl_hi = a.n_slices * (part + 1) / n_parts;
+    const int n_sl = sl_hi - sl_lo;
     const int grp = q / a.qb, ql = q % a.qb;
     const int MK = a.M * a.K;
     for (int i = threadIdx.x; i < MK; i += R8_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
-    if (threadIdx.x < 32) {  // warp 0: counts of all slices, exclusive prefix
+    if (threadIdx.x < 32) {  // warp 0: counts of this part's slices, exclusive prefix
         const int lane = threadIdx.x;
         uint32_t run = 0;
-        for (int s0 = 0; s0 < a.n_slices; s0 += 32) {
+        for (int s0 = 0; s0 < n_sl; s0 += 32) {
             const int s = s0 + lane;
             uint32_t c = 0;
-            if (s < a.n_slices) c = a.cand_cnt[((size_t)s * a.n_groups + grp) * a.qb + ql];
+            if (s < n_sl) c = a.cand_cnt[((size_t)(sl_lo + s) * a.n_groups + grp) * a.qb + ql];
             uint32_t incl = c;
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            if (s < a.n_slices) s_off[s] = run + incl - c;
+            if (s < n_sl) s_off[s] = run + incl - c;
             run += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0) {
-            s_off[a.n_slices] = run;
+            s_off[n_sl] = run;
             s_n = 0u;
             // a valid cap known beforehand bounds the candidates worth keeping (inclusive, any position)
             const float cap = a.cap_in ? a.cap_in[q] : FLT_MAX;
@@ -361,22 +368,22 @@ __global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
         }
     }
     __syncthreads();
-    const int total = (int)s_off[a.n_slices];
+    const int total = (int)s_off[n_sl];
     for (int base = 0; base < total; base += R8_T) {
         const int i = base + threadIdx.x;
         if (i < total) {
-            int lo = 0, hi = a.n_slices;  // slice s with off[s] <= i < off[s+1]
+            int lo = 0, hi = n_sl;  // slice s with off[s] <= i < off[s+1]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (s_off[mid] <= (uint32_t)i) lo = mid;
                 else hi = mid;
             }
-            const size_t item = (size_t)lo * a.n_groups + grp;
+            const size_t item = (size_t)(sl_lo + lo) * a.n_groups + grp;
             const uint32_t pos = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - s_off[lo]));
             const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
             const double d = exact_dist(s_lut, code, a.cstride, a.M, a.K);
             const uint64_t key = ((uint64_t)__float_as_uint((float)d) << 32) | pos;
-            if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;  // < FB_BUF: compacted above FB_BUF - R8_T
+            if (key <= s_thr) s_keys[atomicAdd(&s_n, 1u)] = key;  // < FB_BUF: compacted well below FB_BUF - R8_T
         }
         __syncthreads();
         // compact early (a small sort) so that the k-th key becomes the bound soon: later candidates are
@@ -384,7 +391,38 @@ __global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
         if (s_n > (uint32_t)max(256, 2 * a.topk)) fb_compact(s_keys, &s_n, &s_thr, a.topk);
     }
     fb_compact(s_keys, &s_n, &s_thr, a.topk);
-    const int n = (int)s_n, k = a.topk;
+    const int k = a.topk;
+    if (n_parts > 1) {
+        // leave this part's k best in the scratch list; the last CTA of the query to arrive merges them
+        uint64_t* mine = a.part + ((size_t)q * n_parts + part) * k;
+        for (int i = threadIdx.x; i < k; i += R8_T) mine[i] = i < (int)s_n ? s_keys[i] : ~0ull;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&a.part_done[q], 1u) == (uint32_t)(n_parts - 1);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const uint64_t* all = a.part + (size_t)q * n_parts * k;
+        for (int i = threadIdx.x; i < n_parts * k; i += R8_T) s_keys[i] = __ldcg(all + i);
+        if (threadIdx.x == 0) {
+            s_n = (uint32_t)(n_parts * k);  // empty slots are ~0 keys: they sort to the end
+            s_thr = ~0ull;
+            a.part_done[q] = 0u;  // ready for the next pass
+        }
+        __syncthreads();
+        fb_compact(s_keys, &s_n, &s_thr, k);
+    }
+    int n = (int)s_n;
+    if (n_parts > 1) {  // count the real keys among the k kept
+        __shared__ int s_real;
+        if (threadIdx.x == 0) s_real = 0;
+        __syncthreads();
+        int c = 0;
+        for (int i = threadIdx.x; i < n; i += R8_T) c += s_keys[i] != ~0ull;
+        if (c) atomicAdd(&s_real, c);
+        __syncthreads();
+        n = s_real;
+    }
     if (a.out_key)
         for (int i = threadIdx.x; i < k; i += R8_T)
             a.out_key[(size_t)q * k + i] = i < n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
@@ -408,7 +446,7 @@ __global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
 
 void launch_rescore8(const Rescore8Args& a, cudaStream_t st) {
     const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
-    rescore8_kernel<<<a.Q, R8_T, sm, st>>>(a);
+    rescore8_kernel<<<dim3((unsigned)a.Q, (unsigned)std::max(1, a.n_parts)), R8_T, sm, st>>>(a);
 }
 
 }  // namespace dpq
