@@ -101,7 +101,7 @@ struct dpq_index {
     int opt_parts8 = 0;        // CTAs per query of the exact re-score (0 auto)
     int opt_refine = -1;       // stride of a second, denser sampled coarse pass that tightens the cap before the
                                // full pass (0: none; -1 auto: 4 for the wide shape with topk > 32)
-    int opt_presample = 0;     // nodes scored exactly per query to seed the sample pass (0 auto: 2048, or 8192 for topk > 32)
+    int opt_presample = 0;     // nodes scored exactly per query to seed the sample pass (0 auto: 2048, or 4096 for topk > 32)
     int opt_bcap8 = 0, opt_warps8 = 24, opt_levels8 = 80;  // bcap8 0 = auto (512 narrow, 2048 wide)
     int64_t opt_coarse_min = 100000;  // nodes in the shard from which the coarse search pays (gpurun_out/probe22.log)
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
@@ -598,7 +598,9 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
 static int pick_slices(int n_groups, int n_chunks, int chunks_per_round, int max_slices) {
     double best = -1.0;
     int pick = 1;
-    for (int s = 1; s <= max_slices && s <= std::max(1, n_chunks / chunks_per_round); ++s) {
+    // an item is at least a quarter round: sampled passes are small, and an SM without a CTA costs more than a
+    // partly filled round (ncu: the 1/32 sample pass of the wide shape ran on 54 of 148 SMs)
+    for (int s = 1; s <= max_slices && s <= std::max(1, 4 * n_chunks / chunks_per_round); ++s) {
         const int64_t items = (int64_t)n_groups * s;
         const int64_t waves = (items + 147) / 148;
         const double cpi = (double)n_chunks / s;
@@ -673,6 +675,15 @@ static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk
     r1.K = P.K;
     r1.Q = Q;
     r1.topk = topk;
+    r1.n_parts = std::max(1, std::min(16, 2048 / topk));
+    {
+        if ((rc = ix->d_part8.ensure((size_t)Q * r1.n_parts * topk * 8))) return rc;
+        const bool fresh = ix->d_done8.cap < (size_t)Q * 4;
+        if ((rc = ix->d_done8.ensure((size_t)Q * 4))) return rc;
+        if (fresh) CU(cudaMemsetAsync(ix->d_done8.p, 0, ix->d_done8.cap, st));
+    }
+    r1.part = ix->d_part8.as<uint64_t>();
+    r1.part_done = ix->d_done8.as<uint32_t>();
     const int64_t n_chunks = (P.n_local + 2047) / 2048;
     auto ranges_for = [&](int64_t chunks) { return (int)std::max<int64_t>(1, std::min<int64_t>(chunks, 148 / s1.n_pairs)); };
     CU(cudaMemsetAsync(cnt, 0, (size_t)Q * 16, st));
@@ -999,7 +1010,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the
             // sample (every S-th batch) -> exact re-score -> cap1 = the sample's k-th distance
             dpq::launch_presample(se.lutf, se.codes, P.cstride, P.n_local, P.M, P.K, Q, topk,
-                                  ix->opt_presample > 0 ? ix->opt_presample : (topk > 32 ? 8192 : 2048), cap0, st);
+                                  ix->opt_presample > 0 ? ix->opt_presample : (topk > 32 ? 4096 : 2048), cap0, st);
             dpq::launch_pack8(se.lutf, cap0, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
             s8.bt_stride = S;
             s8.n_slices = g8_slices_s;

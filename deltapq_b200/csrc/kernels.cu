@@ -683,7 +683,9 @@ __global__ void __launch_bounds__(256) fallback_merge_kernel(const FallbackArgs 
     }
 }
 
-// Latency mode: exact re-score of scan1's candidate lists, one CTA per query (same running top-k).
+// Latency mode: exact re-score of scan1's candidate lists.  A query's list is cut into gridDim.y ranges, one
+// CTA each (a handful of queries must still fill the machine); the last CTA of a query to arrive merges the
+// ranges' k best (same running top-k).
 constexpr int R1_T = 256;
 __global__ void __launch_bounds__(R1_T) rescore1_kernel(const Rescore1Args a) {
     extern __shared__ __align__(16) unsigned char fb_smem[];
@@ -691,19 +693,22 @@ __global__ void __launch_bounds__(R1_T) rescore1_kernel(const Rescore1Args a) {
     float* s_lut = reinterpret_cast<float*>(s_keys + FB_BUF);  // [M*K]
     __shared__ uint32_t s_n;
     __shared__ unsigned long long s_thr;
-    const int q = blockIdx.x;
+    __shared__ int s_last, s_real;
+    const int q = blockIdx.x, part = blockIdx.y, n_parts = gridDim.y;
     const int MK = a.M * a.K;
     for (int i = threadIdx.x; i < MK; i += R1_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
     if (threadIdx.x == 0) {
         s_n = 0u;
         s_thr = ~0ull;
+        s_real = 0;
     }
     __syncthreads();
     const int total = (int)min(a.cand_cnt[q], (uint32_t)a.ccap);
+    const int lo = (int)((int64_t)total * part / n_parts), hi = (int)((int64_t)total * (part + 1) / n_parts);
     const uint32_t* cand = a.cand + (size_t)q * a.ccap;
-    for (int base = 0; base < total; base += R1_T) {
+    for (int base = lo; base < hi; base += R1_T) {
         const int i = base + threadIdx.x;
-        if (i < total) {
+        if (i < hi) {
             const uint32_t pos = cand[i];
             const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
             const double d = exact_dist(s_lut, code, a.cstride, a.M, a.K);
@@ -714,13 +719,37 @@ __global__ void __launch_bounds__(R1_T) rescore1_kernel(const Rescore1Args a) {
         if (s_n > (uint32_t)max(256, 2 * a.topk)) fb_compact(s_keys, &s_n, &s_thr, a.topk);  // early: small sorts, tight bound
     }
     fb_compact(s_keys, &s_n, &s_thr, a.topk);
-    const int n = (int)s_n;
+    const int k = a.topk;
+    if (n_parts > 1) {
+        uint64_t* mine = a.part + ((size_t)q * n_parts + part) * k;
+        for (int i = threadIdx.x; i < k; i += R1_T) mine[i] = i < (int)s_n ? s_keys[i] : ~0ull;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&a.part_done[q], 1u) == (uint32_t)(n_parts - 1);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const uint64_t* all = a.part + (size_t)q * n_parts * k;
+        for (int i = threadIdx.x; i < n_parts * k; i += R1_T) s_keys[i] = __ldcg(all + i);
+        if (threadIdx.x == 0) {
+            s_n = (uint32_t)(n_parts * k);  // empty slots are ~0 keys: they sort to the end
+            s_thr = ~0ull;
+            a.part_done[q] = 0u;
+        }
+        __syncthreads();
+        fb_compact(s_keys, &s_n, &s_thr, k);
+    }
+    int c = 0;
+    for (int i = threadIdx.x; i < (int)s_n; i += R1_T) c += s_keys[i] != ~0ull;
+    if (c) atomicAdd(&s_real, c);
+    __syncthreads();
+    const int n = s_real;
     if (a.out_key)
-        for (int i = threadIdx.x; i < a.topk; i += R1_T)
-            a.out_key[(size_t)q * a.topk + i] = i < n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+        for (int i = threadIdx.x; i < k; i += R1_T)
+            a.out_key[(size_t)q * k + i] = i < n ? s_keys[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
     if (threadIdx.x == 0) {
         // the k best found are real nodes: their k-th distance bounds the true k-th from above
-        const float found = n >= a.topk ? __uint_as_float((uint32_t)(s_keys[a.topk - 1] >> 32)) : FLT_MAX;
+        const float found = n >= k ? __uint_as_float((uint32_t)(s_keys[k - 1] >> 32)) : FLT_MAX;
         const float known = a.cap_in ? a.cap_in[q] : FLT_MAX;
         const float cap = fminf(found, known);
         if (a.cap_out) a.cap_out[q] = cap;
@@ -736,7 +765,7 @@ __global__ void __launch_bounds__(R1_T) rescore1_kernel(const Rescore1Args a) {
 
 void launch_rescore1(const Rescore1Args& a, cudaStream_t st) {
     const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
-    rescore1_kernel<<<a.Q, R1_T, sm, st>>>(a);
+    rescore1_kernel<<<dim3((unsigned)a.Q, (unsigned)(a.n_parts > 1 ? a.n_parts : 1)), R1_T, sm, st>>>(a);
 }
 
 void launch_fallback(const FallbackArgs& a, cudaStream_t st) {

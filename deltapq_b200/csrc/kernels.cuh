@@ -376,6 +376,9 @@ struct Rescore1Args {
     uint32_t* n_flagged;
     int max_flagged;
     float* bound;                 // [Q] bound for the fallback
+    int n_parts;                  // CTAs per query (ranges of the candidate list); n_parts * topk <= FB_BUF
+    uint64_t* part;               // [Q][n_parts][topk]
+    uint32_t* part_done;          // [Q] zeroed arrival counters (self-resetting)
 };
 void launch_rescore1(const Rescore1Args& a, cudaStream_t st);
 
