@@ -222,16 +222,30 @@ struct Rescore8Args {
 };
 void launch_rescore8(const Rescore8Args& a, cudaStream_t st);
 
+// Rounds a non-negative double to the nearest float (ties to even) WITHOUT leaving the double domain:
+// adding and subtracting 2^(E+29), E = the operand's exponent, drops exactly the 29 mantissa bits a float
+// lacks, with the double adder's own round-to-nearest-even.  Two DADD + a few integer ops instead of the
+// F2F.F32.F64 / F2F.F64.F32 pair, which run at a quarter of the FP64 add rate and bound the ADC-table
+// kernel.  Zero, float subnormals and the top binade (where the float conversion may overflow) take the
+// conversion itself.
+__device__ __forceinline__ double round_to_float_in_double(double s) {
+    const int e = __double2hiint(s) & 0x7FF00000;
+    if ((unsigned)(e - 0x38100000) <= (unsigned)(0x47D00000 - 0x38100000)) {  // 2^-126 <= s < 2^127
+        const double c = __hiloint2double(e + (29 << 20), 0);
+        return __dsub_rn(__dadd_rn(s, c), c);
+    }
+    return (double)(float)s;
+}
+
 // One ADC table entry in the reference's arithmetic (DCAT.h:3754-3757): float accumulator,
 // each term the double square of the float difference, rounded back to float after every add.
 __device__ __forceinline__ float adc_entry(const float* __restrict__ c, const float* q, int Ds) {
-    float acc = 0.0f;
+    double acc = 0.0;  // always holds a float-representable value
     for (int d = 0; d < Ds; ++d) {
-        float diff = __fsub_rn(c[d], q[d]);
-        double t = __dmul_rn((double)diff, (double)diff);
-        acc = (float)__dadd_rn((double)acc, t);
+        const double diff = (double)__fsub_rn(c[d], q[d]);
+        acc = round_to_float_in_double(__dadd_rn(acc, __dmul_rn(diff, diff)));
     }
-    return acc;
+    return (float)acc;
 }
 
 struct SelectArgs {

@@ -60,18 +60,23 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
     __syncthreads();
     for (int m = 0; m < M; ++m) {
         float acc[LUT2_QPB];
+        {
+            double accd[LUT2_QPB];  // float-representable at every step (round_to_float_in_double)
 #pragma unroll
-        for (int j = 0; j < LUT2_QPB; ++j) acc[j] = 0.0f;
-        if (k < K) {
-            const float* c = cw + ((size_t)m * K + k) * Ds;
-            for (int d = 0; d < Ds; ++d) {
-                const float cv = c[d];
+            for (int j = 0; j < LUT2_QPB; ++j) accd[j] = 0.0;
+            if (k < K) {
+                const float* c = cw + ((size_t)m * K + k) * Ds;
+                for (int d = 0; d < Ds; ++d) {
+                    const float cv = c[d];
 #pragma unroll
-                for (int j = 0; j < LUT2_QPB; ++j) {
-                    const float diff = __fsub_rn(cv, s_q[j * D + m * Ds + d]);
-                    acc[j] = (float)__dadd_rn((double)acc[j], __dmul_rn((double)diff, (double)diff));
+                    for (int j = 0; j < LUT2_QPB; ++j) {
+                        const double diff = (double)__fsub_rn(cv, s_q[j * D + m * Ds + d]);
+                        accd[j] = round_to_float_in_double(__dadd_rn(accd[j], __dmul_rn(diff, diff)));
+                    }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < LUT2_QPB; ++j) acc[j] = (float)accd[j];
         }
 #pragma unroll
         for (int j = 0; j < LUT2_QPB; ++j) {
