@@ -381,7 +381,7 @@ def run_gpu(args):
                 del qn
                 np.savez(os.path.join(tmpd, "multi_probe.npz"), cw=cw, queries=queries0, topk=k, n_codes=args.n_codes)
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "multi_probe.py"), tmpd, str(world), "5"],
-                                   capture_output=True, text=True, timeout=240)
+                                   capture_output=True, text=True, timeout=420)
                 last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
                 multi_cpp = json.loads(last[-1]) if last else {"error": (r.stderr or r.stdout)[-300:], "rc": r.returncode}
             except Exception as e:  # recorded, never fatal

@@ -99,6 +99,7 @@ struct dpq_index {
     int opt_seed = -1;         // 0: sampled 15-bit scan gives the cap (narrow shape default);
                                // 1: exact presample -> sampled coarse scan -> re-score (wide shape default); -1: auto
     int opt_parts8 = 0;        // CTAs per query of the exact re-score (0 auto)
+    int opt_warp_rescore = -1; // -1 auto (narrow shape, topk <= 32), 0 / 1: warp-per-query form of the exact re-score
     int opt_refine = -1;       // stride of a second, denser sampled coarse pass that tightens the cap before the
                                // full pass (0: none; -1 auto: 4 for the wide shape with topk > 32)
     int opt_presample = 0;     // nodes scored exactly per query to seed the sample pass (0 auto: 2048, or 4096 for topk > 32)
@@ -586,6 +587,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "seed") ix->opt_seed = (int)v;
     else if (n == "refine") ix->opt_refine = (int)v;
     else if (n == "parts8") ix->opt_parts8 = std::max(0, std::min(16, (int)v));
+    else if (n == "warp_rescore") ix->opt_warp_rescore = (int)v;
     else if (n == "slices_s") ix->opt_slices_s = (int)v;
     else if (n == "presample") ix->opt_presample = v <= 0 ? 0 : std::max(64, std::min(8192, (int)v));
     else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
@@ -1005,6 +1007,7 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         r8.topk = topk;
         r8.part = ix->d_part8.as<uint64_t>();
         r8.part_done = ix->d_done8.as<uint32_t>();
+        r8.warp_form = ix->opt_warp_rescore >= 0 ? ix->opt_warp_rescore : (P.shape.nf == 8 ? 1 : 0);
         auto parts_for = [&](int slices) { return std::max(1, std::min(std::min(r8_parts, slices), std::max(1, 2048 / topk))); };
         if (seeded) {
             // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the

@@ -216,6 +216,7 @@ struct Rescore8Args {
     uint32_t* n_flagged;
     int max_flagged;
     float* bound;                 // [Q] exact distance bound for the fallback
+    int warp_form;                // 1: short lists may take the warp-per-query kernel (narrow shape, few survivors)
     int n_parts;                  // CTAs per query (ranges of slices); > 1: part / part_done scratch is used
     uint64_t* part;               // [Q][n_parts][topk] per-part results (n_parts * topk <= FB_BUF)
     uint32_t* part_done;          // [Q] zeroed arrival counters (the last CTA of a query merges and resets its counter)
