@@ -229,13 +229,16 @@ void launch_rescore8(const Rescore8Args& a, cudaStream_t st);
 // F2F.F32.F64 / F2F.F64.F32 pair, which run at a quarter of the FP64 add rate and bound the ADC-table
 // kernel.  Zero, float subnormals and the top binade (where the float conversion may overflow) take the
 // conversion itself.
+// (the conversion path is a real call: inlined, the compiler if-converts the branch and executes both
+// paths for every term -- ncu showed three F2F per term again)
+static __device__ __noinline__ double round_to_float_by_conversion(double s) { return (double)(float)s; }
 __device__ __forceinline__ double round_to_float_in_double(double s) {
     const int e = __double2hiint(s) & 0x7FF00000;
     if ((unsigned)(e - 0x38100000) <= (unsigned)(0x47D00000 - 0x38100000)) {  // 2^-126 <= s < 2^127
         const double c = __hiloint2double(e + (29 << 20), 0);
         return __dsub_rn(__dadd_rn(s, c), c);
     }
-    return (double)(float)s;
+    return round_to_float_by_conversion(s);
 }
 
 // One ADC table entry in the reference's arithmetic (DCAT.h:3754-3757): float accumulator,

@@ -7,6 +7,8 @@
 // NCCL is bound at run time (dlopen "libnccl.so.2"), so libdpq.so has no link-time dependency on
 // it and single-GPU users never load it.
 #include <cuda_runtime.h>
+
+#include <chrono>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -38,9 +40,12 @@ struct Nccl {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string load() {
         if (lib) return std::string();
+        // DPQ_NCCL_LIB names a specific library (e.g. the copy a framework already ships); else the system one
+        const char* env = getenv("DPQ_NCCL_LIB");
+        if (env && env[0]) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (lib) break;
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
         }
         if (!lib) return std::string("cannot load libnccl.so.2: ") + dlerror();
 #define DPQ_SYM(field, sym)                                                  \
@@ -73,6 +78,7 @@ struct dpq_multi {
     void* h_stage = nullptr;
     size_t h_cap = 0;
     std::vector<uint32_t> pos2id;  // position -> vector id over the whole position space
+    int64_t open_us = 0, nccl_us = 0;  // wall time of opening the shards / of ncclCommInitAll
 };
 
 #define CUM(call)                                                                                   \
@@ -135,7 +141,9 @@ int finish_multi_open(dpq_multi* m) {
         m->comm.assign((size_t)n_gpus, nullptr);
         std::vector<int> devs((size_t)n_gpus);
         for (int r = 0; r < n_gpus; ++r) devs[(size_t)r] = r;
+        const auto t0 = std::chrono::steady_clock::now();
         ncclResult_t r_ = g_nccl.CommInitAll(m->comm.data(), n_gpus, devs.data());
+        m->nccl_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
         if (r_ != 0) {
             m->comm.clear();
             return dpq::api_fail(DPQ_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r_));
@@ -172,6 +180,7 @@ int dpq_multi_open_file(const char* tree_path, const char* qnode_path, int M, in
     dpq_multi* m = nullptr;
     int rc = begin_multi_open(n_gpus, n_gpus, M, K, &m);
     if (rc) return rc;
+    const auto t_open0 = std::chrono::steady_clock::now();
     {
         // one host thread per shard: the stream decode is sequential (seconds per 10^8 nodes), the
         // shards are independent and the device selection is per thread, so the open takes one decode
@@ -195,6 +204,7 @@ int dpq_multi_open_file(const char* tree_path, const char* qnode_path, int M, in
         for (int r = 0; r < n_gpus && !rc; ++r)
             if (rcs[(size_t)r]) rc = dpq::api_fail(rcs[(size_t)r], errs[(size_t)r]);
     }
+    m->open_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_open0).count();
     if (!rc) rc = finish_multi_open(m);
     if (!rc && qnode_path) {
         const int64_t n_codes = dpq_index_stat(m->ix[0], "n_codes");
@@ -378,6 +388,8 @@ int dpq_multi_search(dpq_multi* m, const float* queries, int Q, int topk, uint32
 }
 
 int64_t dpq_multi_stat(dpq_multi* m, int rank, const char* name) {
+    if (m && name && std::string(name) == "multi_nccl_init_us") return m->nccl_us;
+    if (m && name && std::string(name) == "multi_open_us") return m->open_us;
     if (!m || rank < 0 || rank >= (int)m->ix.size()) return -1;
     return dpq_index_stat(m->ix[(size_t)rank], name);
 }

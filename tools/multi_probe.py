@@ -31,6 +31,7 @@ def main():
         pos, ids, dist = mx.search(queries, k)
     dt = (time.perf_counter() - t0) / steps
     shard_nodes = [mx.stat(r, "n_local") for r in range(n_gpus)]
+    open_parts = {"shards_open_s": round(mx.stat(0, "multi_open_us") / 1e6, 2), "nccl_comm_init_s": round(mx.stat(0, "multi_nccl_init_us") / 1e6, 2)}
     mx.close()
     dpq.set_device(0)
     one = dpq.DeltaTreeIndex.from_file(tree, 8, 256, qnode_path=qnode)
@@ -38,7 +39,7 @@ def main():
     opos, oids, odist = one.search(queries, k)
     one.close()
     same = bool(np.array_equal(pos, opos) and np.array_equal(dist, odist) and np.array_equal(ids, oids))
-    print(json.dumps({"n_gpus": n_gpus, "queries": int(len(queries)), "topk": k, "n_codes": n, "open_s": round(open_s, 2),
+    print(json.dumps({"n_gpus": n_gpus, "queries": int(len(queries)), "topk": k, "n_codes": n, "open_s": round(open_s, 2), "open_breakdown": open_parts,
                       "ms_per_call_host_buffers": dt * 1e3, "queries_per_s": len(queries) / dt,
                       "shard_nodes": shard_nodes, "equals_single_gpu": same,
                       "path": "dpq_multi_open_file / dpq_multi_search (C++ host, NCCL via dlopen, no torch)"}))
