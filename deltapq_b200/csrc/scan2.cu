@@ -47,36 +47,71 @@ constexpr int LUT2_QPB = 8;
 __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw, int M, int K, int Ds,
                                                    const float* __restrict__ queries, int Q,
                                                    float* __restrict__ lutf, double* __restrict__ scale) {
-    extern __shared__ float s_q[];  // [LUT2_QPB][M*Ds]
+    extern __shared__ __align__(16) float s_q[];  // [M*Ds][LUT2_QPB]: the eight queries' values of one dimension are adjacent
     __shared__ int s_max[LUT2_QPB][16];
     const int q0 = blockIdx.x * LUT2_QPB;
     const int k = threadIdx.x;
     const int D = M * Ds;
     for (int i = k; i < LUT2_QPB * D; i += blockDim.x) {
-        const int q = q0 + i / D;
-        s_q[i] = q < Q ? queries[(size_t)q * D + i % D] : 0.0f;
+        const int j = i / D, d = i % D;  // coalesced global read, transposed store
+        const int q = q0 + j;
+        s_q[d * LUT2_QPB + j] = q < Q ? queries[(size_t)q * D + d] : 0.0f;
     }
     if (k < LUT2_QPB * 16) s_max[k / 16][k % 16] = 0;
     __syncthreads();
     for (int m = 0; m < M; ++m) {
         float acc[LUT2_QPB];
-        {
-            double accd[LUT2_QPB];  // float-representable at every step (round_to_float_in_double)
 #pragma unroll
-            for (int j = 0; j < LUT2_QPB; ++j) accd[j] = 0.0;
-            if (k < K) {
-                const float* c = cw + ((size_t)m * K + k) * Ds;
-                for (int d = 0; d < Ds; ++d) {
-                    const float cv = c[d];
+        for (int j = 0; j < LUT2_QPB; ++j) acc[j] = 0.0f;
+        if (k < K) {
+            // The accumulator is rounded to float after every term INSIDE the double domain (add and
+            // subtract 2^(E+29), see round_to_float_in_double): branch free, one F2F per term instead of
+            // three.  The sum only grows, so the rare ranges where that shortcut differs from the float
+            // conversion are detected with one sticky flag per chain -- a nonzero partial sum below
+            // 2^-126 (float subnormals keep fewer bits) or a final value from 2^127 up (the conversion may
+            // overflow) -- and such an entry is recomputed by adc_entry, which takes the conversion path.
+            double accd[LUT2_QPB];
+            bool odd[LUT2_QPB];
 #pragma unroll
-                    for (int j = 0; j < LUT2_QPB; ++j) {
-                        const double diff = (double)__fsub_rn(cv, s_q[j * D + m * Ds + d]);
-                        accd[j] = round_to_float_in_double(__dadd_rn(accd[j], __dmul_rn(diff, diff)));
-                    }
+            for (int j = 0; j < LUT2_QPB; ++j) {
+                accd[j] = 0.0;
+                odd[j] = false;
+            }
+            const float* c = cw + ((size_t)m * K + k) * Ds;
+            const float4* qrow = reinterpret_cast<const float4*>(s_q + (size_t)m * Ds * LUT2_QPB);
+            for (int d = 0; d < Ds; ++d) {
+                const float cv = c[d];
+                const float4 qa = qrow[2 * d], qb = qrow[2 * d + 1];
+                const float qv[LUT2_QPB] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int j = 0; j < LUT2_QPB; ++j) {
+                    const double diff = (double)__fsub_rn(cv, qv[j]);
+                    const double sum = __dadd_rn(accd[j], __dmul_rn(diff, diff));
+                    const int e = __double2hiint(sum) & 0x7FF00000;
+                    odd[j] |= (unsigned)(e - 1) < (unsigned)(0x38100000 - 1);  // 0 < sum < 2^-126
+                    const double big = __hiloint2double(e + (29 << 20), 0);
+                    accd[j] = __dsub_rn(__dadd_rn(sum, big), big);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < LUT2_QPB; ++j) acc[j] = (float)accd[j];
+            for (int j = 0; j < LUT2_QPB; ++j) {
+                if (odd[j] || (__double2hiint(accd[j]) & 0x7FF00000) >= 0x47E00000) {
+                    float qj[64];
+                    float r = 0.0f;
+                    if (Ds <= 64) {
+                        for (int d = 0; d < Ds; ++d) qj[d] = s_q[(m * Ds + d) * LUT2_QPB + j];
+                        r = adc_entry(c, qj, Ds);
+                    } else {  // long sub-vectors: the conversion form, term by term
+                        for (int d = 0; d < Ds; ++d) {
+                            const float diff = __fsub_rn(c[d], s_q[(m * Ds + d) * LUT2_QPB + j]);
+                            r = (float)__dadd_rn((double)r, __dmul_rn((double)diff, (double)diff));
+                        }
+                    }
+                    acc[j] = r;
+                } else {
+                    acc[j] = (float)accd[j];
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < LUT2_QPB; ++j) {

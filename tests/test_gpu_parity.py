@@ -691,3 +691,35 @@ def test_multi_index_single_gpu_and_probe(golden4000, tmp_path, engine):
         assert r.returncode == 0, r.stderr[-500:]
         out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
         assert out["equals_single_gpu"] and out["shard_nodes"] == [n]
+
+
+@pytest.mark.parametrize("scale", [1e-22, 3e-20, 1.0, 2e18, 1.8e19])
+def test_adc_tables_extreme_ranges(scale, engine):
+    """The ADC-table kernels round their accumulator to float inside the double domain; partial sums
+    in the float-subnormal range and from 2^127 up take the conversion path instead.  Both must equal
+    the oracle bit for bit (dpq_adc_tables = adc_entry; a search = lut2_kernel / lut_small_kernel), so
+    the data is scaled into those ranges."""
+    rng = np.random.default_rng(17)
+    M, K, Ds, n = 8, 256, 4, 5000
+    cw = (rng.random((M, K, Ds)).astype(np.float32) * np.float32(scale)).astype(np.float32)
+    queries = (rng.random((40, M * Ds)).astype(np.float32) * np.float32(scale)).astype(np.float32)
+    if scale > 1e19:  # one term per entry, up to 3.2e38: the top binade of float without overflowing the sum
+        cw[:, :, 1:] = 0
+        queries.reshape(40, M, Ds)[:, :, 1:] = 0
+    queries[0] = cw[:, 3, :].reshape(-1)          # exact zeros in every subspace
+    lut = dpq.adc_tables(cw, queries)
+    for i in range(0, 40, 7):
+        assert np.array_equal(lut[i], po.lut(cw, queries[i])), (scale, i)
+    if scale > 1e19:
+        assert np.isfinite(lut).all() and (lut > 1.8e38).any()
+        return  # a node's eight entries would overflow float: tables only
+    codes = rng.integers(0, K, (n, M)).astype(np.uint8)
+    _, _, lay, payload = po.build_tree(codes, cw)
+    ix = dpq.DeltaTreeIndex(payload, n, M, K, pos2id=lay["vec_id"])
+    ix.set_codebook(cw)
+    for qs in (queries, queries[:3]):              # batched tables and the latency-mode tables
+        pos, ids, dist = ix.search(qs, 5)
+        for i in range(0, len(qs), 9):
+            opos, odist, nd = po.scan(payload, n, cw, qs[i], 5, want_node_dist=True)
+            assert np.array_equal(dist[i], odist), (scale, i, dist[i], odist)
+    ix.close()
