@@ -78,7 +78,8 @@ struct dpq_index {
     int Ds = 0;
     // device-resident tree
     DevBuf d_ops, d_chunks, d_anc, d_codes, d_pos2id, d_cw, d_ovf;
-    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_cap0, d_cap1, d_part8, d_done8;
+    DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_cap0, d_cap1, d_part8, d_done8, d_ps_codes;
+    int ps_R = 0;  // presample nodes currently gathered in d_ps_codes
     int last_coarse = 0;
     int last_device_queries = 0;  // queries of the last dpq_index_search_device call (a host-buffer search runs sub-batches)
     int64_t last_items8 = 0;
@@ -615,6 +616,16 @@ static int pick_slices(int n_groups, int n_chunks, int chunks_per_round, int max
     return pick;
 }
 
+// the presample's node set gathered once per (index, R)
+static int ensure_sample_codes(dpq_index* ix, int R) {
+    if (ix->ps_R == R && ix->d_ps_codes.p) return DPQ_OK;
+    int rc = ix->d_ps_codes.ensure((size_t)R * ix->prog.cstride);
+    if (rc) return rc;
+    dpq::launch_gather_sample(ix->d_codes.as<uint8_t>(), ix->prog.cstride, ix->prog.n_local, R, ix->d_ps_codes.as<uint8_t>(), ix->stream);
+    ix->ps_R = R;
+    return DPQ_OK;
+}
+
 // Latency mode: exact tables -> exact presample (cap0) -> [scan1 over every S-th chunk -> exact re-score ->
 // cap1] -> scan1 over the whole shard -> exact re-score -> exact fallback for overflowed lists.
 static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk, uint64_t* d_out_key) {
@@ -651,7 +662,8 @@ static int search_latency(dpq_index* ix, const float* d_queries, int Q, int topk
     CU(cudaEventRecord(ix->ev[1], st));
     float* cap0 = ix->d_cap0.as<float>();
     float* cap1 = ix->d_cap1.as<float>();
-    dpq::launch_presample(ix->d_lutf.as<float>(), ix->d_codes.as<uint8_t>(), P.cstride, P.n_local, P.M, P.K, Q, topk, 2048, cap0, st);
+    if ((rc = ensure_sample_codes(ix, 2048))) return rc;
+    dpq::launch_presample(ix->d_lutf.as<float>(), ix->d_ps_codes.as<uint8_t>(), P.cstride, P.n_local, P.M, P.K, Q, topk, 2048, cap0, st);
     launches += 2;
     uint32_t* cnt = ix->d_cnt1.as<uint32_t>();  // [0..Q) counts, [Q..2Q) overflow flags; a second pair behind for the final pass
     dpq::Scan1Args s1;
@@ -1014,8 +1026,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
         if (seeded) {
             // cap0: exact k-th distance over a small strided set of nodes -> coarse scan of the
             // sample (every S-th batch) -> exact re-score -> cap1 = the sample's k-th distance
-            dpq::launch_presample(se.lutf, se.codes, P.cstride, P.n_local, P.M, P.K, Q, topk,
-                                  ix->opt_presample > 0 ? ix->opt_presample : (topk > 32 ? 4096 : 2048), cap0, st);
+            const int R = ix->opt_presample > 0 ? ix->opt_presample : (topk > 32 ? 4096 : 2048);
+            if ((rc = ensure_sample_codes(ix, R))) return rc;
+            dpq::launch_presample(se.lutf, ix->d_ps_codes.as<uint8_t>(), P.cstride, P.n_local, P.M, P.K, Q, topk, R, cap0, st);
             dpq::launch_pack8(se.lutf, cap0, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
             s8.bt_stride = S;
             s8.n_slices = g8_slices_s;
@@ -1284,7 +1297,7 @@ void dpq_index_close(dpq_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_cand1, &ix->d_cnt1, &ix->d_part8, &ix->d_done8, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
+    for (DevBuf* b : {&ix->d_cap0, &ix->d_cap1, &ix->d_qlut8, &ix->d_cand8, &ix->d_cnt8, &ix->d_ovf8, &ix->d_flagged2, &ix->d_ovf, &ix->d_cand1, &ix->d_cnt1, &ix->d_part8, &ix->d_done8, &ix->d_ps_codes, &ix->d_ops, &ix->d_chunks, &ix->d_anc, &ix->d_codes, &ix->d_pos2id, &ix->d_cw,
                       &ix->d_queries, &ix->d_lutf, &ix->d_scale, &ix->d_qlut, &ix->d_cand, &ix->d_cnt,
                       &ix->d_flagged, &ix->d_ctrl, &ix->d_bound, &ix->d_key, &ix->d_fpart,
                       &ix->d_gthr})

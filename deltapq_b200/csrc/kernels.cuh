@@ -193,9 +193,11 @@ void launch_pack8(const float* d_lutf, const float* d_cap, int M, int K, int Q, 
                   uint32_t* d_ovf, int n_groups, int nf, cudaStream_t st);
 // cap of every query from the key lists of a finished search: cap[q] = distance of out_key[q][topk-1]
 void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap, cudaStream_t st);
-// cap0[q] = exact k-th smallest distance over R evenly strided nodes (float tables, reference
-// arithmetic): a valid, loose upper bound of the true k-th distance that seeds the sample pass
-void launch_presample(const float* d_lutf, const uint8_t* d_codes, int cstride, int64_t n_local, int M, int K, int Q,
+// the presample's nodes (R evenly strided nodes of the shard, R <= 8192) gathered into a compact array [R][cstride]
+void launch_gather_sample(const uint8_t* d_codes, int cstride, int64_t n_local, int R, uint8_t* d_out, cudaStream_t st);
+// cap0[q] = exact k-th smallest distance over those R nodes (float tables, reference arithmetic): a valid,
+// loose upper bound of the true k-th distance that seeds the sample pass
+void launch_presample(const float* d_lutf, const uint8_t* d_sample_codes, int cstride, int64_t n_local, int M, int K, int Q,
                       int topk, int R, float* d_cap, cudaStream_t st);
 cudaError_t launch_scan8(const Scan8Args& a, cudaStream_t st);
 struct Rescore8Args {

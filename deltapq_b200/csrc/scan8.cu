@@ -40,11 +40,27 @@ void launch_cap_from_keys(const uint64_t* d_keys, int topk, int Q, float* d_cap,
     cap_from_keys_kernel<<<(Q + 255) / 256, 256, 0, st>>>(d_keys, topk, Q, d_cap);
 }
 
+// The presample's node set (R evenly strided nodes of the shard) is the same for every query: their codes
+// are gathered once per index into a compact array, so that a query's block reads them with coalesced
+// loads instead of R strided ones (189 us -> see profiles/r2_summary.md at C2).
+__global__ void gather_sample_kernel(const uint8_t* __restrict__ codes, int cstride, int64_t n_local, int R, int64_t stride,
+                                     uint8_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const int64_t node = (int64_t)i * stride;
+    for (int b = 0; b < cstride; ++b) out[(size_t)i * cstride + b] = node < n_local ? codes[(size_t)node * cstride + b] : 0;
+}
+void launch_gather_sample(const uint8_t* d_codes, int cstride, int64_t n_local, int R, uint8_t* d_out, cudaStream_t st) {
+    const int64_t stride = n_local / R > 0 ? n_local / R : 1;
+    gather_sample_kernel<<<(R + 255) / 256, 256, 0, st>>>(d_codes, cstride, n_local, R, stride, d_out);
+}
+
 // One block per query: exact distances of R evenly strided nodes (the query's float table in
-// shared memory), then the k-th smallest by bisection on the float bit patterns (distances are
-// non-negative, so the integer order of the bits is the float order).
+// shared memory; the nodes' codes come from the compact array of launch_gather_sample), then the
+// k-th smallest by bisection on the float bit patterns (distances are non-negative, so the integer
+// order of the bits is the float order).
 template <int PS_T>
-__global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict__ lutf, const uint8_t* __restrict__ codes, int cstride,
+__global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict__ lutf, const uint8_t* __restrict__ sample_codes, int cstride,
                                                          int64_t n_local, int M, int K, int topk, int R,
                                                          float* __restrict__ cap) {
     extern __shared__ float s_lut[];  // M*K
@@ -61,8 +77,7 @@ __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict
         const int i = t * PS_T + threadIdx.x;
         v[t] = 0x7F800000u;  // +inf: never counted
         if (i < R && (int64_t)i * stride < n_local) {
-            const uint8_t* c = codes + (size_t)((int64_t)i * stride) * cstride;
-            const double d = exact_dist(s_lut, c, cstride, M, K);
+            const double d = exact_dist(s_lut, sample_codes + (size_t)i * cstride, cstride, M, K);
             v[t] = __float_as_uint((float)d);
         }
     }
@@ -85,15 +100,14 @@ __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict
     }
     if (threadIdx.x == 0) cap[q] = __uint_as_float(lo);  // FLT_MAX when the sample holds fewer than k nodes
 }
-void launch_presample(const float* d_lutf, const uint8_t* d_codes, int cstride, int64_t n_local, int M, int K, int Q,
+void launch_presample(const float* d_lutf, const uint8_t* d_sample_codes, int cstride, int64_t n_local, int M, int K, int Q,
                       int topk, int R, float* d_cap, cudaStream_t st) {
     // 16 values per thread: 128 threads for R <= 2048, 512 threads up to 8192
     const size_t sm = (size_t)M * K * sizeof(float);
     if (R <= 128 * 16) {
-        presample_kernel<128><<<Q, 128, sm, st>>>(d_lutf, d_codes, cstride, n_local, M, K, topk, R, d_cap);
+        presample_kernel<128><<<Q, 128, sm, st>>>(d_lutf, d_sample_codes, cstride, n_local, M, K, topk, R, d_cap);
     } else {
-        if (R > 512 * 16) R = 512 * 16;
-        presample_kernel<512><<<Q, 512, sm, st>>>(d_lutf, d_codes, cstride, n_local, M, K, topk, R, d_cap);
+        presample_kernel<512><<<Q, 512, sm, st>>>(d_lutf, d_sample_codes, cstride, n_local, M, K, topk, R, d_cap);
     }
 }
 
