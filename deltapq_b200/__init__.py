@@ -21,7 +21,7 @@ SYMBOLS = [
     "dpq_index_set_stream",
     "dpq_index_search", "dpq_index_search_device", "dpq_index_sync", "dpq_merge_topk_device",
     "dpq_malloc", "dpq_free", "dpq_memcpy_h2d", "dpq_memcpy_d2h", "dpq_malloc_host",
-    "dpq_free_host", "dpq_index_stat", "dpq_index_close", "dpq_adc_tables", "dpq_encode", "dpq_encode_u8",
+    "dpq_free_host", "dpq_index_stat", "dpq_index_close", "dpq_adc_tables", "dpq_encode", "dpq_encode_u8", "dpq_encode_stat",
     "dpq_find_edges", "dpq_edge_diffs", "dpq_groundtruth_begin", "dpq_groundtruth_chunk",
     "dpq_groundtruth_finish", "dpq_groundtruth_stat", "dpq_program_compile", "dpq_program_size", "dpq_program_copy",
     "dpq_program_free", "dpq_tree_build", "dpq_tree_from_edges", "dpq_tree_size", "dpq_tree_copy",
@@ -79,6 +79,8 @@ def lib():
     L.dpq_adc_tables.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     L.dpq_encode.argtypes = [vp, i32, i32, i32, vp, i64, i32, vp]
     L.dpq_encode_u8.argtypes = [vp, i32, i32, i32, vp, i64, i32, i64, i64, vp]
+    L.dpq_encode_stat.argtypes = [C.c_char_p]
+    L.dpq_encode_stat.restype = C.c_int64
     L.dpq_find_edges.argtypes = [vp, i64, i32, i32, i32, i32, vp, C.POINTER(C.c_uint32)]
     L.dpq_edge_diffs.argtypes = [vp, i64, i32, vp, i64, vp, C.POINTER(i64)]
     L.dpq_groundtruth_begin.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
@@ -307,6 +309,11 @@ def encode(cw, x):
     codes = np.empty((x.shape[0], M), np.uint8)
     _check(lib().dpq_encode(_ptr(cw), M, K, Ds, _ptr(x), x.shape[0], x.shape[1], _ptr(codes)))
     return codes
+
+
+def encode_stat(name):
+    """dpq_encode_stat: "tc" / "kernel_us" of the last encode call."""
+    return int(lib().dpq_encode_stat(name.encode()))
 
 
 def encode_u8(cw, raw, n, D, row_stride, row_offset):

@@ -1160,8 +1160,23 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
         memcpy(hq, queries, qbytes);
         CU(cudaHostGetDevicePointer(&dq, hq, 0));
     }
+    // result arrays: a caller array that is page-locked is written by the kernel itself (no staging, no
+    // copy afterwards); the others go through the mapped staging buffer
+    auto mapped = [&](void* host) -> uint32_t* {
+        if (!host) return nullptr;
+        void* d = nullptr;
+        cudaPointerAttributes at;
+        const bool ok = cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+                        cudaHostGetDevicePointer(&d, host, 0) == cudaSuccess && d;
+        (void)cudaGetLastError();
+        return ok ? reinterpret_cast<uint32_t*>(d) : nullptr;
+    };
     void* d_stage_out = nullptr;
     CU(cudaHostGetDevicePointer(&d_stage_out, h_pos, 0));
+    uint32_t* const ds = reinterpret_cast<uint32_t*>(d_stage_out);
+    uint32_t* const o_pos = mapped(out_pos);
+    uint32_t* const o_id = mapped(out_id);
+    uint32_t* const o_dist = mapped(out_dist);
     if ((rc = ix->d_key.ensure(kbytes))) return rc;
     const bool want_id = out_id != nullptr;
     if (want_id && ix->has_pos2id && !ix->d_pos2id.p) {  // first host-buffer call: the id table moves to the device
@@ -1171,15 +1186,17 @@ int dpq_index_search(dpq_index* ix, const float* queries, int Q, int topk, uint3
     rc = dpq_index_search_device(ix, reinterpret_cast<const float*>(dq), Q, topk, ix->d_key.as<uint64_t>());
     if (rc) return rc;
     dpq::launch_unpack(ix->d_key.as<uint64_t>(), nk, want_id && ix->has_pos2id ? ix->d_pos2id.as<uint32_t>() : nullptr,
-                       (uint32_t)ix->prog.base_pos, reinterpret_cast<uint32_t*>(d_stage_out), ix->stream);
-    CU(cudaMemcpyAsync(hc, ix->d_ctrl.p, 16, cudaMemcpyDeviceToHost, ix->stream));
+                       (uint32_t)ix->prog.base_pos, out_pos ? (o_pos ? o_pos : ds) : nullptr,
+                       out_id ? (o_id ? o_id : ds + nk) : nullptr, out_dist ? (o_dist ? o_dist : ds + 2 * nk) : nullptr,
+                       ix->d_ctrl.p ? ix->d_ctrl.as<uint32_t>() : nullptr, ds + 3 * nk, ix->stream);
+    CU(cudaGetLastError());
     const auto t_enq = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(ix->stream));  // the one host sync of the call
     const auto t_sync = std::chrono::steady_clock::now();
     ix->last_fallback = (int64_t)hc[0] + hc[2];
-    if (out_pos) memcpy(out_pos, h_pos, nk * 4);
-    if (out_id) memcpy(out_id, h_id, nk * 4);
-    if (out_dist) memcpy(out_dist, h_dist, nk * 4);
+    if (out_pos && !o_pos) memcpy(out_pos, h_pos, nk * 4);
+    if (out_id && !o_id) memcpy(out_id, h_id, nk * 4);
+    if (out_dist && !o_dist) memcpy(out_dist, h_dist, nk * 4);
     const auto t_end = std::chrono::steady_clock::now();
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();

@@ -804,19 +804,22 @@ __global__ void merge_kernel(const uint64_t* __restrict__ keys, int n_lists, int
 }
 
 __global__ void unpack_kernel(const uint64_t* __restrict__ keys, size_t n, const uint32_t* __restrict__ pos2id,
-                              uint32_t base_pos, uint32_t* __restrict__ out) {
+                              uint32_t base_pos, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_id,
+                              uint32_t* __restrict__ out_dist, const uint32_t* __restrict__ ctrl, uint32_t* __restrict__ out_ctrl) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 && out_ctrl) out_ctrl[i] = ctrl ? ctrl[i] : 0u;
     if (i >= n) return;
     const uint64_t k = keys[i];
     const uint32_t pos = (uint32_t)k;
-    out[i] = pos;
-    out[n + i] = (pos2id && pos != 0xFFFFFFFFu) ? pos2id[pos - base_pos] : pos;
-    out[2 * n + i] = (uint32_t)(k >> 32);
+    if (out_pos) out_pos[i] = pos;
+    if (out_id) out_id[i] = (pos2id && pos != 0xFFFFFFFFu) ? pos2id[pos - base_pos] : pos;
+    if (out_dist) out_dist[i] = (uint32_t)(k >> 32);
 }
 
-void launch_unpack(const uint64_t* d_keys, size_t n, const uint32_t* d_pos2id, uint32_t base_pos, uint32_t* out,
-                   cudaStream_t st) {
-    unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_keys, n, d_pos2id, base_pos, out);
+void launch_unpack(const uint64_t* d_keys, size_t n, const uint32_t* d_pos2id, uint32_t base_pos, uint32_t* out_pos,
+                   uint32_t* out_id, uint32_t* out_dist, const uint32_t* d_ctrl, uint32_t* out_ctrl, cudaStream_t st) {
+    unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_keys, n, d_pos2id, base_pos, out_pos, out_id, out_dist, d_ctrl,
+                                                                out_ctrl);
 }
 
 void launch_merge(const uint64_t* d_keys, int n_lists, int Q, int topk, uint64_t* d_out,

@@ -355,10 +355,11 @@ void launch_fallback(const FallbackArgs& a, cudaStream_t st);
 
 void launch_merge(const uint64_t* d_keys, int n_lists, int Q, int topk, uint64_t* d_out,
                   cudaStream_t st);
-// keys (distance bits << 32 | position) -> out[0..n) positions, out[n..2n) ids (pos2id[pos - base_pos], or the
-// position when pos2id is null), out[2n..3n) distance bits; `out` may be device-mapped host memory
-void launch_unpack(const uint64_t* d_keys, size_t n, const uint32_t* d_pos2id, uint32_t base_pos, uint32_t* out,
-                   cudaStream_t st);
+// keys (distance bits << 32 | position) -> positions, ids (pos2id[pos - base_pos], or the position when
+// pos2id is null), distance bits, each to its own array (null = not wanted; device-mapped host memory is
+// fine); the four control words of the search are copied to out_ctrl alongside
+void launch_unpack(const uint64_t* d_keys, size_t n, const uint32_t* d_pos2id, uint32_t base_pos, uint32_t* out_pos,
+                   uint32_t* out_id, uint32_t* out_dist, const uint32_t* d_ctrl, uint32_t* out_ctrl, cudaStream_t st);
 
 // ---- latency mode (scan1.cu): lanes = nodes, two queries per pass over the code array ----
 struct Scan1Args {

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/dpq.h"
+#include "encode_tc.cuh"
 #include "gt_tc.cuh"
 
 namespace dpq {
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ c
         xr[d] = col < D ? x[(size_t)v * D + col] : 0.0f;  // zero padding (pq_tree.cpp:194-198)
     }
     float best = FLT_MAX;
-    int best_k = 0;
+    int best_k = -1;  // nothing below FLT_MAX (overflow, NaN): the reference writes (uchar)-1 (pq_tree.cpp:217, 235)
     for (int k = 0; k < K; ++k) {
         const float* c = s_cw + k * DS;
         float dist = 0.0f;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) encode_kernel_any(const float* __restrict
     __syncthreads();
     if (v >= n) return;
     float best = FLT_MAX;
-    int best_k = 0;
+    int best_k = -1;  // nothing below FLT_MAX (overflow, NaN): the reference writes (uchar)-1 (pq_tree.cpp:217, 235)
     for (int k = 0; k < K; ++k) {
         const float* c = s_cw + k * Ds;
         float dist = 0.0f;
@@ -389,6 +390,75 @@ int gt_tc_range(dpq_gt* st, const float* d_base, int64_t n, int64_t id0, int64_t
     if (ctl[0]) return gt_dense(st, d_base, n, id0, st->d_flag, (int)ctl[0]);  // overflowed candidate lists
     return DPQ_OK;
 }
+
+// ------------------------------------------------------------------------ encode driver -------
+int64_t g_enc_tc = 0, g_enc_kernel_us = 0;
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice;
+}
+
+// One encode call: the codebook on the device, the path choice (tensor cores for Ds in {4, 8, 16} unless
+// DPQ_ENCODE_TC=0, else the SIMT kernel), the kernels' device time.
+struct Encoder {
+    Buf d_cw, d_scratch, d_err;
+    int M = 0, K = 0, Ds = 0, n_sms = 148;
+    bool tc = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    double ms = 0.0;
+    ~Encoder() {
+        for (auto e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+    int init(const float* cw, int M_, int K_, int Ds_) {
+        M = M_, K = K_, Ds = Ds_;
+        g_enc_tc = 0, g_enc_kernel_us = 0;
+        CU(cudaMalloc(&d_cw.p, (size_t)M * K * Ds * 4));
+        CU(cudaMemcpy(d_cw.p, cw, (size_t)M * K * Ds * 4, cudaMemcpyDefault));
+        const char* env = getenv("DPQ_ENCODE_TC");
+        tc = dpq::encode_tc_supported(M, K, Ds) && !(env && env[0] == '0');
+        if (tc) {
+            cudaDeviceProp prop;
+            CU(cudaGetDeviceProperties(&prop, dpq::api_device()));
+            n_sms = prop.multiProcessorCount;
+            CU(cudaMalloc(&d_scratch.p, dpq::encode_tc_scratch_bytes(M)));
+            CU(cudaMalloc(&d_err.p, 4));
+            CU(cudaMemset(d_err.p, 0, 4));
+        }
+        CU(cudaEventCreate(&ev[0]));
+        CU(cudaEventCreate(&ev[1]));
+        return DPQ_OK;
+    }
+    int run(const float* d_x, int64_t n, int D, uint8_t* d_codes) {
+        CU(cudaEventRecord(ev[0], 0));
+        if (tc)
+            CU(dpq::launch_encode_tc((const float*)d_cw.p, M, K, Ds, d_x, n, D, d_codes, (unsigned char*)d_scratch.p,
+                                     (uint32_t*)d_err.p, n_sms, 0));
+        else
+            CU(launch_encode((const float*)d_cw.p, M, K, Ds, d_x, n, D, d_codes, 0));
+        CU(cudaEventRecord(ev[1], 0));
+        CU(cudaEventSynchronize(ev[1]));
+        float t = 0.0f;
+        CU(cudaEventElapsedTime(&t, ev[0], ev[1]));
+        ms += t;
+        return DPQ_OK;
+    }
+    int finish() {
+        if (tc) {
+            uint32_t err = 0;
+            CU(cudaMemcpy(&err, d_err.p, 4, cudaMemcpyDeviceToHost));
+            if (err) return dpq::api_fail(DPQ_ERR_CUDA, "encode: a tensor-core completion barrier never fired");
+        }
+        g_enc_tc = tc ? 1 : 0;
+        g_enc_kernel_us = (int64_t)(ms * 1e3);
+        return DPQ_OK;
+    }
+};
 }  // namespace
 
 extern "C" {
@@ -401,19 +471,23 @@ int dpq_encode(const float* cw, int M, int K, int Ds, const float* x, int64_t n,
     if (rc) return rc;
     if (n == 0) return DPQ_OK;
     CU(cudaSetDevice(dpq::api_device()));
-    Buf d_cw, d_x, d_c;
+    Encoder enc;
+    if ((rc = enc.init(cw, M, K, Ds))) return rc;
+    if (is_device_ptr(x) && is_device_ptr(codes)) {  // device-resident input and output: no staging
+        if ((rc = enc.run(x, n, D, codes))) return rc;
+        return enc.finish();
+    }
+    Buf d_x, d_c;
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 20);
-    CU(cudaMalloc(&d_cw.p, (size_t)M * K * Ds * 4));
     CU(cudaMalloc(&d_x.p, (size_t)chunk * D * 4));
     CU(cudaMalloc(&d_c.p, (size_t)chunk * M));
-    CU(cudaMemcpy(d_cw.p, cw, (size_t)M * K * Ds * 4, cudaMemcpyHostToDevice));
     for (int64_t s = 0; s < n; s += chunk) {
         int64_t c = std::min(chunk, n - s);
         CU(cudaMemcpy(d_x.p, x + (size_t)s * D, (size_t)c * D * 4, cudaMemcpyDefault));
-        CU(launch_encode((const float*)d_cw.p, M, K, Ds, (const float*)d_x.p, c, D, (uint8_t*)d_c.p, 0));
+        if ((rc = enc.run((const float*)d_x.p, c, D, (uint8_t*)d_c.p))) return rc;
         CU(cudaMemcpy(codes + (size_t)s * M, d_c.p, (size_t)c * M, cudaMemcpyDefault));
     }
-    return DPQ_OK;
+    return enc.finish();
 }
 
 int dpq_encode_u8(const float* cw, int M, int K, int Ds, const uint8_t* x, int64_t n, int D, int64_t row_stride,
@@ -425,13 +499,13 @@ int dpq_encode_u8(const float* cw, int M, int K, int Ds, const uint8_t* x, int64
     if (rc) return rc;
     if (n == 0) return DPQ_OK;
     CU(cudaSetDevice(dpq::api_device()));
-    Buf d_cw, d_raw, d_x, d_c;
+    Encoder enc;
+    if ((rc = enc.init(cw, M, K, Ds))) return rc;
+    Buf d_raw, d_x, d_c;
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 20);
-    CU(cudaMalloc(&d_cw.p, (size_t)M * K * Ds * 4));
     CU(cudaMalloc(&d_raw.p, (size_t)chunk * row_stride));
     CU(cudaMalloc(&d_x.p, (size_t)chunk * D * 4));
     CU(cudaMalloc(&d_c.p, (size_t)chunk * M));
-    CU(cudaMemcpy(d_cw.p, cw, (size_t)M * K * Ds * 4, cudaMemcpyHostToDevice));
     for (int64_t s = 0; s < n; s += chunk) {
         const int64_t c = std::min(chunk, n - s);
         // the last record may end before a whole stride (no trailing padding in the caller's buffer)
@@ -439,10 +513,18 @@ int dpq_encode_u8(const float* cw, int M, int K, int Ds, const uint8_t* x, int64
         CU(cudaMemcpy(d_raw.p, x + (size_t)s * row_stride, raw_bytes, cudaMemcpyDefault));
         u8_to_float_kernel<<<(unsigned)((c * D + 255) / 256), 256>>>((const uint8_t*)d_raw.p, c, D, row_stride, row_offset,
                                                                      (float*)d_x.p);
-        CU(launch_encode((const float*)d_cw.p, M, K, Ds, (const float*)d_x.p, c, D, (uint8_t*)d_c.p, 0));
+        if ((rc = enc.run((const float*)d_x.p, c, D, (uint8_t*)d_c.p))) return rc;
         CU(cudaMemcpy(codes + (size_t)s * M, d_c.p, (size_t)c * M, cudaMemcpyDefault));
     }
-    return DPQ_OK;
+    return enc.finish();
+}
+
+int64_t dpq_encode_stat(const char* name) {
+    if (!name) return -1;
+    const std::string s(name);
+    if (s == "tc") return g_enc_tc;                 // 1: the last encode call ran on the tensor cores
+    if (s == "kernel_us") return g_enc_kernel_us;   // device time of its encode kernels (CUDA events)
+    return -1;
 }
 
 int dpq_edge_diffs(const uint8_t* codes, int64_t n_codes, int M, const uint32_t* edges, int64_t n_edges,

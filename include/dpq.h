@@ -185,7 +185,11 @@ int dpq_adc_tables(const float* codewords, int M, int K, int Ds, const float* qu
 
 /* PQTree::EncodePlain (pq_tree.cpp:192-253) over n vectors x[n][D], D <= M*Ds (zero
  * padded): codes[n][M], bit-exact (sequential FP32, no FMA, strict <).  x and codes may be
- * host or device pointers (unified addressing); codewords is a host pointer. */
+ * host or device pointers (unified addressing; device-resident x and codes are used in place);
+ * codewords is a host pointer.  Ds in {4, 8, 16}: the K scores of 128 vectors come from one
+ * tcgen05.mma group (bf16 hi/lo split) used as a filter, and only the centroids within the
+ * rigorous error bound of the best score are re-scored in the reference's arithmetic
+ * (encode_tc.cu; DPQ_ENCODE_TC=0 selects the SIMT kernel); other Ds: SIMT kernel. */
 int dpq_encode(const float* codewords, int M, int K, int Ds, const float* x, int64_t n, int D,
                uint8_t* codes);
 
@@ -195,6 +199,9 @@ int dpq_encode(const float* codewords, int M, int K, int Ds, const float* x, int
  * row_offset = 4.  The conversion runs on the device; a quarter of the bytes cross PCIe. */
 int dpq_encode_u8(const float* codewords, int M, int K, int Ds, const uint8_t* x, int64_t n, int D,
                   int64_t row_stride, int64_t row_offset, uint8_t* codes);
+/* About the calling thread's process-wide last encode call: "tc" (1 = tensor-core path),
+ * "kernel_us" (device time of its encode kernels, CUDA events); -1 for an unknown name. */
+int64_t dpq_encode_stat(const char* name);
 
 /* find_edges_by_diff_approx (DCAT.h:1207-1332) with the canonical stable-sort tie rule:
  * edges[n_codes-1][2] = (parent id, child id) in emission order, *root_id. */

@@ -1,6 +1,8 @@
 """GPU: the CUDA path (through the C ABI, libdpq.so) against the oracle and the reference
 fixtures.  Integer/byte results bit-exact; distances bit-exact where the reference's double
 accumulation is exact, else within 1e-5 relative; ids modulo ties at 1e-5."""
+import os
+
 import numpy as np
 import pytest
 
@@ -413,6 +415,85 @@ def test_encode_bit_exact(golden4000, golden_m16):
     cw = dg.roundtrip_codebook(rng.random((4, 100, 7)).astype(np.float32))   # odd Ds, padding
     x = rng.random((33, 27)).astype(np.float32)
     assert np.array_equal(dpq.encode(cw, x), po.encode(cw, x))
+
+
+def test_encode_tensor_core_filter_is_exact():
+    """encode_tc.cu: the tcgen05 scores only FILTER; the code written is the reference loop's
+    (pq_tree.cpp:215-237) on inputs built to break a filter: duplicated centroids (ties go to the
+    lowest id), vectors equal to centroids, midpoints of centroid pairs (exact ties in real
+    arithmetic), near-ties a few ulps apart, magnitudes from 1e-30 to 1e18, zero vectors, zero
+    padding (D < M * Ds), K < 256, ragged n, NaN / inf components."""
+    rng = np.random.default_rng(11)
+    for M, K, Ds, n in ((8, 256, 16, 3001), (16, 256, 8, 1500), (4, 100, 16, 700), (8, 7, 4, 513), (3, 33, 8, 129)):
+        cw = rng.normal(size=(M, K, Ds)).astype(np.float32) * 40 + 60
+        cw[:, K // 2] = cw[:, 1]                      # duplicate centroid
+        if K > 6:
+            cw[:, 5] = np.nextafter(cw[:, 4], np.float32(np.inf))   # one ulp apart
+        D = M * Ds
+        x = rng.normal(size=(n, D)).astype(np.float32) * 40 + 60
+        xs = x.reshape(n, M, Ds)
+        pick = rng.integers(0, K, size=(n, M))
+        own = cw[np.arange(M)[None, :], pick]         # [n][M][Ds]
+        xs[0:200] = own[0:200]                        # exactly a centroid (possibly the duplicated one)
+        other = cw[np.arange(M)[None, :], (pick + 1) % K]
+        xs[200:400] = (own[200:400] + other[200:400]) * np.float32(0.5)   # midpoints
+        xs[400:420] = 0.0
+        x = xs.reshape(n, D)
+        for scale in (1.0, 1e-3, 1e4):
+            cws, xq = (cw * np.float32(scale)).astype(np.float32), (x * np.float32(scale)).astype(np.float32)
+            got = dpq.encode(cws, xq)
+            assert dpq.encode_stat("tc") == 1
+            assert np.array_equal(got, po.encode(cws, xq)), (M, K, Ds, scale)
+        # the bound cannot be trusted out here: every centroid becomes a candidate, still the reference's answer
+        for cs, xsc in ((1e-30, 1e-30), (1e18, 1e18), (1e-30, 1e6), (1e10, 1e-20)):
+            cws, xq = (cw * np.float32(cs)).astype(np.float32), (x[:300] * np.float32(xsc)).astype(np.float32)
+            assert np.array_equal(dpq.encode(cws, xq), po.encode(cws, xq)), (M, K, Ds, cs, xsc)
+        xq = x[:300].copy()
+        xq[3, 1] = np.nan
+        xq[7, 0] = np.inf
+        xq[9, D - 1] = -np.inf
+        cwn = cw.copy()
+        cwn[0, 2, 0] = np.nan
+        assert np.array_equal(dpq.encode(cw, xq), po.encode(cw, xq))
+        assert np.array_equal(dpq.encode(cwn, xq), po.encode(cwn, xq))
+        # zero padding: D < M * Ds
+        for cut in (3, 4):
+            xc = x[:257, :D - cut].copy()
+            assert np.array_equal(dpq.encode(cw, xc), po.encode(cw, xc))
+    # SIFT-shaped integers (every component exact in bf16 hi + lo), and the SIMT kernel on the same input
+    cw = dg.roundtrip_codebook((rng.random((8, 256, 16)) * 140).astype(np.float32))
+    x = rng.integers(0, 256, size=(40000, 128)).astype(np.float32)
+    got = dpq.encode(cw, x)
+    assert dpq.encode_stat("tc") == 1 and dpq.encode_stat("kernel_us") >= 0
+    os.environ["DPQ_ENCODE_TC"] = "0"
+    try:
+        simt = dpq.encode(cw, x)
+        assert dpq.encode_stat("tc") == 0
+    finally:
+        del os.environ["DPQ_ENCODE_TC"]
+    assert np.array_equal(got, simt)
+    assert np.array_equal(got[:4000], po.encode(cw, x[:4000]))
+
+
+def test_search_into_page_locked_result_arrays(golden4000):
+    """dpq_index_search: caller arrays that are page-locked are written by the unpack kernel itself;
+    pageable ones go through the staging buffer -- same content either way, also mixed."""
+    g = golden4000
+    ix = _open(g)
+    q = g["queries"]
+    Q, k = len(q), 10
+    ref = ix.search(q, k)
+    pinned = tuple(dpq.pinned_array((Q, k), dt) for dt in (np.uint32, np.uint32, np.float32))
+    for a in pinned:
+        a[...] = 0
+    got = ix.search(q, k, out=pinned)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    mixed = (np.zeros((Q, k), np.uint32), dpq.pinned_array((Q, k), np.uint32), np.zeros((Q, k), np.float32))
+    got = ix.search(q, k, out=mixed)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    ix.close()
 
 
 def test_edge_diffs(golden4000):

@@ -40,6 +40,16 @@ try:
     for _ in range(3):
         t = time.perf_counter(); dpq.encode_device(cw, dx.ptr.value, N, base.shape[1], dc.ptr.value); dt_ = time.perf_counter() - t
         t_dev = dt_ if t_dev is None else min(t_dev, dt_)
+    enc_tc, enc_kernel_us = dpq.encode_stat("tc"), dpq.encode_stat("kernel_us")
+    assert np.array_equal(dc.download(np.uint8, (N, M)), codes)
+    # the SIMT encoder on the same device-resident input
+    os.environ["DPQ_ENCODE_TC"] = "0"
+    t_simt = None
+    for _ in range(2):
+        t = time.perf_counter(); dpq.encode_device(cw, dx.ptr.value, N, base.shape[1], dc.ptr.value); dt_ = time.perf_counter() - t
+        t_simt = dt_ if t_simt is None else min(t_simt, dt_)
+    simt_kernel_us = dpq.encode_stat("kernel_us")
+    del os.environ["DPQ_ENCODE_TC"]
     assert np.array_equal(dc.download(np.uint8, (N, M)), codes)
     dx.free(); dc.free()
     Ds = cw.shape[2]
@@ -50,7 +60,10 @@ try:
     t = time.perf_counter(); gid, gd = dpq.groundtruth(base, queries, 10); t_gt = time.perf_counter() - t
     out = dict(N=N, M=M, encode_s=round(t_enc, 3), encode_vec_per_s=round(N / t_enc),
                encode_device_resident_s=round(t_dev, 4), encode_device_resident_vec_per_s=round(N / t_dev),
-               encode_fp32_issue_frac=round(fp32_ops / t_dev / (148 * 128 * 1.965e9), 3),
+               encode_tensor_core_path=enc_tc, encode_kernel_us=enc_kernel_us,
+               encode_kernel_vec_per_s=round(N / max(enc_kernel_us, 1) * 1e6),
+               encode_simt_device_resident_s=round(t_simt, 4), encode_simt_kernel_us=simt_kernel_us,
+               encode_simt_fp32_issue_frac=round(fp32_ops / max(simt_kernel_us, 1) * 1e6 / (148 * 128 * 1.965e9), 3),
                find_edges_s=round(t_edges, 3), tree_build_s=round(t_tree, 3),
                groundtruth_s=round(t_gt, 3), groundtruth_ms_per_query=round(t_gt / NQ * 1e3, 2),
                tree_edge_stage_s=round(tree["edge_us"] / 1e6, 3), tree_layout_stage_s=round(tree["layout_us"] / 1e6, 3),
