@@ -48,6 +48,22 @@ constexpr int ET_B_BYTES = ET_N * 128;     // 32 KB
 constexpr uint32_t ET_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ET_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr int ET_SMEM_MIN = 80 * 1024;  // > 228 KB / 3: at most two CTAs per SM, 256 TMEM columns each
 
+// bounded spin on the MMA completion barrier (a few seconds at most: a failure is reported, never a hang)
+__device__ __forceinline__ bool wait_mma(uint64_t* bar, uint32_t phase) {
+    for (uint32_t spin = 0; spin < (1u << 21); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
 __device__ __forceinline__ uint16_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float bf16_val(uint16_t b) { return __bfloat162float(__ushort_as_bfloat16(b)); }
 
@@ -213,7 +229,7 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
         }
         float xnext[DS];  // the next tile's row travels while the MMAs run
         if (t + 1 < t_hi) load_row<DS>(a, row + ET_ROWS, m, xnext);
-        ok = umma::mbar_wait_bounded(s_bar, phase);
+        ok = wait_mma(s_bar, phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (!ok) break;
@@ -258,7 +274,9 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
         int best_k = -1;  // nothing below FLT_MAX (overflow, NaN): the reference writes (uchar)-1 (pq_tree.cpp:217, 235)
 #pragma unroll
         for (int b = 0; b < ET_N / 32; ++b) {
-            if (b * 32 < K && !(bm[b] < lim)) {
+            // tcgen05.ld is warp-collective (.sync.aligned): the skip must be decided by the whole warp.  A row
+            // without a candidate in this block gets hits == 0 from the test below anyway.
+            if (b * 32 < K && __any_sync(0xffffffffu, !(bm[b] < lim))) {
                 uint32_t v[32];
                 umma::tmem_ld32(tlane + (uint32_t)(b * 32), v);
                 umma::tmem_ld_wait();
@@ -275,6 +293,7 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
                         best_k = k;
                     }
                 }
+                __syncwarp();  // the rows' candidate loops differ in length: reconverge before the next collective load
             }
         }
         if (row < a.n) a.codes[(size_t)row * a.M + m] = (uint8_t)best_k;

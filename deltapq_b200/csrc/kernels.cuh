@@ -249,7 +249,7 @@ __device__ __forceinline__ float adc_entry(const float* __restrict__ c, const fl
     double acc = 0.0;  // always holds a float-representable value
     for (int d = 0; d < Ds; ++d) {
         const double diff = (double)__fsub_rn(c[d], q[d]);
-        acc = round_to_float_in_double(__dadd_rn(acc, __dmul_rn(diff, diff)));
+        acc = round_to_float_in_double(__fma_rn(diff, diff, acc));  // diff * diff is exact in double: same rounding as multiply, add
     }
     return (float)acc;
 }

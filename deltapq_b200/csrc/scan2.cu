@@ -71,14 +71,15 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
             // 2^-126 (float subnormals keep fewer bits) or a final value from 2^127 up (the conversion may
             // overflow) -- and such an entry is recomputed by adc_entry, which takes the conversion path.
             double accd[LUT2_QPB];
-            bool odd[LUT2_QPB];
+            unsigned emin[LUT2_QPB];  // smallest (exponent field - 1) seen by the chain; a zero sum wraps to the top
 #pragma unroll
             for (int j = 0; j < LUT2_QPB; ++j) {
                 accd[j] = 0.0;
-                odd[j] = false;
+                emin[j] = 0xFFFFFFFFu;
             }
             const float* c = cw + ((size_t)m * K + k) * Ds;
             const float4* qrow = reinterpret_cast<const float4*>(s_q + (size_t)m * Ds * LUT2_QPB);
+#pragma unroll 4
             for (int d = 0; d < Ds; ++d) {
                 const float cv = c[d];
                 const float4 qa = qrow[2 * d], qb = qrow[2 * d + 1];
@@ -86,16 +87,19 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
 #pragma unroll
                 for (int j = 0; j < LUT2_QPB; ++j) {
                     const double diff = (double)__fsub_rn(cv, qv[j]);
-                    const double sum = __dadd_rn(accd[j], __dmul_rn(diff, diff));
+                    // diff is a widened float: diff * diff is exact in double, so one fused multiply-add
+                    // rounds exactly like the reference's multiply then add
+                    const double sum = __fma_rn(diff, diff, accd[j]);
                     const int e = __double2hiint(sum) & 0x7FF00000;
-                    odd[j] |= (unsigned)(e - 1) < (unsigned)(0x38100000 - 1);  // 0 < sum < 2^-126
+                    emin[j] = min(emin[j], (unsigned)e - 1u);
                     const double big = __hiloint2double(e + (29 << 20), 0);
                     accd[j] = __dsub_rn(__dadd_rn(sum, big), big);
                 }
             }
 #pragma unroll
             for (int j = 0; j < LUT2_QPB; ++j) {
-                if (odd[j] || (__double2hiint(accd[j]) & 0x7FF00000) >= 0x47E00000) {
+                // 0 < some partial sum < 2^-126, or a final value from 2^127 up: the conversion path decides
+                if (emin[j] < 0x38100000u - 1u || (__double2hiint(accd[j]) & 0x7FF00000) >= 0x47E00000) {
                     float qj[64];
                     float r = 0.0f;
                     if (Ds <= 64) {

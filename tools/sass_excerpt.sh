@@ -13,6 +13,7 @@ cuobjdump -sass "$SO" 2>/dev/null | awk '
   }
   END{for(k in c) print c[k], k}' | sort -k2,2 -k3,3 | while read n fn m; do printf "%6d  %-28s %s\n" "$n" "$m" "$(echo "$fn" | c++filt | cut -c1-90)"; done
 echo
-echo "# first tensor-core / TMEM / TMA instructions of gt_tc_filter2_kernel and the table load of scan8_kernel<8>"
+echo "# first tensor-core / TMEM / TMA instructions of gt_tc_filter2_kernel, the table load of scan8_kernel<8>, the MMA group and TMEM loads of encode_tc_kernel<16>"
 cuobjdump -sass "$SO" 2>/dev/null | awk '/Function : /{fn=$3} fn ~ /gt_tc_filter2_kernel/ && /UTCHMMA|LDTM|UBLKCP|SYNCS/{print "gt_tc_filter2: " $0}' | grep -v "^\s*$" | cut -c1-140 | grep "UTCHMMA\|LDTM\|UBLKCP" | head -14
 cuobjdump -sass "$SO" 2>/dev/null | awk '/Function : /{fn=$3} fn ~ /scan8_kernelILi8E/ && /UBLKCP|SYNCS|LDS.128/{print "scan8<8>: " $0}' | cut -c1-140 | head -14
+cuobjdump -sass "$SO" 2>/dev/null | awk '/Function : /{fn=$3} fn ~ /encode_tc_kernelILi16E/ && /UTCHMMA|LDTM|UTCBAR/{print "encode_tc<16>: " $0}' | cut -c1-140 | head -10
