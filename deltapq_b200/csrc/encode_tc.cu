@@ -46,6 +46,7 @@ constexpr int ET_N = 256;     // centroid columns = MMA N = TMEM columns
 constexpr int ET_A_BYTES = ET_ROWS * 128;  // 16 KB
 constexpr int ET_B_BYTES = ET_N * 128;     // 32 KB
 constexpr uint32_t ET_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ET_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr int ET_QCAP = 16;   // candidate queue per row (bytes of shared memory)
 constexpr int ET_SMEM_MIN = 80 * 1024;  // > 228 KB / 3: at most two CTAs per SM, 256 TMEM columns each
 
 // bounded spin on the MMA completion barrier (a few seconds at most: a failure is reported, never a hang)
@@ -161,7 +162,7 @@ __device__ __forceinline__ float ref_dist(const float (&x)[DS], const float* __r
 }
 
 // CTA = (range of 128-vector tiles, subspace m); thread r owns row r of the tile = TMEM lane r.
-template <int DS>
+template <int DS, bool FULLK>  // FULLK: K == 256, no column masks
 __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
     constexpr int KSTEPS = (3 * DS + 3 + 15) / 16;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
     float* s_cw = reinterpret_cast<float*>(smem + ET_B_BYTES + ET_A_BYTES);  // [K][DS] exact centroids
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + ET_B_BYTES + ET_A_BYTES + ET_N * DS * 4);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+    uint8_t* s_queue = reinterpret_cast<uint8_t*>(s_bar + 2);  // [ET_ROWS][ET_QCAP]
 
     const int r = threadIdx.x, warp = r >> 5, m = blockIdx.y, K = a.K;
     const int64_t n_tiles = (a.n + ET_ROWS - 1) / ET_ROWS;
@@ -240,17 +242,17 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
 #pragma unroll
         for (int b = 0; b < ET_N / 32; ++b) {
             bm[b] = -FLT_MAX;
-            if (b * 32 < K) {
+            if (FULLK || b * 32 < K) {
                 uint32_t v[32];
                 umma::tmem_ld32(tlane + (uint32_t)(b * 32), v);
                 umma::tmem_ld_wait();
                 float m0 = -FLT_MAX, m1 = -FLT_MAX, m2 = -FLT_MAX, m3 = -FLT_MAX;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    m0 = fmaxf(m0, b * 32 + j < K ? __uint_as_float(v[j]) : -FLT_MAX);
-                    m1 = fmaxf(m1, b * 32 + j + 1 < K ? __uint_as_float(v[j + 1]) : -FLT_MAX);
-                    m2 = fmaxf(m2, b * 32 + j + 2 < K ? __uint_as_float(v[j + 2]) : -FLT_MAX);
-                    m3 = fmaxf(m3, b * 32 + j + 3 < K ? __uint_as_float(v[j + 3]) : -FLT_MAX);
+                    m0 = fmaxf(m0, FULLK || b * 32 + j < K ? __uint_as_float(v[j]) : -FLT_MAX);
+                    m1 = fmaxf(m1, FULLK || b * 32 + j + 1 < K ? __uint_as_float(v[j + 1]) : -FLT_MAX);
+                    m2 = fmaxf(m2, FULLK || b * 32 + j + 2 < K ? __uint_as_float(v[j + 2]) : -FLT_MAX);
+                    m3 = fmaxf(m3, FULLK || b * 32 + j + 3 < K ? __uint_as_float(v[j + 3]) : -FLT_MAX);
                 }
                 bm[b] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 vmax = fmaxf(vmax, bm[b]);
@@ -263,39 +265,69 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
         // upper bound of d_true(kb), the float evaluation's own rounding included
         const float dkb = fmaxf(fmaf(-2.0f, vmax, x2) + 2.0f * E, 0.0f) + 1e-6f * (x2 + 2.0f * fabsf(vmax));
         const float thr = 1.01f * (2.0f * E + 1.5f * gam * dkb);
-        float lim = vmax - thr;
+        const float lim = vmax - thr;
         // not finite, or small enough for operands / products to be flushed or the bound to underflow:
         // every column is a candidate (the loop below is then the reference's loop)
-        if (!(scale < 1e30f) || !(scale > 1e-25f) || !(cmax > 1e-25f) || !(x2 < 1e30f) || !(thr < 1e30f))
-            lim = -__int_as_float(0x7f800000);
+        const bool every = !(scale < 1e30f) || !(scale > 1e-25f) || !(cmax > 1e-25f) || !(x2 < 1e30f) || !(thr < 1e30f) ||
+                           !(lim == lim);
 
-        // pass 2: exact re-score of the candidates, ascending centroid id, strict <  (pq_tree.cpp:225-233)
-        float best = FLT_MAX;
-        int best_k = -1;  // nothing below FLT_MAX (overflow, NaN): the reference writes (uchar)-1 (pq_tree.cpp:217, 235)
+        // pass 2: the row's candidate columns, ascending, into its private queue.  Groups of four columns are
+        // tested by their maximum first: a row has one to three candidates among 256 columns, so nearly every
+        // group is dismissed with one compare.  Rows whose bound cannot be trusted skip this and take every column.
+        int nc = every ? ET_QCAP + 1 : 0;
+        uint8_t* queue = s_queue + r * ET_QCAP;
 #pragma unroll
         for (int b = 0; b < ET_N / 32; ++b) {
             // tcgen05.ld is warp-collective (.sync.aligned): the skip must be decided by the whole warp.  A row
-            // without a candidate in this block gets hits == 0 from the test below anyway.
-            if (b * 32 < K && __any_sync(0xffffffffu, !(bm[b] < lim))) {
+            // without a candidate in this block dismisses its eight groups below.
+            if ((FULLK || b * 32 < K) && __any_sync(0xffffffffu, !every && !(bm[b] < lim))) {
                 uint32_t v[32];
                 umma::tmem_ld32(tlane + (uint32_t)(b * 32), v);
                 umma::tmem_ld_wait();
-                uint32_t hits = 0;
+                if (!every) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) hits |= (!(__uint_as_float(v[j]) < lim) ? 1u : 0u) << j;
-                if (K - b * 32 < 32) hits &= (1u << (K - b * 32)) - 1u;
-                while (hits) {
-                    const int k = b * 32 + __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const float dist = ref_dist<DS>(x, s_cw + k * DS);
-                    if (dist < best) {
-                        best = dist;
-                        best_k = k;
+                    for (int g = 0; g < 8; ++g) {
+                        const float g4 = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
+                                               fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+                        if (!(g4 < lim)) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int k = b * 32 + 4 * g + i;
+                                if ((FULLK || k < K) && !(__uint_as_float(v[4 * g + i]) < lim)) {
+                                    if (nc < ET_QCAP) queue[nc] = (uint8_t)k;
+                                    ++nc;
+                                }
+                            }
+                        }
                     }
                 }
-                __syncwarp();  // the rows' candidate loops differ in length: reconverge before the next collective load
+                __syncwarp();  // the rows' work differs: reconverge before the next collective load
             }
         }
+        // exact re-score, ascending centroid id, strict <  (pq_tree.cpp:225-233).  Every row walks ITS queue, so
+        // a warp runs as many rounds as its longest queue; a row with more candidates than the queue holds
+        // (duplicated centroids en masse, untrusted bound) runs the reference loop over all K columns.
+        float best = FLT_MAX;
+        int best_k = -1;  // nothing below FLT_MAX (overflow, NaN): the reference writes (uchar)-1 (pq_tree.cpp:217, 235)
+        if (nc > ET_QCAP) {
+            for (int k = 0; k < K; ++k) {
+                const float dist = ref_dist<DS>(x, s_cw + k * DS);
+                if (dist < best) {
+                    best = dist;
+                    best_k = k;
+                }
+            }
+        } else {
+            for (int i = 0; i < nc; ++i) {
+                const int k = queue[i];
+                const float dist = ref_dist<DS>(x, s_cw + k * DS);
+                if (dist < best) {
+                    best = dist;
+                    best_k = k;
+                }
+            }
+        }
+        __syncwarp();
         if (row < a.n) a.codes[(size_t)row * a.M + m] = (uint8_t)best_k;
 #pragma unroll
         for (int d = 0; d < DS; ++d) x[d] = xnext[d];
@@ -313,15 +345,16 @@ cudaError_t launch_ds(const EncTcArgs& a, int n_sms, cudaStream_t st) {
     encode_tc_prep_kernel<DS><<<a.M, ET_N, 0, st>>>(a.cw, a.K, const_cast<unsigned char*>(a.bsplit), const_cast<float*>(a.cmax));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int smem = ET_B_BYTES + ET_A_BYTES + ET_N * DS * 4 + 64;
+    int smem = ET_B_BYTES + ET_A_BYTES + ET_N * DS * 4 + 16 + ET_ROWS * ET_QCAP;
     if (smem < ET_SMEM_MIN) smem = ET_SMEM_MIN;
-    e = cudaFuncSetAttribute(encode_tc_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    auto kernel = a.K == ET_N ? encode_tc_kernel<DS, true> : encode_tc_kernel<DS, false>;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int64_t n_tiles = (a.n + ET_ROWS - 1) / ET_ROWS;
     int64_t gx = (2LL * n_sms + a.M - 1) / a.M;  // two CTAs per SM
     if (gx > n_tiles) gx = n_tiles;
     if (gx < 1) gx = 1;
-    encode_tc_kernel<DS><<<dim3((unsigned)gx, (unsigned)a.M), ET_ROWS, smem, st>>>(a);
+    kernel<<<dim3((unsigned)gx, (unsigned)a.M), ET_ROWS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

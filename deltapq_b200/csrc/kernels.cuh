@@ -301,6 +301,29 @@ __device__ __forceinline__ double exact_dist(const float* __restrict__ lut, cons
     return d;
 }
 
+// Upper bound of exact_dist from float adds only (no conversions): the float sum of M non-negative
+// entries is within (M - 1) * 2^-24 of the real sum, the exact value within 2^-24 of it.
+__device__ __forceinline__ float dist_upper_bound(const float* __restrict__ lut, const uint8_t* __restrict__ code, int cstride,
+                                                  int M, int K) {
+    float d = 0.0f;
+    if (cstride == 8) {
+        const uint2 w = *reinterpret_cast<const uint2*>(code);
+        const uint32_t ww[2] = {w.x, w.y};
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+            if (m < M) d += lut[m * K + ((ww[m >> 2] >> (8 * (m & 3))) & 0xFFu)];
+    } else if (cstride == 16) {
+        const uint4 w = *reinterpret_cast<const uint4*>(code);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            if (m < M) d += lut[m * K + ((ww[m >> 2] >> (8 * (m & 3))) & 0xFFu)];
+    } else {
+        for (int m = 0; m < M; ++m) d += lut[m * K + code[m]];
+    }
+    return __fmul_ru(d, 1.0f + 1.0f / 131072.0f);  // M <= 64 terms: 2^-17 covers 64 * 2^-24 with room
+}
+
 // Block-wide running top-k used by the exact kernels (fallback, re-score): s_keys[0 .. *s_n) holds
 // candidate keys (distance bits << 32 | position, unique); the call sorts them (bitonic, whole CTA),
 // keeps the topk smallest and makes the k-th key the new exclusive bound *s_thr.  Every thread of

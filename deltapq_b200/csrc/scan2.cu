@@ -79,9 +79,7 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
             }
             const float* c = cw + ((size_t)m * K + k) * Ds;
             const float4* qrow = reinterpret_cast<const float4*>(s_q + (size_t)m * Ds * LUT2_QPB);
-#pragma unroll 4
-            for (int d = 0; d < Ds; ++d) {
-                const float cv = c[d];
+            auto term = [&](int d, float cv) {
                 const float4 qa = qrow[2 * d], qb = qrow[2 * d + 1];
                 const float qv[LUT2_QPB] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
@@ -95,6 +93,22 @@ __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw,
                     const double big = __hiloint2double(e + (29 << 20), 0);
                     accd[j] = __dsub_rn(__dadd_rn(sum, big), big);
                 }
+            };
+            if ((Ds & 3) == 0) {
+                // the centroid's values arrive four at a time, the next four in flight while these are used
+                // (ncu: the scalar loads of the codebook were the kernel's top stall, long_scoreboard)
+                const float4* c4 = reinterpret_cast<const float4*>(c);
+                float4 nxt = __ldg(c4);
+                for (int d4 = 0; d4 < Ds / 4; ++d4) {
+                    const float4 cur = nxt;
+                    if (d4 + 1 < Ds / 4) nxt = __ldg(c4 + d4 + 1);
+                    term(4 * d4, cur.x);
+                    term(4 * d4 + 1, cur.y);
+                    term(4 * d4 + 2, cur.z);
+                    term(4 * d4 + 3, cur.w);
+                }
+            } else {
+                for (int d = 0; d < Ds; ++d) term(d, c[d]);
             }
 #pragma unroll
             for (int j = 0; j < LUT2_QPB; ++j) {
