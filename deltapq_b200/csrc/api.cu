@@ -835,7 +835,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     const size_t n_items = (size_t)g.n_groups * g.n_slices;
     const int max_flagged = Q;
     if ((rc = ix->d_lutf.ensure((size_t)Q * MK * 4))) return rc;
-    if ((rc = ix->d_scale.ensure((size_t)g.n_groups * g.qpg * 8))) return rc;
+    // [padded Q] doubles (15-bit scale), then [Q][16] floats (per-subspace table maxima)
+    const size_t scale_bytes = (size_t)g.n_groups * g.qpg * 8;
+    if ((rc = ix->d_scale.ensure(scale_bytes + (size_t)Q * 16 * 4))) return rc;
     if (P.v2) {
         if ((rc = ix->d_cand.ensure(n_items * g.qpg * g.bcap * 8))) return rc;
         if ((rc = ix->d_cnt.ensure(n_items * g.qpg * 4))) return rc;
@@ -888,10 +890,11 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     CU(cudaMemsetAsync(ctrl, 0, 64, st));
     if (P.v2) {
         dpq::launch_lut2(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
-                         ix->d_scale.as<double>(), seeded ? nullptr : ix->d_qlut.as<uint16_t>(),
+                         ix->d_scale.as<double>(), reinterpret_cast<float*>(ix->d_scale.as<char>() + scale_bytes),
+                         seeded ? nullptr : ix->d_qlut.as<uint16_t>(),
                          ix->d_gthr.as<uint32_t>(), ix->d_ovf.as<uint32_t>(), g.n_groups, P.shape,
                          (uint32_t)ix->opt_dbg_bound, st);
-        launches += seeded ? 1 : 2;
+        launches += seeded ? 1 : 3;
     } else {
         dpq::launch_lut(ix->d_cw.as<float>(), P.M, P.K, ix->Ds, d_queries, Q, ix->d_lutf.as<float>(),
                         ix->d_scale.as<double>(), ix->d_qlut.as<uint32_t>(), ix->d_gthr.as<uint32_t>(), g, st);

@@ -144,8 +144,9 @@ struct Scan2Args {
     int kp, bcap, trigger, epoch, ramp;
 };
 // d_qlut == nullptr: float tables only (the coarse pipeline quantises them itself)
+// d_mmax: [Q][16] floats of scratch (per-subspace table maxima; d_scale is derived from it when d_qlut is set)
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
-                 double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
+                 double* d_scale, float* d_mmax, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  const V2Shape& sh, uint32_t bound0, cudaStream_t st);
 cudaError_t launch_scan2(const Scan2Args& a, cudaStream_t st);
 // small batches: exact tables + per-subspace maxima mmax[Q][16], one block per (query, subspace)

@@ -40,111 +40,110 @@ constexpr int MAXQB = 64;  // s_thr / s_cnt slots (56 or 24 used)
 
 // ------------------------------------------------------------------------ ADC tables ---
 // Exact float tables [Q][M*K] (reference arithmetic, DCAT.h:3754-3757, same expression as
-// adc_entry) + per-query fixed-point scale.  Block = 8 queries x one thread per centroid: every
-// codebook value is loaded once and feeds eight independent accumulation chains (the chain is
-// a dependent float -> double -> float sequence, so the eight queries are the ILP).
+// adc_entry).  Block = (8 queries, one subspace) x one thread per centroid: every codebook value is
+// loaded once and feeds eight independent accumulation chains (the chain is a dependent
+// float -> double -> float sequence, so the eight queries are the ILP).  One subspace per block keeps
+// the grid at (Q / 8) * M short blocks: with whole queries per block (1250 blocks of 256 threads at
+// C2, four or five resident per SM) the last wave ran a third full.
+// mmax[q][16]: the per-subspace maxima of the table (scale2_kernel derives the 15-bit scale from them).
 constexpr int LUT2_QPB = 8;
 __global__ void __launch_bounds__(256) lut2_kernel(const float* __restrict__ cw, int M, int K, int Ds,
                                                    const float* __restrict__ queries, int Q,
-                                                   float* __restrict__ lutf, double* __restrict__ scale) {
-    extern __shared__ __align__(16) float s_q[];  // [M*Ds][LUT2_QPB]: the eight queries' values of one dimension are adjacent
-    __shared__ int s_max[LUT2_QPB][16];
+                                                   float* __restrict__ lutf, float* __restrict__ mmax) {
+    extern __shared__ __align__(16) float s_q[];  // [Ds][LUT2_QPB]: the eight queries' values of one dimension are adjacent
+    __shared__ int s_max[LUT2_QPB];
     const int q0 = blockIdx.x * LUT2_QPB;
+    const int m = blockIdx.y;
     const int k = threadIdx.x;
     const int D = M * Ds;
-    for (int i = k; i < LUT2_QPB * D; i += blockDim.x) {
-        const int j = i / D, d = i % D;  // coalesced global read, transposed store
+    for (int i = k; i < LUT2_QPB * Ds; i += blockDim.x) {
+        const int j = i / Ds, d = i % Ds;  // contiguous global reads per query, transposed store
         const int q = q0 + j;
-        s_q[d * LUT2_QPB + j] = q < Q ? queries[(size_t)q * D + d] : 0.0f;
+        s_q[d * LUT2_QPB + j] = q < Q ? queries[(size_t)q * D + m * Ds + d] : 0.0f;
     }
-    if (k < LUT2_QPB * 16) s_max[k / 16][k % 16] = 0;
+    if (k < LUT2_QPB) s_max[k] = 0;
     __syncthreads();
-    for (int m = 0; m < M; ++m) {
-        float acc[LUT2_QPB];
+    float acc[LUT2_QPB];
 #pragma unroll
-        for (int j = 0; j < LUT2_QPB; ++j) acc[j] = 0.0f;
-        if (k < K) {
-            // The accumulator is rounded to float after every term INSIDE the double domain (add and
-            // subtract 2^(E+29), see round_to_float_in_double): branch free, one F2F per term instead of
-            // three.  The sum only grows, so the rare ranges where that shortcut differs from the float
-            // conversion are detected with one sticky flag per chain -- a nonzero partial sum below
-            // 2^-126 (float subnormals keep fewer bits) or a final value from 2^127 up (the conversion may
-            // overflow) -- and such an entry is recomputed by adc_entry, which takes the conversion path.
-            double accd[LUT2_QPB];
-            unsigned emin[LUT2_QPB];  // smallest (exponent field - 1) seen by the chain; a zero sum wraps to the top
+    for (int j = 0; j < LUT2_QPB; ++j) acc[j] = 0.0f;
+    if (k < K) {
+        // The accumulator is rounded to float after every term INSIDE the double domain (add and
+        // subtract 2^(E+29), see round_to_float_in_double): branch free, one F2F per term instead of
+        // three.  The sum only grows, so the rare ranges where that shortcut differs from the float
+        // conversion are detected per chain -- a nonzero partial sum below 2^-126 (float subnormals
+        // keep fewer bits) or a final value from 2^127 up (the conversion may overflow) -- and such an
+        // entry is recomputed by adc_entry, which takes the conversion path.
+        double accd[LUT2_QPB];
+        unsigned emin[LUT2_QPB];  // smallest (exponent field - 1) seen by the chain; a zero sum wraps to the top
 #pragma unroll
-            for (int j = 0; j < LUT2_QPB; ++j) {
-                accd[j] = 0.0;
-                emin[j] = 0xFFFFFFFFu;
-            }
-            const float* c = cw + ((size_t)m * K + k) * Ds;
-            const float4* qrow = reinterpret_cast<const float4*>(s_q + (size_t)m * Ds * LUT2_QPB);
-            auto term = [&](int d, float cv) {
-                const float4 qa = qrow[2 * d], qb = qrow[2 * d + 1];
-                const float qv[LUT2_QPB] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-                for (int j = 0; j < LUT2_QPB; ++j) {
-                    const double diff = (double)__fsub_rn(cv, qv[j]);
-                    // diff is a widened float: diff * diff is exact in double, so one fused multiply-add
-                    // rounds exactly like the reference's multiply then add
-                    const double sum = __fma_rn(diff, diff, accd[j]);
-                    const int e = __double2hiint(sum) & 0x7FF00000;
-                    emin[j] = min(emin[j], (unsigned)e - 1u);
-                    const double big = __hiloint2double(e + (29 << 20), 0);
-                    accd[j] = __dsub_rn(__dadd_rn(sum, big), big);
-                }
-            };
-            if ((Ds & 3) == 0) {
-                // the centroid's values arrive four at a time, the next four in flight while these are used
-                // (ncu: the scalar loads of the codebook were the kernel's top stall, long_scoreboard)
-                const float4* c4 = reinterpret_cast<const float4*>(c);
-                float4 nxt = __ldg(c4);
-                for (int d4 = 0; d4 < Ds / 4; ++d4) {
-                    const float4 cur = nxt;
-                    if (d4 + 1 < Ds / 4) nxt = __ldg(c4 + d4 + 1);
-                    term(4 * d4, cur.x);
-                    term(4 * d4 + 1, cur.y);
-                    term(4 * d4 + 2, cur.z);
-                    term(4 * d4 + 3, cur.w);
-                }
-            } else {
-                for (int d = 0; d < Ds; ++d) term(d, c[d]);
-            }
+        for (int j = 0; j < LUT2_QPB; ++j) {
+            accd[j] = 0.0;
+            emin[j] = 0xFFFFFFFFu;
+        }
+        const float* c = cw + ((size_t)m * K + k) * Ds;
+        const float4* qrow = reinterpret_cast<const float4*>(s_q);
+        auto term = [&](int d, float cv) {
+            const float4 qa = qrow[2 * d], qb = qrow[2 * d + 1];
+            const float qv[LUT2_QPB] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
             for (int j = 0; j < LUT2_QPB; ++j) {
-                // 0 < some partial sum < 2^-126, or a final value from 2^127 up: the conversion path decides
-                if (emin[j] < 0x38100000u - 1u || (__double2hiint(accd[j]) & 0x7FF00000) >= 0x47E00000) {
-                    float qj[64];
-                    float r = 0.0f;
-                    if (Ds <= 64) {
-                        for (int d = 0; d < Ds; ++d) qj[d] = s_q[(m * Ds + d) * LUT2_QPB + j];
-                        r = adc_entry(c, qj, Ds);
-                    } else {  // long sub-vectors: the conversion form, term by term
-                        for (int d = 0; d < Ds; ++d) {
-                            const float diff = __fsub_rn(c[d], s_q[(m * Ds + d) * LUT2_QPB + j]);
-                            r = (float)__dadd_rn((double)r, __dmul_rn((double)diff, (double)diff));
-                        }
-                    }
-                    acc[j] = r;
-                } else {
-                    acc[j] = (float)accd[j];
-                }
+                const double diff = (double)__fsub_rn(cv, qv[j]);
+                // diff is a widened float: diff * diff is exact in double, so one fused multiply-add
+                // rounds exactly like the reference's multiply then add
+                const double sum = __fma_rn(diff, diff, accd[j]);
+                const int e = __double2hiint(sum) & 0x7FF00000;
+                emin[j] = min(emin[j], (unsigned)e - 1u);
+                const double big = __hiloint2double(e + (29 << 20), 0);
+                accd[j] = __dsub_rn(__dadd_rn(sum, big), big);
             }
+        };
+        if ((Ds & 3) == 0) {  // the centroid's values four at a time, the next four in flight
+            const float4* c4 = reinterpret_cast<const float4*>(c);
+            float4 nxt = __ldg(c4);
+            for (int d4 = 0; d4 < Ds / 4; ++d4) {
+                const float4 cur = nxt;
+                if (d4 + 1 < Ds / 4) nxt = __ldg(c4 + d4 + 1);
+                term(4 * d4, cur.x);
+                term(4 * d4 + 1, cur.y);
+                term(4 * d4 + 2, cur.z);
+                term(4 * d4 + 3, cur.w);
+            }
+        } else {
+            for (int d = 0; d < Ds; ++d) term(d, c[d]);
         }
 #pragma unroll
         for (int j = 0; j < LUT2_QPB; ++j) {
-            if (k < K && q0 + j < Q) lutf[(size_t)(q0 + j) * M * K + m * K + k] = acc[j];
-            int vi = __float_as_int(acc[j]);  // >= 0: integer order == float order
-            for (int o = 16; o; o >>= 1) vi = max(vi, __shfl_xor_sync(0xffffffffu, vi, o));
-            if ((k & 31) == 0) atomicMax(&s_max[j][m], vi);
+            // 0 < some partial sum < 2^-126, or a final value from 2^127 up: the conversion path decides
+            if (emin[j] < 0x38100000u - 1u || (__double2hiint(accd[j]) & 0x7FF00000) >= 0x47E00000) {
+                float r = 0.0f;
+                for (int d = 0; d < Ds; ++d) {
+                    const float diff = __fsub_rn(c[d], s_q[d * LUT2_QPB + j]);
+                    r = (float)__dadd_rn((double)r, __dmul_rn((double)diff, (double)diff));
+                }
+                acc[j] = r;
+            } else {
+                acc[j] = (float)accd[j];
+            }
         }
     }
-    __syncthreads();
-    if (k < LUT2_QPB && q0 + k < Q) {
-        double sum = 0.0;
-        for (int m = 0; m < M; ++m) sum += (double)__int_as_float(s_max[k][m]);
-        scale[q0 + k] = sum > 0.0 ? (double)(32767 - 16) / sum : 1.0;
+#pragma unroll
+    for (int j = 0; j < LUT2_QPB; ++j) {
+        if (k < K && q0 + j < Q) lutf[(size_t)(q0 + j) * M * K + m * K + k] = acc[j];
+        int vi = __float_as_int(acc[j]);  // >= 0: integer order == float order
+        vi = __reduce_max_sync(0xffffffffu, vi);
+        if ((k & 31) == 0) atomicMax(&s_max[j], vi);
     }
+    __syncthreads();
+    if (k < LUT2_QPB && q0 + k < Q) mmax[(size_t)(q0 + k) * 16 + m] = __int_as_float(s_max[k]);
+}
+
+// 15-bit fixed-point scale per query from the per-subspace maxima (the 15-bit scan only)
+__global__ void scale2_kernel(const float* __restrict__ mmax, int M, int Q, double* __restrict__ scale) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    double sum = 0.0;
+    for (int m = 0; m < M; ++m) sum += (double)mmax[(size_t)q * 16 + m];
+    scale[q] = sum > 0.0 ? (double)(32767 - 16) / sum : 1.0;
 }
 
 // Small batches (latency mode): one block per (query, subspace), so that even a single query spreads
@@ -205,12 +204,14 @@ __global__ void __launch_bounds__(256) pack2_kernel(const float* __restrict__ lu
 }
 
 void launch_lut2(const float* d_cw, int M, int K, int Ds, const float* d_queries, int Q, float* d_lutf,
-                 double* d_scale, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
+                 double* d_scale, float* d_mmax, uint16_t* d_qlut, uint32_t* d_gthr, uint32_t* d_ovf, int n_groups,
                  const V2Shape& sh, uint32_t bound0, cudaStream_t st) {
-    const size_t lsm = (size_t)LUT2_QPB * M * Ds * sizeof(float);
+    const size_t lsm = (size_t)LUT2_QPB * Ds * sizeof(float);
     if (lsm > 48 * 1024) cudaFuncSetAttribute(lut2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
-    lut2_kernel<<<(Q + LUT2_QPB - 1) / LUT2_QPB, 256, lsm, st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf, d_scale);
+    lut2_kernel<<<dim3((unsigned)((Q + LUT2_QPB - 1) / LUT2_QPB), (unsigned)M), 256, lsm, st>>>(d_cw, M, K, Ds, d_queries, Q, d_lutf,
+                                                                                            d_mmax);
     if (!d_qlut) return;
+    scale2_kernel<<<(Q + 255) / 256, 256, 0, st>>>(d_mmax, M, Q, d_scale);
     pack2_kernel<<<dim3((unsigned)n_groups, (unsigned)(sh.rows / 64)), 256, 0, st>>>(d_lutf, d_scale, M, K, Q, sh.qb(), sh.rows,
                                                                                     d_qlut, d_gthr, d_ovf, bound0);
 }
