@@ -46,7 +46,7 @@ constexpr int ET_N = 256;     // centroid columns = MMA N = TMEM columns
 constexpr int ET_A_BYTES = ET_ROWS * 128;  // 16 KB
 constexpr int ET_B_BYTES = ET_N * 128;     // 32 KB
 constexpr uint32_t ET_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ET_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-constexpr int ET_QCAP = 16;   // candidate queue per row (bytes of shared memory)
+constexpr int ET_THREADS = 256;  // two threads per row: column halves
 constexpr int ET_SMEM_MIN = 80 * 1024;  // > 228 KB / 3: at most two CTAs per SM, 256 TMEM columns each
 
 // bounded spin on the MMA completion barrier (a few seconds at most: a failure is reported, never a hang)
@@ -129,26 +129,6 @@ __global__ void __launch_bounds__(ET_N) encode_tc_prep_kernel(const float* __res
     }
 }
 
-template <int DS>
-__device__ __forceinline__ void load_row(const EncTcArgs& a, int64_t row, int m, float (&x)[DS]) {
-    if (row >= a.n) {
-#pragma unroll
-        for (int d = 0; d < DS; ++d) x[d] = 0.0f;
-        return;
-    }
-    const float* p = a.x + (size_t)row * a.D + (size_t)m * DS;
-    if (a.vec_ok && (m + 1) * DS <= a.D) {
-#pragma unroll
-        for (int d = 0; d < DS; d += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p + d));
-            x[d] = v.x, x[d + 1] = v.y, x[d + 2] = v.z, x[d + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int d = 0; d < DS; ++d) x[d] = m * DS + d < a.D ? __ldg(p + d) : 0.0f;  // zero padding (pq_tree.cpp:194-198)
-    }
-}
-
 // the reference's distance, op for op (pq_tree.cpp:215-237): never contracted into FMAs
 template <int DS>
 __device__ __forceinline__ float ref_dist(const float (&x)[DS], const float* __restrict__ c) {
@@ -161,23 +141,65 @@ __device__ __forceinline__ float ref_dist(const float (&x)[DS], const float* __r
     return dist;
 }
 
-// CTA = (range of 128-vector tiles, subspace m); thread r owns row r of the tile = TMEM lane r.
+// rows of tile `t` (this CTA's subspace) -> s_x[row][XS] (zero beyond n and beyond D: pq_tree.cpp:194-198).
+// Aligned input: 16-byte cp.async copies, completed with cp.async.wait_group by the caller, so the next
+// tile's rows travel while this tile is scored.  Thread (r, h) moves the chunks c of row r with c % 2 == h.
+template <int DS>
+__device__ __forceinline__ void stage_rows(const EncTcArgs& a, int64_t t, int m, float* s_x, int r, int h) {
+    constexpr int XS = DS + 4;
+    const int64_t row = t * ET_ROWS + r;
+    if (a.vec_ok && (m + 1) * DS <= a.D) {
+        const bool valid = row < a.n;
+        const float* src = a.x + (valid ? (size_t)row * a.D + (size_t)m * DS : 0);
+#pragma unroll
+        for (int c = 0; c < DS / 4; ++c)
+            if ((c & 1) == h)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(s_x + r * XS + 4 * c)), "l"(src + 4 * c),
+                             "r"(valid ? 16 : 0)
+                             : "memory");
+    } else {
+#pragma unroll
+        for (int c = 0; c < DS / 4; ++c)
+            if ((c & 1) == h)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int d = 4 * c + i;
+                    s_x[r * XS + d] = (row < a.n && m * DS + d < a.D) ? __ldg(a.x + (size_t)row * a.D + (size_t)m * DS + d) : 0.0f;
+                }
+    }
+}
+
+// CTA = (range of 128-vector tiles, subspace m), 256 threads: thread t owns row r = t & 127 (= TMEM lane)
+// and the column half h = t >> 7 (128 centroids), so that an SM holds 16 warps (two CTAs of 256 TMEM
+// columns): the first version (128 threads, 8 warps per SM) issued 44 % of its cycles (ncu, stall "wait").
+// Per tile: A' from the staged rows -> 1..4 tcgen05.mma (one elected thread) -> every thread reads its 128
+// scores ONCE (four tcgen05.ld), keeping the maximum of each group of four columns (32 registers, a
+// by-product of the max tree) -> the halves exchange their row maxima -> groups whose maximum reaches the
+// candidate limit are re-scored in the reference's arithmetic, four columns each, ascending -> the halves
+// exchange (distance, id).  A second pass over TMEM for the individual columns cost more than re-scoring
+// three extra columns per candidate (tcgen05.ld is warp-collective: a warp visits the union of its rows'
+// candidate blocks, i.e. nearly all of them).
 template <int DS, bool FULLK>  // FULLK: K == 256, no column masks
-__global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
+__global__ void __launch_bounds__(ET_THREADS, 2) encode_tc_kernel(const EncTcArgs a) {
     constexpr int KSTEPS = (3 * DS + 3 + 15) / 16;
+    constexpr int PIECES = 2 * KSTEPS;
+    constexpr int XS = DS + 4;  // row stride of the staged rows: 16-byte accesses of 8 consecutive rows hit 8 bank groups
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + ET_B_BYTES;
     float* s_cw = reinterpret_cast<float*>(smem + ET_B_BYTES + ET_A_BYTES);  // [K][DS] exact centroids
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + ET_B_BYTES + ET_A_BYTES + ET_N * DS * 4);
+    float* s_xb = s_cw + ET_N * DS;                                           // [2][ET_ROWS][XS] staged rows
+    float* s_vmax = s_xb + 2 * ET_ROWS * XS;                                  // [256] row maxima per half
+    float* s_best = s_vmax + ET_THREADS;                                      // [128] upper half's best distance
+    int* s_bestk = reinterpret_cast<int*>(s_best + ET_ROWS);                  // [128] and its centroid
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bestk + ET_ROWS);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
-    uint8_t* s_queue = reinterpret_cast<uint8_t*>(s_bar + 2);  // [ET_ROWS][ET_QCAP]
 
-    const int r = threadIdx.x, warp = r >> 5, m = blockIdx.y, K = a.K;
+    const int tid = threadIdx.x, r = tid & (ET_ROWS - 1), h = tid >> 7, warp = tid >> 5, m = blockIdx.y, K = a.K;
     const int64_t n_tiles = (a.n + ET_ROWS - 1) / ET_ROWS;
     const int64_t t_lo = n_tiles * blockIdx.x / gridDim.x, t_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
 
-    if (r == 0) {
+    if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -189,26 +211,34 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
     {  // the subspace's B' block (already in the shared-memory layout) and its exact centroids
         const uint4* src = reinterpret_cast<const uint4*>(a.bsplit + (size_t)m * ET_B_BYTES);
         uint4* dst = reinterpret_cast<uint4*>(sB);
-        for (int i = r; i < ET_B_BYTES / 16; i += ET_ROWS) dst[i] = __ldg(src + i);
-        for (int i = r; i < K * DS; i += ET_ROWS) s_cw[i] = a.cw[(size_t)m * K * DS + i];
+        for (int i = tid; i < ET_B_BYTES / 16; i += ET_THREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < K * DS; i += ET_THREADS) s_cw[i] = a.cw[(size_t)m * K * DS + i];
     }
+    if (t_lo < t_hi) stage_rows<DS>(a, t_lo, m, s_xb, r, h);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(h * (ET_N / 2));
 
     const float cmax = a.cmax[m];
     const float gam = (float)(DS + 3) * 5.97e-8f;  // (Ds + 3) * 2^-24 * 1.001
     uint32_t phase = 0;
     bool ok = (smem_u32(smem) & 1023u) == 0;  // the swizzle is a function of the absolute address
 
-    float x[DS];
-    if (t_lo < t_hi) load_row<DS>(a, t_lo * ET_ROWS + r, m, x);
     for (int64_t t = t_lo; t < t_hi && ok; ++t) {
-        const int64_t row = t * ET_ROWS + r;
+        const float* s_x = s_xb + (int)((t - t_lo) & 1) * ET_ROWS * XS + r * XS;
+        float* s_xnext = s_xb + (int)((t - t_lo + 1) & 1) * ET_ROWS * XS;
         float xn2 = 0.0f;
         {
+            float x[DS];
+#pragma unroll
+            for (int d = 0; d < DS; d += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(s_x + d);
+                x[d] = v.x, x[d + 1] = v.y, x[d + 2] = v.z, x[d + 3] = v.w;
+            }
             uint16_t hi[DS], lo[DS];
             const uint16_t one[3] = {0x3F80, 0x3F80, 0x3F80};
 #pragma unroll
@@ -217,11 +247,22 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
                 lo[d] = bf16_bits(x[d] - bf16_val(hi[d]));
                 xn2 = fmaf(x[d], x[d], xn2);
             }
-            store_row<DS, false>(sA, r, hi, lo, one);
+            // the two halves write alternate 16-byte pieces of the row
+#pragma unroll
+            for (int p = 0; p < PIECES; ++p) {
+                if ((p & 1) == h) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        w[i] = (uint32_t)row_elem<DS, false>(p * 8 + 2 * i, hi, lo, one) |
+                               ((uint32_t)row_elem<DS, false>(p * 8 + 2 * i + 1, hi, lo, one) << 16);
+                    *reinterpret_cast<uint4*>(sA + umma::swz_off(r, p)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> MMA reads
         __syncthreads();
-        if (r == 0) {
+        if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(sA), sb = smem_u32(sB);
 #pragma unroll
@@ -229,35 +270,38 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
                 umma::mma_bf16<ET_IDESC>(tmem, umma::smem_desc(sa + 32 * k), umma::smem_desc(sb + 32 * k), k != 0);
             umma::commit(s_bar);
         }
-        float xnext[DS];  // the next tile's row travels while the MMAs run
-        if (t + 1 < t_hi) load_row<DS>(a, row + ET_ROWS, m, xnext);
+        if (t + 1 < t_hi) stage_rows<DS>(a, t + 1, m, s_xnext, r, h);  // the next tile's rows travel meanwhile
+        asm volatile("cp.async.commit_group;" ::: "memory");
         ok = wait_mma(s_bar, phase);
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (!ok) break;
 
-        // pass 1: best score of the row, and of each block of 32 columns
-        float bm[ET_N / 32];
+        // this thread's 128 scores, once: the maximum of every group of four columns, and of the half row
+        float gm[ET_N / 8];
         float vmax = -FLT_MAX;
 #pragma unroll
-        for (int b = 0; b < ET_N / 32; ++b) {
-            bm[b] = -FLT_MAX;
-            if (FULLK || b * 32 < K) {
-                uint32_t v[32];
-                umma::tmem_ld32(tlane + (uint32_t)(b * 32), v);
-                umma::tmem_ld_wait();
-                float m0 = -FLT_MAX, m1 = -FLT_MAX, m2 = -FLT_MAX, m3 = -FLT_MAX;
+        for (int b = 0; b < ET_N / 64; ++b) {
+            uint32_t v[32];
+            umma::tmem_ld32(tlane + (uint32_t)(b * 32), v);
+            umma::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    m0 = fmaxf(m0, FULLK || b * 32 + j < K ? __uint_as_float(v[j]) : -FLT_MAX);
-                    m1 = fmaxf(m1, FULLK || b * 32 + j + 1 < K ? __uint_as_float(v[j + 1]) : -FLT_MAX);
-                    m2 = fmaxf(m2, FULLK || b * 32 + j + 2 < K ? __uint_as_float(v[j + 2]) : -FLT_MAX);
-                    m3 = fmaxf(m3, FULLK || b * 32 + j + 3 < K ? __uint_as_float(v[j + 3]) : -FLT_MAX);
+            for (int g = 0; g < 8; ++g) {
+                float g4 = -FLT_MAX;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = h * (ET_N / 2) + b * 32 + 4 * g + i;  // padded columns (k >= K) hold 0: masked
+                    g4 = fmaxf(g4, FULLK || k < K ? __uint_as_float(v[4 * g + i]) : -FLT_MAX);
                 }
-                bm[b] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                vmax = fmaxf(vmax, bm[b]);
+                gm[b * 8 + g] = g4;
+                vmax = fmaxf(vmax, g4);
             }
         }
+        s_vmax[tid] = vmax;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // TMEM and sA are free from here on
+        vmax = fmaxf(s_vmax[r], s_vmax[r + ET_ROWS]);
+
         // candidate limit (see the header): everything not provably worse than the best column
         const float xlen = sqrtf(xn2) * 1.0001f, x2 = xn2 * 1.0001f;
         const float scale = fmaf(xlen, cmax, 0.5f * cmax * cmax);
@@ -270,71 +314,54 @@ __global__ void __launch_bounds__(ET_ROWS) encode_tc_kernel(const EncTcArgs a) {
         // every column is a candidate (the loop below is then the reference's loop)
         const bool every = !(scale < 1e30f) || !(scale > 1e-25f) || !(cmax > 1e-25f) || !(x2 < 1e30f) || !(thr < 1e30f) ||
                            !(lim == lim);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < ET_N / 8; ++j) mask |= (!(gm[j] < lim) ? 1u : 0u) << j;
+        if (every) mask = 0xFFFFFFFFu;
 
-        // pass 2: the row's candidate columns, ascending, into its private queue.  Groups of four columns are
-        // tested by their maximum first: a row has one to three candidates among 256 columns, so nearly every
-        // group is dismissed with one compare.  Rows whose bound cannot be trusted skip this and take every column.
-        int nc = every ? ET_QCAP + 1 : 0;
-        uint8_t* queue = s_queue + r * ET_QCAP;
+        // exact re-score of the candidate groups, ascending centroid id, strict <  (pq_tree.cpp:225-233).  Every
+        // row walks ITS groups, so a warp runs as many rounds as its row with the most groups (one, mostly).
+        float best = FLT_MAX;
+        int best_k = -1;  // nothing below FLT_MAX (overflow, NaN): the reference writes (uchar)-1 (pq_tree.cpp:217, 235)
+        if (mask) {
+            float x[DS];
 #pragma unroll
-        for (int b = 0; b < ET_N / 32; ++b) {
-            // tcgen05.ld is warp-collective (.sync.aligned): the skip must be decided by the whole warp.  A row
-            // without a candidate in this block dismisses its eight groups below.
-            if ((FULLK || b * 32 < K) && __any_sync(0xffffffffu, !every && !(bm[b] < lim))) {
-                uint32_t v[32];
-                umma::tmem_ld32(tlane + (uint32_t)(b * 32), v);
-                umma::tmem_ld_wait();
-                if (!every) {
+            for (int d = 0; d < DS; d += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(s_x + d);
+                x[d] = v.x, x[d + 1] = v.y, x[d + 2] = v.z, x[d + 3] = v.w;
+            }
+            while (mask) {
+                const int g = __ffs(mask) - 1;
+                mask &= mask - 1;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float g4 = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
-                                               fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
-                        if (!(g4 < lim)) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int k = b * 32 + 4 * g + i;
-                                if ((FULLK || k < K) && !(__uint_as_float(v[4 * g + i]) < lim)) {
-                                    if (nc < ET_QCAP) queue[nc] = (uint8_t)k;
-                                    ++nc;
-                                }
-                            }
+                for (int i = 0; i < 4; ++i) {
+                    const int k = h * (ET_N / 2) + 4 * g + i;
+                    if (FULLK || k < K) {
+                        const float dist = ref_dist<DS>(x, s_cw + k * DS);
+                        if (dist < best) {
+                            best = dist;
+                            best_k = k;
                         }
                     }
                 }
-                __syncwarp();  // the rows' work differs: reconverge before the next collective load
             }
         }
-        // exact re-score, ascending centroid id, strict <  (pq_tree.cpp:225-233).  Every row walks ITS queue, so
-        // a warp runs as many rounds as its longest queue; a row with more candidates than the queue holds
-        // (duplicated centroids en masse, untrusted bound) runs the reference loop over all K columns.
-        float best = FLT_MAX;
-        int best_k = -1;  // nothing below FLT_MAX (overflow, NaN): the reference writes (uchar)-1 (pq_tree.cpp:217, 235)
-        if (nc > ET_QCAP) {
-            for (int k = 0; k < K; ++k) {
-                const float dist = ref_dist<DS>(x, s_cw + k * DS);
-                if (dist < best) {
-                    best = dist;
-                    best_k = k;
-                }
-            }
-        } else {
-            for (int i = 0; i < nc; ++i) {
-                const int k = queue[i];
-                const float dist = ref_dist<DS>(x, s_cw + k * DS);
-                if (dist < best) {
-                    best = dist;
-                    best_k = k;
-                }
-            }
+        if (h == 1) {
+            s_best[r] = best;
+            s_bestk[r] = best_k;
         }
-        __syncwarp();
-        if (row < a.n) a.codes[(size_t)row * a.M + m] = (uint8_t)best_k;
-#pragma unroll
-        for (int d = 0; d < DS; ++d) x[d] = xnext[d];
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // every row is read before the next tile's MMA overwrites the columns (and sA)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the next tile's rows have landed (this thread's copies)
+        __syncthreads();                                      // ... everyone's; and the upper half's results
+        if (h == 0) {
+            // the lower half holds the smaller ids: the upper half wins only with a strictly smaller distance
+            if (s_best[r] < best) best_k = s_bestk[r];
+            const int64_t row = t * ET_ROWS + r;
+            if (row < a.n) a.codes[(size_t)row * a.M + m] = (uint8_t)best_k;
+        }
+        // s_best / s_bestk are rewritten only after the next tile's two barriers
     }
-    if (!ok && r == 0) atomicExch(a.error, 1u);
+    if (!ok && tid == 0) atomicExch(a.error, 1u);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)ET_N) : "memory");
@@ -345,7 +372,7 @@ cudaError_t launch_ds(const EncTcArgs& a, int n_sms, cudaStream_t st) {
     encode_tc_prep_kernel<DS><<<a.M, ET_N, 0, st>>>(a.cw, a.K, const_cast<unsigned char*>(a.bsplit), const_cast<float*>(a.cmax));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int smem = ET_B_BYTES + ET_A_BYTES + ET_N * DS * 4 + 16 + ET_ROWS * ET_QCAP;
+    int smem = ET_B_BYTES + ET_A_BYTES + ET_N * DS * 4 + 2 * ET_ROWS * (DS + 4) * 4 + ET_THREADS * 4 + ET_ROWS * 8 + 64;
     if (smem < ET_SMEM_MIN) smem = ET_SMEM_MIN;
     auto kernel = a.K == ET_N ? encode_tc_kernel<DS, true> : encode_tc_kernel<DS, false>;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -354,7 +381,7 @@ cudaError_t launch_ds(const EncTcArgs& a, int n_sms, cudaStream_t st) {
     int64_t gx = (2LL * n_sms + a.M - 1) / a.M;  // two CTAs per SM
     if (gx > n_tiles) gx = n_tiles;
     if (gx < 1) gx = 1;
-    kernel<<<dim3((unsigned)gx, (unsigned)a.M), ET_ROWS, smem, st>>>(a);
+    kernel<<<dim3((unsigned)gx, (unsigned)a.M), ET_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -423,9 +423,7 @@ struct Encoder {
         const char* env = getenv("DPQ_ENCODE_TC");
         tc = dpq::encode_tc_supported(M, K, Ds) && !(env && env[0] == '0');
         if (tc) {
-            cudaDeviceProp prop;
-            CU(cudaGetDeviceProperties(&prop, dpq::api_device()));
-            n_sms = prop.multiProcessorCount;
+            CU(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dpq::api_device()));  // (cudaGetDeviceProperties takes milliseconds)
             CU(cudaMalloc(&d_scratch.p, dpq::encode_tc_scratch_bytes(M)));
             CU(cudaMalloc(&d_err.p, 4));
             CU(cudaMemset(d_err.p, 0, 4));
