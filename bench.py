@@ -425,6 +425,10 @@ def run_gpu(args):
         cpu_base, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
             cpu_base, parity = cpu_baseline(payload, args.n_codes, cw, queries, args.cpu_baseline_queries, out_pos, out_dist)
+        elif not args.no_cpu_baseline:
+            # N > 1: the CPU baseline is an N = 1 number, the parity check is not: rank 0's answers for a short
+            # sample of its own batch against the reference CPU scan (about a second; the other ranks wait)
+            _, parity = cpu_baseline(payload, args.n_codes, cw, queries, min(100, args.cpu_baseline_queries), out_pos, out_dist)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
         if os.path.exists(tpath):
