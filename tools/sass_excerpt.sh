@@ -9,7 +9,7 @@ cuobjdump -sass "$SO" 2>/dev/null | awk '
   /Function : /{fn=$3; next}
   /^[ \t]*\/\*[0-9a-f]+\*\//{
      m=$2; if (m ~ /^@/) m=$3;
-     if (fn ~ /^_ZN3dpq/ && m ~ /^(UTCHMMA|UTCQMMA|UTCBAR|LDTM|STTM|UBLKCP|UTMALDG|SYNCS|LDS\.128|LDS\.64|ATOMS|CCTL|UTCCP)/) { c[fn" "m]++ }
+     if (fn ~ /^_ZN3dpq/ && m ~ /^(UTCHMMA|UTCQMMA|UTCBAR|LDTM|STTM|UBLKCP|UTMALDG|SYNCS|LDS\.128|LDS\.64|ATOMS|CCTL|UTCCP|FMNMX3|LDGSTS|REDUX|DFMA)/) { c[fn" "m]++ }
   }
   END{for(k in c) print c[k], k}' | sort -k2,2 -k3,3 | while read n fn m; do printf "%6d  %-28s %s\n" "$n" "$m" "$(echo "$fn" | c++filt | cut -c1-90)"; done
 echo
