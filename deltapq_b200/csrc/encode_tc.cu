@@ -134,9 +134,14 @@ template <int DS>
 __device__ __forceinline__ float ref_dist(const float (&x)[DS], const float* __restrict__ c) {
     float dist = 0.0f;
 #pragma unroll
-    for (int d = 0; d < DS; ++d) {
-        const float diff = __fsub_rn(x[d], c[d]);
-        dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+    for (int d = 0; d < DS; d += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(c + d);  // rows are 16-byte aligned
+        const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float diff = __fsub_rn(x[d + i], cv[i]);
+            dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+        }
     }
     return dist;
 }
@@ -187,8 +192,10 @@ __global__ void __launch_bounds__(ET_THREADS, 2) encode_tc_kernel(const EncTcArg
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + ET_B_BYTES;
-    float* s_cw = reinterpret_cast<float*>(smem + ET_B_BYTES + ET_A_BYTES);  // [K][DS] exact centroids
-    float* s_xb = s_cw + ET_N * DS;                                           // [2][ET_ROWS][XS] staged rows
+    float* s_cw = reinterpret_cast<float*>(smem + ET_B_BYTES + ET_A_BYTES);  // [K][XS] exact centroids, rows padded like s_x:
+    // the rows of a warp's 32 different candidates then spread over the banks (ncu, unpadded: 60 % of the
+    // kernel's shared-memory wavefronts were bank conflicts, top stall short_scoreboard)
+    float* s_xb = s_cw + ET_N * XS;                                           // [2][ET_ROWS][XS] staged rows
     float* s_vmax = s_xb + 2 * ET_ROWS * XS;                                  // [256] row maxima per half
     float* s_best = s_vmax + ET_THREADS;                                      // [128] upper half's best distance
     int* s_bestk = reinterpret_cast<int*>(s_best + ET_ROWS);                  // [128] and its centroid
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(ET_THREADS, 2) encode_tc_kernel(const EncTcArg
         const uint4* src = reinterpret_cast<const uint4*>(a.bsplit + (size_t)m * ET_B_BYTES);
         uint4* dst = reinterpret_cast<uint4*>(sB);
         for (int i = tid; i < ET_B_BYTES / 16; i += ET_THREADS) dst[i] = __ldg(src + i);
-        for (int i = tid; i < K * DS; i += ET_THREADS) s_cw[i] = a.cw[(size_t)m * K * DS + i];
+        for (int i = tid; i < K * DS; i += ET_THREADS) s_cw[(i / DS) * XS + i % DS] = a.cw[(size_t)m * K * DS + i];
     }
     if (t_lo < t_hi) stage_rows<DS>(a, t_lo, m, s_xb, r, h);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -239,24 +246,45 @@ __global__ void __launch_bounds__(ET_THREADS, 2) encode_tc_kernel(const EncTcArg
                 const float4 v = *reinterpret_cast<const float4*>(s_x + d);
                 x[d] = v.x, x[d + 1] = v.y, x[d + 2] = v.z, x[d + 3] = v.w;
             }
-            uint16_t hi[DS], lo[DS];
-            const uint16_t one[3] = {0x3F80, 0x3F80, 0x3F80};
 #pragma unroll
-            for (int d = 0; d < DS; ++d) {
-                hi[d] = bf16_bits(x[d]);
-                lo[d] = bf16_bits(x[d] - bf16_val(hi[d]));
-                xn2 = fmaf(x[d], x[d], xn2);
-            }
-            // the two halves write alternate 16-byte pieces of the row
+            for (int d = 0; d < DS; ++d) xn2 = fmaf(x[d], x[d], xn2);
+            if constexpr (DS == 16) {
+                // the two halves write alternate 16-byte pieces of the row: pieces h, 2 + h (hi) and 4 + h (lo)
+                // hold dimensions 8h .. 8h + 7, so each half converts only its eight values
+                const float4 u0 = *reinterpret_cast<const float4*>(s_x + 8 * h), u1 = *reinterpret_cast<const float4*>(s_x + 8 * h + 4);
+                const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                uint32_t wh[4], wl[4];
 #pragma unroll
-            for (int p = 0; p < PIECES; ++p) {
-                if ((p & 1) == h) {
-                    uint32_t w[4];
+                for (int i = 0; i < 4; ++i) {
+                    const uint16_t h0 = bf16_bits(u[2 * i]), h1 = bf16_bits(u[2 * i + 1]);
+                    const uint16_t l0 = bf16_bits(u[2 * i] - bf16_val(h0)), l1 = bf16_bits(u[2 * i + 1] - bf16_val(h1));
+                    wh[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    wl[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                const uint4 ph = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                *reinterpret_cast<uint4*>(sA + umma::swz_off(r, h)) = ph;
+                *reinterpret_cast<uint4*>(sA + umma::swz_off(r, 2 + h)) = ph;
+                *reinterpret_cast<uint4*>(sA + umma::swz_off(r, 4 + h)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                *reinterpret_cast<uint4*>(sA + umma::swz_off(r, 6 + h)) =
+                    h == 0 ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);  // 1 1 1 0 ...
+            } else {
+                uint16_t hi[DS], lo[DS];
+                const uint16_t one[3] = {0x3F80, 0x3F80, 0x3F80};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        w[i] = (uint32_t)row_elem<DS, false>(p * 8 + 2 * i, hi, lo, one) |
-                               ((uint32_t)row_elem<DS, false>(p * 8 + 2 * i + 1, hi, lo, one) << 16);
-                    *reinterpret_cast<uint4*>(sA + umma::swz_off(r, p)) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int d = 0; d < DS; ++d) {
+                    hi[d] = bf16_bits(x[d]);
+                    lo[d] = bf16_bits(x[d] - bf16_val(hi[d]));
+                }
+#pragma unroll
+                for (int p = 0; p < PIECES; ++p) {
+                    if ((p & 1) == h) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            w[i] = (uint32_t)row_elem<DS, false>(p * 8 + 2 * i, hi, lo, one) |
+                                   ((uint32_t)row_elem<DS, false>(p * 8 + 2 * i + 1, hi, lo, one) << 16);
+                        *reinterpret_cast<uint4*>(sA + umma::swz_off(r, p)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
                 }
             }
         }
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(ET_THREADS, 2) encode_tc_kernel(const EncTcArg
                 for (int i = 0; i < 4; ++i) {
                     const int k = h * (ET_N / 2) + 4 * g + i;
                     if (FULLK || k < K) {
-                        const float dist = ref_dist<DS>(x, s_cw + k * DS);
+                        const float dist = ref_dist<DS>(x, s_cw + k * XS);
                         if (dist < best) {
                             best = dist;
                             best_k = k;
@@ -372,7 +400,7 @@ cudaError_t launch_ds(const EncTcArgs& a, int n_sms, cudaStream_t st) {
     encode_tc_prep_kernel<DS><<<a.M, ET_N, 0, st>>>(a.cw, a.K, const_cast<unsigned char*>(a.bsplit), const_cast<float*>(a.cmax));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int smem = ET_B_BYTES + ET_A_BYTES + ET_N * DS * 4 + 2 * ET_ROWS * (DS + 4) * 4 + ET_THREADS * 4 + ET_ROWS * 8 + 64;
+    int smem = ET_B_BYTES + ET_A_BYTES + ET_N * (DS + 4) * 4 + 2 * ET_ROWS * (DS + 4) * 4 + ET_THREADS * 4 + ET_ROWS * 8 + 64;
     if (smem < ET_SMEM_MIN) smem = ET_SMEM_MIN;
     auto kernel = a.K == ET_N ? encode_tc_kernel<DS, true> : encode_tc_kernel<DS, false>;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
