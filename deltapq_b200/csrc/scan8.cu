@@ -142,16 +142,32 @@ __global__ void __launch_bounds__(256) pack8_kernel(const float* __restrict__ lu
         if (blockIdx.y == 0) ovf[grp * QB + threadIdx.x] = 0u;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * QB; i += blockDim.x) {
-        const int ql = i >> 6, r = i & 63;
-        const int q = grp * QB + ql, row = row0 + r;
-        const int m = row >> 8, c = row & 255;
-        uint8_t v = 0;
-        if (q < Q && m < M && c < K) {
-            const double x = (double)lutf[(size_t)q * MK + m * K + c] * s_inv[ql];
-            v = x >= (double)SAT ? (uint8_t)SAT : (uint8_t)__double2int_rn(x);
+    // 28 entries per thread, seven loads in flight at a time (one load per round trip made the kernel
+    // latency-bound: 53 us for 82 MB of L2-resident tables)
+    constexpr int PER = 64 * QB / 256, BATCH = 7;
+    static_assert(PER % BATCH == 0, "tile shape");
+#pragma unroll 1
+    for (int it0 = 0; it0 < PER; it0 += BATCH) {
+        float f[BATCH];  // negative = no such entry (table entries are sums of squares)
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int i = (it0 + u) * 256 + threadIdx.x;
+            const int ql = i >> 6, r = i & 63;
+            const int q = grp * QB + ql, row = row0 + r;
+            const int m = row >> 8, c = row & 255;
+            f[u] = (q < Q && m < M && c < K) ? __ldg(lutf + (size_t)q * MK + m * K + c) : -1.0f;
         }
-        tile[r * QB + ql] = v;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int i = (it0 + u) * 256 + threadIdx.x;
+            const int ql = i >> 6, r = i & 63;
+            uint8_t v = 0;
+            if (f[u] >= 0.0f) {
+                const double x = (double)f[u] * s_inv[ql];
+                v = x >= (double)SAT ? (uint8_t)SAT : (uint8_t)__double2int_rn(x);
+            }
+            tile[r * QB + ql] = v;
+        }
     }
     __syncthreads();
     uint32_t* dst = reinterpret_cast<uint32_t*>(qlut8 + ((size_t)grp * ROWS + row0) * ROWB);
