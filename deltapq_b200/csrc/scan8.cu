@@ -67,11 +67,18 @@ template <int PS_T>
 __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict__ lutf, const uint8_t* __restrict__ sample_codes, int cstride,
                                                          int64_t n_local, int M, int K, int topk, int R,
                                                          float* __restrict__ cap) {
-    extern __shared__ float s_lut[];  // M*K
+    extern __shared__ __align__(16) float s_lut[];  // M*K
     __shared__ int s_cnt[2][PS_T / 32];
     const int q = blockIdx.x;
     const int MK = M * K;
-    for (int i = threadIdx.x; i < MK; i += PS_T) s_lut[i] = lutf[(size_t)q * MK + i];
+    if ((MK & 3) == 0) {  // 16-byte loads, all of a thread's in flight together
+        const float4* src = reinterpret_cast<const float4*>(lutf + (size_t)q * MK);
+        float4* dst = reinterpret_cast<float4*>(s_lut);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < MK / 4; i += PS_T) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < MK; i += PS_T) s_lut[i] = lutf[(size_t)q * MK + i];
+    }
     __syncthreads();
     constexpr int PER = 16;  // R <= PS_T * PER
     constexpr int DROP = 17;  // pattern bits below the bucket
@@ -542,10 +549,15 @@ __global__ void __launch_bounds__(R8W_WARPS * 32) rescore8w_kernel(const Rescore
     // inclusive bound: a valid cap known beforehand, then the k-th best key so far
     const float known = a.cap_in ? a.cap_in[q] : FLT_MAX;
     uint64_t bound = ((uint64_t)__float_as_uint(known) << 32) | 0xFFFFFFFFull;
-    for (int i0 = 0; i0 < total; i0 += 32) {
-        uint64_t key = ~0ull;
-        const int i = i0 + lane;
-        if (i < total) {
+    // Two candidates per lane per round, every load of both issued before either is used (indices are
+    // clamped instead of branched around): a round is a chain of three dependent memory round trips
+    // (position -> code -> table entries), and one candidate per lane left the warp waiting on each of them.
+    constexpr int U = 2;
+    for (int i0 = 0; i0 < total; i0 += 32 * U) {
+        uint32_t pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = min(i0 + 32 * u + lane, total - 1);
             int lo = 0, hi = a.n_slices;  // slice s with off[s] <= i < off[s+1]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -553,23 +565,32 @@ __global__ void __launch_bounds__(R8W_WARPS * 32) rescore8w_kernel(const Rescore
                 else hi = mid;
             }
             const size_t item = (size_t)lo * a.n_groups + grp;
-            const uint32_t pos = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - off[lo]));
-            const uint8_t* code = a.codes + (size_t)((int64_t)pos - a.base_pos) * a.cstride;
-            key = ((uint64_t)__float_as_uint((float)exact_dist(lut, code, a.cstride, a.M, a.K)) << 32) | pos;
+            pos[u] = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - off[lo]));
         }
-        const bool take = key <= bound;
-        const uint32_t mk = __ballot_sync(0xffffffffu, take);
-        if (mk) {
-            if (n + 32 > R8W_BUF) {  // make room: reduce to the k best, tighten the bound
-                n = r8w_compact(buf, n, k, lane);
-                if (n == k) bound = buf[k - 1] - 1ull;
+        uint64_t keys[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint8_t* code = a.codes + (size_t)((int64_t)pos[u] - a.base_pos) * a.cstride;
+            keys[u] = ((uint64_t)__float_as_uint((float)exact_dist(lut, code, a.cstride, a.M, a.K)) << 32) | pos[u];
+            if (i0 + 32 * u + lane >= total) keys[u] = ~0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t key = keys[u];
+            const bool take = key <= bound;
+            const uint32_t mk = __ballot_sync(0xffffffffu, take);
+            if (mk) {
+                if (n + 32 > R8W_BUF) {  // make room: reduce to the k best, tighten the bound
+                    n = r8w_compact(buf, n, k, lane);
+                    if (n == k) bound = buf[k - 1] - 1ull;
+                    __syncwarp();
+                }
+                const bool still = take && key <= bound;
+                const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
+                if (still) buf[n + __popc(mk2 & ((1u << lane) - 1u))] = key;
+                n += __popc(mk2);
                 __syncwarp();
             }
-            const bool still = take && key <= bound;
-            const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
-            if (still) buf[n + __popc(mk2 & ((1u << lane) - 1u))] = key;
-            n += __popc(mk2);
-            __syncwarp();
         }
     }
     n = r8w_compact(buf, n, k, lane);
