@@ -81,6 +81,7 @@ struct dpq_index {
     DevBuf d_qlut8, d_cand8, d_cnt8, d_ovf8, d_flagged2, d_cap0, d_cap1, d_part8, d_done8, d_ps_codes;
     int ps_R = 0;  // presample nodes currently gathered in d_ps_codes
     int last_coarse = 0;
+    int last_sample_stride = 0, last_refine_stride = 0;  // strides of the sampled coarse passes of the last search
     int last_device_queries = 0;  // queries of the last dpq_index_search_device call (a host-buffer search runs sub-batches)
     int64_t last_items8 = 0;
     int n_chunks = 0;
@@ -799,11 +800,21 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     int S_auto = P.n_local >= 2000000 ? 64 : (P.n_local >= 1000000 ? 32 : (P.n_local >= 400000 ? 16 : 8));
     // wide shape, short lists: a denser sample (1M codes, M = 16, top-10: 2.42 ms at 16 vs 2.8 ms at 32)
     if (P.shape.nf == 16 && topk <= 32 && S_auto > 16 && P.n_local < 2000000) S_auto = 16;
-    const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : S_auto);
+    // Large shards, seeded pipeline: a 1/64 sample of 10^8..10^9 nodes is millions of nodes, far too many to scan
+    // under the presample's loose cap (0.5 % quantile: tens of thousands of survivors per query, appended and
+    // re-scored: 0.36 s of a 1.10 s step on a 250M-node shard).  Two levels instead: a ~64K-node sample under
+    // the presample cap, then the 1/64 sample under THAT cap (the refine pass below), then the whole shard.
+    int S_big = 0;
+    if (coarse && ix->opt_seed != 0 && ix->opt_sample == 0 && ix->opt_refine < 0 && P.n_local / 64 > 262144) {
+        S_big = 128;
+        while (S_big < 16384 && P.n_local / S_big > 98304) S_big <<= 1;
+    }
+    const int S = !coarse ? 1 : (ix->opt_sample > 0 ? ix->opt_sample : (S_big ? S_big : S_auto));
     const int n_chunks_sample = (((ix->n_chunks + spw - 1) / spw + S - 1) / S) * spw;  // chunks the sample pass walks
     int rc = P.v2 ? choose_geometry2(ix, Q, topk, &g, coarse ? n_chunks_sample : -1) : choose_geometry(ix, Q, topk, &g);
     if (rc) return rc;
     ix->last_coarse = coarse ? 1 : 0;
+    ix->last_sample_stride = coarse ? S : 0;
     ix->last_device_queries = Q;
     // geometry of the coarse passes: 112-query groups, 4 strands per warp
     const int warps8 = ix->opt_warps8;
@@ -815,8 +826,9 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
     // second refinement level: a denser sampled coarse pass (stride S2 < S) under the first cap.  Long result
     // lists need it: the cap of a 1/S sample is about the (k S)-th distance of the tree, and the coarse filter
     // passes a multiple of that many nodes (26K survivors per query at top-100, S = 32, M = 16).
-    int S2 = ix->opt_refine >= 0 ? ix->opt_refine : (P.shape.nf == 16 && topk > 32 ? 8 : 0);
+    int S2 = ix->opt_refine >= 0 ? ix->opt_refine : (S_big ? 64 : (P.shape.nf == 16 && topk > 32 ? 8 : 0));
     if (!coarse || S2 < 2 || S2 >= S) S2 = 0;
+    ix->last_refine_stride = S2;
     const int n_chunks_refine8 = S2 ? (((ix->n_chunks + 3) / 4 + S2 - 1) / S2) * 4 : 0;
     int g8_groups = 0, g8_slices = 1, g8_slices_s = 1, g8_slices_r = 1;
     if (coarse) {
@@ -1267,6 +1279,8 @@ int64_t dpq_index_stat(dpq_index* ix, const char* name) {
     if (n == "last_launches") return ix->last_launches;
     if (n == "engine") return P.v2 ? 2 : 1;
     if (n == "last_coarse") return ix->last_coarse;
+    if (n == "last_sample_stride") return ix->last_sample_stride;
+    if (n == "last_refine_stride") return ix->last_refine_stride;
     if (n == "last_latency") return ix->last_latency;
     if (n == "last_host_enqueue_us") return ix->host_us[0];
     if (n == "last_host_wait_us") return ix->host_us[1];

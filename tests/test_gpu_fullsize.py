@@ -266,3 +266,38 @@ def test_latency_mode_small_and_odd_trees(sift1m):
         b = ix.search(q, 10)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
         ix.close()
+
+
+def test_two_level_sample_on_a_large_shard():
+    """Shards of tens of millions of nodes and more (the 10^9-code tree over 1..8 GPUs): the seeded pipeline
+    samples in two levels (~64K nodes under the presample cap, then every 64th batch under that cap) before
+    the full pass.  Same answers as the 15-bit sample pass (`seed=0`) and as plain ADC over the codes."""
+    n, M, K, Q, k = 20_000_000, 8, 256, 300, 10
+    rng = np.random.default_rng(5)
+    codes = rng.integers(0, K, size=(n, M), dtype=np.uint8)
+    cw = dg.roundtrip_codebook((rng.random((M, K, 16)) * 120).astype(np.float32))
+    queries = (rng.random((Q, 128)) * 120).astype(np.float32)
+    dcodes = dpq.DeviceBuffer(codes.nbytes).upload(codes)
+    dt = dpq.DeviceTree(dcodes.ptr.value, n, M, cw)
+    ix = dt.shard(0, 1)
+    ix.set_codebook(cw)
+    pos, ids, dist = ix.search(queries, k)
+    assert ix.stat("last_coarse") == 1 and ix.stat("last_fallback") == 0
+    assert ix.stat("last_sample_stride") >= 128 and ix.stat("last_refine_stride") == 64
+    ix.set_option("seed", 0)
+    pos0, ids0, dist0 = ix.search(queries, k)
+    assert ix.stat("last_sample_stride") == 64 and ix.stat("last_refine_stride") == 0
+    assert np.array_equal(dist, dist0) and np.array_equal(pos, pos0) and np.array_equal(ids, ids0)
+    # plain ADC over the codes for a few queries: distance = float(double sum of the float table entries)
+    lut = dpq.adc_tables(cw, queries[:3])
+    for i in range(3):
+        d = np.zeros(n, np.float64)
+        for m in range(M):
+            d += lut[i, m][codes[:, m]].astype(np.float64)
+        d32 = d.astype(np.float32)
+        best = np.sort(d32, kind="stable")[:k]
+        assert np.array_equal(dist[i], best)
+        assert np.array_equal(d32[ids[i]], dist[i])
+    ix.close()
+    dt.free()
+    dcodes.free()
