@@ -1,6 +1,6 @@
 """Developer probe: BASELINE configs[2] shape (SIFT1M-shaped, M=16 K=256, top-100) or, with a
 third argument "gist", configs[3] shape (GIST-shaped 960-d floats in [0,1), M=16 K=256).
-Usage: python tools/perf_probe_m16.py N Q [gist]"""
+Usage: python tools/perf_probe_m16.py [N=1000000] [Q=2000] [gist]"""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -8,7 +8,9 @@ import numpy as np
 import datagen as dg
 import deltapq_b200 as dpq
 from oracle import pyoracle as po
-N = int(sys.argv[1]); Q = int(sys.argv[2]); M = 16; K = 256; topk = 100
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+Q = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+M = 16; K = 256; topk = 100
 gist = len(sys.argv) > 3 and sys.argv[3] == "gist"
 gen, D = (dg.gist_like, 960) if gist else (dg.sift_like, 128)
 base = gen(N, D, seed=1)
