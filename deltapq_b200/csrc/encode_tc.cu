@@ -10,9 +10,10 @@
 // A' row (vector)   = [ x_hi | x_hi | x_lo | 1 1 1 | 0.. ]   (bf16, 64 columns = one 128-byte swizzle row)
 // B' row (centroid) = [ c_hi | c_lo | c_hi | n1 n2 n3 | 0.. ],  n1 + n2 + n3 = -||c||^2 / 2 split three ways
 // so that A'.B' = x_hi.c_hi + x_hi.c_lo + x_lo.c_hi - ||c||^2 / 2 = v_k up to a rigorously bounded error E.
-// The MMA result is a FILTER: every centroid whose score is within the bound of the best score is
-// re-scored in the reference's own arithmetic, in ascending centroid order with strict <, so the
-// code written is the reference's, bit for bit, whatever the tensor cores rounded (tests compare
+// The MMA result is a FILTER: every centroid whose score is within the bound of the best score (in
+// practice: every group of four consecutive centroids whose best score is) is re-scored in the
+// reference's own arithmetic, in ascending centroid order with strict <, so the code written is the
+// reference's, bit for bit, whatever the tensor cores rounded (tests compare
 // with the SIMT kernel and the oracle on adversarial inputs: duplicated centroids, exact ties,
 // huge / tiny magnitudes, non-finite values).
 //

@@ -62,6 +62,8 @@ try:
                encode_device_resident_s=round(t_dev, 4), encode_device_resident_vec_per_s=round(N / t_dev),
                encode_tensor_core_path=enc_tc, encode_kernel_us=enc_kernel_us,
                encode_kernel_vec_per_s=round(N / max(enc_kernel_us, 1) * 1e6),
+               encode_useful_tflops=round(2.0 * N * 256 * M * Ds / max(enc_kernel_us, 1) / 1e6, 1),   # 2 N K D
+               encode_mma_issued_tflops=round(2.0 * N * M * 256 * 64 / max(enc_kernel_us, 1) / 1e6, 1),  # hi.hi + hi.lo + lo.hi + norm, K padded to 64
                encode_simt_device_resident_s=round(t_simt, 4), encode_simt_kernel_us=simt_kernel_us,
                encode_simt_fp32_issue_frac=round(fp32_ops / max(simt_kernel_us, 1) * 1e6 / (148 * 128 * 1.965e9), 3),
                find_edges_s=round(t_edges, 3), tree_build_s=round(t_tree, 3),
