@@ -10,8 +10,8 @@ The tree is produced by the product's own pipeline (GPU encode, GPU edge search,
 layout + stream writer); only the cpu_baseline leg / --impl reference touch oracle/.
 
 N > 1 (torchrun, one rank per GPU).  Primary number: the 16 MB tree is replicated and the
-QUERIES are the sharded units (10K per GPU per step, weak scaling), result keys all-gathered
-over NCCL.  Secondary block "tree_sharded": the same tree sharded by whole depth-1 subtrees
+QUERIES are the sharded units (10K per GPU per step, weak scaling): independent batches, no
+data-path collective.  Secondary block "tree_sharded": the same tree sharded by whole depth-1 subtrees
 (the 1B-code design), every rank scans its shard for the same 10K queries, the
 per-rank top-k key lists are all-gathered over NCCL and merged on the device (strong scaling);
 its merged result is checked against the unsharded one in the same run.
@@ -269,8 +269,9 @@ def run_gpu(args):
 
     # Primary mode.  The 1M-code tree is 16 MB on the device: every GPU holds the whole tree
     # and answers ITS OWN batch of 10K queries (the units of work are queries: weak scaling,
-    # per-GPU batch fixed); the per-rank result keys are all-gathered so every rank ends with
-    # all N x 10K answers.  N = 1 is the plain single-GPU run.
+    # per-GPU batch fixed).  The batches are independent, so the primary step has no collective
+    # (the exchange step of the path -- all-gather of key lists + merge -- is what the tree_sharded
+    # and c5 blocks below measure).  N = 1 is the plain single-GPU run.
     ix = open_index(0, 1)
     t_setup = time.perf_counter() - t_setup
     if world > 1:
@@ -285,8 +286,6 @@ def run_gpu(args):
 
     def step_device():
         ix.search_device(d_q.data_ptr(), Q, k, d_key.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(d_all.view(-1), d_key.view(-1))
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -463,7 +462,7 @@ def run_gpu(args):
                        "device_bytes_per_node": ix.stat("device_bytes_per_node"),
                        "disk_bytes_per_node": round(n_bytes_total / args.n_codes, 3),
                        "sharding": "whole tree on one GPU" if world == 1 else
-                                   f"queries sharded: {world} replicas of the tree, {Q} queries per GPU per step, NCCL all-gather of the result keys",
+                                   f"queries sharded: {world} replicas of the tree, {Q} independent queries per GPU per step, no data-path collective",
                        "l2": "256 MiB buffer written before every timed step (L2 flush, outside the events)",
                        "tree": "built by libdpq (GPU encode + GPU edge search + GPU DFS layout and stream)",
                        "setup_s": round(t_setup, 1), "opts": args.opts or "default"},
