@@ -486,6 +486,8 @@ __global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
     }
 }
 
+// (Measured and rejected: two interleaved queries per warp, so that 10 000 queries fit one wave of resident
+// warps -- 235 us against 168 us at C2: candidate counts are heavy tailed, the longest query decides.)
 // Short lists (topk <= 32) with a few hundred survivors per query: ONE WARP per query, no barriers: the
 // keys live in a small shared-memory buffer that is reduced by rank counting whenever it fills.  (The
 // CTA-per-query form above pays a table load and ~50 barrier stages of sorting per query: 289 us against
@@ -518,135 +520,99 @@ __device__ __forceinline__ int r8w_compact(uint64_t* buf, int n, int k, int lane
     return keep;
 }
 
-// NQ queries per warp, interleaved.  One query per warp needs Q warps; an SM holds 64, so 10 000 queries are
-// 1.06 waves of 9 472 warps and the launch takes two query times.  With two queries per warp every warp is
-// resident at once and the two queries' memory round trips overlap.
-template <int NQ>
-__global__ void __launch_bounds__(R8W_WARPS * 32, NQ == 2 ? 10 : 12) rescore8w_kernel(const Rescore8Args a) {  // NQ = 2: 40 warps per SM = 11 840 queries in one wave
-    __shared__ uint64_t s_buf[R8W_WARPS][NQ][R8W_BUF];
-    __shared__ uint32_t s_off[R8W_WARPS][NQ][R8_MAXSL + 1];  // exclusive prefix of the per-slice counts
+__global__ void __launch_bounds__(R8W_WARPS * 32) rescore8w_kernel(const Rescore8Args a) {
+    __shared__ uint64_t s_buf[R8W_WARPS][R8W_BUF];
+    __shared__ uint32_t s_off[R8W_WARPS][R8_MAXSL + 1];  // exclusive prefix of the per-slice counts
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q0 = (blockIdx.x * R8W_WARPS + w) * NQ;
-    if (q0 >= a.Q) return;
-    const int k = a.topk;
-    int total[NQ], n[NQ], grp[NQ], ql[NQ];
-    uint64_t bound[NQ];
-    float known[NQ];
-    const float* lut[NQ];
-    int max_total = 0;
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-        const int q = min(q0 + j, a.Q - 1);  // a missing partner repeats the last query and is not written
-        grp[j] = q / a.qb, ql[j] = q % a.qb;
-        lut[j] = a.lutf + (size_t)q * a.M * a.K;
-        uint32_t* off = s_off[w][j];
-        uint32_t run = 0;
-        for (int s0 = 0; s0 < a.n_slices; s0 += 32) {
-            const int s = s0 + lane;
-            uint32_t c = 0;
-            if (s < a.n_slices) c = a.cand_cnt[((size_t)s * a.n_groups + grp[j]) * a.qb + ql[j]];
-            uint32_t incl = c;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (s < a.n_slices) off[s] = run + incl - c;
-            run += __shfl_sync(0xffffffffu, incl, 31);
+    const int q = blockIdx.x * R8W_WARPS + w;
+    if (q >= a.Q) return;
+    const int grp = q / a.qb, ql = q % a.qb;
+    const float* lut = a.lutf + (size_t)q * a.M * a.K;
+    uint64_t* buf = s_buf[w];
+    uint32_t* off = s_off[w];
+    uint32_t run = 0;
+    for (int s0 = 0; s0 < a.n_slices; s0 += 32) {
+        const int s = s0 + lane;
+        uint32_t c = 0;
+        if (s < a.n_slices) c = a.cand_cnt[((size_t)s * a.n_groups + grp) * a.qb + ql];
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        if (lane == 0) off[a.n_slices] = run;
-        total[j] = q0 + j < a.Q ? (int)run : 0;
-        max_total = max(max_total, total[j]);
-        n[j] = 0;
-        // inclusive bound: a valid cap known beforehand, then the k-th best key so far
-        known[j] = a.cap_in ? a.cap_in[q] : FLT_MAX;
-        bound[j] = ((uint64_t)__float_as_uint(known[j]) << 32) | 0xFFFFFFFFull;
+        if (s < a.n_slices) off[s] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) off[a.n_slices] = run;
     __syncwarp();
-    // Two candidates per lane per query per round, every load issued before any is used (indices are
+    const int total = (int)run;
+    const int k = a.topk;
+    int n = 0;
+    // inclusive bound: a valid cap known beforehand, then the k-th best key so far
+    const float known = a.cap_in ? a.cap_in[q] : FLT_MAX;
+    uint64_t bound = ((uint64_t)__float_as_uint(known) << 32) | 0xFFFFFFFFull;
+    // Two candidates per lane per round, every load of both issued before either is used (indices are
     // clamped instead of branched around): a round is a chain of three dependent memory round trips
     // (position -> code -> table entries), and one candidate per lane left the warp waiting on each of them.
     constexpr int U = 2;
-    for (int i0 = 0; i0 < max_total; i0 += 32 * U) {
-        uint32_t pos[NQ][U];
+    for (int i0 = 0; i0 < total; i0 += 32 * U) {
+        uint32_t pos[U];
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-            const uint32_t* off = s_off[w][j];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = max(0, min(i0 + 32 * u + lane, total[j] - 1));
-                int lo = 0, hi = a.n_slices;  // slice s with off[s] <= i < off[s+1]
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (off[mid] <= (uint32_t)i) lo = mid;
-                    else hi = mid;
-                }
-                const size_t item = (size_t)lo * a.n_groups + grp[j];
-                // (a query without candidates reads slot 0 of its first list: allocated, possibly stale, unused)
-                pos[j][u] = __ldcg(a.cand + (item * a.qb + ql[j]) * (size_t)a.bcap + ((uint32_t)i - off[lo]));
+        for (int u = 0; u < U; ++u) {
+            const int i = min(i0 + 32 * u + lane, total - 1);
+            int lo = 0, hi = a.n_slices;  // slice s with off[s] <= i < off[s+1]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (off[mid] <= (uint32_t)i) lo = mid;
+                else hi = mid;
             }
+            const size_t item = (size_t)lo * a.n_groups + grp;
+            pos[u] = __ldcg(a.cand + (item * a.qb + ql) * (size_t)a.bcap + ((uint32_t)i - off[lo]));
         }
-        uint64_t keys[NQ][U];
+        uint64_t keys[U];
 #pragma unroll
-        for (int j = 0; j < NQ; ++j)
+        for (int u = 0; u < U; ++u) {
+            const uint8_t* code = a.codes + (size_t)((int64_t)pos[u] - a.base_pos) * a.cstride;
+            keys[u] = ((uint64_t)__float_as_uint((float)exact_dist(lut, code, a.cstride, a.M, a.K)) << 32) | pos[u];
+            if (i0 + 32 * u + lane >= total) keys[u] = ~0ull;
+        }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                keys[j][u] = ~0ull;
-                if (i0 + 32 * u + lane < total[j]) {
-                    const uint8_t* code = a.codes + (size_t)((int64_t)pos[j][u] - a.base_pos) * a.cstride;
-                    keys[j][u] = ((uint64_t)__float_as_uint((float)exact_dist(lut[j], code, a.cstride, a.M, a.K)) << 32) | pos[j][u];
-                }
-            }
-#pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-            uint64_t* buf = s_buf[w][j];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint64_t key = keys[j][u];
-                const bool take = key <= bound[j];
-                const uint32_t mk = __ballot_sync(0xffffffffu, take);
-                if (mk) {
-                    if (n[j] + 32 > R8W_BUF) {  // make room: reduce to the k best, tighten the bound
-                        n[j] = r8w_compact(buf, n[j], k, lane);
-                        if (n[j] == k) bound[j] = buf[k - 1] - 1ull;
-                        __syncwarp();
-                    }
-                    const bool still = take && key <= bound[j];
-                    const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
-                    if (still) buf[n[j] + __popc(mk2 & ((1u << lane) - 1u))] = key;
-                    n[j] += __popc(mk2);
+        for (int u = 0; u < U; ++u) {
+            const uint64_t key = keys[u];
+            const bool take = key <= bound;
+            const uint32_t mk = __ballot_sync(0xffffffffu, take);
+            if (mk) {
+                if (n + 32 > R8W_BUF) {  // make room: reduce to the k best, tighten the bound
+                    n = r8w_compact(buf, n, k, lane);
+                    if (n == k) bound = buf[k - 1] - 1ull;
                     __syncwarp();
                 }
+                const bool still = take && key <= bound;
+                const uint32_t mk2 = __ballot_sync(0xffffffffu, still);
+                if (still) buf[n + __popc(mk2 & ((1u << lane) - 1u))] = key;
+                n += __popc(mk2);
+                __syncwarp();
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-        const int q = q0 + j;
-        if (q >= a.Q) break;
-        uint64_t* buf = s_buf[w][j];
-        const int nn = r8w_compact(buf, n[j], k, lane);
-        if (a.out_key)
-            for (int i = lane; i < k; i += 32)
-                a.out_key[(size_t)q * k + i] = i < nn ? buf[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
-        const float found = nn >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
-        if (lane == 0 && a.cap_out) a.cap_out[q] = fminf(found, known[j]);
-        if (lane == 0 && a.flagged) {
-            a.bound[q] = fminf(found, known[j]);
-            if (a.ovf[(size_t)grp[j] * a.qb + ql[j]]) {
-                const uint32_t slot = atomicAdd(a.n_flagged, 1u);
-                if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;
-            }
+    n = r8w_compact(buf, n, k, lane);
+    if (a.out_key)
+        for (int i = lane; i < k; i += 32)
+            a.out_key[(size_t)q * k + i] = i < n ? buf[i] : (((uint64_t)__float_as_uint(FLT_MAX) << 32) | 0xFFFFFFFFull);
+    const float found = n >= k ? __uint_as_float((uint32_t)(buf[k - 1] >> 32)) : FLT_MAX;
+    if (lane == 0 && a.cap_out) a.cap_out[q] = fminf(found, known);
+    if (lane == 0 && a.flagged) {
+        a.bound[q] = fminf(found, known);
+        if (a.ovf[(size_t)grp * a.qb + ql]) {
+            const uint32_t slot = atomicAdd(a.n_flagged, 1u);
+            if (slot < (uint32_t)a.max_flagged) a.flagged[slot] = (uint32_t)q;
         }
     }
 }
 
 void launch_rescore8(const Rescore8Args& a, cudaStream_t st) {
     if (a.n_parts <= 1 && a.topk <= 32 && a.warp_form) {
-        // one query per warp while that fits one wave (48 resident warps per SM at its register count), else two
-        if (a.Q <= 7000)
-            rescore8w_kernel<1><<<(a.Q + R8W_WARPS - 1) / R8W_WARPS, R8W_WARPS * 32, 0, st>>>(a);
-        else
-            rescore8w_kernel<2><<<((a.Q + 1) / 2 + R8W_WARPS - 1) / R8W_WARPS, R8W_WARPS * 32, 0, st>>>(a);
+        rescore8w_kernel<<<(a.Q + R8W_WARPS - 1) / R8W_WARPS, R8W_WARPS * 32, 0, st>>>(a);
         return;
     }
     const size_t sm = (size_t)FB_BUF * sizeof(uint64_t) + (size_t)a.M * a.K * sizeof(float);
