@@ -106,6 +106,7 @@ struct dpq_index {
                                // full pass (0: none; -1 auto: 4 for the wide shape with topk > 32)
     int opt_presample = 0;     // nodes scored exactly per query to seed the sample pass (0 auto: 2048, or 4096 for topk > 32)
     int opt_bcap8 = 0, opt_warps8 = 24, opt_levels8 = 80;  // bcap8 0 = auto (512 narrow, 2048 wide)
+    int opt_stight = 100;      // percent of the presample cap the first sampled pass accepts (100 = all of it)
     int64_t opt_coarse_min = 100000;  // nodes in the shard from which the coarse search pays (gpurun_out/probe22.log)
     int opt_dbg_bound = 0x8000;  // developer probe: initial exclusive bound (results are wrong below 0x8000)
     int chunk_nodes = 512;
@@ -593,6 +594,7 @@ int dpq_index_set_option(dpq_index* ix, const char* name, int64_t v) {
     else if (n == "slices_s") ix->opt_slices_s = (int)v;
     else if (n == "presample") ix->opt_presample = v <= 0 ? 0 : std::max(64, std::min(8192, (int)v));
     else if (n == "levels8") ix->opt_levels8 = std::max(31, std::min(123, (int)v));
+    else if (n == "stight") ix->opt_stight = std::max(50, std::min(100, (int)v));
     else return fail(DPQ_ERR_ARG, "unknown option " + n);
     return DPQ_OK;
 }
@@ -1044,7 +1046,12 @@ int dpq_index_search_device(dpq_index* ix, const float* d_queries, int Q, int to
             const int R = ix->opt_presample > 0 ? ix->opt_presample : (topk > 32 ? 4096 : 2048);
             if ((rc = ensure_sample_codes(ix, R))) return rc;
             dpq::launch_presample(se.lutf, ix->d_ps_codes.as<uint8_t>(), P.cstride, P.n_local, P.M, P.K, Q, topk, R, cap0, st);
-            dpq::launch_pack8(se.lutf, cap0, P.M, P.K, Q, levels8, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups, c8.nf, st);
+            // The first sampled pass only has to FIND k nodes below the presample cap, not all of them: quantising
+            // with levels8 * 100 / stight levels per cap while the test constant stays at levels8 accepts distances
+            // up to ~stight % of cap0 -- fewer survivors to append and re-score.  A query whose sample holds fewer than
+            // k such nodes keeps cap0 (valid, looser).
+            dpq::launch_pack8(se.lutf, cap0, P.M, P.K, Q, levels8 * 100 / ix->opt_stight, ix->d_qlut8.as<uint8_t>(), s8.ovf, g8_groups,
+                              c8.nf, st);
             s8.bt_stride = S;
             s8.n_slices = g8_slices_s;
             CU(dpq::launch_scan8(s8, st));
