@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(FB_T) fallback_kernel(const FallbackArgs a) {
     const int64_t lo = a.n_local * slice / n_slices, hi = a.n_local * (slice + 1) / n_slices;
     for (int f = blockIdx.y; f < n_flagged; f += gridDim.y) {
         const uint32_t q = a.flagged[f];
-        for (int i = threadIdx.x; i < MK; i += FB_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
+        stage_table(s_lut, a.lutf + (size_t)q * MK, MK, threadIdx.x, FB_T);
         if (threadIdx.x == 0) {
             s_n = 0u;
             // inclusive bound: every node with distance <= bound[q] (any position) is a candidate
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(R1_T) rescore1_kernel(const Rescore1Args a) {
     __shared__ int s_last, s_real;
     const int q = blockIdx.x, part = blockIdx.y, n_parts = gridDim.y;
     const int MK = a.M * a.K;
-    for (int i = threadIdx.x; i < MK; i += R1_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
+    stage_table(s_lut, a.lutf + (size_t)q * MK, MK, threadIdx.x, R1_T);
     if (threadIdx.x == 0) {
         s_n = 0u;
         s_thr = ~0ull;

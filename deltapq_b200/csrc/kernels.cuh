@@ -277,6 +277,19 @@ struct SelectArgs {
 };
 void launch_select(const SelectArgs& a, cudaStream_t st);
 
+// A query's float table [M*K] -> shared memory, 16 bytes per load and a thread's loads in flight together
+// (s_lut 16-byte aligned; the table rows of lutf are when M*K is a multiple of four)
+__device__ __forceinline__ void stage_table(float* s_lut, const float* __restrict__ src, int MK, int tid, int T) {
+    if ((MK & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(s_lut);
+#pragma unroll 4
+        for (int i = tid; i < MK / 4; i += T) d4[i] = __ldg(s4 + i);
+    } else {
+        for (int i = tid; i < MK; i += T) s_lut[i] = src[i];
+    }
+}
+
 // Exact distance of one node in the reference's arithmetic: float table entries summed in double.
 // The node's code is fetched with ONE vector load when the stride is 8 or 16 bytes (the code-array
 // engine): sixteen byte loads per candidate, each lane on another line, made the exact kernels

@@ -71,14 +71,7 @@ __global__ void __launch_bounds__(PS_T) presample_kernel(const float* __restrict
     __shared__ int s_cnt[2][PS_T / 32];
     const int q = blockIdx.x;
     const int MK = M * K;
-    if ((MK & 3) == 0) {  // 16-byte loads, all of a thread's in flight together
-        const float4* src = reinterpret_cast<const float4*>(lutf + (size_t)q * MK);
-        float4* dst = reinterpret_cast<float4*>(s_lut);
-#pragma unroll 4
-        for (int i = threadIdx.x; i < MK / 4; i += PS_T) dst[i] = __ldg(src + i);
-    } else {
-        for (int i = threadIdx.x; i < MK; i += PS_T) s_lut[i] = lutf[(size_t)q * MK + i];
-    }
+    stage_table(s_lut, lutf + (size_t)q * MK, MK, threadIdx.x, PS_T);
     __syncthreads();
     constexpr int PER = 16;  // R <= PS_T * PER
     constexpr int DROP = 17;  // pattern bits below the bucket
@@ -385,7 +378,7 @@ __global__ void __launch_bounds__(R8_T) rescore8_kernel(const Rescore8Args a) {
     const int n_sl = sl_hi - sl_lo;
     const int grp = q / a.qb, ql = q % a.qb;
     const int MK = a.M * a.K;
-    for (int i = threadIdx.x; i < MK; i += R8_T) s_lut[i] = a.lutf[(size_t)q * MK + i];
+    stage_table(s_lut, a.lutf + (size_t)q * MK, MK, threadIdx.x, R8_T);
     if (threadIdx.x < 32) {  // warp 0: counts of this part's slices, exclusive prefix
         const int lane = threadIdx.x;
         uint32_t run = 0;
