@@ -96,8 +96,10 @@ int dpq_index_set_stream(dpq_index* idx, void* cuda_stream);
 /* Tuning knobs (optional): "slices", "warps", "slack" (extra candidates re-scored exactly),
  * "epoch", "trigger", "ramp" (candidate collection of the 15-bit scan); "coarse" (-1 auto, 0 off,
  * 1 on), "sample", "seed" (1: the sample pass is a coarse scan seeded by an exact presample),
- * "refine" (stride of a second, denser sample pass), "levels8", "bcap8", "warps8", "coarse_min"
- * (coarse search); "latency" (-1 auto, 0 off, 1 on: lanes = nodes scan for a handful of queries);
+ * "refine" (stride of a second, denser sample pass; automatic on shards above 16.8M nodes), "stight"
+ * (percent of the presample cap the first sampled pass accepts, default 100), "presample", "parts8",
+ * "levels8", "bcap8", "warps8", "coarse_min" (coarse search); "latency" (-1 auto, 0 off, 1 on: lanes =
+ * nodes scan for a handful of queries);
  * first-generation engine only: "pack" (1 = 31-bit, 2 = 2x15-bit filter). */
 int dpq_index_set_option(dpq_index* idx, const char* name, int64_t value);
 
